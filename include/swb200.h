@@ -1,0 +1,184 @@
+/*
+ * swb200.h — C ABI of the B200-native swiftwatcher filtering/segmentation path.
+ *
+ * The reference (joshuacwnewton/swiftwatcher) is pure Python and has no FFI on
+ * this path; its seam is FrameQueue.preprocess_queue / FrameQueue.segment_queue
+ * (swiftwatcher/data_structures.py:171-217), which call the free functions of
+ * swiftwatcher/image_filtering.py once per 21-frame batch
+ * (swiftwatcher/__main__.py:77-78).  Every entry point below names the
+ * reference function(s) it replaces.  Plain pointers and sizes only; no
+ * torch / C++ types cross this boundary.  All functions return SWB_OK (0) or a
+ * negative error code; the message is available through swb_last_error().
+ * Nothing here ever falls back to the CPU: without a CUDA device every compute
+ * entry point fails with SWB_ERR_CUDA.
+ */
+#ifndef SWB200_H
+#define SWB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SWB_OK            0
+#define SWB_ERR_INVALID  -1   /* bad argument / configuration            */
+#define SWB_ERR_CUDA     -2   /* CUDA runtime error, or no device        */
+#define SWB_ERR_CAPACITY -3   /* more frames / segments than configured  */
+#define SWB_ERR_STATE    -4   /* call order (collect before submit, ...) */
+
+#define SWB_MEM_HOST   0      /* pointer is host memory (pinned or pageable) */
+#define SWB_MEM_DEVICE 1      /* pointer is device memory on cfg.device       */
+
+#define SWB_LABELS_I32 0      /* int32 labels 1..n, OpenCV numbering                         */
+#define SWB_LABELS_U8  1      /* reference behaviour: labels.astype(uint8)                   */
+                              /* (image_filtering.py:329) and regionprops of THAT image      */
+
+#define SWB_HALO_CARRY (-1)   /* n_halo value: use the history carried from the last submit  */
+
+#define SWB_OUT_MASK    1     /* flags: materialise the uint8 {0,255} foreground mask  */
+#define SWB_OUT_LABELS  2     /* flags: materialise the dense label image              */
+
+/* Pipeline configuration: the literals the reference hard-codes at its call
+ * sites (data_structures.py:194-206, __main__.py:78) made explicit. */
+typedef struct swb_config {
+    int32_t device;          /* CUDA device ordinal                                          */
+    int32_t frame_h;         /* full frame height (rows)                                     */
+    int32_t frame_w;         /* full frame width (pixels)                                    */
+    int32_t channels;        /* 3 = BGR interleaved uint8, 1 = already grayscale             */
+    int64_t frame_pitch;     /* bytes per frame row; 0 = frame_w * channels                  */
+    int64_t frame_stride;    /* bytes per frame; 0 = frame_h * frame_pitch                   */
+    int32_t roi_x0, roi_y0;  /* crop_region[0] = (x0, y0)   (image_filtering.py:199-203)     */
+    int32_t roi_x1, roi_y1;  /* crop_region[1] = (x1, y1), exclusive                         */
+    int32_t median_n;        /* temporal median window, odd, 1..9 (BASELINE: 5, 9)           */
+    int32_t threshold;       /* thresh_to_zero threshold, 15 at data_structures.py:198       */
+    int32_t morph_size;      /* square structuring element: 0 (none), 3 or 5                 */
+    int32_t do_open;         /* grey_opening  (data_structures.py:202)                       */
+    int32_t do_close;        /* grey_closing after the opening (BASELINE "open/close")       */
+    int32_t label_mode;      /* SWB_LABELS_I32 | SWB_LABELS_U8                               */
+    int32_t out_flags;       /* SWB_OUT_MASK | SWB_OUT_LABELS                                */
+    int32_t max_frames;      /* max output frames per submit                                 */
+    int32_t max_segments;    /* max segment rows per submit (0 = 1024 per frame)             */
+    int32_t reserved[3];
+} swb_config;
+
+/* One row of the per-frame segment table: what skimage.measure.regionprops
+ * (image_filtering.py:332-335) exposes and swiftwatcher consumes.
+ * centroid = (sum_row / area, sum_col / area) in float64 reproduces
+ * numpy's coords.mean(axis=0) bit-exactly (integer sums, one rounding). */
+typedef struct swb_segment {
+    int32_t frame;           /* output frame index within the submit (0-based)   */
+    int32_t label;           /* label value in the label image                   */
+    int32_t area;            /* pixel count                                      */
+    int32_t bbox[4];         /* (min_row, min_col, max_row, max_col), half-open  */
+    int32_t reserved;
+    int64_t sum_row;         /* sum of row coordinates over the segment's pixels */
+    int64_t sum_col;         /* sum of column coordinates                        */
+} swb_segment;
+
+typedef struct swb_ctx swb_ctx;
+
+/* Library / error plumbing ------------------------------------------------- */
+const char* swb_version(void);
+/* Message of the last error on `ctx` (or, with ctx == NULL, of the last failed
+ * call that had no context).  The reference has no error convention on this
+ * path (cv2.error / IndexError); the Python wrapper raises RuntimeError. */
+const char* swb_last_error(const swb_ctx* ctx);
+int swb_device_count(int32_t* count);
+
+/* Context ------------------------------------------------------------------ */
+/* One context per (GPU, video); owns all device memory and a stream.  Not
+ * thread-safe.  Replaces the FrameQueue batch state (data_structures.py:116-124). */
+int swb_create(const swb_config* cfg, swb_ctx** out);
+int swb_destroy(swb_ctx* ctx);
+/* Forget the carried temporal history (start of a new video). */
+int swb_reset(swb_ctx* ctx);
+/* Launch on an external CUDA stream (cudaStream_t passed as void*) instead of
+ * the context's own; NULL restores the own stream. */
+int swb_set_stream(swb_ctx* ctx, void* cuda_stream);
+
+/* The hot path ------------------------------------------------------------- */
+/* Replaces FrameQueue.preprocess_queue + segment_queue
+ * (data_structures.py:171-217): crop_frame, convert_grayscale, [rolling
+ * median + absdiff per BASELINE.json in place of rpca + bilateral_blur],
+ * thresh_to_zero, grayscale_opening[/closing], cc_labeling,
+ * get_segment_properties for `n_frames` consecutive frames.
+ *
+ * `frames` points at n_halo + n_frames full frames (oldest first) laid out as
+ * cfg.frame_stride / frame_pitch say.  The first n_halo frames are temporal
+ * history only (0 <= n_halo <= median_n - 1); history that is not supplied is
+ * the earliest supplied frame replicated.  n_halo == SWB_HALO_CARRY uses the
+ * history the context carried over from the previous submit instead.
+ * Asynchronous on the context's stream; the caller keeps `frames` alive until
+ * swb_collect / swb_sync returns. */
+int swb_submit(swb_ctx* ctx, const uint8_t* frames, int32_t n_frames,
+               int32_t n_halo, int32_t mem_kind);
+
+/* Waits for the last submit and copies its segment table to host memory.
+ * rows: capacity `cap` rows, ordered by (frame, label); per_frame_counts:
+ * n_frames entries (may be NULL).  Replaces get_segment_properties over the
+ * queue (data_structures.py:210). */
+int swb_collect(swb_ctx* ctx, swb_segment* rows, int64_t cap, int64_t* n_rows,
+                int32_t* per_frame_counts);
+int swb_sync(swb_ctx* ctx);
+
+/* Dense per-frame outputs of the last submit, frames [t0, t0 + n):
+ * mask: uint8 {0,255}, == (opened > 0) of data_structures.py:202-204;
+ * labels: int32 (SWB_LABELS_I32) or uint8 (SWB_LABELS_U8), data_structures.py:206.
+ * dst is tightly packed [n][roi_h][roi_w]. */
+int swb_get_masks(swb_ctx* ctx, int32_t t0, int32_t n, uint8_t* dst, int32_t mem_kind);
+int swb_get_labels(swb_ctx* ctx, int32_t t0, int32_t n, void* dst, int32_t mem_kind);
+/* Bit-packed final mask (1 bit/pixel, little-endian bit order inside uint32
+ * words, words_per_row = ceil(roi_w / 32)), tightly packed. */
+int swb_get_mask_bits(swb_ctx* ctx, int32_t t0, int32_t n, uint32_t* dst, int32_t mem_kind);
+/* Zero-copy views of the context-owned output buffers (device pointers). */
+int swb_device_views(swb_ctx* ctx, uint8_t** mask, int64_t* mask_pitch,
+                     void** labels, int64_t* labels_pitch_elems,
+                     swb_segment** rows, int32_t** per_frame_counts);
+
+/* Per-kernel device timing of the last submit (CUDA events on the launch
+ * stream).  names: up to `cap` static strings; ms: milliseconds. */
+int swb_enable_timing(swb_ctx* ctx, int32_t on);
+int swb_get_timing(swb_ctx* ctx, const char** names, float* ms, int32_t cap, int32_t* n);
+/* Number of kernels launched by this context since creation. */
+int64_t swb_launch_count(const swb_ctx* ctx);
+
+/* Batched segment crops for the classifier: extract_segment_images
+ * (image_filtering.py:338-369) for every row of the last submit's table, as
+ * fixed crop x crop x channels tiles gathered from the full frames that were
+ * submitted; out-of-frame pixels are zero.  dst: [n_rows][crop][crop][channels]. */
+int swb_gather_crops(swb_ctx* ctx, int32_t crop, uint8_t* dst, int32_t mem_kind);
+
+/* Single-stage entry points: one reference function each, host buffers in/out,
+ * tightly packed.  They exist so that each reference function has a drop-in
+ * with the same meaning; the fused swb_submit path is the fast one. -------- */
+/* convert_grayscale, image_filtering.py:188-196 (cv2 BGR2GRAY, 15-bit fixed point). */
+int swb_stage_gray(int32_t device, const uint8_t* bgr, int32_t h, int32_t w, uint8_t* out);
+/* rolling temporal median of n (odd, <= 9) gray frames [n][h][w] (no reference fn). */
+int swb_stage_median(int32_t device, const uint8_t* stack, int32_t n, int32_t h, int32_t w, uint8_t* out);
+/* cv2.absdiff (no reference fn). */
+int swb_stage_absdiff(int32_t device, const uint8_t* a, const uint8_t* b, int32_t h, int32_t w, uint8_t* out);
+/* thresh_to_zero, image_filtering.py:310-316. */
+int swb_stage_thresh_to_zero(int32_t device, const uint8_t* in, int32_t h, int32_t w, int32_t thresh, uint8_t* out);
+/* grayscale_opening (closing=0), image_filtering.py:319-322, or its dual (closing=1);
+ * flat se_h x se_w structuring element, scipy 'reflect' border. */
+int swb_stage_grey_morph(int32_t device, const uint8_t* in, int32_t h, int32_t w,
+                         int32_t se_h, int32_t se_w, int32_t closing, uint8_t* out);
+/* cc_labeling, image_filtering.py:325-329: 8-connected, OpenCV numbering.
+ * out_i32 and/or out_u8 may be NULL. */
+int swb_stage_cc_label(int32_t device, const uint8_t* in, int32_t h, int32_t w,
+                       int32_t* out_i32, uint8_t* out_u8, int32_t* n_labels);
+/* get_segment_properties, image_filtering.py:332-335, on a uint8 or int32
+ * label image (elem_size 1 or 4).  Rows ordered by label. */
+int swb_stage_regionprops(int32_t device, const void* labels, int32_t elem_size,
+                          int32_t h, int32_t w, swb_segment* rows, int32_t cap, int32_t* n_rows);
+
+/* Synthetic video (bench / tests): frames t0..t0+n-1 of the seeded generator,
+ * bit-identical to oracle/synth.py.  dst: [n][h][w][3] uint8. */
+int swb_synth_frames(int32_t device, uint8_t* dst, int32_t mem_kind, uint32_t seed, uint32_t video,
+                     int32_t t0, int32_t n, int32_t h, int32_t w, int32_t n_birds);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWB200_H */

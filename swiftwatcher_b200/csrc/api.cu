@@ -1,0 +1,775 @@
+// C ABI of libswb200 (include/swb200.h): context, buffers, streams, launch order.
+// Host side only; the kernels live in fg_bits.cu / morph_mask.cu / ccl.cu /
+// stages.cu / synth.cu.  There is no CPU fallback anywhere in this file: every
+// compute entry point needs a CUDA device and reports SWB_ERR_CUDA without one.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "swb_internal.cuh"
+
+using namespace swb;
+
+namespace {
+
+thread_local std::string g_error;
+
+constexpr int N_TIMERS = 6;
+const char* const TIMER_NAMES[N_TIMERS] = {"fg_bits",   "morph_mask", "ccl_merge",
+                                           "ccl_rank",  "ccl_label",  "write_labels"};
+
+}  // namespace
+
+struct swb_ctx {
+    swb_config cfg;
+    Geom g;
+    MorphCfg morph;
+    int X0a;
+    int label_elem;
+    int cap_rows;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    // device buffers
+    uint8_t* in_buf = nullptr;      // host-mode staging: [N-1 + max_frames][h][in_pitch]
+    size_t in_buf_bytes = 0;
+    long long in_pitch = 0, in_stride = 0;
+    uint8_t* hist[2] = {nullptr, nullptr};
+    int hist_cur = 0;
+    bool hist_has = false;
+    uint16_t* raw_bits = nullptr;
+    uint32_t* fbits = nullptr;
+    uint8_t* mask = nullptr;
+    void* labels = nullptr;
+    CclBuffers ccl{};
+    // host staging (pinned)
+    int32_t* h_segoff = nullptr;
+    int32_t* h_overflow = nullptr;
+    // state of the last submit
+    int last_T = 0;
+    bool pending = false;
+    const uint8_t* last_frames_dev = nullptr;   // frame 0 (first OUTPUT frame) of full frames on device, or null
+    long long last_stride = 0, last_pitch = 0;
+    int64_t launches = 0;
+    // timing
+    bool timing = false;
+    cudaEvent_t ev[N_TIMERS + 1] = {};
+    bool ev_valid = false;
+    std::string error;
+};
+
+namespace {
+
+int fail(swb_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->error = buf;
+    g_error = buf;
+    return code;
+}
+
+#define CU(ctx, call)                                                                         \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return fail(ctx, SWB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                                  \
+    } while (0)
+
+int select_device(swb_ctx* ctx, int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        return fail(ctx, SWB_ERR_CUDA, "no CUDA device available (%s); libswb200 has no CPU path",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= n) return fail(ctx, SWB_ERR_INVALID, "device %d out of range [0,%d)", device, n);
+    CU(ctx, cudaSetDevice(device));
+    return SWB_OK;
+}
+
+template <typename T>
+cudaError_t dalloc(T** p, size_t count) {
+    return cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(count, 1) * sizeof(T));
+}
+
+void make_geom(int roi_x0, int roi_y0, int roi_x1, int roi_y1, Geom& g, int& X0a) {
+    X0a = roi_x0 & ~31;
+    g.h = roi_y1 - roi_y0;
+    g.w = roi_x1 - roi_x0;
+    g.dx = roi_x0 - X0a;
+    g.wa = ((roi_x1 + 31) & ~31) - X0a;
+    g.wpr_raw = g.wa / 32;
+    g.wpr = (g.w + 31) / 32;
+    g.mpitch = g.wpr * 32;
+    g.BH = (g.h + 1) / 2;
+    g.BW = 16 * g.wpr;
+}
+
+int make_morph(swb_ctx* ctx, int size, int do_open, int do_close, MorphCfg& m) {
+    memset(&m, 0, sizeof(m));
+    if (size == 0 || (!do_open && !do_close)) {
+        m.radius = 1;
+        m.n_ops = 0;
+        return SWB_OK;
+    }
+    if (size != 3 && size != 5) return fail(ctx, SWB_ERR_INVALID, "morph_size must be 0, 3 or 5 (got %d)", size);
+    m.radius = size / 2;
+    int k = 0;
+    if (do_open) { m.is_erode[k++] = 1; m.is_erode[k++] = 0; }
+    if (do_close) { m.is_erode[k++] = 0; m.is_erode[k++] = 1; }
+    m.n_ops = k;
+    return SWB_OK;
+}
+
+void free_ctx_buffers(swb_ctx* c) {
+    cudaFree(c->in_buf);
+    cudaFree(c->hist[0]);
+    cudaFree(c->hist[1]);
+    cudaFree(c->raw_bits);
+    cudaFree(c->fbits);
+    cudaFree(c->mask);
+    cudaFree(c->labels);
+    cudaFree(c->ccl.parent);
+    cudaFree(c->ccl.blocklabel);
+    cudaFree(c->ccl.rootbits);
+    cudaFree(c->ccl.wordbase);
+    cudaFree(c->ccl.rowcount);
+    cudaFree(c->ccl.nseg);
+    cudaFree(c->ccl.segoff);
+    cudaFree(c->ccl.rows);
+    cudaFree(c->ccl.overflow);
+    if (c->h_segoff) cudaFreeHost(c->h_segoff);
+    if (c->h_overflow) cudaFreeHost(c->h_overflow);
+    for (auto& e : c->ev)
+        if (e) cudaEventDestroy(e);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+}
+
+int alloc_ccl(swb_ctx* ctx, CclBuffers& b, const Geom& g, int T, int cap_rows) {
+    const size_t nblk = (size_t)T * g.BH * g.BW;
+    const size_t nwords = (size_t)T * g.BH * g.wpr;
+    CU(ctx, dalloc(&b.parent, nblk));
+    CU(ctx, dalloc(&b.blocklabel, nblk));
+    CU(ctx, dalloc(&b.rootbits, nwords));
+    CU(ctx, dalloc(&b.wordbase, nwords));
+    CU(ctx, dalloc(&b.rowcount, (size_t)T * g.BH));
+    CU(ctx, dalloc(&b.nseg, (size_t)T));
+    CU(ctx, dalloc(&b.segoff, (size_t)T + 1));
+    CU(ctx, dalloc(&b.rows, (size_t)cap_rows));
+    CU(ctx, dalloc(&b.overflow, 1));
+    b.cap_rows = cap_rows;
+    return SWB_OK;
+}
+
+// reference behaviour for label_mode U8: regionprops of labels.astype(uint8)
+// (image_filtering.py:329,335): components whose int32 labels agree mod 256 form
+// one region; labels that are 0 mod 256 disappear into the background.
+int64_t merge_u8(const swb_segment* in, const int32_t* off, int T, swb_segment* out, int64_t cap,
+                 int32_t* counts, bool& overflow) {
+    int64_t n_out = 0;
+    overflow = false;
+    std::vector<swb_segment> acc(256);
+    std::vector<char> used(256);
+    for (int f = 0; f < T; ++f) {
+        std::fill(used.begin(), used.end(), 0);
+        for (int32_t i = off[f]; i < off[f + 1]; ++i) {
+            const swb_segment& s = in[i];
+            const int v = s.label & 0xFF;
+            if (v == 0) continue;
+            if (!used[v]) {
+                used[v] = 1;
+                acc[v] = s;
+                acc[v].label = v;
+            } else {
+                swb_segment& a = acc[v];
+                a.area += s.area;
+                a.bbox[0] = std::min(a.bbox[0], s.bbox[0]);
+                a.bbox[1] = std::min(a.bbox[1], s.bbox[1]);
+                a.bbox[2] = std::max(a.bbox[2], s.bbox[2]);
+                a.bbox[3] = std::max(a.bbox[3], s.bbox[3]);
+                a.sum_row += s.sum_row;
+                a.sum_col += s.sum_col;
+            }
+        }
+        int32_t cnt = 0;
+        for (int v = 1; v < 256; ++v) {
+            if (!used[v]) continue;
+            if (n_out < cap) out[n_out] = acc[v];
+            else overflow = true;
+            ++n_out;
+            ++cnt;
+        }
+        if (counts) counts[f] = cnt;
+    }
+    return n_out;
+}
+
+}  // namespace
+
+namespace {
+struct DevTmp {
+    std::vector<void*> ptrs;
+    ~DevTmp() {
+        for (void* p : ptrs) cudaFree(p);
+    }
+    template <typename T>
+    cudaError_t alloc(T** p, size_t count) {
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(count, 1) * sizeof(T));
+        if (e == cudaSuccess) ptrs.push_back(*p);
+        return e;
+    }
+};
+}  // namespace
+
+
+extern "C" {
+
+const char* swb_version(void) { return "swb200 0.1 (sm_100a)"; }
+
+const char* swb_last_error(const swb_ctx* ctx) { return ctx ? ctx->error.c_str() : g_error.c_str(); }
+
+int swb_device_count(int32_t* count) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (count) *count = (e == cudaSuccess) ? n : 0;
+    if (e != cudaSuccess) return fail(nullptr, SWB_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return SWB_OK;
+}
+
+int swb_create(const swb_config* cfg, swb_ctx** out) {
+    if (!cfg || !out) return fail(nullptr, SWB_ERR_INVALID, "null argument");
+    *out = nullptr;
+    swb_config c = *cfg;
+    if (c.frame_h <= 0 || c.frame_w <= 0) return fail(nullptr, SWB_ERR_INVALID, "bad frame size %dx%d", c.frame_w, c.frame_h);
+    if (c.channels != 1 && c.channels != 3) return fail(nullptr, SWB_ERR_INVALID, "channels must be 1 or 3");
+    if (c.frame_pitch == 0) c.frame_pitch = (int64_t)c.frame_w * c.channels;
+    if (c.frame_stride == 0) c.frame_stride = (int64_t)c.frame_h * c.frame_pitch;
+    if (c.frame_pitch < (int64_t)c.frame_w * c.channels || c.frame_stride < c.frame_pitch * c.frame_h)
+        return fail(nullptr, SWB_ERR_INVALID, "frame_pitch / frame_stride too small");
+    if (c.roi_x0 == 0 && c.roi_x1 == 0 && c.roi_y0 == 0 && c.roi_y1 == 0) {
+        c.roi_x1 = c.frame_w;
+        c.roi_y1 = c.frame_h;
+    }
+    if (c.roi_x0 < 0 || c.roi_y0 < 0 || c.roi_x1 > c.frame_w || c.roi_y1 > c.frame_h || c.roi_x1 <= c.roi_x0 ||
+        c.roi_y1 <= c.roi_y0)
+        return fail(nullptr, SWB_ERR_INVALID, "ROI [(%d,%d),(%d,%d)] not inside the %dx%d frame", c.roi_x0, c.roi_y0,
+                    c.roi_x1, c.roi_y1, c.frame_w, c.frame_h);
+    if (c.median_n < 1 || c.median_n > 9 || (c.median_n & 1) == 0)
+        return fail(nullptr, SWB_ERR_INVALID, "median_n must be odd and in 1..9 (got %d)", c.median_n);
+    if (c.threshold < 0 || c.threshold > 255) return fail(nullptr, SWB_ERR_INVALID, "threshold must be in 0..255");
+    if (c.label_mode != SWB_LABELS_I32 && c.label_mode != SWB_LABELS_U8)
+        return fail(nullptr, SWB_ERR_INVALID, "bad label_mode %d", c.label_mode);
+    if (c.max_frames <= 0 || c.max_frames > 32768) return fail(nullptr, SWB_ERR_INVALID, "max_frames must be in 1..32768");
+    if (c.max_segments <= 0) c.max_segments = 1024 * c.max_frames;
+
+    swb_ctx* ctx = new swb_ctx();
+    ctx->cfg = c;
+    int rc = make_morph(ctx, c.morph_size, c.do_open, c.do_close, ctx->morph);
+    if (rc != SWB_OK) { delete ctx; return rc; }
+    make_geom(c.roi_x0, c.roi_y0, c.roi_x1, c.roi_y1, ctx->g, ctx->X0a);
+    ctx->label_elem = (c.label_mode == SWB_LABELS_U8) ? 1 : 4;
+    ctx->cap_rows = c.max_segments;
+
+    auto bail = [&](int code) {
+        std::string msg = ctx->error;
+        free_ctx_buffers(ctx);
+        delete ctx;
+        g_error = msg;
+        return code;
+    };
+    rc = select_device(ctx, c.device);
+    if (rc != SWB_OK) return bail(rc);
+
+    const Geom& g = ctx->g;
+    const int T = c.max_frames;
+    const int nh = c.median_n - 1;
+#define CUB(call)                                                                                   \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess) {                                                                   \
+            fail(ctx, SWB_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__));               \
+            return bail(SWB_ERR_CUDA);                                                              \
+        }                                                                                           \
+    } while (0)
+    CUB(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    if (nh > 0) {
+        CUB(dalloc(&ctx->hist[0], (size_t)nh * g.h * g.wa));
+        CUB(dalloc(&ctx->hist[1], (size_t)nh * g.h * g.wa));
+    }
+    CUB(dalloc(&ctx->raw_bits, (size_t)T * g.h * g.wpr_raw * 2 + 8));
+    CUB(dalloc(&ctx->fbits, (size_t)T * g.h * g.wpr));
+    if (c.out_flags & SWB_OUT_MASK) CUB(dalloc(&ctx->mask, (size_t)T * g.h * g.mpitch));
+    if (c.out_flags & SWB_OUT_LABELS)
+        CUB(cudaMalloc(&ctx->labels, (size_t)T * g.h * g.mpitch * ctx->label_elem));
+    rc = alloc_ccl(ctx, ctx->ccl, g, T, ctx->cap_rows);
+    if (rc != SWB_OK) return bail(rc);
+    CUB(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_segoff), ((size_t)T + 1) * sizeof(int32_t)));
+    CUB(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_overflow), sizeof(int32_t)));
+    for (auto& e : ctx->ev) CUB(cudaEventCreate(&e));
+#undef CUB
+    *out = ctx;
+    return SWB_OK;
+}
+
+int swb_destroy(swb_ctx* ctx) {
+    if (!ctx) return SWB_OK;
+    cudaSetDevice(ctx->cfg.device);
+    cudaStreamSynchronize(ctx->stream);
+    free_ctx_buffers(ctx);
+    delete ctx;
+    return SWB_OK;
+}
+
+int swb_reset(swb_ctx* ctx) {
+    if (!ctx) return fail(nullptr, SWB_ERR_INVALID, "null context");
+    ctx->hist_has = false;
+    return SWB_OK;
+}
+
+int swb_set_stream(swb_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return fail(nullptr, SWB_ERR_INVALID, "null context");
+    CU(ctx, cudaSetDevice(ctx->cfg.device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return SWB_OK;
+}
+
+int swb_submit(swb_ctx* ctx, const uint8_t* frames, int32_t n_frames, int32_t n_halo, int32_t mem_kind) {
+    if (!ctx) return fail(nullptr, SWB_ERR_INVALID, "null context");
+    const swb_config& c = ctx->cfg;
+    const Geom& g = ctx->g;
+    const int N = c.median_n;
+    if (!frames) return fail(ctx, SWB_ERR_INVALID, "null frames");
+    if (n_frames <= 0 || n_frames > c.max_frames)
+        return fail(ctx, SWB_ERR_CAPACITY, "n_frames %d outside 1..max_frames (%d)", n_frames, c.max_frames);
+    if (n_halo != SWB_HALO_CARRY && (n_halo < 0 || n_halo > N - 1))
+        return fail(ctx, SWB_ERR_INVALID, "n_halo %d outside 0..%d", n_halo, N - 1);
+    if (mem_kind != SWB_MEM_HOST && mem_kind != SWB_MEM_DEVICE) return fail(ctx, SWB_ERR_INVALID, "bad mem_kind");
+    CU(ctx, cudaSetDevice(c.device));
+    cudaStream_t s = ctx->stream;
+    const int inline_halo = n_halo == SWB_HALO_CARRY ? 0 : n_halo;
+    const int n_total = inline_halo + n_frames;
+    const int C = c.channels;
+
+    FrameSrc src{};
+    bool aligned;
+    if (mem_kind == SWB_MEM_HOST) {
+        // stage only the (32-pixel aligned) ROI columns / rows of every frame
+        const long long in_pitch = (long long)g.wa * C;
+        const long long in_stride = in_pitch * g.h;
+        const size_t need = (size_t)in_stride * (c.max_frames + N - 1) + 256;
+        if (!ctx->in_buf) {
+            CU(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->in_buf), need));
+            ctx->in_buf_bytes = need;
+            ctx->in_pitch = in_pitch;
+            ctx->in_stride = in_stride;
+        }
+        const int copy_px = std::min(g.wa, c.frame_w - ctx->X0a);
+        const uint8_t* sbase = frames + (long long)c.roi_y0 * c.frame_pitch + (long long)ctx->X0a * C;
+        if (copy_px == c.frame_w && g.h == c.frame_h && c.frame_pitch == in_pitch && c.frame_stride == in_stride) {
+            CU(ctx, cudaMemcpyAsync(ctx->in_buf, frames, (size_t)in_stride * n_total, cudaMemcpyHostToDevice, s));
+        } else if (c.frame_stride % c.frame_pitch == 0) {
+            cudaMemcpy3DParms p;
+            memset(&p, 0, sizeof(p));
+            p.srcPtr = make_cudaPitchedPtr(const_cast<uint8_t*>(sbase), (size_t)c.frame_pitch,
+                                           (size_t)c.frame_pitch, (size_t)(c.frame_stride / c.frame_pitch));
+            p.dstPtr = make_cudaPitchedPtr(ctx->in_buf, (size_t)in_pitch, (size_t)in_pitch, (size_t)g.h);
+            p.extent = make_cudaExtent((size_t)copy_px * C, (size_t)g.h, (size_t)n_total);
+            p.kind = cudaMemcpyHostToDevice;
+            CU(ctx, cudaMemcpy3DAsync(&p, s));
+        } else {
+            for (int f = 0; f < n_total; ++f)
+                CU(ctx, cudaMemcpy2DAsync(ctx->in_buf + (long long)f * in_stride, (size_t)in_pitch,
+                                          sbase + (long long)f * c.frame_stride, (size_t)c.frame_pitch,
+                                          (size_t)copy_px * C, (size_t)g.h, cudaMemcpyHostToDevice, s));
+        }
+        src.cur = ctx->in_buf + (long long)inline_halo * in_stride;
+        src.frame_stride = in_stride;
+        src.pitch = in_pitch;
+        src.avail_w = g.wa;
+        aligned = true;
+        const bool full = (ctx->X0a == 0 && c.roi_y0 == 0 && g.h == c.frame_h && g.wa >= c.frame_w);
+        ctx->last_frames_dev = full ? src.cur : nullptr;
+        ctx->last_stride = in_stride;
+        ctx->last_pitch = in_pitch;
+    } else {
+        const uint8_t* f0 = frames + (long long)inline_halo * c.frame_stride;
+        src.cur = f0 + (long long)c.roi_y0 * c.frame_pitch + (long long)ctx->X0a * C;
+        src.frame_stride = c.frame_stride;
+        src.pitch = c.frame_pitch;
+        src.avail_w = c.frame_w - ctx->X0a;
+        aligned = (reinterpret_cast<uintptr_t>(src.cur) % 16 == 0) && (c.frame_pitch % 16 == 0) &&
+                  (c.frame_stride % 16 == 0) && (ctx->X0a + g.wa <= c.frame_w);
+        ctx->last_frames_dev = f0;
+        ctx->last_stride = c.frame_stride;
+        ctx->last_pitch = c.frame_pitch;
+    }
+    src.n_inline_halo = inline_halo;
+    src.hist_valid = (n_halo == SWB_HALO_CARRY && ctx->hist_has && N > 1) ? 1 : 0;
+    src.hist = ctx->hist[ctx->hist_cur];
+    src.hist_out = (N > 1) ? ctx->hist[ctx->hist_cur ^ 1] : nullptr;
+
+    int launches = 0;
+    if (ctx->timing) CU(ctx, cudaEventRecord(ctx->ev[0], s));
+    CU(ctx, launch_fg_bits(s, src, C, N, n_frames, g, c.threshold, ctx->raw_bits, aligned, &launches));
+    if (ctx->timing) CU(ctx, cudaEventRecord(ctx->ev[1], s));
+    CU(ctx, launch_morph_mask(s, reinterpret_cast<const uint32_t*>(ctx->raw_bits), n_frames, g, ctx->morph,
+                              ctx->fbits, ctx->mask, &launches));
+    if (ctx->timing) CU(ctx, cudaEventRecord(ctx->ev[2], s));
+    CU(ctx, cudaMemsetAsync(ctx->ccl.overflow, 0, sizeof(int32_t), s));
+    CU(ctx, launch_ccl(s, ctx->fbits, n_frames, g, ctx->ccl, ctx->labels, ctx->label_elem, &launches,
+                       ctx->timing ? &ctx->ev[3] : nullptr, 4));
+    ctx->ev_valid = ctx->timing;
+    ctx->launches += launches;
+    if (N > 1) {
+        ctx->hist_cur ^= 1;
+        ctx->hist_has = true;
+    }
+    ctx->last_T = n_frames;
+    ctx->pending = true;
+    return SWB_OK;
+}
+
+int swb_sync(swb_ctx* ctx) {
+    if (!ctx) return fail(nullptr, SWB_ERR_INVALID, "null context");
+    CU(ctx, cudaSetDevice(ctx->cfg.device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SWB_OK;
+}
+
+int swb_collect(swb_ctx* ctx, swb_segment* rows, int64_t cap, int64_t* n_rows, int32_t* per_frame_counts) {
+    if (!ctx) return fail(nullptr, SWB_ERR_INVALID, "null context");
+    if (!ctx->pending) return fail(ctx, SWB_ERR_STATE, "swb_collect without a preceding swb_submit");
+    CU(ctx, cudaSetDevice(ctx->cfg.device));
+    cudaStream_t s = ctx->stream;
+    const int T = ctx->last_T;
+    CU(ctx, cudaMemcpyAsync(ctx->h_segoff, ctx->ccl.segoff, ((size_t)T + 1) * sizeof(int32_t),
+                            cudaMemcpyDeviceToHost, s));
+    CU(ctx, cudaMemcpyAsync(ctx->h_overflow, ctx->ccl.overflow, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CU(ctx, cudaStreamSynchronize(s));
+    const int64_t total = ctx->h_segoff[T];
+    if (*ctx->h_overflow || total > ctx->cap_rows)
+        return fail(ctx, SWB_ERR_CAPACITY, "%lld segments in this submit exceed max_segments (%d)", (long long)total,
+                    ctx->cap_rows);
+    if (ctx->cfg.label_mode == SWB_LABELS_I32) {
+        if (n_rows) *n_rows = total;
+        if (per_frame_counts)
+            for (int f = 0; f < T; ++f) per_frame_counts[f] = ctx->h_segoff[f + 1] - ctx->h_segoff[f];
+        if (total > cap) return fail(ctx, SWB_ERR_CAPACITY, "%lld rows do not fit the caller's %lld", (long long)total, (long long)cap);
+        if (total > 0 && rows) {
+            CU(ctx, cudaMemcpyAsync(rows, ctx->ccl.rows, (size_t)total * sizeof(swb_segment), cudaMemcpyDeviceToHost, s));
+            CU(ctx, cudaStreamSynchronize(s));
+        }
+    } else {
+        std::vector<swb_segment> tmp((size_t)std::max<int64_t>(total, 1));
+        if (total > 0) {
+            CU(ctx, cudaMemcpyAsync(tmp.data(), ctx->ccl.rows, (size_t)total * sizeof(swb_segment),
+                                    cudaMemcpyDeviceToHost, s));
+            CU(ctx, cudaStreamSynchronize(s));
+        }
+        bool ovf = false;
+        const int64_t n = merge_u8(tmp.data(), ctx->h_segoff, T, rows, rows ? cap : 0, per_frame_counts, ovf);
+        if (n_rows) *n_rows = n;
+        if (ovf && rows) return fail(ctx, SWB_ERR_CAPACITY, "%lld rows do not fit the caller's %lld", (long long)n, (long long)cap);
+    }
+    return SWB_OK;
+}
+
+static int copy_out(swb_ctx* ctx, const void* src, size_t elem, int32_t t0, int32_t n, void* dst, int32_t mem_kind) {
+    const Geom& g = ctx->g;
+    if (!ctx->pending) return fail(ctx, SWB_ERR_STATE, "no submit to read from");
+    if (!src) return fail(ctx, SWB_ERR_STATE, "this output was not enabled in swb_config.out_flags");
+    if (t0 < 0 || n < 0 || t0 + n > ctx->last_T) return fail(ctx, SWB_ERR_INVALID, "frame range [%d,%d) outside 0..%d", t0, t0 + n, ctx->last_T);
+    if (n == 0) return SWB_OK;
+    CU(ctx, cudaSetDevice(ctx->cfg.device));
+    const uint8_t* sp = static_cast<const uint8_t*>(src) + (size_t)t0 * g.h * g.mpitch * elem;
+    CU(ctx, cudaMemcpy2DAsync(dst, (size_t)g.w * elem, sp, (size_t)g.mpitch * elem, (size_t)g.w * elem,
+                              (size_t)n * g.h, mem_kind == SWB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                              ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SWB_OK;
+}
+
+int swb_get_masks(swb_ctx* ctx, int32_t t0, int32_t n, uint8_t* dst, int32_t mem_kind) {
+    if (!ctx || !dst) return fail(ctx, SWB_ERR_INVALID, "null argument");
+    return copy_out(ctx, ctx->mask, 1, t0, n, dst, mem_kind);
+}
+
+int swb_get_labels(swb_ctx* ctx, int32_t t0, int32_t n, void* dst, int32_t mem_kind) {
+    if (!ctx || !dst) return fail(ctx, SWB_ERR_INVALID, "null argument");
+    return copy_out(ctx, ctx->labels, (size_t)ctx->label_elem, t0, n, dst, mem_kind);
+}
+
+int swb_get_mask_bits(swb_ctx* ctx, int32_t t0, int32_t n, uint32_t* dst, int32_t mem_kind) {
+    if (!ctx || !dst) return fail(ctx, SWB_ERR_INVALID, "null argument");
+    if (!ctx->pending) return fail(ctx, SWB_ERR_STATE, "no submit to read from");
+    if (t0 < 0 || n < 0 || t0 + n > ctx->last_T) return fail(ctx, SWB_ERR_INVALID, "bad frame range");
+    CU(ctx, cudaSetDevice(ctx->cfg.device));
+    const Geom& g = ctx->g;
+    const size_t per = (size_t)g.h * g.wpr;
+    CU(ctx, cudaMemcpyAsync(dst, ctx->fbits + per * t0, per * n * sizeof(uint32_t),
+                            mem_kind == SWB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SWB_OK;
+}
+
+int swb_device_views(swb_ctx* ctx, uint8_t** mask, int64_t* mask_pitch, void** labels, int64_t* labels_pitch_elems,
+                     swb_segment** rows, int32_t** per_frame_counts) {
+    if (!ctx) return fail(nullptr, SWB_ERR_INVALID, "null context");
+    if (mask) *mask = ctx->mask;
+    if (mask_pitch) *mask_pitch = ctx->g.mpitch;
+    if (labels) *labels = ctx->labels;
+    if (labels_pitch_elems) *labels_pitch_elems = ctx->g.mpitch;
+    if (rows) *rows = ctx->ccl.rows;
+    if (per_frame_counts) *per_frame_counts = ctx->ccl.nseg;
+    return SWB_OK;
+}
+
+int swb_enable_timing(swb_ctx* ctx, int32_t on) {
+    if (!ctx) return fail(nullptr, SWB_ERR_INVALID, "null context");
+    ctx->timing = on != 0;
+    ctx->ev_valid = false;
+    return SWB_OK;
+}
+
+int swb_get_timing(swb_ctx* ctx, const char** names, float* ms, int32_t cap, int32_t* n) {
+    if (!ctx) return fail(nullptr, SWB_ERR_INVALID, "null context");
+    if (!ctx->ev_valid) return fail(ctx, SWB_ERR_STATE, "timing not enabled for the last submit");
+    CU(ctx, cudaSetDevice(ctx->cfg.device));
+    CU(ctx, cudaEventSynchronize(ctx->ev[N_TIMERS]));
+    const int k = std::min<int>(cap, N_TIMERS);
+    for (int i = 0; i < k; ++i) {
+        if (names) names[i] = TIMER_NAMES[i];
+        if (ms) CU(ctx, cudaEventElapsedTime(&ms[i], ctx->ev[i], ctx->ev[i + 1]));
+    }
+    if (n) *n = k;
+    return SWB_OK;
+}
+
+int64_t swb_launch_count(const swb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int swb_gather_crops(swb_ctx* ctx, int32_t crop, uint8_t* dst, int32_t mem_kind) {
+    if (!ctx || !dst) return fail(ctx, SWB_ERR_INVALID, "null argument");
+    if (!ctx->pending) return fail(ctx, SWB_ERR_STATE, "no submit to read from");
+    if (!ctx->last_frames_dev)
+        return fail(ctx, SWB_ERR_STATE, "full frames are not resident on the device (host submit with a partial ROI); "
+                                        "crop on the host instead");
+    if (crop <= 0 || crop > 256) return fail(ctx, SWB_ERR_INVALID, "crop must be in 1..256");
+    if (ctx->cfg.label_mode != SWB_LABELS_I32)
+        return fail(ctx, SWB_ERR_STATE, "swb_gather_crops needs label_mode SWB_LABELS_I32");
+    const swb_config& c = ctx->cfg;
+    CU(ctx, cudaSetDevice(c.device));
+    cudaStream_t s = ctx->stream;
+    const int T = ctx->last_T;
+    CU(ctx, cudaMemcpyAsync(ctx->h_segoff, ctx->ccl.segoff, ((size_t)T + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CU(ctx, cudaStreamSynchronize(s));
+    const int total = std::min<int>(ctx->h_segoff[T], ctx->cap_rows);
+    if (total == 0) return SWB_OK;
+    const size_t bytes = (size_t)total * crop * crop * c.channels;
+    uint8_t* d = dst;
+    uint8_t* tmp = nullptr;
+    if (mem_kind == SWB_MEM_HOST) {
+        CU(ctx, cudaMalloc(reinterpret_cast<void**>(&tmp), bytes));
+        d = tmp;
+    }
+    cudaError_t e = launch_gather_crops_n(s, ctx->last_frames_dev, ctx->last_stride, ctx->last_pitch, c.channels,
+                                          c.frame_h, c.frame_w, c.roi_x0, c.roi_y0, ctx->ccl.rows, total, crop, d);
+    ctx->launches += 1;
+    if (e == cudaSuccess && tmp) e = cudaMemcpyAsync(dst, tmp, bytes, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (tmp) cudaFree(tmp);
+    if (e != cudaSuccess) return fail(ctx, SWB_ERR_CUDA, "gather_crops: %s", cudaGetErrorString(e));
+    return SWB_OK;
+}
+
+// ---- single-stage entry points -------------------------------------------------------
+#define STAGE_PROLOGUE()                                   \
+    do {                                                   \
+        int rc__ = select_device(nullptr, device);         \
+        if (rc__ != SWB_OK) return rc__;                   \
+    } while (0)
+
+int swb_stage_gray(int32_t device, const uint8_t* bgr, int32_t h, int32_t w, uint8_t* out) {
+    if (!bgr || !out || h <= 0 || w <= 0) return fail(nullptr, SWB_ERR_INVALID, "bad argument");
+    STAGE_PROLOGUE();
+    DevTmp t;
+    uint8_t *d_in, *d_out;
+    const size_t n = (size_t)h * w;
+    CU(nullptr, t.alloc(&d_in, n * 3));
+    CU(nullptr, t.alloc(&d_out, n));
+    CU(nullptr, cudaMemcpy(d_in, bgr, n * 3, cudaMemcpyHostToDevice));
+    CU(nullptr, launch_stage_gray(0, d_in, h, w, d_out));
+    CU(nullptr, cudaMemcpy(out, d_out, n, cudaMemcpyDeviceToHost));
+    return SWB_OK;
+}
+
+int swb_stage_median(int32_t device, const uint8_t* stack, int32_t n, int32_t h, int32_t w, uint8_t* out) {
+    if (!stack || !out || h <= 0 || w <= 0) return fail(nullptr, SWB_ERR_INVALID, "bad argument");
+    if (n < 1 || n > 9 || !(n & 1)) return fail(nullptr, SWB_ERR_INVALID, "n must be odd and in 1..9");
+    STAGE_PROLOGUE();
+    DevTmp t;
+    uint8_t *d_in, *d_out;
+    const size_t npx = (size_t)h * w;
+    CU(nullptr, t.alloc(&d_in, npx * n));
+    CU(nullptr, t.alloc(&d_out, npx));
+    CU(nullptr, cudaMemcpy(d_in, stack, npx * n, cudaMemcpyHostToDevice));
+    CU(nullptr, launch_stage_median(0, d_in, n, h, w, d_out));
+    CU(nullptr, cudaMemcpy(out, d_out, npx, cudaMemcpyDeviceToHost));
+    return SWB_OK;
+}
+
+int swb_stage_absdiff(int32_t device, const uint8_t* a, const uint8_t* b, int32_t h, int32_t w, uint8_t* out) {
+    if (!a || !b || !out || h <= 0 || w <= 0) return fail(nullptr, SWB_ERR_INVALID, "bad argument");
+    STAGE_PROLOGUE();
+    DevTmp t;
+    uint8_t *d_a, *d_b, *d_out;
+    const size_t n = (size_t)h * w;
+    CU(nullptr, t.alloc(&d_a, n));
+    CU(nullptr, t.alloc(&d_b, n));
+    CU(nullptr, t.alloc(&d_out, n));
+    CU(nullptr, cudaMemcpy(d_a, a, n, cudaMemcpyHostToDevice));
+    CU(nullptr, cudaMemcpy(d_b, b, n, cudaMemcpyHostToDevice));
+    CU(nullptr, launch_stage_absdiff(0, d_a, d_b, (long long)n, d_out));
+    CU(nullptr, cudaMemcpy(out, d_out, n, cudaMemcpyDeviceToHost));
+    return SWB_OK;
+}
+
+int swb_stage_thresh_to_zero(int32_t device, const uint8_t* in, int32_t h, int32_t w, int32_t thresh, uint8_t* out) {
+    if (!in || !out || h <= 0 || w <= 0) return fail(nullptr, SWB_ERR_INVALID, "bad argument");
+    STAGE_PROLOGUE();
+    DevTmp t;
+    uint8_t *d_in, *d_out;
+    const size_t n = (size_t)h * w;
+    CU(nullptr, t.alloc(&d_in, n));
+    CU(nullptr, t.alloc(&d_out, n));
+    CU(nullptr, cudaMemcpy(d_in, in, n, cudaMemcpyHostToDevice));
+    CU(nullptr, launch_stage_thresh(0, d_in, (long long)n, thresh, d_out));
+    CU(nullptr, cudaMemcpy(out, d_out, n, cudaMemcpyDeviceToHost));
+    return SWB_OK;
+}
+
+int swb_stage_grey_morph(int32_t device, const uint8_t* in, int32_t h, int32_t w, int32_t se_h, int32_t se_w,
+                         int32_t closing, uint8_t* out) {
+    if (!in || !out || h <= 0 || w <= 0) return fail(nullptr, SWB_ERR_INVALID, "bad argument");
+    if (se_h < 1 || se_w < 1 || !(se_h & 1) || !(se_w & 1) || se_h > 31 || se_w > 31)
+        return fail(nullptr, SWB_ERR_INVALID, "structuring element must be odd-sized, 1..31 (got %dx%d)", se_h, se_w);
+    STAGE_PROLOGUE();
+    DevTmp t;
+    uint8_t *d_a, *d_b;
+    const size_t n = (size_t)h * w;
+    CU(nullptr, t.alloc(&d_a, n));
+    CU(nullptr, t.alloc(&d_b, n));
+    CU(nullptr, cudaMemcpy(d_a, in, n, cudaMemcpyHostToDevice));
+    // opening = erosion (min) then dilation (max); closing is the dual
+    CU(nullptr, launch_stage_minmax(0, d_a, h, w, se_h, se_w, closing ? 1 : 0, d_b));
+    CU(nullptr, launch_stage_minmax(0, d_b, h, w, se_h, se_w, closing ? 0 : 1, d_a));
+    CU(nullptr, cudaMemcpy(out, d_a, n, cudaMemcpyDeviceToHost));
+    return SWB_OK;
+}
+
+int swb_stage_cc_label(int32_t device, const uint8_t* in, int32_t h, int32_t w, int32_t* out_i32, uint8_t* out_u8,
+                       int32_t* n_labels) {
+    if (!in || h <= 0 || w <= 0) return fail(nullptr, SWB_ERR_INVALID, "bad argument");
+    STAGE_PROLOGUE();
+    Geom g;
+    int X0a;
+    make_geom(0, 0, w, h, g, X0a);
+    DevTmp t;
+    uint8_t* d_in;
+    uint32_t* d_bits;
+    int32_t* d_lab;
+    const size_t n = (size_t)h * w;
+    CU(nullptr, t.alloc(&d_in, n));
+    CU(nullptr, t.alloc(&d_bits, (size_t)g.h * g.wpr));
+    CU(nullptr, t.alloc(&d_lab, (size_t)g.h * g.mpitch));
+    CclBuffers b{};
+    const int cap = g.BH * g.BW;   // every 2x2 block its own component at most
+    {
+        const size_t nblk = (size_t)g.BH * g.BW, nwords = (size_t)g.BH * g.wpr;
+        CU(nullptr, t.alloc(&b.parent, nblk));
+        CU(nullptr, t.alloc(&b.blocklabel, nblk));
+        CU(nullptr, t.alloc(&b.rootbits, nwords));
+        CU(nullptr, t.alloc(&b.wordbase, nwords));
+        CU(nullptr, t.alloc(&b.rowcount, (size_t)g.BH));
+        CU(nullptr, t.alloc(&b.nseg, 1));
+        CU(nullptr, t.alloc(&b.segoff, 2));
+        CU(nullptr, t.alloc(&b.rows, (size_t)cap));
+        CU(nullptr, t.alloc(&b.overflow, 1));
+        b.cap_rows = cap;
+    }
+    CU(nullptr, cudaMemcpy(d_in, in, n, cudaMemcpyHostToDevice));
+    CU(nullptr, cudaMemset(b.overflow, 0, sizeof(int32_t)));
+    CU(nullptr, launch_pack_bits(0, d_in, h, w, d_bits, g.wpr));
+    CU(nullptr, launch_ccl(0, d_bits, 1, g, b, d_lab, 4, nullptr, nullptr, 0));
+    std::vector<int32_t> lab((size_t)h * w);
+    CU(nullptr, cudaMemcpy2D(lab.data(), (size_t)w * 4, d_lab, (size_t)g.mpitch * 4, (size_t)w * 4, (size_t)h,
+                             cudaMemcpyDeviceToHost));
+    int32_t nseg = 0;
+    CU(nullptr, cudaMemcpy(&nseg, b.nseg, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (n_labels) *n_labels = nseg;
+    if (out_i32) memcpy(out_i32, lab.data(), lab.size() * sizeof(int32_t));
+    if (out_u8)
+        for (size_t i = 0; i < lab.size(); ++i) out_u8[i] = (uint8_t)lab[i];   // labels.astype(np.uint8)
+    return SWB_OK;
+}
+
+int swb_stage_regionprops(int32_t device, const void* labels, int32_t elem_size, int32_t h, int32_t w,
+                          swb_segment* rows, int32_t cap, int32_t* n_rows) {
+    if (!labels || !rows || h <= 0 || w <= 0 || (elem_size != 1 && elem_size != 4))
+        return fail(nullptr, SWB_ERR_INVALID, "bad argument");
+    STAGE_PROLOGUE();
+    const size_t n = (size_t)h * w;
+    int64_t maxlab = 0;
+    if (elem_size == 1) {
+        const uint8_t* p = static_cast<const uint8_t*>(labels);
+        for (size_t i = 0; i < n; ++i) maxlab = std::max<int64_t>(maxlab, p[i]);
+    } else {
+        const int32_t* p = static_cast<const int32_t*>(labels);
+        for (size_t i = 0; i < n; ++i) maxlab = std::max<int64_t>(maxlab, p[i]);
+    }
+    if (n_rows) *n_rows = 0;
+    if (maxlab <= 0) return SWB_OK;
+    DevTmp t;
+    uint8_t* d_lab;
+    swb_segment* d_acc;
+    CU(nullptr, t.alloc(&d_lab, n * elem_size));
+    CU(nullptr, t.alloc(&d_acc, (size_t)maxlab));
+    CU(nullptr, cudaMemcpy(d_lab, labels, n * elem_size, cudaMemcpyHostToDevice));
+    CU(nullptr, launch_stage_props(0, d_lab, elem_size, h, w, d_acc, (int)maxlab));
+    std::vector<swb_segment> acc((size_t)maxlab);
+    CU(nullptr, cudaMemcpy(acc.data(), d_acc, acc.size() * sizeof(swb_segment), cudaMemcpyDeviceToHost));
+    int32_t k = 0;
+    for (const swb_segment& s : acc) {
+        if (s.area <= 0) continue;   // label value absent: find_objects yields None (skipped)
+        if (k >= cap) return fail(nullptr, SWB_ERR_CAPACITY, "more than %d regions", cap);
+        rows[k++] = s;
+    }
+    if (n_rows) *n_rows = k;
+    return SWB_OK;
+}
+
+int swb_synth_frames(int32_t device, uint8_t* dst, int32_t mem_kind, uint32_t seed, uint32_t video, int32_t t0,
+                     int32_t n, int32_t h, int32_t w, int32_t n_birds) {
+    if (!dst || n <= 0 || h <= 0 || w <= 0 || n_birds < 0 || n > 65535) return fail(nullptr, SWB_ERR_INVALID, "bad argument");
+    STAGE_PROLOGUE();
+    const size_t bytes = (size_t)n * h * w * 3;
+    if (mem_kind == SWB_MEM_DEVICE) {
+        CU(nullptr, launch_synth(0, dst, seed, video, t0, n, h, w, n_birds));
+        CU(nullptr, cudaDeviceSynchronize());
+    } else {
+        DevTmp t;
+        uint8_t* d;
+        CU(nullptr, t.alloc(&d, bytes));
+        CU(nullptr, launch_synth(0, d, seed, video, t0, n, h, w, n_birds));
+        CU(nullptr, cudaMemcpy(dst, d, bytes, cudaMemcpyDeviceToHost));
+    }
+    return SWB_OK;
+}
+
+}  // extern "C"

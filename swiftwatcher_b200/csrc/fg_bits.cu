@@ -1,0 +1,305 @@
+// K1 — temporal foreground kernel.
+//
+// crop_frame + convert_grayscale (image_filtering.py:199-203, :188-196), then the
+// rolling temporal median / absdiff / threshold that BASELINE.json puts in place
+// of rpca + bilateral_blur (data_structures.py:191-200; thresh_to_zero is
+// image_filtering.py:310-316), fused into one pass that reads every BGR byte
+// once and emits one bit per pixel.
+//
+// Design: march through time, not space.  A thread owns 16 horizontally
+// adjacent pixels and walks a run of consecutive frames; the last N gray
+// values of its pixels live in registers as packed u16x2 lanes (pixel k in
+// the low half, pixel k+8 in the high half of register k), so the gray ring
+// never touches HBM.  The median is a min/max network on VIMNMX.U16x2 (native
+// on sm_100a; the u8x4 video min/max are emulated).  The time
+// loop is unrolled by N so ring slots are static register names.
+//
+// Work unit = (256-thread column group, temporal sub-chunk of Ts frames); each
+// sub-chunk re-reads its N-1 preceding frames as warm-up.
+#include "swb_internal.cuh"
+
+namespace swb {
+
+namespace {
+
+__device__ __forceinline__ uint32_t vmin2(uint32_t a, uint32_t b) { return __vminu2(a, b); }
+__device__ __forceinline__ uint32_t vmax2(uint32_t a, uint32_t b) { return __vmaxu2(a, b); }
+__device__ __forceinline__ uint32_t med3(uint32_t x, uint32_t y, uint32_t z) {
+    return vmax2(vmin2(x, y), vmin2(vmax2(x, y), z));
+}
+__device__ __forceinline__ void cswap(uint32_t& a, uint32_t& b) {
+    uint32_t lo = vmin2(a, b);
+    b = vmax2(a, b);
+    a = lo;
+}
+
+// Median of N packed u16x2 values (order statistic (N-1)/2), any odd N <= 9.
+template <int N>
+__device__ __forceinline__ uint32_t median_lanes(const uint32_t (&v)[N]) {
+    if constexpr (N == 1) {
+        return v[0];
+    } else if constexpr (N == 3) {
+        return med3(v[0], v[1], v[2]);
+    } else if constexpr (N == 5) {
+        // med5 = med3(e, max(min(a,b), min(c,d)), min(max(a,b), max(c,d)))
+        uint32_t lo = vmax2(vmin2(v[0], v[1]), vmin2(v[2], v[3]));
+        uint32_t hi = vmin2(vmax2(v[0], v[1]), vmax2(v[2], v[3]));
+        return med3(v[4], lo, hi);
+    } else if constexpr (N == 9) {
+        // sort three triples, then med3(max of mins, med of meds, min of maxes)
+        uint32_t a[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) a[i] = v[i];
+#pragma unroll
+        for (int c = 0; c < 9; c += 3) {
+            cswap(a[c], a[c + 1]);
+            cswap(a[c + 1], a[c + 2]);
+            cswap(a[c], a[c + 1]);
+        }
+        uint32_t lo = vmax2(vmax2(a[0], a[3]), a[6]);
+        uint32_t hi = vmin2(vmin2(a[2], a[5]), a[8]);
+        uint32_t mid = med3(a[1], a[4], a[7]);
+        return med3(lo, mid, hi);
+    } else {
+        // odd-even transposition sort; the compiler prunes the unused outputs
+        uint32_t a[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) a[i] = v[i];
+#pragma unroll
+        for (int r = 0; r < N; ++r) {
+#pragma unroll
+            for (int i = (r & 1); i + 1 < N; i += 2) cswap(a[i], a[i + 1]);
+        }
+        return a[N / 2];
+    }
+}
+
+// cv2 4.13 BGR2GRAY: (3735 B + 19235 G + 9798 R + 2^14) >> 15, evaluated with all
+// terms doubled so that the result is byte 2 of the sum (sum < 2^24).
+__device__ __forceinline__ uint32_t gray_sum(uint32_t b, uint32_t g, uint32_t r) {
+    return 7470u * b + 38470u * g + 19596u * r + 32768u;
+}
+
+// 48 BGR bytes (12 words, 16 pixels) -> 8 registers of (gray[k], gray[k+8]) u16x2.
+__device__ __forceinline__ void bgr48_to_lanes(const uint32_t (&w)[12], uint32_t (&out)[8]) {
+    uint32_t s[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int o = 3 * i;
+        uint32_t b = (w[o >> 2] >> (8 * (o & 3))) & 0xFFu;
+        uint32_t g = (w[(o + 1) >> 2] >> (8 * ((o + 1) & 3))) & 0xFFu;
+        uint32_t r = (w[(o + 2) >> 2] >> (8 * ((o + 2) & 3))) & 0xFFu;
+        s[i] = gray_sum(b, g, r);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) out[k] = __byte_perm(s[k], s[k + 8], 0x7632);
+}
+
+// 16 gray bytes (4 words) -> lanes
+__device__ __forceinline__ void gray16_to_lanes(const uint32_t (&w)[4], uint32_t (&out)[8]) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        // byte k (word k>>2) into bits 0..7, byte k+8 (word (k>>2)+2) into bits 16..23
+        uint32_t lo = (w[k >> 2] >> (8 * (k & 3))) & 0xFFu;
+        uint32_t hi = (w[(k >> 2) + 2] >> (8 * (k & 3))) & 0xFFu;
+        out[k] = lo | (hi << 16);
+    }
+}
+
+__device__ __forceinline__ uint4 lanes_to_gray16(const uint32_t (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        // bytes 4q..4q+3 (low halves) and 8+4q..8+4q+3 (high halves)
+        uint32_t lo01 = __byte_perm(v[4 * q + 0], v[4 * q + 1], 0x0040);  // b0=v0.b0 b1=v1.b0
+        uint32_t lo23 = __byte_perm(v[4 * q + 2], v[4 * q + 3], 0x0040);
+        uint32_t hi01 = __byte_perm(v[4 * q + 0], v[4 * q + 1], 0x0062);  // b0=v0.b2 b1=v1.b2
+        uint32_t hi23 = __byte_perm(v[4 * q + 2], v[4 * q + 3], 0x0062);
+        w[q] = __byte_perm(lo01, lo23, 0x5410);
+        w[q + 2] = __byte_perm(hi01, hi23, 0x5410);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+template <int C, bool ALIGNED>
+struct RawPixels {
+    uint32_t w[C == 3 ? 12 : 4];
+};
+
+// Load the 16 pixels of this thread from a BGR/gray source row.
+template <int C, bool ALIGNED>
+__device__ __forceinline__ void load_raw(RawPixels<C, ALIGNED>& p, const uint8_t* ptr, int avail_px) {
+    constexpr int NW = (C == 3) ? 12 : 4;
+    if constexpr (ALIGNED) {
+        const uint4* q = reinterpret_cast<const uint4*>(ptr);
+#pragma unroll
+        for (int i = 0; i < NW / 4; ++i) {
+            uint4 v = __ldcs(q + i);
+            p.w[4 * i + 0] = v.x;
+            p.w[4 * i + 1] = v.y;
+            p.w[4 * i + 2] = v.z;
+            p.w[4 * i + 3] = v.w;
+        }
+    } else {
+        // guarded byte loads: pixels at or beyond avail_px read as 0
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                int byte = 4 * i + b;
+                int px = byte / C;
+                if (px < avail_px) v |= (uint32_t)ptr[byte] << (8 * b);
+            }
+            p.w[i] = v;
+        }
+    }
+}
+
+template <int C, bool ALIGNED>
+__device__ __forceinline__ void raw_to_lanes(const RawPixels<C, ALIGNED>& p, uint32_t (&out)[8]) {
+    if constexpr (C == 3) bgr48_to_lanes(p.w, out);
+    else gray16_to_lanes(p.w, out);
+}
+
+// |x - m| > thresh per u16 lane -> 16 result bits (bit k = pixel k)
+__device__ __forceinline__ uint32_t fg_bits16(const uint32_t (&cur)[8], const uint32_t (&med)[8],
+                                              uint32_t bias /* (0x7FFF - thresh) * 0x10001 */) {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        uint32_t d = vmax2(cur[k], med[k]) - vmin2(cur[k], med[k]);  // per-lane |x-m|, no borrow
+        uint32_t t = d + bias;                                       // bit 15 / 31 = (d > thresh)
+        acc |= (t >> (15 - k)) & (0x00010001u << k);
+    }
+    return (acc & 0xFFu) | ((acc >> 8) & 0xFF00u);
+}
+
+template <int N, int C, bool ALIGNED>
+__global__ void __launch_bounds__(256)
+k_fg_bits(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint16_t* __restrict__ raw_bits) {
+    const int gpr = wa >> 4;  // 16-pixel groups per row
+    const int G = h * gpr;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    const int row = g / gpr;
+    const int col = g - row * gpr;
+    const int t_start = blockIdx.y * Ts;
+    const int t_end = min(T, t_start + Ts);
+    const int n_out = t_end - t_start;
+    if (n_out <= 0) return;
+
+    const long long pix_off = (long long)row * src.pitch + (long long)col * 16 * C;
+    const int avail_px = src.avail_w - col * 16;
+    const uint32_t bias = (uint32_t)(0x7FFF - thresh) * 0x00010001u;
+
+    uint32_t ring[N][8];
+
+    auto load_frame = [&](int j, uint32_t (&dst)[8]) {
+        // frame j relative to the first output frame of this submit
+        if (j < 0 && src.hist_valid) {
+            const int slot = j + (N - 1);
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(
+                src.hist + ((long long)slot * h + row) * wa + col * 16));
+            uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+            gray16_to_lanes(w4, dst);
+        } else {
+            if (j < -src.n_inline_halo) j = -src.n_inline_halo;  // replicate earliest frame
+            RawPixels<C, ALIGNED> p;
+            load_raw<C, ALIGNED>(p, src.cur + (long long)j * src.frame_stride + pix_off, avail_px);
+            raw_to_lanes<C, ALIGNED>(p, dst);
+        }
+    };
+
+    // warm-up: frames t_start-(N-1) .. t_start-1 into slots 0..N-2
+#pragma unroll
+    for (int s = 0; s < N - 1; ++s) load_frame(t_start - (N - 1) + s, ring[s]);
+
+    RawPixels<C, ALIGNED> nxt;
+    load_raw<C, ALIGNED>(nxt, src.cur + (long long)t_start * src.frame_stride + pix_off, avail_px);
+
+    const bool write_hist = (src.hist_out != nullptr) && (t_end == T);
+    uint16_t* out = raw_bits + ((long long)t_start * h + row) * gpr + col;
+    const long long out_step = (long long)h * gpr;
+
+    for (int base = 0; base < n_out; base += N) {
+#pragma unroll
+        for (int p = 0; p < N; ++p) {
+            const int k = base + p;
+            if (k < n_out) {
+                const int slot = (N - 1 + p) % N;  // static after unrolling
+                raw_to_lanes<C, ALIGNED>(nxt, ring[slot]);
+                if (k + 1 < n_out)
+                    load_raw<C, ALIGNED>(nxt, src.cur + (long long)(t_start + k + 1) * src.frame_stride + pix_off,
+                                         avail_px);
+                uint32_t med[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    uint32_t v[N];
+#pragma unroll
+                    for (int s = 0; s < N; ++s) v[s] = ring[s][q];
+                    med[q] = median_lanes<N>(v);
+                }
+                out[(long long)k * out_step] = (uint16_t)fg_bits16(ring[slot], med, bias);
+                if (write_hist && k == n_out - 1) {
+                    // last N-1 gray frames, oldest first: hist[s] = frame (T-1) - (N-2-s)
+#pragma unroll
+                    for (int s = 0; s < N - 1; ++s) {
+                        const int m = N - 2 - s;                  // frames back from the newest
+                        const int hs = ((slot - m) % N + N) % N;  // static
+                        *reinterpret_cast<uint4*>(src.hist_out + ((long long)s * h + row) * wa + col * 16) =
+                            lanes_to_gray16(ring[hs]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int N>
+cudaError_t launch_n(cudaStream_t s, const FrameSrc& src, int channels, int T, int Ts, const Geom& g,
+                     int thresh, uint16_t* raw_bits, bool aligned) {
+    const int G = g.h * (g.wa >> 4);
+    dim3 grid((G + 255) / 256, (T + Ts - 1) / Ts);
+    dim3 block(256);
+    if (channels == 3) {
+        if (aligned) k_fg_bits<N, 3, true><<<grid, block, 0, s>>>(src, T, Ts, g.h, g.wa, thresh, raw_bits);
+        else k_fg_bits<N, 3, false><<<grid, block, 0, s>>>(src, T, Ts, g.h, g.wa, thresh, raw_bits);
+    } else {
+        if (aligned) k_fg_bits<N, 1, true><<<grid, block, 0, s>>>(src, T, Ts, g.h, g.wa, thresh, raw_bits);
+        else k_fg_bits<N, 1, false><<<grid, block, 0, s>>>(src, T, Ts, g.h, g.wa, thresh, raw_bits);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+// Temporal sub-chunk length: long enough that the N-1 warm-up frames are a few
+// percent of the work, short enough that the grid has several waves of CTAs.
+static int pick_ts(int T, int n_col_blocks, int median_n) {
+    const int target_ctas = 148 * 2 * 4;
+    int ts = T;
+    while (ts > 32 && (long long)n_col_blocks * ((T + ts - 1) / ts) < target_ctas) ts = (ts + 1) / 2;
+    const int min_ts = 16 * (median_n - 1) > 0 ? 16 * (median_n - 1) : 1;  // <= ~6% warm-up
+    if (ts < min_ts) ts = min_ts;
+    if (ts > T) ts = T;
+    if (ts < 1) ts = 1;
+    return ts;
+}
+
+cudaError_t launch_fg_bits(cudaStream_t s, const FrameSrc& src, int channels, int median_n, int T,
+                           const Geom& g, int thresh, uint16_t* raw_bits, bool aligned, int* n_launches) {
+    const int G = g.h * (g.wa >> 4);
+    const int Ts = pick_ts(T, (G + 255) / 256, median_n);
+    if (n_launches) *n_launches += 1;
+    switch (median_n) {
+        case 1: return launch_n<1>(s, src, channels, T, Ts, g, thresh, raw_bits, aligned);
+        case 3: return launch_n<3>(s, src, channels, T, Ts, g, thresh, raw_bits, aligned);
+        case 5: return launch_n<5>(s, src, channels, T, Ts, g, thresh, raw_bits, aligned);
+        case 7: return launch_n<7>(s, src, channels, T, Ts, g, thresh, raw_bits, aligned);
+        case 9: return launch_n<9>(s, src, channels, T, Ts, g, thresh, raw_bits, aligned);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace swb

@@ -1,0 +1,91 @@
+// Internal declarations shared by the swb200 translation units (not installed).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/swb200.h"
+
+namespace swb {
+
+// Geometry of the processed region (the ROI of crop_frame, image_filtering.py:199-203).
+//
+// Two coordinate systems are used on the device:
+//  * "raw" coordinates: the ROI widened to 32-pixel alignment in the source
+//    frame, x in [X0a, X0a + wa), X0a = roi_x0 & ~31.  The temporal kernel works
+//    here so that every thread reads 48 contiguous, 16-byte aligned BGR bytes.
+//  * "roi" coordinates: x in [0, w) exactly as the reference sees the cropped
+//    frame.  The morphology kernel realigns raw bits by dx = roi_x0 - X0a, and
+//    every later buffer (final bits, mask, labels, 2x2 blocks) is ROI-local.
+struct Geom {
+    int h, w;        // ROI height / width
+    int dx;          // roi_x0 - X0a, 0..31
+    int wa;          // raw width in pixels, multiple of 32, >= dx + w
+    int wpr_raw;     // wa / 32
+    int wpr;         // ceil(w / 32): words per row of the final bit mask
+    int mpitch;      // wpr * 32: row pitch (elements) of mask / label images
+    int BH;          // ceil(h / 2): 2x2-block rows
+    int BW;          // 16 * wpr:    2x2-block columns (padded)
+};
+
+// Where the temporal kernel finds frame j (j = 0 is the first output frame).
+struct FrameSrc {
+    const uint8_t* cur;        // frame 0, ROI row 0, raw column 0 (byte address)
+    long long frame_stride;    // bytes between frames
+    long long pitch;           // bytes between rows
+    int n_inline_halo;         // frames -n_inline_halo..-1 are readable at cur + j*stride
+    int hist_valid;            // frames j < 0 come from `hist` (gray) instead
+    const uint8_t* hist;       // [N-1][h][wa] gray; slot s holds frame s-(N-1)
+    uint8_t* hist_out;         // where to leave the last N-1 gray frames (or null)
+    int avail_w;               // pixels readable from raw column 0 in a row (guarded path)
+};
+
+struct MorphCfg {
+    int radius;      // 0 (no morphology), 1 (3x3) or 2 (5x5)
+    int n_ops;       // 0, 2 (open) or 4 (open + close) / 2 (close only)
+    int is_erode[4]; // op sequence
+};
+
+// ---- launchers (each returns the cudaError_t of the launch) ---------------
+cudaError_t launch_fg_bits(cudaStream_t s, const FrameSrc& src, int channels, int median_n,
+                           int T, const Geom& g, int thresh, uint16_t* raw_bits, bool aligned,
+                           int* n_launches);
+cudaError_t launch_morph_mask(cudaStream_t s, const uint32_t* raw_bits, int T, const Geom& g,
+                              const MorphCfg& m, uint32_t* fbits, uint8_t* mask, int* n_launches);
+
+struct CclBuffers {
+    int* parent;          // [T][BH][BW]
+    int* blocklabel;      // [T][BH][BW]
+    uint32_t* rootbits;   // [T][BH][wpr]
+    uint32_t* wordbase;   // [T][BH][wpr]
+    uint32_t* rowcount;   // [T][BH]  (becomes exclusive row base after the scan)
+    int32_t* nseg;        // [T] segments per frame
+    int32_t* segoff;      // [T+1] exclusive prefix of nseg
+    swb_segment* rows;    // [cap_rows]
+    int cap_rows;
+    int32_t* overflow;    // device flag: 1 when total rows > cap_rows
+};
+cudaError_t launch_ccl(cudaStream_t s, const uint32_t* fbits, int T, const Geom& g,
+                       const CclBuffers& b, void* labels, int label_elem_size,
+                       int* n_launches, cudaEvent_t* stage_events, int n_stage_events);
+
+cudaError_t launch_pack_bits(cudaStream_t s, const uint8_t* img, int h, int w, uint32_t* fbits,
+                             int wpr);
+cudaError_t launch_gather_crops_n(cudaStream_t s, const uint8_t* frames, long long frame_stride,
+                                  long long pitch, int channels, int frame_h, int frame_w,
+                                  int roi_x0, int roi_y0, const swb_segment* rows, int n_rows,
+                                  int crop, uint8_t* dst);
+
+// single-stage kernels (stages.cu)
+cudaError_t launch_stage_gray(cudaStream_t s, const uint8_t* bgr, int h, int w, uint8_t* out);
+cudaError_t launch_stage_median(cudaStream_t s, const uint8_t* stack, int n, int h, int w, uint8_t* out);
+cudaError_t launch_stage_absdiff(cudaStream_t s, const uint8_t* a, const uint8_t* b, long long n, uint8_t* out);
+cudaError_t launch_stage_thresh(cudaStream_t s, const uint8_t* in, long long n, int thresh, uint8_t* out);
+cudaError_t launch_stage_minmax(cudaStream_t s, const uint8_t* in, int h, int w, int se_h, int se_w,
+                                int is_max, uint8_t* out);
+cudaError_t launch_stage_props(cudaStream_t s, const void* labels, int elem_size, int h, int w,
+                               swb_segment* acc, int cap);
+cudaError_t launch_synth(cudaStream_t s, uint8_t* dst, uint32_t seed, uint32_t video, int t0, int n,
+                         int h, int w, int n_birds);
+
+}  // namespace swb

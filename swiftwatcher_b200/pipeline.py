@@ -1,0 +1,226 @@
+"""FilterContext — the fused, batched filtering + segmentation path.
+
+Host-side mirror of what ``FrameQueue.preprocess_queue`` + ``segment_queue``
+do per batch in the reference (swiftwatcher/data_structures.py:171-217), with
+the rolling-median background model BASELINE.json names.  All compute happens
+in libswb200 (CUDA); this file only marshals buffers.
+"""
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import (HALO_CARRY, LABELS_I32, LABELS_U8, MEM_DEVICE, MEM_HOST, OUT_LABELS,
+                   OUT_MASK, SEGMENT_DTYPE, SwbConfig, check, ptr)
+
+
+class RegionProperties:
+    """What swiftwatcher reads from a skimage ``_RegionProperties``
+    (image_filtering.py:332-335): label, area, bbox (min_row, min_col, max_row,
+    max_col) half-open, centroid (row, col) float64 — as plain attributes so
+    that ``Segment.__init__`` (data_structures.py:28-30) can copy them."""
+
+    __slots__ = ("label", "area", "bbox", "centroid")
+
+    def __init__(self, label, area, bbox, centroid):
+        self.label = label
+        self.area = area
+        self.bbox = bbox
+        self.centroid = centroid
+
+    def __repr__(self):
+        return ("RegionProperties(label=%d, area=%d, bbox=%r, centroid=%r)"
+                % (self.label, self.area, self.bbox, self.centroid))
+
+
+def centroids(rows):
+    """(k, 2) float64 centroids: integer coordinate sums / area, one rounding —
+    the same value numpy's ``coords.mean(axis=0)`` yields."""
+    area = rows["area"].astype(np.float64)
+    return np.stack([rows["sum_row"].astype(np.float64) / area,
+                     rows["sum_col"].astype(np.float64) / area], axis=1)
+
+
+def props_from_rows(rows):
+    """Segment-table rows (one frame) -> list[RegionProperties], label order."""
+    cen = centroids(rows) if len(rows) else np.zeros((0, 2))
+    return [RegionProperties(int(r["label"]), int(r["area"]),
+                             tuple(int(v) for v in r["bbox"]),
+                             (cen[i, 0], cen[i, 1]))
+            for i, r in enumerate(rows)]
+
+
+class FilterContext:
+    """One context per (GPU, video).  Not thread-safe (include/swb200.h)."""
+
+    def __init__(self, frame_shape, crop_region=None, median_n=5, threshold=15,
+                 morph_size=3, do_open=True, do_close=False, label_mode="u8",
+                 max_frames=21, max_segments=0, device=0, want_mask=True,
+                 want_labels=True, frame_pitch=0, frame_stride=0):
+        """frame_shape: (H, W, 3) BGR or (H, W) gray.  crop_region: the
+        reference's ``[(x0, y0), (x1, y1)]`` (image_filtering.py:199-203);
+        None = whole frame."""
+        self._lib = _lib.load()
+        h, w = int(frame_shape[0]), int(frame_shape[1])
+        ch = int(frame_shape[2]) if len(frame_shape) == 3 else 1
+        if crop_region is None:
+            crop_region = [(0, 0), (w, h)]
+        (x0, y0), (x1, y1) = crop_region
+        cfg = SwbConfig()
+        cfg.device = device
+        cfg.frame_h, cfg.frame_w, cfg.channels = h, w, ch
+        cfg.frame_pitch, cfg.frame_stride = frame_pitch, frame_stride
+        cfg.roi_x0, cfg.roi_y0, cfg.roi_x1, cfg.roi_y1 = int(x0), int(y0), int(x1), int(y1)
+        cfg.median_n, cfg.threshold = median_n, threshold
+        cfg.morph_size = morph_size
+        cfg.do_open, cfg.do_close = int(bool(do_open)), int(bool(do_close))
+        cfg.label_mode = LABELS_U8 if label_mode in ("u8", LABELS_U8) else LABELS_I32
+        cfg.out_flags = (OUT_MASK if want_mask else 0) | (OUT_LABELS if want_labels else 0)
+        cfg.max_frames = max_frames
+        cfg.max_segments = max_segments
+        self.cfg = cfg
+        self.frame_shape = (h, w, ch) if ch == 3 else (h, w)
+        self.frame_bytes = (frame_stride or (frame_pitch or w * ch) * h)
+        self.roi_h, self.roi_w = int(y1) - int(y0), int(x1) - int(x0)
+        self.crop_region = [(int(x0), int(y0)), (int(x1), int(y1))]
+        self.median_n = median_n
+        self.max_frames = max_frames
+        self.label_dtype = np.uint8 if cfg.label_mode == LABELS_U8 else np.int32
+        self._ctx = C.c_void_p()
+        check(self._lib.swb_create(C.byref(cfg), C.byref(self._ctx)))
+        self._n_last = 0
+        self._keepalive = None
+
+    # -- lifetime ---------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self._lib.swb_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def reset(self):
+        check(self._lib.swb_reset(self._ctx), self._ctx)
+
+    def set_stream(self, cuda_stream):
+        """Launch on an external CUDA stream handle (int), e.g.
+        ``torch.cuda.current_stream().cuda_stream``."""
+        check(self._lib.swb_set_stream(self._ctx, C.c_void_p(cuda_stream or 0)), self._ctx)
+
+    # -- the hot path --------------------------------------------------------
+    def submit(self, frames, n_halo=HALO_CARRY, n_frames=None):
+        """frames: numpy (n_halo + n, H, W[, 3]) uint8 (host) or a CUDA torch
+        tensor of that shape (device, zero-copy).  Asynchronous."""
+        if isinstance(frames, np.ndarray):
+            if frames.dtype != np.uint8 or not frames.flags["C_CONTIGUOUS"]:
+                raise ValueError("frames must be C-contiguous uint8")
+            kind = MEM_HOST
+        elif hasattr(frames, "data_ptr"):
+            if not frames.is_contiguous() or frames.element_size() != 1:
+                raise ValueError("frames must be a contiguous uint8 tensor")
+            kind = MEM_DEVICE if frames.is_cuda else MEM_HOST
+        else:
+            raise TypeError("frames must be a numpy array or a torch tensor")
+        total = int(frames.shape[0])
+        halo = 0 if n_halo == HALO_CARRY else int(n_halo)
+        n = total - halo if n_frames is None else int(n_frames)
+        if tuple(frames.shape[1:]) != tuple(self.frame_shape) and not (self.cfg.frame_pitch or self.cfg.frame_stride):
+            raise ValueError("frame shape %r != configured %r" % (tuple(frames.shape[1:]), self.frame_shape))
+        self._keepalive = frames
+        check(self._lib.swb_submit(self._ctx, ptr(frames), n, n_halo, kind), self._ctx)
+        self._n_last = n
+        return n
+
+    def submit_ptr(self, address, n_frames, n_halo, mem_kind=MEM_DEVICE):
+        check(self._lib.swb_submit(self._ctx, C.c_void_p(address), n_frames, n_halo, mem_kind), self._ctx)
+        self._n_last = n_frames
+
+    def sync(self):
+        check(self._lib.swb_sync(self._ctx), self._ctx)
+
+    def collect(self, cap=None):
+        """-> (rows, counts): the segment table (SEGMENT_DTYPE, ordered by frame
+        then label) and segments per frame, for the last submit."""
+        n = self._n_last
+        cap = int(cap if cap is not None else max(self.cfg.max_segments, 1024 * self.max_frames))
+        rows = np.empty(cap, dtype=SEGMENT_DTYPE)
+        counts = np.zeros(n, dtype=np.int32)
+        n_rows = C.c_int64(0)
+        check(self._lib.swb_collect(self._ctx, ptr(rows), cap, C.byref(n_rows), ptr(counts)), self._ctx)
+        return rows[:n_rows.value], counts
+
+    def collect_props(self):
+        """-> list (per frame) of list[RegionProperties]."""
+        rows, counts = self.collect()
+        out, o = [], 0
+        for c in counts:
+            out.append(props_from_rows(rows[o:o + c]))
+            o += c
+        return out
+
+    def masks(self, t0=0, n=None):
+        n = self._n_last - t0 if n is None else n
+        out = np.empty((n, self.roi_h, self.roi_w), dtype=np.uint8)
+        check(self._lib.swb_get_masks(self._ctx, t0, n, ptr(out), MEM_HOST), self._ctx)
+        return out
+
+    def labels(self, t0=0, n=None):
+        n = self._n_last - t0 if n is None else n
+        out = np.empty((n, self.roi_h, self.roi_w), dtype=self.label_dtype)
+        check(self._lib.swb_get_labels(self._ctx, t0, n, ptr(out), MEM_HOST), self._ctx)
+        return out
+
+    def mask_bits(self, t0=0, n=None):
+        n = self._n_last - t0 if n is None else n
+        wpr = (self.roi_w + 31) // 32
+        out = np.empty((n, self.roi_h, wpr), dtype=np.uint32)
+        check(self._lib.swb_get_mask_bits(self._ctx, t0, n, ptr(out), MEM_HOST), self._ctx)
+        return out
+
+    def gather_crops(self, n_rows, crop=24, out=None):
+        """(n_rows, crop, crop, C) uint8 crops for the last submit's table
+        (device-resident full frames only)."""
+        ch = self.cfg.channels
+        if out is None:
+            out = np.empty((n_rows, crop, crop, ch), dtype=np.uint8)
+        kind = MEM_DEVICE if (hasattr(out, "is_cuda") and out.is_cuda) else MEM_HOST
+        check(self._lib.swb_gather_crops(self._ctx, crop, ptr(out), kind), self._ctx)
+        return out
+
+    # -- instrumentation --------------------------------------------------------
+    def enable_timing(self, on=True):
+        check(self._lib.swb_enable_timing(self._ctx, int(on)), self._ctx)
+
+    def timing(self):
+        names = (C.c_char_p * 8)()
+        ms = (C.c_float * 8)()
+        n = C.c_int32(0)
+        check(self._lib.swb_get_timing(self._ctx, names, ms, 8, C.byref(n)), self._ctx)
+        return {names[i].decode(): float(ms[i]) for i in range(n.value)}
+
+    def launch_count(self):
+        return int(self._lib.swb_launch_count(self._ctx))
+
+
+def synth_frames(seed, video, t0, n, h, w, n_birds, device=0, out=None):
+    """Synthetic frames from the CUDA generator (twin of oracle/synth.py).
+    ``out``: optional CUDA uint8 torch tensor (n, h, w, 3); else numpy."""
+    lib = _lib.load()
+    if out is None:
+        out = np.empty((n, h, w, 3), dtype=np.uint8)
+        kind = MEM_HOST
+    else:
+        kind = MEM_DEVICE if getattr(out, "is_cuda", False) else MEM_HOST
+    check(lib.swb_synth_frames(device, ptr(out), kind, seed, video, t0, n, h, w, n_birds))
+    return out

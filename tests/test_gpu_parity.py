@@ -1,0 +1,421 @@
+"""GPU suite (B200): the CUDA path through the C ABI against the oracle on the
+same seeded inputs, against the committed golden vectors, and through
+size-independent properties at BASELINE.json's full sizes."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import reference_path as rp
+from oracle import synth
+
+import swiftwatcher_b200 as swb
+from swiftwatcher_b200 import chunking
+from swiftwatcher_b200 import data_structures as ds
+from swiftwatcher_b200 import image_filtering as img
+from swiftwatcher_b200.pipeline import centroids, synth_frames
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu(lib):
+    assert swb.device_count() > 0, "GPU tests need a CUDA device (no CPU fallback exists)"
+
+
+def table_from_rows(rows):
+    cen = centroids(rows) if len(rows) else np.zeros((0, 2))
+    tab = np.zeros((len(rows), 8))
+    tab[:, 0] = rows["label"]
+    tab[:, 1] = rows["area"]
+    tab[:, 2:6] = rows["bbox"]
+    tab[:, 6:8] = cen
+    return tab
+
+
+def check_against_oracle(frames, region, n=5, thresh=15, se=3, do_open=True, do_close=False,
+                         mode="i32", history=None, ctx=None, n_halo=None, submit_frames=None):
+    """Run the CUDA path and the oracle on the same frames; compare masks and
+    labels bit-exactly, tables exactly (centroids within 1e-5 relative is the
+    stated tolerance; integer sums make them equal)."""
+    par = rp.PathParams(region, n, thresh, se, do_open, do_close, mode)
+    want = rp.run_path(frames, par, history=history)
+    own = ctx is None
+    if own:
+        ctx = swb.FilterContext(frames.shape[1:], region, median_n=n, threshold=thresh,
+                                morph_size=se, do_open=do_open, do_close=do_close,
+                                label_mode=mode, max_frames=max(len(frames), 1))
+    try:
+        if submit_frames is None:
+            if history is not None:
+                submit_frames = np.ascontiguousarray(np.concatenate([np.stack(history), frames]))
+                n_halo = len(history)
+            else:
+                submit_frames, n_halo = frames, (0 if n_halo is None else n_halo)
+        ctx.submit(submit_frames, n_halo=n_halo)
+        rows, counts = ctx.collect()
+        masks, labels = ctx.masks(), ctx.labels()
+    finally:
+        if own:
+            ctx.close()
+    assert len(want) == len(counts)
+    o = 0
+    for t, rec in enumerate(want):
+        assert np.array_equal(masks[t], rec["mask"]), "mask differs at frame %d" % t
+        assert labels.dtype == rec["labels"].dtype
+        assert np.array_equal(labels[t], rec["labels"]), "labels differ at frame %d" % t
+        assert counts[t] == len(rec["props"]), "segment count differs at frame %d" % t
+        got = table_from_rows(rows[o:o + counts[t]])
+        exp = rp.props_table(rec["props"])
+        assert np.array_equal(got[:, :6], exp[:, :6]), "label/area/bbox differ at frame %d" % t
+        np.testing.assert_allclose(got[:, 6:], exp[:, 6:], rtol=1e-5, atol=0)   # north_star tolerance
+        assert np.array_equal(got[:, 6:], exp[:, 6:])                           # and in fact bit-exact
+        assert np.all(rows["frame"][o:o + counts[t]] == t)
+        o += counts[t]
+    return want
+
+
+# ---------------------------------------------------------------------------------
+# synthetic generator twin
+# ---------------------------------------------------------------------------------
+def test_synth_cuda_equals_numpy():
+    for (seed, video, t0, n, h, w, birds) in [(1, 0, 0, 3, 72, 128, 20), (7, 3, 1000, 2, 50, 77, 9),
+                                              (2, 1, 54000, 1, 33, 40, 0)]:
+        got = synth_frames(seed, video, t0, n, h, w, birds)
+        want = synth.synth_video(seed, video, t0, n, h, w, birds)
+        assert np.array_equal(got, want)
+
+
+# ---------------------------------------------------------------------------------
+# single-stage drop-ins against the golden vectors produced by the reference
+# ---------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def kats(golden_dir):
+    return np.load(os.path.join(golden_dir, "stage_kats.npz"))
+
+
+def test_stage_gray(kats):
+    assert np.array_equal(img.convert_grayscale(kats["gray_in"]), kats["gray_out"])
+    g = kats["gray_out"]
+    assert img.convert_grayscale(g) is g
+    rng = np.random.default_rng(0)
+    big = rng.integers(0, 256, (257, 513, 3), dtype=np.uint8)
+    assert np.array_equal(img.convert_grayscale(big), rp.convert_grayscale(big))
+
+
+def test_stage_threshold(kats):
+    assert np.array_equal(img.thresh_to_zero(kats["thresh_in"], 15), kats["thresh_out"])
+    probe = np.array([[14, 15, 16, 255]], np.uint8)
+    assert img.thresh_to_zero(probe, 15).tolist() == [[0, 0, 16, 255]]
+
+
+def test_stage_morphology(kats):
+    m = kats["open_in"]
+    assert np.array_equal(img.grayscale_opening(m, (3, 3)), kats["open3_out"])
+    assert np.array_equal(img.grayscale_opening(m, (5, 5)), kats["open5_out"])
+    assert np.array_equal(img.grayscale_closing(m, (3, 3)), kats["close3_out"])
+    assert np.array_equal(img.grayscale_closing(m, (5, 5)), kats["close5_out"])
+    assert np.array_equal(img.grayscale_opening(m, (3, 5)), rp.grayscale_opening(m, (3, 5)))
+
+
+def test_stage_median_absdiff():
+    rng = np.random.default_rng(4)
+    stack = rng.integers(0, 256, (9, 61, 83), dtype=np.uint8)
+    for n in (1, 3, 5, 7, 9):
+        assert np.array_equal(img.temporal_median(list(stack[:n])), rp.temporal_median(list(stack[:n])))
+    assert np.array_equal(img.absdiff(stack[0], stack[1]), rp.absdiff(stack[0], stack[1]))
+
+
+def test_stage_cc_labeling(kats):
+    assert np.array_equal(img.cc_labeling(kats["cc_diag_in"], 4), kats["cc_diag_out"])
+    assert np.array_equal(img.cc_labeling(kats["cc_blobs_in"], 4), kats["cc_blobs_out"])
+    assert np.array_equal(img.cc_labeling(kats["cc_many_in"], 4), kats["cc_many_out"])
+    assert np.array_equal(img.cc_labeling_i32(kats["cc_many_in"]), kats["cc_many_i32"])
+
+
+def test_stage_cc_labeling_random_shapes():
+    rng = np.random.default_rng(5)
+    for _ in range(12):
+        h, w = int(rng.integers(1, 90)), int(rng.integers(1, 200))
+        a = (rng.random((h, w)) < rng.uniform(0.02, 0.7)).astype(np.uint8) * 200
+        assert np.array_equal(img.cc_labeling_i32(a), rp.cc_labeling_i32(a)), (h, w)
+    for a in (np.zeros((5, 7), np.uint8), np.full((64, 96), 9, np.uint8), np.eye(33, dtype=np.uint8)):
+        assert np.array_equal(img.cc_labeling_i32(a), rp.cc_labeling_i32(a))
+
+
+def test_stage_cc_labeling_serpentine():
+    """Long snake: deep union-find chains across many words and rows."""
+    a = np.zeros((101, 300), np.uint8)
+    a[::4, :] = 1
+    a[2::8, -1] = 1
+    a[6::8, 0] = 1
+    a[1::8, -1] = 1; a[3::8, -1] = 1
+    a[5::8, 0] = 1; a[7::8, 0] = 1
+    assert np.array_equal(img.cc_labeling_i32(a), rp.cc_labeling_i32(a))
+
+
+def test_stage_regionprops(kats):
+    for key, tab in (("cc_blobs_out", "props_blobs"), ("cc_many_out", "props_many")):
+        props = img.get_segment_properties(kats[key])
+        got = np.array([(p.label, p.area, *p.bbox, *p.centroid) for p in props])
+        assert np.array_equal(got, kats[tab])
+    props = img.get_segment_properties(kats["cc_many_i32"])
+    want = rp.regionprops(kats["cc_many_i32"])
+    assert [(p.label, p.area, p.bbox, p.centroid) for p in props] == \
+           [(p.label, p.area, p.bbox, tuple(p.centroid)) for p in want]
+    assert img.get_segment_properties(np.zeros((4, 4), np.uint8)) == []
+
+
+# ---------------------------------------------------------------------------------
+# the fused path against the golden vectors (reference functions' outputs)
+# ---------------------------------------------------------------------------------
+PATH_CASES = ["path_roi_n5_open3", "path_full_n9_oc5", "path_dense_n5_open3"]
+
+
+@pytest.mark.parametrize("name", PATH_CASES)
+@pytest.mark.parametrize("mode", ["u8", "i32"])
+def test_fused_path_against_golden(golden_dir, name, mode):
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    c = [int(v) for v in z["cfg"]]
+    seed, video, H, W, birds, T = c[:6]
+    roi = [(c[6], c[7]), (c[8], c[9])]
+    frames = synth_frames(seed, video, 0, T, H, W, birds)      # CUDA generator
+    assert np.array_equal(frames.reshape(T, -1).sum(axis=1), z["frame_sums"])
+    with swb.FilterContext(frames.shape[1:], roi, median_n=c[10], threshold=c[11], morph_size=c[12],
+                           do_open=bool(c[13]), do_close=bool(c[14]), label_mode=mode,
+                           max_frames=T) as ctx:
+        ctx.submit(frames, n_halo=0)
+        rows, counts = ctx.collect()
+        masks, labels, bits = ctx.masks(), ctx.labels(), ctx.mask_bits()
+    w = roi[1][0] - roi[0][0]
+    want_bits = np.unpackbits(z["masks_packed"], axis=2, bitorder="little")[:, :, :w].astype(bool)
+    assert np.array_equal(masks > 0, want_bits)
+    assert set(np.unique(masks)) <= {0, 255}
+    got_bits = np.unpackbits(bits.view(np.uint8), axis=2, bitorder="little")[:, :, :w].astype(bool)
+    assert np.array_equal(got_bits, want_bits)
+    assert np.array_equal(labels, z["labels_" + mode])
+    assert np.array_equal(counts, z["counts_" + mode])
+    assert np.array_equal(table_from_rows(rows), z["props_" + mode])
+
+
+# ---------------------------------------------------------------------------------
+# the fused path against the oracle: edge cases
+# ---------------------------------------------------------------------------------
+def test_unaligned_roi_and_odd_frame_width():
+    # W % 16 != 0 -> guarded loads; ROI x0 odd -> bit realignment; ROI touching borders
+    frames = synth.synth_video(21, 0, 0, 9, 75, 203, 40)
+    for region in ([(33, 7), (190, 70)], [(0, 0), (203, 75)], [(1, 1), (34, 74)], [(170, 3), (203, 75)]):
+        check_against_oracle(frames, region, n=5, mode="i32")
+
+
+def test_aligned_width_unaligned_roi():
+    frames = synth.synth_video(22, 0, 0, 8, 64, 256, 40)
+    for region in ([(37, 5), (229, 60)], [(32, 0), (256, 64)], [(95, 9), (97, 11)]):
+        check_against_oracle(frames, region, n=5, mode="u8")
+
+
+@pytest.mark.parametrize("n", [1, 3, 5, 7, 9])
+def test_median_windows(n):
+    frames = synth.synth_video(23, 1, 0, 2 * n + 3, 48, 96, 20)
+    check_against_oracle(frames, [(0, 0), (96, 48)], n=n, mode="i32")
+
+
+@pytest.mark.parametrize("se,do_open,do_close", [(0, False, False), (3, True, True), (3, False, True),
+                                                  (5, True, False), (5, True, True)])
+def test_morphology_variants(se, do_open, do_close):
+    frames = synth.synth_video(24, 0, 0, 8, 70, 130, 45)
+    check_against_oracle(frames, [(3, 2), (128, 69)], se=se or 3, do_open=do_open, do_close=do_close)
+
+
+def test_thresholds():
+    frames = synth.synth_video(25, 0, 0, 7, 40, 64, 12)
+    for th in (0, 3, 15, 99, 255):
+        check_against_oracle(frames, [(0, 0), (64, 40)], thresh=th)
+
+
+def test_random_noise_frames_many_tiny_components():
+    rng = np.random.default_rng(11)
+    frames = rng.integers(0, 256, (7, 66, 131, 3), dtype=np.uint8)
+    check_against_oracle(frames, [(0, 0), (131, 66)], thresh=60, se=0, do_open=False, mode="i32")
+    check_against_oracle(frames, [(0, 0), (131, 66)], thresh=60, se=0, do_open=False, mode="u8")
+    check_against_oracle(frames, [(2, 3), (130, 61)], thresh=40, se=3, do_open=True, do_close=True)
+
+
+def test_gray_input_frames():
+    rng = np.random.default_rng(12)
+    frames = rng.integers(0, 256, (6, 50, 90), dtype=np.uint8)
+    check_against_oracle(frames, [(5, 5), (85, 45)], thresh=50)
+
+
+def test_blank_and_full_foreground():
+    frames = np.zeros((7, 40, 70, 3), np.uint8)
+    check_against_oracle(frames, [(0, 0), (70, 40)])
+    frames[5:] = 255          # every pixel becomes foreground: one frame-filling component
+    check_against_oracle(frames, [(0, 0), (70, 40)], mode="i32")
+
+
+def test_explicit_halo_equals_whole():
+    frames = synth.synth_video(26, 0, 0, 16, 60, 100, 30)
+    region = [(4, 4), (99, 58)]
+    whole = check_against_oracle(frames, region, n=5)
+    part = check_against_oracle(frames[9:], region, n=5, history=list(frames[5:9]))
+    for a, b in zip(whole[9:], part):
+        assert np.array_equal(a["labels"], b["labels"])
+    # a short halo replicates the earliest supplied frame (oracle window policy)
+    check_against_oracle(frames[9:], region, n=5, history=list(frames[7:9]))
+
+
+def test_carried_history_across_submits():
+    """Stateful streaming: submits with SWB_HALO_CARRY continue the rolling
+    median exactly as one long submit would (FrameQueue's 21-frame batches)."""
+    frames = synth.synth_video(27, 0, 0, 19, 54, 120, 30)
+    region = [(7, 3), (117, 50)]
+    par = rp.PathParams(region, 5, 15, 3, True, False, "i32")
+    want = rp.run_path(frames, par)
+    with swb.FilterContext(frames.shape[1:], region, label_mode="i32", max_frames=8) as ctx:
+        t = 0
+        for n in (1, 2, 8, 3, 5):
+            ctx.submit(np.ascontiguousarray(frames[t:t + n]))     # n_halo = CARRY
+            labels = ctx.labels()
+            for i in range(n):
+                assert np.array_equal(labels[i], want[t + i]["labels"]), (t, i)
+            t += n
+        ctx.reset()
+        ctx.submit(np.ascontiguousarray(frames[10:14]))
+        fresh = rp.run_path(frames[10:14], par)
+        assert np.array_equal(ctx.labels()[3], fresh[3]["labels"])
+
+
+def test_device_resident_input_zero_copy():
+    import torch
+    frames = synth.synth_video(28, 0, 0, 10, 72, 160, 30)
+    dev = torch.from_numpy(frames).cuda()
+    for region in ([(0, 0), (160, 72)], [(19, 5), (150, 70)]):
+        par = rp.PathParams(region, 5, 15, 3, True, False, "i32")
+        want = rp.run_path(frames[4:], par, history=list(frames[:4]))
+        with swb.FilterContext(frames.shape[1:], region, label_mode="i32", max_frames=6) as ctx:
+            ctx.submit(dev, n_halo=4)
+            labels = ctx.labels()
+            rows, counts = ctx.collect()
+        for t, rec in enumerate(want):
+            assert np.array_equal(labels[t], rec["labels"])
+            assert counts[t] == len(rec["props"])
+
+
+def test_capacity_errors_are_loud():
+    frames = synth.synth_video(29, 0, 0, 6, 40, 64, 30)
+    with swb.FilterContext(frames.shape[1:], None, label_mode="i32", max_frames=4, max_segments=3) as ctx:
+        with pytest.raises(swb.SwbError) as e:
+            ctx.submit(frames)
+        assert e.value.code == -3
+        ctx.submit(np.ascontiguousarray(frames[:4]), n_halo=0)
+        with pytest.raises(swb.SwbError) as e:
+            ctx.collect()
+        assert e.value.code == -3
+
+
+def test_gather_crops_matches_reference_slicing():
+    import torch
+    frames = synth.synth_video(30, 0, 0, 8, 120, 200, 25)
+    dev = torch.from_numpy(frames).cuda()
+    region = [(20, 10), (180, 110)]
+    with swb.FilterContext(frames.shape[1:], region, label_mode="i32", max_frames=8) as ctx:
+        ctx.submit(dev, n_halo=0)
+        rows, counts = ctx.collect()
+        crops = ctx.gather_crops(len(rows), 24)
+    checked = 0
+    for r, crop in zip(rows, crops):
+        bh, bw = r["bbox"][2] - r["bbox"][0], r["bbox"][3] - r["bbox"][1]
+        if bh > 24 or bw > 24:
+            continue
+        seg = rp.RegionProperties(int(r["label"]), int(r["area"]), tuple(r["bbox"]), (0, 0))
+        b = rp.expand_bbox(seg.bbox, (24, 24), region)
+        if b[0] < 0 or b[1] < 0 or b[2] > 120 or b[3] > 200:
+            continue        # the reference wraps/truncates here; the tile is zero-padded instead
+        want = rp.extract_segment_images([seg], frames[r["frame"]], (24, 24), region)[0]
+        assert np.array_equal(crop, want)
+        checked += 1
+    assert checked > 10
+
+
+# ---------------------------------------------------------------------------------
+# the drop-in FrameQueue flow (data_structures.py:171-217, __main__.py:71-96)
+# ---------------------------------------------------------------------------------
+def test_framequeue_drop_in_flow():
+    frames = synth.synth_video(31, 0, 0, 30, 90, 160, 30)
+    region = [(16, 8), (150, 80)]
+    par = rp.PathParams(region, 5, 15, 3, True, False, "u8")
+    want = rp.run_path(frames, par, want_images=True)
+    queue = ds.FrameQueue(queue_size=21)
+    t = 0
+    seen = 0
+    while t < len(frames):
+        batch = list(frames[t:t + 21])
+        queue.push_list_of_frames(batch, list(range(t, t + len(batch))), ["00:00:00.000"] * len(batch))
+        queue.preprocess_queue(region, (300, 150))
+        queue.segment_queue((24, 24), region)
+        while not queue.is_empty():
+            f = queue.pop_frame()
+            rec = want[f.frame_number]
+            assert np.array_equal(f.get_processed_frame("cc_labeling"), rec["labels"])
+            assert np.array_equal(f.get_processed_frame("mask"), rec["mask"])
+            assert np.shares_memory(f.get_processed_frame("crop"), f.frame)
+            assert f.get_num_segments() == len(rec["props"])
+            for s, p, c in zip(f.segments, rec["props"], rec["crops"]):
+                assert (s.label, s.area, s.bbox) == (p.label, p.area, p.bbox)
+                assert s.centroid == tuple(p.centroid)
+                assert np.array_equal(s.segment_image, c)
+                assert s.parent_frame_number == f.frame_number
+            seen += 1
+        t += 21
+    assert seen == len(frames) and queue.frames_processed == len(frames)
+
+
+# ---------------------------------------------------------------------------------
+# full-size properties (BASELINE.json configs 2 and 3): no oracle at this size
+# ---------------------------------------------------------------------------------
+def _full_size_properties(H, W, n, se, do_close, T, birds):
+    import torch
+    halo = n - 1
+    dev = torch.empty((halo + T, H, W, 3), dtype=torch.uint8, device="cuda")
+    synth_frames(3, 0, 100, halo + T, H, W, birds, out=dev)
+    with swb.FilterContext((H, W, 3), None, median_n=n, morph_size=se, do_close=do_close,
+                           label_mode="i32", max_frames=T) as ctx:
+        ctx.submit(dev, n_halo=halo)
+        rows, counts = ctx.collect()
+        masks, labels = ctx.masks(), ctx.labels()
+        # temporal chunks with halo == one submit (the multi-GPU partition, run on one GPU)
+        rows2, counts2, _, _ = chunking.run_rank(
+            ctx, lambda a, b: dev[a:b], halo + T, 0, 1, chunk_frames=max(T // 3, 1))
+    assert counts.sum() == len(rows) and counts.min() > 0
+    assert np.array_equal((labels > 0), (masks == 255))
+    assert rows["area"].sum() == int((masks == 255).sum())            # checksum of checksums
+    o = 0
+    for t in range(T):
+        r = rows[o:o + counts[t]]
+        assert np.array_equal(r["label"], np.arange(1, counts[t] + 1))
+        assert labels[t].max() == counts[t]
+        # spot-check a few segments exactly against the dense label image
+        for k in (0, counts[t] // 2, counts[t] - 1):
+            ys, xs = np.nonzero(labels[t] == r["label"][k])
+            assert r["area"][k] == len(ys)
+            assert tuple(r["bbox"][k]) == (ys.min(), xs.min(), ys.max() + 1, xs.max() + 1)
+            assert r["sum_row"][k] == ys.sum() and r["sum_col"][k] == xs.sum()
+        o += counts[t]
+    # run_rank processed frames [0, halo+T) of `dev` as a video of its own: its frames
+    # halo.. coincide with the submit above (full window available in both)
+    keep = rows2["frame"] >= halo
+    r2 = rows2[keep].copy()
+    r2["frame"] -= halo
+    assert np.array_equal(counts2[halo:], counts)
+    assert np.array_equal(r2, rows)
+    # frame 0 label image against the oracle's labeller (per-frame, affordable)
+    assert np.array_equal(labels[0], rp.cc_labeling_i32(masks[0]))
+
+
+def test_full_size_1080p_n5_open3():
+    _full_size_properties(1080, 1920, 5, 3, False, 6, 300)
+
+
+def test_full_size_4k_n9_openclose5():
+    _full_size_properties(2160, 3840, 9, 5, True, 3, 600)
