@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py — frames/sec of the filtering + segmentation hot path (BASELINE.json).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W     # the reference's CPU path (oracle port)
+    torchrun --nproc-per-node N bench.py --gpus N ...        # one rank per GPU
+
+A step is one pass of the hot path over one chunk of synthetic video: by
+default BASELINE.json configs[1] (1080p full frame, N=5 median, 3x3 opening,
+int32 labels) in chunks of 512 frames (3.2 GB of BGR, >> the 126 MB L2, so no
+L2 flush is needed between steps).  Inputs are generated on the device by the
+seeded CUDA generator before the timed region.  `value` is device-timed (CUDA
+events on the launch stream, max over ranks); `e2e` runs the same chunks
+through the C ABI from pinned HOST buffers (H2D copy and D2H of the segment
+table inside the timed region).
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # BASELINE.json configs[1]
+    "1080p_full_n5_open3": dict(H=1080, W=1920, roi=None, N=5, se=3, do_close=False, birds=300, chunk=512),
+    # BASELINE.json configs[2]
+    "4k_full_n9_oc5": dict(H=2160, W=3840, roi=None, N=9, se=5, do_close=True, birds=600, chunk=128),
+    # BASELINE.json configs[0] geometry (the reference's CPU-runnable case)
+    "1080p_roi320x240_n5_open3": dict(H=1080, W=1920, roi=[(800, 400), (1120, 640)], N=5, se=3,
+                                      do_close=False, birds=300, chunk=512),
+    # BASELINE.json configs[4] filtering part (dense swarm, ~500 segments/frame)
+    "1080p_dense_n5_open3": dict(H=1080, W=1920, roi=None, N=5, se=3, do_close=False, birds=2500, chunk=256),
+}
+DEFAULT_CONFIG = "1080p_full_n5_open3"
+SEED = 2
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax = float(parts[2])
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def algorithmic_bytes(cfg, h, w):
+    """Per OUTPUT frame.  Whole path: read BGR once,
+    write the uint8 mask once, write int32 labels once = 8*h*w."""
+    hw = h * w
+    return {
+        "path": 8 * hw,
+        "fg_bits": 3 * hw + hw // 8,            # BGR read + 1 bit/px write
+        "morph_mask": hw // 8 + hw // 8 + hw,   # bits read, bits write, uint8 mask write
+        "ccl_merge": hw // 8, "ccl_rank": hw // 8, "ccl_label": hw // 8,
+        "write_labels": hw // 8 + 4 * hw,       # bits read + int32 label write
+    }
+
+
+def cpu_baseline_sample(cfg, n_frames, threads=None):
+    """The reference's CPU path (oracle port: the same cv2/scipy calls the
+    reference makes + np.median/absdiff) on `n_frames` frames of the workload."""
+    import cv2
+    from oracle import reference_path as rp
+    from oracle import synth
+    if threads:
+        cv2.setNumThreads(threads)
+    H, W = cfg["H"], cfg["W"]
+    roi = cfg["roi"] or [(0, 0), (W, H)]
+    halo = cfg["N"] - 1
+    frames = synth.synth_video(SEED, 0, 1000, halo + n_frames, H, W, cfg["birds"])
+    par = rp.PathParams(roi, cfg["N"], 15, cfg["se"], True, cfg["do_close"], "u8")
+    t0 = time.perf_counter()
+    out = rp.run_path(frames[halo:], par, history=list(frames[:halo]), want_images=True)
+    dt = time.perf_counter() - t0
+    segs = sum(len(o["props"]) for o in out)
+    return n_frames / dt, dt, segs, cv2.getNumThreads()
+
+
+def run_reference(args, cfg, name):
+    """--impl reference: the reference's own CPU implementation of the path
+    (oracle port; /root/reference is pure Python over cv2/scipy/skimage and does
+    not exist on the GPU box), all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = max(2, min(8, int(24 // max(args.steps, 1)) or 2)) if cfg["H"] >= 1080 and cfg["roi"] is None else 64
+    for _ in range(min(args.warmup, 1)):
+        cpu_baseline_sample(cfg, 2)
+    t_total, n_total, segs, threads = 0.0, 0, 0, 0
+    for _ in range(args.steps):
+        fps, dt, s, threads = cpu_baseline_sample(cfg, sample)
+        t_total += dt
+        n_total += sample
+        segs += s
+    value = n_total / t_total
+    line = {
+        "impl": "reference", "metric": "frames/sec (filter + label hot path)", "value": value,
+        "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": name, "frames_per_step": sample, "median_n": cfg["N"], "morph": cfg["se"]},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": "port",
+                         "sample": "%d steps x %d frames of %s on the host CPU (oracle port of the reference's "
+                                   "cv2/scipy path; cv2 thread pool, numpy/scipy single-threaded)"
+                                   % (args.steps, sample, name)},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "host_cpus": os.cpu_count(),
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default=DEFAULT_CONFIG, choices=sorted(CONFIGS))
+    ap.add_argument("--chunk", type=int, default=0, help="frames per step (0 = config default)")
+    ap.add_argument("--label-mode", default="i32", choices=["i32", "u8"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-frames", type=int, default=0)
+    args = ap.parse_args()
+    cfg = dict(CONFIGS[args.config])
+    if args.chunk:
+        cfg["chunk"] = args.chunk
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        run_reference(args, cfg, args.config)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import swiftwatcher_b200 as swb
+    from swiftwatcher_b200.pipeline import synth_frames
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if swb.device_count() < 1:
+        raise RuntimeError("bench.py needs a CUDA device: libswb200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    H, W, N, T = cfg["H"], cfg["W"], cfg["N"], cfg["chunk"]
+    roi = cfg["roi"]
+    halo = N - 1
+    rh, rw = (H, W) if roi is None else (roi[1][1] - roi[0][1], roi[1][0] - roi[0][0])
+    frame_bytes = H * W * 3
+
+    # ---- inputs resident in HBM: n_buf distinct chunks of this rank's part of the video
+    n_buf = max(1, min(4, int(24e9 // ((halo + T) * frame_bytes))))
+    bufs = []
+    for b in range(n_buf):
+        t0 = 1000 + (rank * 64 + b) * T          # each rank works on its own temporal chunk
+        x = torch.empty((halo + T, H, W, 3), dtype=torch.uint8, device="cuda")
+        synth_frames(SEED, 0, t0 - halo, halo + T, H, W, cfg["birds"], device=local_rank, out=x)
+        bufs.append(x)
+    torch.cuda.synchronize()
+
+    ctx = swb.FilterContext((H, W, 3), roi, median_n=N, threshold=15, morph_size=cfg["se"], do_open=True,
+                            do_close=cfg["do_close"], label_mode=args.label_mode, max_frames=T,
+                            max_segments=T * 4096, device=local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        ctx.submit(bufs[i % n_buf], n_halo=halo)
+    ctx.sync()
+    rows, counts = ctx.collect()
+    segs_per_frame = float(counts.mean())
+
+    # ---- timed region: K steps, device-timed on the launch stream
+    sampler = ClockSampler(local_rank)
+    launches0 = ctx.launch_count()
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for i in range(args.steps):
+        ctx.submit(bufs[i % n_buf], n_halo=halo)
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    fps = world * args.steps * T / (ms * 1e-3)
+
+    # ---- per-kernel durations (CUDA events between launches, same stream)
+    ctx.enable_timing(True)
+    per_kernel = {}
+    reps = min(args.steps, 8)
+    for i in range(reps):
+        ctx.submit(bufs[i % n_buf], n_halo=halo)
+        ctx.sync()
+        for k, v in ctx.timing().items():
+            per_kernel[k] = per_kernel.get(k, 0.0) + v / reps
+    ctx.enable_timing(False)
+    peak, peak_src = measured_peak()
+    alg = algorithmic_bytes(cfg, rh, rw)
+    dom = max(per_kernel, key=per_kernel.get)
+    kernels = {k: {"ms": round(v, 4), "alg_gbs": round(alg[k] * T / (v * 1e-3) / 1e9, 1) if v > 0 else None}
+               for k, v in per_kernel.items()}
+    dom_ach = alg[dom] * T / (per_kernel[dom] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": round(dom_ach, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(dom_ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg[dom] * T,
+                "path_achieved": round(alg["path"] * fps / world / 1e9, 1),
+                "path_frac": round(alg["path"] * fps / world / 1e9 / peak, 4), "kernels": kernels}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            roofline["traffic"] = json.load(open(traffic_file)).get(args.config, {}).get(dom)
+        except Exception:
+            pass
+
+    # ---- end to end through the C ABI with HOST buffers
+    e2e = None
+    if not args.no_e2e:
+        ctx_h = swb.FilterContext((H, W, 3), roi, median_n=N, threshold=15, morph_size=cfg["se"], do_open=True,
+                                  do_close=cfg["do_close"], label_mode=args.label_mode, max_frames=T,
+                                  max_segments=T * 4096, device=local_rank)
+        host = torch.empty((halo + T, H, W, 3), dtype=torch.uint8, pin_memory=True)
+        host.copy_(bufs[0])
+        torch.cuda.synchronize()
+        ctx_h.submit(host, n_halo=halo)
+        rows_h, counts_h = ctx_h.collect()
+        d2h = 0
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.e2e_steps):
+            ctx_h.submit(host, n_halo=halo)
+            rows_h, counts_h = ctx_h.collect()
+            d2h = rows_h.nbytes + counts_h.nbytes + 4 * (T + 1)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        if roi is None:
+            h2d = (halo + T) * frame_bytes
+        else:
+            x0a = roi[0][0] & ~31
+            wa = ((roi[1][0] + 31) & ~31) - x0a
+            h2d = (halo + T) * rh * min(wa, W - x0a) * 3
+        e2e = {"value": world * args.e2e_steps * T / dt, "unit": "frames/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps,
+               "note": "pinned host frames -> swb_submit (H2D) -> swb_collect (D2H segment table); PCIe-bound"}
+        ctx_h.close()
+        del host
+
+    # ---- the reference's CPU path on this box's host cores (rank 0, N=1 only)
+    cpu = None
+    if not args.no_cpu and world == 1:
+        n_cpu = args.cpu_frames or (16 if roi is None and H >= 1080 else 300)
+        if H > 1080:
+            n_cpu = args.cpu_frames or 4
+        cpu_fps, cpu_dt, _, threads = cpu_baseline_sample(cfg, n_cpu)
+        cpu = {"value": cpu_fps, "unit": "frames/s", "cores": threads, "kind": "port",
+               "sample": "%d frames of %s (%.1f s) through oracle/reference_path.py: the reference's cv2/scipy calls "
+                         "+ np.median/absdiff; cv2 pool of %d threads, numpy/scipy stages single-threaded; "
+                         "host has %d CPUs" % (n_cpu, args.config, cpu_dt, threads, os.cpu_count())}
+
+    if rank == 0:
+        line = {
+            "metric": "frames/sec (filter + label hot path)", "value": fps, "unit": "frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": args.config, "frame": [H, W, 3], "roi": roi, "median_n": N,
+                       "threshold": 15, "morph": cfg["se"], "open": True, "close": cfg["do_close"],
+                       "labels": args.label_mode, "frames_per_step": T, "halo_frames": halo,
+                       "resident_chunks": n_buf, "segments_per_frame": round(segs_per_frame, 1),
+                       "l2": "inputs (%.1f GB/step) >> 126 MB L2; no flush" % ((halo + T) * frame_bytes / 1e9),
+                       "partition": "temporal chunks, %d-frame halo, no collective" % halo},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
