@@ -228,8 +228,8 @@ def main():
     ctx = swb.FilterContext((H, W, 3), roi, median_n=N, threshold=15, morph_size=cfg["se"], do_open=True,
                             do_close=cfg["do_close"], label_mode=args.label_mode, max_frames=T,
                             max_segments=T * 4096, device=local_rank)
-    stream = torch.cuda.current_stream()
-    ctx.set_stream(stream.cuda_stream)
+    stream = torch.cuda.Stream()          # a real (non-default) stream: the library launches on it and the
+    ctx.set_stream(stream.cuda_stream)    # CUDA events below are recorded on it
 
     def barrier():
         if world > 1:

@@ -20,6 +20,8 @@ thread_local std::string g_error;
 constexpr int N_TIMERS = 6;
 const char* const TIMER_NAMES[N_TIMERS] = {"fg_bits",   "morph_mask", "ccl_merge",
                                            "ccl_rank",  "ccl_label",  "write_labels"};
+// ccl_merge = local + boundary (or init + merge); ccl_rank = roots + scan + offsets + seg_init;
+// ccl_label = label + props_final
 
 }  // namespace
 
@@ -107,7 +109,8 @@ void make_geom(int roi_x0, int roi_y0, int roi_x1, int roi_y1, Geom& g, int& X0a
     g.wpr = (g.w + 31) / 32;
     g.mpitch = g.wpr * 32;
     g.BH = (g.h + 1) / 2;
-    g.BW = 16 * g.wpr;
+    g.wpr4 = (g.wpr + 3) & ~3;
+    g.BW = 16 * g.wpr4;
 }
 
 int make_morph(swb_ctx* ctx, int size, int do_open, int do_close, MorphCfg& m) {
@@ -136,13 +139,13 @@ void free_ctx_buffers(swb_ctx* c) {
     cudaFree(c->labels);
     cudaFree(c->ccl.parent);
     cudaFree(c->ccl.blocklabel);
-    cudaFree(c->ccl.rootbits);
-    cudaFree(c->ccl.wordbase);
     cudaFree(c->ccl.rowcount);
     cudaFree(c->ccl.nseg);
     cudaFree(c->ccl.segoff);
     cudaFree(c->ccl.rows);
     cudaFree(c->ccl.overflow);
+    cudaFree(c->ccl.parts);
+    cudaFree(c->ccl.pcount);
     if (c->h_segoff) cudaFreeHost(c->h_segoff);
     if (c->h_overflow) cudaFreeHost(c->h_overflow);
     for (auto& e : c->ev)
@@ -152,17 +155,17 @@ void free_ctx_buffers(swb_ctx* c) {
 
 int alloc_ccl(swb_ctx* ctx, CclBuffers& b, const Geom& g, int T, int cap_rows) {
     const size_t nblk = (size_t)T * g.BH * g.BW;
-    const size_t nwords = (size_t)T * g.BH * g.wpr;
     CU(ctx, dalloc(&b.parent, nblk));
     CU(ctx, dalloc(&b.blocklabel, nblk));
-    CU(ctx, dalloc(&b.rootbits, nwords));
-    CU(ctx, dalloc(&b.wordbase, nwords));
     CU(ctx, dalloc(&b.rowcount, (size_t)T * g.BH));
     CU(ctx, dalloc(&b.nseg, (size_t)T));
     CU(ctx, dalloc(&b.segoff, (size_t)T + 1));
     CU(ctx, dalloc(&b.rows, (size_t)cap_rows));
     CU(ctx, dalloc(&b.overflow, 1));
     b.cap_rows = cap_rows;
+    b.cap_parts = 2 * cap_rows + 4096;
+    CU(ctx, dalloc(&b.parts, (size_t)b.cap_parts));
+    CU(ctx, dalloc(&b.pcount, 1));
     return SWB_OK;
 }
 
@@ -303,7 +306,7 @@ int swb_create(const swb_config* cfg, swb_ctx** out) {
         CUB(dalloc(&ctx->hist[1], (size_t)nh * g.h * g.wa));
     }
     CUB(dalloc(&ctx->raw_bits, (size_t)T * g.h * g.wpr_raw * 2 + 8));
-    CUB(dalloc(&ctx->fbits, (size_t)T * g.h * g.wpr));
+    CUB(dalloc(&ctx->fbits, (size_t)T * g.h * g.wpr4));
     if (c.out_flags & SWB_OUT_MASK) CUB(dalloc(&ctx->mask, (size_t)T * g.h * g.mpitch));
     if (c.out_flags & SWB_OUT_LABELS)
         CUB(cudaMalloc(&ctx->labels, (size_t)T * g.h * g.mpitch * ctx->label_elem));
@@ -512,9 +515,9 @@ int swb_get_mask_bits(swb_ctx* ctx, int32_t t0, int32_t n, uint32_t* dst, int32_
     if (t0 < 0 || n < 0 || t0 + n > ctx->last_T) return fail(ctx, SWB_ERR_INVALID, "bad frame range");
     CU(ctx, cudaSetDevice(ctx->cfg.device));
     const Geom& g = ctx->g;
-    const size_t per = (size_t)g.h * g.wpr;
-    CU(ctx, cudaMemcpyAsync(dst, ctx->fbits + per * t0, per * n * sizeof(uint32_t),
-                            mem_kind == SWB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpy2DAsync(dst, (size_t)g.wpr * 4, ctx->fbits + (size_t)t0 * g.h * g.wpr4, (size_t)g.wpr4 * 4,
+                              (size_t)g.wpr * 4, (size_t)n * g.h,
+                              mem_kind == SWB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return SWB_OK;
 }
@@ -686,26 +689,27 @@ int swb_stage_cc_label(int32_t device, const uint8_t* in, int32_t h, int32_t w, 
     int32_t* d_lab;
     const size_t n = (size_t)h * w;
     CU(nullptr, t.alloc(&d_in, n));
-    CU(nullptr, t.alloc(&d_bits, (size_t)g.h * g.wpr));
+    CU(nullptr, t.alloc(&d_bits, (size_t)g.h * g.wpr4));
     CU(nullptr, t.alloc(&d_lab, (size_t)g.h * g.mpitch));
     CclBuffers b{};
     const int cap = g.BH * g.BW;   // every 2x2 block its own component at most
     {
-        const size_t nblk = (size_t)g.BH * g.BW, nwords = (size_t)g.BH * g.wpr;
+        const size_t nblk = (size_t)g.BH * g.BW;
         CU(nullptr, t.alloc(&b.parent, nblk));
         CU(nullptr, t.alloc(&b.blocklabel, nblk));
-        CU(nullptr, t.alloc(&b.rootbits, nwords));
-        CU(nullptr, t.alloc(&b.wordbase, nwords));
         CU(nullptr, t.alloc(&b.rowcount, (size_t)g.BH));
         CU(nullptr, t.alloc(&b.nseg, 1));
         CU(nullptr, t.alloc(&b.segoff, 2));
         CU(nullptr, t.alloc(&b.rows, (size_t)cap));
         CU(nullptr, t.alloc(&b.overflow, 1));
         b.cap_rows = cap;
+        b.cap_parts = 2 * cap + 4096;
+        CU(nullptr, t.alloc(&b.parts, (size_t)b.cap_parts));
+        CU(nullptr, t.alloc(&b.pcount, 1));
     }
     CU(nullptr, cudaMemcpy(d_in, in, n, cudaMemcpyHostToDevice));
     CU(nullptr, cudaMemset(b.overflow, 0, sizeof(int32_t)));
-    CU(nullptr, launch_pack_bits(0, d_in, h, w, d_bits, g.wpr));
+    CU(nullptr, launch_pack_bits(0, d_in, h, w, d_bits, g.wpr4));
     CU(nullptr, launch_ccl(0, d_bits, 1, g, b, d_lab, 4, nullptr, nullptr, 0));
     std::vector<int32_t> lab((size_t)h * w);
     CU(nullptr, cudaMemcpy2D(lab.data(), (size_t)w * 4, d_lab, (size_t)g.mpitch * 4, (size_t)w * 4, (size_t)h,

@@ -123,7 +123,7 @@ k_morph_mask(const uint32_t* __restrict__ raw_bits, Geom g, MorphCfg m, uint32_t
         // final bit words: lane = word
         {
             const int j = tx0 + lane;
-            if (j < g.wpr) fbits[((long long)f * g.h + y) * g.wpr + j] = srow[lane];
+            if (j < g.wpr4) fbits[((long long)f * g.h + y) * g.wpr4 + j] = srow[lane];
         }
         if (mask != nullptr) {
             uint8_t* mrow = mask + ((long long)f * g.h + y) * g.mpitch + (long long)tx0 * 32;

@@ -23,9 +23,10 @@ struct Geom {
     int wa;          // raw width in pixels, multiple of 32, >= dx + w
     int wpr_raw;     // wa / 32
     int wpr;         // ceil(w / 32): words per row of the final bit mask
+    int wpr4;        // wpr rounded up to 4: row pitch (words) of the final bit mask (zero padded)
     int mpitch;      // wpr * 32: row pitch (elements) of mask / label images
     int BH;          // ceil(h / 2): 2x2-block rows
-    int BW;          // 16 * wpr:    2x2-block columns (padded)
+    int BW;          // 16 * wpr4:   2x2-block columns (padded)
 };
 
 // Where the temporal kernel finds frame j (j = 0 is the first output frame).
@@ -53,24 +54,34 @@ cudaError_t launch_fg_bits(cudaStream_t s, const FrameSrc& src, int channels, in
 cudaError_t launch_morph_mask(cudaStream_t s, const uint32_t* raw_bits, int T, const Geom& g,
                               const MorphCfg& m, uint32_t* fbits, uint8_t* mask, int* n_launches);
 
+// Regionprops partial sums of one tile-local component (ccl.cu, tiled path).
+struct Partial {
+    int frame, root;               // frame index; global block id of the tile-local root
+    int area;
+    int minr, minc, maxr, maxc;    // inclusive
+    unsigned sr, sc;               // sums of row / column coordinates within the tile
+    int pad[3];
+};
+
 struct CclBuffers {
     int* parent;          // [T][BH][BW]
     int* blocklabel;      // [T][BH][BW]
-    uint32_t* rootbits;   // [T][BH][wpr]
-    uint32_t* wordbase;   // [T][BH][wpr]
     uint32_t* rowcount;   // [T][BH]  (becomes exclusive row base after the scan)
     int32_t* nseg;        // [T] segments per frame
     int32_t* segoff;      // [T+1] exclusive prefix of nseg
     swb_segment* rows;    // [cap_rows]
     int cap_rows;
-    int32_t* overflow;    // device flag: 1 when total rows > cap_rows
+    int32_t* overflow;    // device flag: 1 when total rows > cap_rows (or partials > cap_parts)
+    Partial* parts;       // [cap_parts] tile-local regionprops partial sums
+    int* pcount;          // number of partials appended
+    int cap_parts;
 };
 cudaError_t launch_ccl(cudaStream_t s, const uint32_t* fbits, int T, const Geom& g,
                        const CclBuffers& b, void* labels, int label_elem_size,
                        int* n_launches, cudaEvent_t* stage_events, int n_stage_events);
 
 cudaError_t launch_pack_bits(cudaStream_t s, const uint8_t* img, int h, int w, uint32_t* fbits,
-                             int wpr);
+                             int wpr4);
 cudaError_t launch_gather_crops_n(cudaStream_t s, const uint8_t* frames, long long frame_stride,
                                   long long pitch, int channels, int frame_h, int frame_w,
                                   int roi_x0, int roi_y0, const swb_segment* rows, int n_rows,

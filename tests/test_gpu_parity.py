@@ -34,7 +34,8 @@ def table_from_rows(rows):
 
 
 def check_against_oracle(frames, region, n=5, thresh=15, se=3, do_open=True, do_close=False,
-                         mode="i32", history=None, ctx=None, n_halo=None, submit_frames=None):
+                         mode="i32", history=None, ctx=None, n_halo=None, submit_frames=None,
+                         max_segments=0):
     """Run the CUDA path and the oracle on the same frames; compare masks and
     labels bit-exactly, tables exactly (centroids within 1e-5 relative is the
     stated tolerance; integer sums make them equal)."""
@@ -44,7 +45,7 @@ def check_against_oracle(frames, region, n=5, thresh=15, se=3, do_open=True, do_
     if own:
         ctx = swb.FilterContext(frames.shape[1:], region, median_n=n, threshold=thresh,
                                 morph_size=se, do_open=do_open, do_close=do_close,
-                                label_mode=mode, max_frames=max(len(frames), 1))
+                                label_mode=mode, max_frames=max(len(frames), 1), max_segments=max_segments)
     try:
         if submit_frames is None:
             if history is not None:
@@ -239,6 +240,37 @@ def test_random_noise_frames_many_tiny_components():
     check_against_oracle(frames, [(0, 0), (131, 66)], thresh=60, se=0, do_open=False, mode="i32")
     check_against_oracle(frames, [(0, 0), (131, 66)], thresh=60, se=0, do_open=False, mode="u8")
     check_against_oracle(frames, [(2, 3), (130, 61)], thresh=40, se=3, do_open=True, do_close=True)
+
+
+def test_wide_frame_uses_global_union_find():
+    """Frames wider than 4096 pixels take the non-tiled labelling path."""
+    rng = np.random.default_rng(13)
+    frames = np.zeros((6, 24, 4300), np.uint8)
+    frames[5] = (rng.random((24, 4300)) < 0.3) * 200
+    frames[5, 10, :] = 200                       # one component spanning the whole width
+    check_against_oracle(frames, [(0, 0), (4300, 24)], thresh=50, se=0, do_open=False, mode="i32")
+
+
+def test_tall_narrow_frames_cross_tile_boundaries():
+    """Narrow ROIs use tall shared-memory tiles (up to 256 block rows): components
+    crossing several tile boundaries, U shapes joined only through a lower tile."""
+    h, w = 1300, 40
+    frames = np.zeros((6, h, w), np.uint8)
+    img0 = np.zeros((h, w), np.uint8)
+    img0[5:1290, 3] = 200                        # long vertical bars
+    img0[100:1200, 20] = 200
+    img0[1200, 3:21] = 200                       # joined near the bottom: a tall U
+    img0[300:305, 30:35] = 200
+    img0[511:514, 8:12] = 200                    # straddles the first tile boundary (row 512)
+    rng = np.random.default_rng(14)
+    img0[rng.random((h, w)) < 0.03] = 200
+    frames[5] = img0
+    check_against_oracle(frames, [(0, 0), (w, h)], thresh=50, se=0, do_open=False, mode="i32")
+    for ww in (70, 200, 300, 600):
+        fr = np.zeros((6, 700, ww), np.uint8)
+        fr[5] = (rng.random((700, ww)) < 0.25) * 255
+        check_against_oracle(fr, [(0, 0), (ww, 700)], thresh=50, se=0, do_open=False, mode="i32",
+                             max_segments=100000)
 
 
 def test_gray_input_frames():
