@@ -20,8 +20,8 @@ thread_local std::string g_error;
 constexpr int N_TIMERS = 6;
 const char* const TIMER_NAMES[N_TIMERS] = {"fg_bits",   "morph_mask", "ccl_merge",
                                            "ccl_rank",  "ccl_label",  "write_labels"};
-// ccl_merge = local + boundary (or init + merge); ccl_rank = roots + scan + offsets + seg_init;
-// ccl_label = label + props_final
+// ccl_merge = local + boundary (or init + merge); ccl_rank = root ranking + scans + seg_init;
+// ccl_label = props_final (regionprops into the table)
 
 }  // namespace
 
@@ -138,14 +138,13 @@ void free_ctx_buffers(swb_ctx* c) {
     cudaFree(c->mask);
     cudaFree(c->labels);
     cudaFree(c->ccl.parent);
-    cudaFree(c->ccl.blocklabel);
     cudaFree(c->ccl.rowcount);
     cudaFree(c->ccl.nseg);
     cudaFree(c->ccl.segoff);
     cudaFree(c->ccl.rows);
-    cudaFree(c->ccl.overflow);
     cudaFree(c->ccl.parts);
     cudaFree(c->ccl.pcount);
+    cudaFree(c->ccl.rootlist);
     if (c->h_segoff) cudaFreeHost(c->h_segoff);
     if (c->h_overflow) cudaFreeHost(c->h_overflow);
     for (auto& e : c->ev)
@@ -156,16 +155,16 @@ void free_ctx_buffers(swb_ctx* c) {
 int alloc_ccl(swb_ctx* ctx, CclBuffers& b, const Geom& g, int T, int cap_rows) {
     const size_t nblk = (size_t)T * g.BH * g.BW;
     CU(ctx, dalloc(&b.parent, nblk));
-    CU(ctx, dalloc(&b.blocklabel, nblk));
-    CU(ctx, dalloc(&b.rowcount, (size_t)T * g.BH));
+    CU(ctx, dalloc(&b.rowcount, (size_t)2 * T * g.BH));
     CU(ctx, dalloc(&b.nseg, (size_t)T));
     CU(ctx, dalloc(&b.segoff, (size_t)T + 1));
     CU(ctx, dalloc(&b.rows, (size_t)cap_rows));
-    CU(ctx, dalloc(&b.overflow, 1));
     b.cap_rows = cap_rows;
     b.cap_parts = 2 * cap_rows + 4096;
     CU(ctx, dalloc(&b.parts, (size_t)b.cap_parts));
-    CU(ctx, dalloc(&b.pcount, 1));
+    CU(ctx, dalloc(&b.pcount, 2));
+    b.overflow = b.pcount + 1;
+    CU(ctx, dalloc(&b.rootlist, (size_t)cap_rows));
     return SWB_OK;
 }
 
@@ -425,7 +424,6 @@ int swb_submit(swb_ctx* ctx, const uint8_t* frames, int32_t n_frames, int32_t n_
     CU(ctx, launch_morph_mask(s, reinterpret_cast<const uint32_t*>(ctx->raw_bits), n_frames, g, ctx->morph,
                               ctx->fbits, ctx->mask, &launches));
     if (ctx->timing) CU(ctx, cudaEventRecord(ctx->ev[2], s));
-    CU(ctx, cudaMemsetAsync(ctx->ccl.overflow, 0, sizeof(int32_t), s));
     CU(ctx, launch_ccl(s, ctx->fbits, n_frames, g, ctx->ccl, ctx->labels, ctx->label_elem, &launches,
                        ctx->timing ? &ctx->ev[3] : nullptr, 4));
     ctx->ev_valid = ctx->timing;
@@ -696,19 +694,18 @@ int swb_stage_cc_label(int32_t device, const uint8_t* in, int32_t h, int32_t w, 
     {
         const size_t nblk = (size_t)g.BH * g.BW;
         CU(nullptr, t.alloc(&b.parent, nblk));
-        CU(nullptr, t.alloc(&b.blocklabel, nblk));
-        CU(nullptr, t.alloc(&b.rowcount, (size_t)g.BH));
+        CU(nullptr, t.alloc(&b.rowcount, (size_t)2 * g.BH));
         CU(nullptr, t.alloc(&b.nseg, 1));
         CU(nullptr, t.alloc(&b.segoff, 2));
         CU(nullptr, t.alloc(&b.rows, (size_t)cap));
-        CU(nullptr, t.alloc(&b.overflow, 1));
         b.cap_rows = cap;
         b.cap_parts = 2 * cap + 4096;
         CU(nullptr, t.alloc(&b.parts, (size_t)b.cap_parts));
-        CU(nullptr, t.alloc(&b.pcount, 1));
+        CU(nullptr, t.alloc(&b.pcount, 2));
+        b.overflow = b.pcount + 1;
+        CU(nullptr, t.alloc(&b.rootlist, (size_t)cap));
     }
     CU(nullptr, cudaMemcpy(d_in, in, n, cudaMemcpyHostToDevice));
-    CU(nullptr, cudaMemset(b.overflow, 0, sizeof(int32_t)));
     CU(nullptr, launch_pack_bits(0, d_in, h, w, d_bits, g.wpr4));
     CU(nullptr, launch_ccl(0, d_bits, 1, g, b, d_lab, 4, nullptr, nullptr, 0));
     std::vector<int32_t> lab((size_t)h * w);

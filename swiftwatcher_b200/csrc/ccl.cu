@@ -11,29 +11,33 @@
 // pixel blocks (all foreground pixels of a block are mutually 8-adjacent),
 // links larger roots under smaller ones (so a root IS the minimum block of
 // its component) and the final label is 1 + the rank of the root among all
-// roots in raster order — a bit count over root flags, no sort.
+// roots in raster order — counts and prefix sums, no sort.
 //
 // Foreground is sparse (birds), so every array indexed by block is allocated
 // dense but only touched where the mask is set; the only dense traffic is the
-// final label image write.
+// final label image write.  The unit of work is a RUN: a maximal chain of
+// horizontally touching blocks inside one 32-pixel word.  Only run starts take
+// part in the union-find; per-run regionprops come from popcounts (area, row
+// sums) and bit-plane popcounts (column sums), independent of the run length.
 //
 // Tiled path (frames up to 4096 pixels wide; one CTA = full-width tile of 8..256
 // block rows held in shared memory):
-//   ccl_local     tile-local union-find in shared memory (init, merge, compress);
-//                 writes parent[b] = tile-local root and one regionprops partial
+//   ccl_local     tile-local union-find in shared memory; writes parent[b] =
+//                 tile-local root for every block and one regionprops partial
 //                 sum per tile-local component (shared-memory atomics)
 //   ccl_boundary  global unions between the first block row of a tile and the
 //                 last block row of the tile above (atomicMin union-find)
 // Wide path (wider frames): ccl_init + ccl_merge do everything globally and
 //   ccl_label also accumulates the regionprops with global atomics.
 // Then, both paths:
-//   ccl_roots     roots get parent = -(1 + rank in their block row); per-row counts
+// Ranking: tiled path from the compact partial list (root_count / root_place / root_rank:
+//   roots per block row, then label = 1 + roots in earlier rows + smaller roots in the
+//   same row, parent[root] = -label); wide path by a dense warp-per-row scan (ccl_roots).
 //   ccl_scan      per-frame exclusive scan of row counts -> segments per frame
 //   ccl_offsets   exclusive scan over frames -> row offsets of the segment table
 //   seg_init      initialise the table rows (frame, label, empty bbox)
-//   ccl_label     per block: root -> label (dense-allocated, sparsely written)
 //   props_final   adds every partial sum to its component's table row
-//   write_labels  dense int32 / uint8 label image from bits + block labels
+//   write_labels  dense int32 / uint8 label image: bits + parent walk to the tagged root
 #include "swb_internal.cuh"
 
 namespace swb {
@@ -69,6 +73,77 @@ __device__ __forceinline__ bool my_group(const Geom& g, int& f, int& by, int& q)
     return q < (g.wpr4 >> 2) && by < g.BH;
 }
 
+// ---- runs inside one word ---------------------------------------------------------
+// P = A | B (pixel columns occupied in the block row); block k = bits 2k, 2k+1.
+__device__ __forceinline__ uint32_t occ_bits(uint32_t P) { return (P | (P >> 1)) & EVEN; }      // bit 2k: block k occupied
+__device__ __forceinline__ uint32_t link_bits(uint32_t P) { return P & (P << 1) & EVEN; }      // bit 2k: block k touches k-1
+__device__ __forceinline__ uint32_t run_starts(uint32_t P) { return occ_bits(P) & ~link_bits(P); }
+// first block of the run that contains (occupied) block k
+__device__ __forceinline__ int run_start_of(uint32_t RS, int k) {
+    return (31 - __clz((int)(RS & ((2u << (2 * k)) - 1u)))) >> 1;
+}
+// pixel mask (both pixel columns of every block) of the run starting at block k0
+__device__ __forceinline__ uint32_t run_mask(uint32_t H, int k0) {
+    const uint32_t hs = (k0 == 15) ? 0u : (H >> (2 * k0 + 2));
+    const uint32_t t = ~(hs | 0xAAAAAAAAu);                 // lowest set even bit = first block not linked
+    const int len = 1 + ((__ffs((int)t) - 1) >> 1);        // t != 0: zeros are shifted in at the top
+    const uint32_t m = (len >= 16) ? 0xFFFFFFFFu : ((1u << (2 * len)) - 1u);
+    return m << (2 * k0);
+}
+// sum of the bit positions of the set bits of w
+__device__ __forceinline__ uint32_t pos_sum(uint32_t w) {
+    return __popc(w & 0xAAAAAAAAu) + 2 * __popc(w & 0xCCCCCCCCu) + 4 * __popc(w & 0xF0F0F0F0u) +
+           8 * __popc(w & 0xFF00FF00u) + 16 * __popc(w & 0xFFFF0000u);
+}
+
+struct RunStats {
+    uint32_t area, sr, sc;
+    int minr, minc, maxr, maxc;   // inclusive
+};
+// regionprops partial sums of the pixels Am (row y0) and Bm (row y0 + 1), word origin column x0
+__device__ __forceinline__ RunStats run_stats(uint32_t Am, uint32_t Bm, int y0, int x0) {
+    RunStats s;
+    const uint32_t na = __popc(Am), nb = __popc(Bm);
+    const uint32_t Pm = Am | Bm;
+    s.area = na + nb;
+    s.sr = na * (uint32_t)y0 + nb * (uint32_t)(y0 + 1);
+    s.sc = pos_sum(Am) + pos_sum(Bm) + s.area * (uint32_t)x0;
+    s.minr = Am ? y0 : y0 + 1;
+    s.maxr = Bm ? y0 + 1 : y0;
+    s.minc = x0 + __ffs((int)Pm) - 1;
+    s.maxc = x0 + 31 - __clz((int)Pm);
+    return s;
+}
+
+// Iterate the runs of a 4-word group in run-major order, so that the n-th runs of all
+// lanes of a warp are processed together whatever word they sit in.  RS[] holds the
+// remaining run-start flags; selects keep everything in registers.
+struct RunIter {
+    uint32_t RS[4];
+    __device__ __forceinline__ void init(const Group& gr) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) RS[i] = run_starts(gr.A[i] | gr.B[i]);
+    }
+    // next run: word i, first block k0, that word's rows A / B
+    __device__ __forceinline__ bool next(const Group& gr, int& i, int& k0, uint32_t& A, uint32_t& B) {
+        if ((RS[0] | RS[1] | RS[2] | RS[3]) == 0u) return false;
+        i = RS[0] ? 0 : (RS[1] ? 1 : (RS[2] ? 2 : 3));
+        const uint32_t rs = i == 0 ? RS[0] : (i == 1 ? RS[1] : (i == 2 ? RS[2] : RS[3]));
+        k0 = (__ffs((int)rs) - 1) >> 1;
+        const uint32_t rest = rs & (rs - 1);
+        RS[0] = i == 0 ? rest : RS[0];
+        RS[1] = i == 1 ? rest : RS[1];
+        RS[2] = i == 2 ? rest : RS[2];
+        RS[3] = i == 3 ? rest : RS[3];
+        A = i == 0 ? gr.A[0] : (i == 1 ? gr.A[1] : (i == 2 ? gr.A[2] : gr.A[3]));
+        B = i == 0 ? gr.B[0] : (i == 1 ? gr.B[1] : (i == 2 ? gr.B[2] : gr.B[3]));
+        return true;
+    }
+};
+
+// ------------------------------------------------------------------------------------
+// Global union-find (wide path and tile boundaries)
+// ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_ccl_init(const uint32_t* __restrict__ fbits, Geom g, int* __restrict__ parent) {
     int f, by, q;
@@ -82,8 +157,8 @@ k_ccl_init(const uint32_t* __restrict__ fbits, Geom g, int* __restrict__ parent)
     for (int i = 0; i < 4; ++i) {
         const uint32_t P = gr.A[i] | gr.B[i];
         if (!P) continue;
-        uint32_t O = (P | (P >> 1)) & EVEN;         // bit 2k: block k occupied
-        const uint32_t H = P & (P << 1) & EVEN;     // bit 2k: block k touches block k-1 (same word)
+        uint32_t O = occ_bits(P);
+        const uint32_t H = link_bits(P);
         const int base = by * g.BW + 16 * (4 * q + i);
         int start = 0;
         while (O) {
@@ -119,6 +194,25 @@ __device__ void unite(int* par, int a, int b) {
     }
 }
 
+// contact bits between word A (pixel row 2by) and the pixel row above it (Bp, with its
+// left / right neighbour words BpL / BpR); links implied by others are dropped
+struct Contacts {
+    uint32_t UP, UL, UR;   // bit 2k: block k <-> up block k / k-1 / k+1
+};
+__device__ __forceinline__ Contacts contacts(uint32_t A, uint32_t P, uint32_t BpL, uint32_t Bp, uint32_t BpR) {
+    Contacts c;
+    const uint32_t Bp_l = __funnelshift_l(BpL, Bp, 1);       // bit x = Bp[x-1]
+    const uint32_t Bp_r = __funnelshift_r(Bp, BpR, 1);       // bit x = Bp[x+1]
+    c.UP = (Bp | (Bp >> 1)) & (A | (A >> 1)) & EVEN;         // block k      <-> up block k
+    c.UL = Bp_l & A & EVEN;                                  // pixel 2k     <-> up pixel 2k-1
+    c.UR = ((Bp_r & A) >> 1) & EVEN;                         // pixel 2k+1   <-> up pixel 2k+2
+    const uint32_t H = link_bits(P);
+    c.UL &= ~(c.UP & Bp);                    // up blocks k-1,k already joined through Bp[2k-1],Bp[2k]
+    c.UR &= ~(c.UP & (Bp >> 1));             // up blocks k,k+1 already joined through Bp[2k+1],Bp[2k+2]
+    c.UP &= ~(H & (c.UP << 2) & Bp_l & Bp);  // cur k-1~k, up k-1~k and cur k-1 ~ up k-1
+    return c;
+}
+
 // Unions between the blocks of group (by, q) and the block row above: only the
 // bottom pixel row (2by - 1) of that row matters.
 __device__ void vertical_links(const Group& gr, const uint32_t* fb, const Geom& g, int by, int q, int* par) {
@@ -139,38 +233,26 @@ __device__ void vertical_links(const Group& gr, const uint32_t* fb, const Geom& 
     for (int i = 0; i < 4; ++i) {
         const uint32_t A = gr.A[i];
         if (!A) continue;
-        const uint32_t Bp = U[i + 1];
-        const uint32_t Bp_l = __funnelshift_l(U[i], Bp, 1);      // bit x = Bp[x-1]
-        const uint32_t Bp_r = __funnelshift_r(Bp, U[i + 2], 1);  // bit x = Bp[x+1]
-        const uint32_t P = A | gr.B[i];
-        uint32_t UP = (Bp | (Bp >> 1)) & (A | (A >> 1)) & EVEN;  // block k <-> up block k
-        uint32_t UL = Bp_l & A & EVEN;                           // pixel 2k   <-> up pixel 2k-1
-        uint32_t UR = ((Bp_r & A) >> 1) & EVEN;                  // pixel 2k+1 <-> up pixel 2k+2
-        // drop links implied by others
-        const uint32_t H = P & (P << 1) & EVEN;
-        UL &= ~(UP & Bp);                    // up blocks k-1,k already joined through Bp[2k-1],Bp[2k]
-        UR &= ~(UP & (Bp >> 1));             // up blocks k,k+1 already joined through Bp[2k+1],Bp[2k+2]
-        UP &= ~(H & (UP << 2) & Bp_l & Bp);  // cur k-1~k, up k-1~k and cur k-1 ~ up k-1
+        Contacts c = contacts(A, A | gr.B[i], U[i], U[i + 1], U[i + 2]);
         const int base = by * g.BW + 16 * (4 * q + i);
         const int upbase = base - g.BW;
-        while (UP) {
-            const int k = (__ffs(UP) - 1) >> 1;
-            UP &= UP - 1;
+        while (c.UP) {
+            const int k = (__ffs(c.UP) - 1) >> 1;
+            c.UP &= c.UP - 1;
             unite(par, base + k, upbase + k);
         }
-        while (UL) {
-            const int k = (__ffs(UL) - 1) >> 1;
-            UL &= UL - 1;
+        while (c.UL) {
+            const int k = (__ffs(c.UL) - 1) >> 1;
+            c.UL &= c.UL - 1;
             unite(par, base + k, upbase + k - 1);
         }
-        while (UR) {
-            const int k = (__ffs(UR) - 1) >> 1;
-            UR &= UR - 1;
+        while (c.UR) {
+            const int k = (__ffs(c.UR) - 1) >> 1;
+            c.UR &= c.UR - 1;
             unite(par, base + k, upbase + k + 1);
         }
     }
 }
-
 
 __global__ void __launch_bounds__(256)
 k_ccl_merge(const uint32_t* __restrict__ fbits, Geom g, int* parent) {
@@ -202,8 +284,245 @@ k_ccl_merge(const uint32_t* __restrict__ fbits, Geom g, int* parent) {
     vertical_links(gr, fb, g, by, q, par);
 }
 
-// warp per (frame, block row): every root (parent[b] == b) gets parent[b] =
-// -(1 + its rank among the roots of this block row); rowcount = roots in the row.
+// Global unions between the first block row of every tile (tile_rows apart) and the
+// row above it.  grid = (ceil(Q / 32), n_boundaries, T), 32 threads.
+__global__ void __launch_bounds__(32)
+k_ccl_boundary(const uint32_t* __restrict__ fbits, Geom g, int tile_rows, int* parent) {
+    const int q = blockIdx.x * 32 + threadIdx.x;
+    const int by = (blockIdx.y + 1) * tile_rows;
+    const int f = blockIdx.z;
+    if (q >= (g.wpr4 >> 2) || by >= g.BH) return;
+    const uint32_t* fb = fbits + (long long)f * g.h * g.wpr4;
+    const uint4 a4 = __ldg(reinterpret_cast<const uint4*>(fb + (long long)(2 * by) * g.wpr4) + q);
+    if ((a4.x | a4.y | a4.z | a4.w) == 0u) return;
+    Group gr;
+    load_group(gr, fb, g, by, q);
+    int* par = parent + (long long)f * g.BH * g.BW;
+    vertical_links(gr, fb, g, by, q, par);
+}
+
+// ------------------------------------------------------------------------------------
+// Tiled path: tile-local union-find in shared memory
+// ------------------------------------------------------------------------------------
+constexpr uint32_t TAG = 0x8000u;  // sp[] entry of a claimed root: TAG | slot
+constexpr uint32_t NOSLOT = 0x7FFFu;
+
+__device__ __forceinline__ int find_s(const unsigned short* sp, int x) {
+    int p = (int)((const volatile unsigned short*)sp)[x];
+    while (p != x) {
+        x = p;
+        p = (int)((const volatile unsigned short*)sp)[x];
+    }
+    return x;
+}
+// union in shared memory: link the larger root under the smaller with a 16-bit CAS
+__device__ void unite_s(unsigned short* sp, int a, int b) {
+    while (true) {
+        a = find_s(sp, a);
+        b = find_s(sp, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }   // a > b
+        const unsigned short old = atomicCAS(&sp[a], (unsigned short)a, (unsigned short)b);
+        if (old == (unsigned short)a) return;
+    }
+}
+
+__device__ __forceinline__ void emit_partial(Partial* parts, int idx, int f, int root, uint32_t area, int minr,
+                                             int minc, int maxr, int maxc, uint32_t sr, uint32_t sc, int flags) {
+    Partial p;
+    p.frame = f; p.root = root; p.area = (int)area;
+    p.minr = minr; p.minc = minc; p.maxr = maxr; p.maxc = maxc;
+    p.sr = sr; p.sc = sc; p.flags = flags; p.pad[0] = p.pad[1] = 0;
+    parts[idx] = p;
+}
+
+// BX = groups (of 4 words) per tile row, a power of two >= Q = wpr4 / 4; BY = 256 / BX block rows.
+// Tile-local block index: l = ty * ROWB + 16 * word + k (contiguous along a tile row), so the
+// left neighbour of a block is l - 1 and the block above it is l - ROWB.
+template <int BX>
+__global__ void __launch_bounds__(256)
+k_ccl_local(const uint32_t* __restrict__ fbits, Geom g, int* __restrict__ parent, Partial* __restrict__ parts,
+            int* __restrict__ pcount, int cap_parts, int32_t* __restrict__ overflow) {
+    constexpr int BY = 256 / BX;
+    constexpr int ROWB = BX * 64;            // blocks per tile row
+    constexpr int SW = BX * 4 + 2;           // words per tile row + one halo word each side
+    // tile-local components with a shared-memory accumulator: what fits in the 48 KB static limit
+    constexpr int MAXR = ((49152 - 32768 - 8 * BY * SW - 16) / 30) / 32 * 32;
+    __shared__ unsigned short sp[256 * 64];  // tile-local parents, used at run starts only (32 KB)
+    __shared__ uint32_t sP[BY * SW];         // A | B of every word
+    __shared__ uint32_t sB[BY * SW];         // bottom pixel row (B) of every word
+    __shared__ uint32_t st_area[MAXR], st_sr[MAXR], st_sc[MAXR];
+    __shared__ int st_minr[MAXR], st_minc[MAXR], st_maxr[MAXR], st_maxc[MAXR];
+    __shared__ unsigned short sroot[MAXR];
+    __shared__ int s_n, s_base;
+
+    const int tid = threadIdx.x;
+    const int tx = tid % BX, ty = tid / BX;
+    const int f = blockIdx.y;
+    const int by0 = blockIdx.x * BY;
+    const int by = by0 + ty;
+    const int Q = g.wpr4 >> 2;
+    const uint32_t* fb = fbits + (long long)f * g.h * g.wpr4;
+
+    Group gr;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) gr.A[i] = gr.B[i] = 0u;
+    if (tx < Q && by < g.BH) load_group(gr, fb, g, by, tx);
+    const uint32_t any = gr.any();
+    const int w0 = ty * SW + 1 + 4 * tx;     // smem index of this thread's word 0
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        sP[w0 + i] = gr.A[i] | gr.B[i];
+        sB[w0 + i] = gr.B[i];
+    }
+    if (tx == 0) { sP[ty * SW] = 0u; sB[ty * SW] = 0u; }
+    if (tx == BX - 1) { sP[ty * SW + SW - 1] = 0u; sB[ty * SW + SW - 1] = 0u; }
+    if (tid == 0) s_n = 0;
+
+    // ---- phase 1: every run start is its own parent
+    const int l0 = tid * 64;
+    RunIter it;
+    int i, k0;
+    uint32_t A, B;
+    if (any) {
+        it.init(gr);
+        while (it.next(gr, i, k0, A, B)) sp[l0 + i * 16 + k0] = (unsigned short)(l0 + i * 16 + k0);
+    }
+    if (!__syncthreads_or((int)any)) return;    // empty tile: nothing to write anywhere
+
+    // ---- phase 2: unions with the word to the left and with the block row above (same tile).
+    // Contacts are evaluated once per word (at its first run), unions dedup'd per run pair.
+    if (any) {
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const uint32_t Aw = gr.A[w];
+            const uint32_t P = Aw | gr.B[w];
+            if (!P) continue;
+            const int lw = l0 + w * 16;                  // tile-local index of block 0 of this word
+            if (P & 1u) {
+                const uint32_t Pl = sP[w0 + w - 1];
+                if (Pl >> 31) unite_s(sp, lw, lw - 16 + run_start_of(run_starts(Pl), 15));
+            }
+            if (ty == 0 || !Aw) continue;
+            const int wu = w0 + w - SW;                  // the word above
+            Contacts c = contacts(Aw, P, sB[wu - 1], sB[wu], sB[wu + 1]);
+            if ((c.UP | c.UL | c.UR) == 0u) continue;
+            const uint32_t RS = run_starts(P);
+            const uint32_t RSu = run_starts(sP[wu]);
+            const int lu = lw - ROWB;                    // block 0 of the word above
+            int last_a = -1, last_b = -1;
+            while (c.UP) {
+                const int k = (__ffs((int)c.UP) - 1) >> 1;
+                c.UP &= c.UP - 1;
+                const int a = lw + run_start_of(RS, k), b = lu + run_start_of(RSu, k);
+                if (a != last_a || b != last_b) unite_s(sp, a, b);
+                last_a = a; last_b = b;
+            }
+            while (c.UL) {
+                const int k = (__ffs((int)c.UL) - 1) >> 1;
+                c.UL &= c.UL - 1;
+                const int a = lw + run_start_of(RS, k);
+                const int b = (k > 0) ? lu + run_start_of(RSu, k - 1)
+                                      : lu - 16 + run_start_of(run_starts(sP[wu - 1]), 15);
+                if (a != last_a || b != last_b) unite_s(sp, a, b);
+                last_a = a; last_b = b;
+            }
+            while (c.UR) {
+                const int k = (__ffs((int)c.UR) - 1) >> 1;
+                c.UR &= c.UR - 1;
+                const int a = lw + run_start_of(RS, k);
+                const int b = (k < 15) ? lu + run_start_of(RSu, k + 1) : lu + 16;   // block 0 starts a run
+                if (a != last_a || b != last_b) unite_s(sp, a, b);
+                last_a = a; last_b = b;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 3: roots claim an accumulator slot (entry becomes TAG | slot)
+    if (any) {
+        it.init(gr);
+        while (it.next(gr, i, k0, A, B)) {
+            const int l = l0 + i * 16 + k0;
+            if ((int)sp[l] == l) {
+                const int slot = atomicAdd(&s_n, 1);
+                if (slot < MAXR) {
+                    sroot[slot] = (unsigned short)l;
+                    st_area[slot] = 0u; st_sr[slot] = 0u; st_sc[slot] = 0u;
+                    st_minr[slot] = 0x7FFFFFFF; st_minc[slot] = 0x7FFFFFFF;
+                    st_maxr[slot] = -1; st_maxc[slot] = -1;
+                    sp[l] = (unsigned short)(TAG | (uint32_t)slot);
+                } else {
+                    sp[l] = (unsigned short)(TAG | NOSLOT);
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 4: per run: root, global parent of every block, regionprops partial sums
+    if (any) {
+        int* par = parent + (long long)f * g.BH * g.BW + (long long)by * g.BW + tx * 64;
+        it.init(gr);
+        while (it.next(gr, i, k0, A, B)) {
+            // root of the run: walk to the tagged entry
+            int x = l0 + i * 16 + k0;
+            uint32_t p = sp[x];
+            while (!(p & TAG)) {
+                x = (int)p;
+                p = sp[x];
+            }
+            const uint32_t slot = p & NOSLOT;
+            const int rgid = (by0 + x / ROWB) * g.BW + (x % ROWB);    // tile-local -> global block id
+            const uint32_t P = A | B;
+            const uint32_t m = run_mask(link_bits(P), k0);
+            uint32_t O = occ_bits(P & m);
+            while (O) {
+                par[i * 16 + ((__ffs((int)O) - 1) >> 1)] = rgid;
+                O &= O - 1;
+            }
+            const RunStats s = run_stats(A & m, B & m, 2 * by, 32 * (4 * tx + i));
+            if (slot < (uint32_t)MAXR) {
+                atomicAdd(&st_area[slot], s.area);
+                atomicAdd(&st_sr[slot], s.sr);
+                atomicAdd(&st_sc[slot], s.sc);
+                atomicMin(&st_minr[slot], s.minr);
+                atomicMin(&st_minc[slot], s.minc);
+                atomicMax(&st_maxr[slot], s.maxr);
+                atomicMax(&st_maxc[slot], s.maxc);
+            } else {   // more than MAXR components in this tile: one partial per run, straight to global
+                const int idx = atomicAdd(pcount, 1);
+                const int own = (by0 + ty) * g.BW + tx * 64 + i * 16 + k0;
+                if (idx < cap_parts) emit_partial(parts, idx, f, rgid, s.area, s.minr, s.minc, s.maxr, s.maxc,
+                                                  s.sr, s.sc, own == rgid ? 2 : 1);
+                else *overflow = 1;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 5: one partial per tile-local component -> global list
+    const int n = min(s_n, MAXR);
+    if (tid == 0) s_base = atomicAdd(pcount, n);
+    __syncthreads();
+    for (int s = tid; s < n; s += 256) {
+        const int idx = s_base + s;
+        if (idx < cap_parts) {
+            const int rl = (int)sroot[s];
+            const int rgid = (by0 + rl / ROWB) * g.BW + (rl % ROWB);
+            emit_partial(parts, idx, f, rgid, st_area[s], st_minr[s], st_minc[s], st_maxr[s], st_maxc[s], st_sr[s],
+                         st_sc[s], 0);
+        } else {
+            *overflow = 1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// Ranking, labels, table
+// ------------------------------------------------------------------------------------
+// warp per (frame, block row): every root (a run start with parent[b] == b) gets
+// parent[b] = -(1 + its rank among the roots of this block row); rowcount = roots in the row.
 __global__ void __launch_bounds__(256)
 k_ccl_roots(const uint32_t* __restrict__ fbits, int T, Geom g, int* __restrict__ parent,
             uint32_t* __restrict__ rowcount) {
@@ -225,20 +544,19 @@ k_ccl_roots(const uint32_t* __restrict__ fbits, int T, Geom g, int* __restrict__
             if (gr.any()) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const uint32_t P = gr.A[i] | gr.B[i];
-                    uint32_t o = (P | (P >> 1)) & EVEN;
+                    uint32_t rs = run_starts(gr.A[i] | gr.B[i]);
                     const int base = by * g.BW + 16 * (4 * q + i);
-                    while (o) {
-                        const int b = __ffs(o) - 1;
-                        o &= o - 1;
+                    while (rs) {
+                        const int b = __ffs((int)rs) - 1;
+                        rs &= rs - 1;
                         if (par[base + (b >> 1)] == base + (b >> 1)) RB[i] |= 1u << b;
                     }
                 }
             }
         }
         const uint32_t cnt = __popc(RB[0]) + __popc(RB[1]) + __popc(RB[2]) + __popc(RB[3]);
-        const uint32_t any = __ballot_sync(0xFFFFFFFFu, cnt != 0u);
-        if (any == 0u) continue;                      // warp-uniform
+        const uint32_t anyroot = __ballot_sync(0xFFFFFFFFu, cnt != 0u);
+        if (anyroot == 0u) continue;                      // warp-uniform
         uint32_t incl = cnt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -252,7 +570,7 @@ k_ccl_roots(const uint32_t* __restrict__ fbits, int T, Geom g, int* __restrict__
                 uint32_t r = RB[i];
                 const int base = by * g.BW + 16 * (4 * q + i);
                 while (r) {
-                    const int b = __ffs(r) - 1;
+                    const int b = __ffs((int)r) - 1;
                     r &= r - 1;
                     par[base + (b >> 1)] = -(int)(1u + rank);
                     ++rank;
@@ -353,35 +671,34 @@ k_seg_init(int T, const int32_t* __restrict__ nseg, const int32_t* __restrict__ 
     }
 }
 
-struct Acc {
-    int label;        // 0 = empty
-    int area;
-    int minr, minc, maxr, maxc;   // inclusive max here; +1 applied at flush
-    long long sr, sc;
-};
-
-__device__ __forceinline__ void flush(const Acc& a, swb_segment* rows, long long off, int cap_rows) {
-    if (a.label == 0) return;
-    const long long r = off + a.label - 1;
-    if (r >= cap_rows) return;
-    swb_segment* s = rows + r;
-    atomicAdd(&s->area, a.area);
-    atomicMin(&s->bbox[0], a.minr);
-    atomicMin(&s->bbox[1], a.minc);
-    atomicMax(&s->bbox[2], a.maxr + 1);
-    atomicMax(&s->bbox[3], a.maxc + 1);
-    atomicAdd(reinterpret_cast<unsigned long long*>(&s->sum_row), (unsigned long long)a.sr);
-    atomicAdd(reinterpret_cast<unsigned long long*>(&s->sum_col), (unsigned long long)a.sc);
+__device__ __forceinline__ void add_to_row(swb_segment* s, uint32_t area, int minr, int minc, int maxr, int maxc,
+                                           unsigned long long sr, unsigned long long sc) {
+    atomicAdd(&s->area, (int)area);
+    atomicMin(&s->bbox[0], minr);
+    atomicMin(&s->bbox[1], minc);
+    atomicMax(&s->bbox[2], maxr + 1);
+    atomicMax(&s->bbox[3], maxc + 1);
+    atomicAdd(reinterpret_cast<unsigned long long*>(&s->sum_row), sr);
+    atomicAdd(reinterpret_cast<unsigned long long*>(&s->sum_col), sc);
 }
 
-// per occupied block: follow parents to the root (negative entry = -(1 + rank in
-// its row)), label = rowbase[root row] + 1 + rank; regionprops partial sums of
-// consecutive blocks with the same label are flushed with one set of atomics.
-template <bool PROPS>
+// label of an occupied block: walk parents to the tagged root.  Tiled path: the tag is
+// -label.  Wide path: the tag is -(1 + rank in the block row) and rowbase is added.
+__device__ __forceinline__ int label_of(const int* par, int x, const uint32_t* rbase, int BW) {
+    int v = par[x];
+    while (v >= 0) {
+        x = v;
+        v = par[x];
+    }
+    return rbase ? (int)rbase[x / BW] - v : -v;
+}
+
+// Wide path only: per run, add the run's regionprops to its component's table row
+// with global atomics (roots are tagged -(1 + rank in their block row)).
 __global__ void __launch_bounds__(256)
-k_ccl_label(const uint32_t* __restrict__ fbits, Geom g, const int* __restrict__ parent,
-            const uint32_t* __restrict__ rowbase, const int32_t* __restrict__ segoff,
-            int* __restrict__ blocklabel, swb_segment* rows, int cap_rows) {
+k_ccl_props_wide(const uint32_t* __restrict__ fbits, Geom g, const int* __restrict__ parent,
+                 const uint32_t* __restrict__ rowbase, const int32_t* __restrict__ segoff, swb_segment* rows,
+                 int cap_rows) {
     int f, by, q;
     if (!my_group(g, f, by, q)) return;
     const uint32_t* fb = fbits + (long long)f * g.h * g.wpr4;
@@ -389,392 +706,91 @@ k_ccl_label(const uint32_t* __restrict__ fbits, Geom g, const int* __restrict__ 
     load_group(gr, fb, g, by, q);
     if (!gr.any()) return;
     const int* par = parent + (long long)f * g.BH * g.BW;
-    int* bl = blocklabel + (long long)f * g.BH * g.BW;
     const uint32_t* rbase = rowbase + (long long)f * g.BH;
     const long long off = segoff[f];
-
-    Acc acc;
-    acc.label = 0;
-    int last_parent = 0x7FFFFFFF, last_label = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const uint32_t A = gr.A[i], B = gr.B[i];
-        const uint32_t P = A | B;
-        if (!P) continue;
-        const int base = by * g.BW + 16 * (4 * q + i);
-        uint32_t O = (P | (P >> 1)) & EVEN;
-        while (O) {
-            const int b = __ffs(O) - 1;
-            O &= O - 1;
-            const int k = b >> 1;
-            const int p0 = par[base + k];
-            int label;
-            if (p0 == last_parent) {
-                label = last_label;
-            } else {
-                int x = base + k, p = p0;
-                while (p >= 0) {
-                    x = p;
-                    p = par[x];
-                }
-                label = (int)rbase[x / g.BW] - p;
-                last_parent = p0;
-                last_label = label;
-            }
-            bl[base + k] = label;
-            if constexpr (PROPS) {
-                const int a0 = (A >> b) & 1, a1 = (A >> (b + 1)) & 1;
-                const int c0 = (B >> b) & 1, c1 = (B >> (b + 1)) & 1;
-                const int y0 = 2 * by, x0 = 32 * (4 * q + i) + b;
-                const int area = a0 + a1 + c0 + c1;
-                const int minr = (a0 | a1) ? y0 : y0 + 1;
-                const int maxr = (c0 | c1) ? y0 + 1 : y0;
-                const int minc = (a0 | c0) ? x0 : x0 + 1;
-                const int maxc = (a1 | c1) ? x0 + 1 : x0;
-                const long long sr = (long long)(a0 + a1) * y0 + (long long)(c0 + c1) * (y0 + 1);
-                const long long sc = (long long)(a0 + c0) * x0 + (long long)(a1 + c1) * (x0 + 1);
-                if (label != acc.label) {
-                    flush(acc, rows, off, cap_rows);
-                    acc.label = label;
-                    acc.area = area;
-                    acc.minr = minr; acc.maxr = maxr; acc.minc = minc; acc.maxc = maxc;
-                    acc.sr = sr; acc.sc = sc;
-                } else {
-                    acc.area += area;
-                    acc.minr = min(acc.minr, minr); acc.maxr = max(acc.maxr, maxr);
-                    acc.minc = min(acc.minc, minc); acc.maxc = max(acc.maxc, maxc);
-                    acc.sr += sr; acc.sc += sc;
-                }
-            }
-        }
-    }
-    if constexpr (PROPS) flush(acc, rows, off, cap_rows);
-}
-
-// ------------------------------------------------------------------------------------
-// Tiled path
-// ------------------------------------------------------------------------------------
-constexpr int MAXR = 256;          // tile-local components with a shared-memory accumulator
-constexpr uint32_t TAG = 0x8000u;  // sp[] entry of a claimed root: TAG | slot
-constexpr uint32_t NOSLOT = 0x7FFFu;
-
-__device__ __forceinline__ uint32_t ld_s(const unsigned short* sp, int i) {
-    return ((const volatile unsigned short*)sp)[i];
-}
-__device__ __forceinline__ int find_s(const unsigned short* sp, int x) {
-    int p = (int)ld_s(sp, x);
-    while (p != x) {
-        x = p;
-        p = (int)ld_s(sp, x);
-    }
-    return x;
-}
-// union in shared memory: link the larger root under the smaller with a 16-bit CAS
-__device__ void unite_s(unsigned short* sp, int a, int b) {
-    while (true) {
-        a = find_s(sp, a);
-        b = find_s(sp, b);
-        if (a == b) return;
-        if (a < b) { int t = a; a = b; b = t; }   // a > b
-        const unsigned short old = atomicCAS(&sp[a], (unsigned short)a, (unsigned short)b);
-        if (old == (unsigned short)a) return;
+    RunIter it;
+    it.init(gr);
+    int i, k0;
+    uint32_t A, B;
+    while (it.next(gr, i, k0, A, B)) {
+        const int label = label_of(par, by * g.BW + 16 * (4 * q + i) + k0, rbase, g.BW);
+        const uint32_t m = run_mask(link_bits(A | B), k0);
+        const RunStats s = run_stats(A & m, B & m, 2 * by, 32 * (4 * q + i));
+        const long long r = off + label - 1;
+        if (r < cap_rows) add_to_row(rows + r, s.area, s.minr, s.minc, s.maxr, s.maxc, s.sr, s.sc);
     }
 }
 
-struct PartAcc {
-    uint32_t slot;   // NOSLOT + 1 = empty
-    int root;
-    uint32_t area, sr, sc;
-    int minr, minc, maxr, maxc;
-};
-
-__device__ __forceinline__ void emit_partial(Partial* parts, int idx, int f, int root, uint32_t area, int minr,
-                                             int minc, int maxr, int maxc, uint32_t sr, uint32_t sc) {
-    Partial p;
-    p.frame = f; p.root = root; p.area = (int)area;
-    p.minr = minr; p.minc = minc; p.maxr = maxr; p.maxc = maxc;
-    p.sr = sr; p.sc = sc; p.pad[0] = p.pad[1] = p.pad[2] = 0;
-    parts[idx] = p;
+// Ranking from the partial list (tiled path).  Every component has exactly one
+// "representative" partial: the slot partial of the tile that holds its root, or the
+// overflow partial of the run that starts at the root (flags 0 / 2).  A representative
+// whose root survived the boundary merges (parent[root] == root) is a component.
+__device__ __forceinline__ bool is_root_partial(const Partial& p, const int* par) {
+    return p.flags != 1 && par[p.root] == p.root;
 }
 
-// BX = groups (of 4 words) per tile row, a power of two >= Q = wpr4 / 4; BY = 256 / BX block rows.
-template <int BX>
+// pass 1: roots per block row
 __global__ void __launch_bounds__(256)
-k_ccl_local(const uint32_t* __restrict__ fbits, Geom g, int* __restrict__ parent, Partial* __restrict__ parts,
-            int* __restrict__ pcount, int cap_parts, int32_t* __restrict__ overflow) {
-    constexpr int BY = 256 / BX;
-    constexpr int ROWB = BX * 64;            // blocks per tile row
-    constexpr int SBW = BX * 4 + 2;          // bottom-row words + one halo word each side
-    __shared__ unsigned short sp[256 * 64];  // tile-local parents (32 KB)
-    __shared__ uint32_t sB[BY * SBW];
-    __shared__ uint32_t sPw3[256];
-    __shared__ uint32_t st_area[MAXR], st_sr[MAXR], st_sc[MAXR];
-    __shared__ int st_minr[MAXR], st_minc[MAXR], st_maxr[MAXR], st_maxc[MAXR];
-    __shared__ unsigned short sroot[MAXR];
-    __shared__ int s_n, s_base;
-
-    const int tid = threadIdx.x;
-    const int tx = tid % BX, ty = tid / BX;
-    const int f = blockIdx.y;
-    const int by0 = blockIdx.x * BY;
-    const int by = by0 + ty;
-    const int Q = g.wpr4 >> 2;
-    const uint32_t* fb = fbits + (long long)f * g.h * g.wpr4;
-
-    Group gr;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) gr.A[i] = gr.B[i] = 0u;
-    if (tx < Q && by < g.BH) load_group(gr, fb, g, by, tx);
-    const uint32_t any = gr.any();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) sB[ty * SBW + 1 + 4 * tx + i] = gr.B[i];
-    if (tx == 0) sB[ty * SBW] = 0u;
-    if (tx == BX - 1) sB[ty * SBW + SBW - 1] = 0u;
-    sPw3[tid] = gr.A[3] | gr.B[3];
-    if (tid == 0) s_n = 0;
-
-    // ---- phase 1: parent = first block of the horizontal run (inside the thread's 128 pixels)
-    const int l0 = tid * 64;
-    if (any) {
-        int start = 0;
-        uint32_t Pprev = 0u;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint32_t P = gr.A[i] | gr.B[i];
-            uint32_t O = (P | (P >> 1)) & EVEN;
-            const uint32_t H = (P & ((P << 1) | (Pprev >> 31))) & EVEN;   // bit 2k: block k touches block k-1
-            while (O) {
-                const int b = __ffs(O) - 1;
-                O &= O - 1;
-                const int pos = i * 16 + (b >> 1);
-                if (!((H >> b) & 1u)) start = pos;
-                sp[l0 + pos] = (unsigned short)(l0 + start);
-            }
-            Pprev = P;
-        }
-    }
-    if (!__syncthreads_or((int)any)) return;    // empty tile: nothing to write anywhere
-
-    // ---- phase 2: unions with the left neighbour thread and with the block row above (same tile)
-    if (any) {
-        if (((gr.A[0] | gr.B[0]) & 1u) && tx > 0 && (sPw3[tid - 1] >> 31)) unite_s(sp, l0, l0 - 1);
-        if (ty > 0) {
-            const uint32_t* up = &sB[(ty - 1) * SBW + 4 * tx];   // up[0] = word 4tx-1 of the row above
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const uint32_t A = gr.A[i];
-                if (!A) continue;
-                const uint32_t Bp = up[i + 1];
-                const uint32_t Bp_l = __funnelshift_l(up[i], Bp, 1);
-                const uint32_t Bp_r = __funnelshift_r(Bp, up[i + 2], 1);
-                const uint32_t P = A | gr.B[i];
-                uint32_t UP = (Bp | (Bp >> 1)) & (A | (A >> 1)) & EVEN;
-                uint32_t UL = Bp_l & A & EVEN;
-                uint32_t UR = ((Bp_r & A) >> 1) & EVEN;
-                const uint32_t H = P & (P << 1) & EVEN;
-                UL &= ~(UP & Bp);
-                UR &= ~(UP & (Bp >> 1));
-                UP &= ~(H & (UP << 2) & Bp_l & Bp);
-                const int base = l0 + i * 16;
-                while (UP) {
-                    const int k = (__ffs(UP) - 1) >> 1;
-                    UP &= UP - 1;
-                    unite_s(sp, base + k, base + k - ROWB);
-                }
-                while (UL) {
-                    const int k = (__ffs(UL) - 1) >> 1;
-                    UL &= UL - 1;
-                    unite_s(sp, base + k, base + k - ROWB - 1);
-                }
-                while (UR) {
-                    const int k = (__ffs(UR) - 1) >> 1;
-                    UR &= UR - 1;
-                    unite_s(sp, base + k, base + k - ROWB + 1);
-                }
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- phase 3a: full path compression (every entry points at its root)
-    if (any) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint32_t P = gr.A[i] | gr.B[i];
-            uint32_t O = (P | (P >> 1)) & EVEN;
-            while (O) {
-                const int pos = i * 16 + ((__ffs(O) - 1) >> 1);
-                O &= O - 1;
-                const int r = find_s(sp, l0 + pos);
-                sp[l0 + pos] = (unsigned short)r;
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- phase 3b: roots claim an accumulator slot
-    if (any) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint32_t P = gr.A[i] | gr.B[i];
-            uint32_t O = (P | (P >> 1)) & EVEN;
-            while (O) {
-                const int pos = i * 16 + ((__ffs(O) - 1) >> 1);
-                O &= O - 1;
-                const int l = l0 + pos;
-                if ((int)sp[l] == l) {
-                    const int slot = atomicAdd(&s_n, 1);
-                    if (slot < MAXR) {
-                        sroot[slot] = (unsigned short)l;
-                        st_area[slot] = 0u; st_sr[slot] = 0u; st_sc[slot] = 0u;
-                        st_minr[slot] = 0x7FFFFFFF; st_minc[slot] = 0x7FFFFFFF;
-                        st_maxr[slot] = -1; st_maxc[slot] = -1;
-                        sp[l] = (unsigned short)(TAG | (uint32_t)slot);
-                    } else {
-                        sp[l] = (unsigned short)(TAG | NOSLOT);
-                    }
-                }
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- phase 3c: global parent = tile-local root; regionprops partial sums per root
-    if (any) {
-        int* par = parent + (long long)f * g.BH * g.BW;
-        const int grow = by * g.BW;              // global id of this block row's block 0
-        PartAcc acc;
-        acc.slot = NOSLOT + 1;
-        auto flush_acc = [&]() {
-            if (acc.slot == NOSLOT + 1) return;
-            if (acc.slot < (uint32_t)MAXR) {
-                atomicAdd(&st_area[acc.slot], acc.area);
-                atomicAdd(&st_sr[acc.slot], acc.sr);
-                atomicAdd(&st_sc[acc.slot], acc.sc);
-                atomicMin(&st_minr[acc.slot], acc.minr);
-                atomicMin(&st_minc[acc.slot], acc.minc);
-                atomicMax(&st_maxr[acc.slot], acc.maxr);
-                atomicMax(&st_maxc[acc.slot], acc.maxc);
-            } else {   // more than MAXR components in this tile: one partial per run, straight to global
-                const int idx = atomicAdd(pcount, 1);
-                if (idx < cap_parts) emit_partial(parts, idx, f, acc.root, acc.area, acc.minr, acc.minc, acc.maxr,
-                                                  acc.maxc, acc.sr, acc.sc);
-                else *overflow = 1;
-            }
-        };
-        int last_e = -1;
-        uint32_t last_slot = 0;
-        int last_root = 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint32_t A = gr.A[i], B = gr.B[i];
-            const uint32_t P = A | B;
-            uint32_t O = (P | (P >> 1)) & EVEN;
-            while (O) {
-                const int b = __ffs(O) - 1;
-                O &= O - 1;
-                const int pos = i * 16 + (b >> 1);
-                const int l = l0 + pos;
-                const int e = (int)sp[l];
-                uint32_t slot;
-                int rl;                               // tile-local index of the root
-                if (e == last_e && !(e & TAG)) {
-                    slot = last_slot; rl = last_root;
-                } else if (e & TAG) {
-                    slot = (uint32_t)e & NOSLOT; rl = l;
-                } else {
-                    slot = (uint32_t)sp[e] & NOSLOT; rl = e;
-                    last_e = e; last_slot = slot; last_root = rl;
-                }
-                // tile-local index -> global block id: rows are contiguous runs of ROWB blocks
-                const int rgid = (by0 + rl / ROWB) * g.BW + (rl % ROWB);
-                par[grow + tx * 64 + pos] = rgid;
-                const int a0 = (A >> b) & 1, a1 = (A >> (b + 1)) & 1;
-                const int c0 = (B >> b) & 1, c1 = (B >> (b + 1)) & 1;
-                const int y0 = 2 * by, x0 = 2 * (tx * 64 + pos);
-                const uint32_t area = a0 + a1 + c0 + c1;
-                const int minr = (a0 | a1) ? y0 : y0 + 1;
-                const int maxr = (c0 | c1) ? y0 + 1 : y0;
-                const int minc = (a0 | c0) ? x0 : x0 + 1;
-                const int maxc = (a1 | c1) ? x0 + 1 : x0;
-                const uint32_t sr = (uint32_t)((a0 + a1) * y0 + (c0 + c1) * (y0 + 1));
-                const uint32_t sc = (uint32_t)((a0 + c0) * x0 + (a1 + c1) * (x0 + 1));
-                if (slot != acc.slot || (slot == NOSLOT && rgid != acc.root)) {
-                    flush_acc();
-                    acc.slot = slot; acc.root = rgid;
-                    acc.area = area; acc.sr = sr; acc.sc = sc;
-                    acc.minr = minr; acc.maxr = maxr; acc.minc = minc; acc.maxc = maxc;
-                } else {
-                    acc.area += area; acc.sr += sr; acc.sc += sc;
-                    acc.minr = min(acc.minr, minr); acc.maxr = max(acc.maxr, maxr);
-                    acc.minc = min(acc.minc, minc); acc.maxc = max(acc.maxc, maxc);
-                }
-            }
-        }
-        flush_acc();
-    }
-    __syncthreads();
-
-    // ---- phase 3d: one partial per tile-local component -> global list
-    const int n = min(s_n, MAXR);
-    if (tid == 0) s_base = atomicAdd(pcount, n);
-    __syncthreads();
-    for (int s = tid; s < n; s += 256) {
-        const int idx = s_base + s;
-        if (idx < cap_parts) {
-            const int rl = (int)sroot[s];
-            const int rgid = (by0 + rl / ROWB) * g.BW + (rl % ROWB);
-            emit_partial(parts, idx, f, rgid, st_area[s], st_minr[s], st_minc[s], st_maxr[s], st_maxc[s], st_sr[s],
-                         st_sc[s]);
-        } else {
-            *overflow = 1;
-        }
+k_root_count(const Partial* __restrict__ parts, const int* __restrict__ pcount, int cap_parts, Geom g,
+             const int* __restrict__ parent, uint32_t* __restrict__ rowcount) {
+    const int n = min(*pcount, cap_parts);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const Partial p = parts[i];
+        if (is_root_partial(p, parent + (long long)p.frame * g.BH * g.BW))
+            atomicAdd(&rowcount[(long long)p.frame * g.BH + p.root / g.BW], 1u);
     }
 }
 
-// Global unions between the first block row of every tile (tile_rows apart) and the
-// row above it.  grid = (ceil(Q / 32), n_boundaries, T), 32 threads.
-__global__ void __launch_bounds__(32)
-k_ccl_boundary(const uint32_t* __restrict__ fbits, Geom g, int tile_rows, int* parent) {
-    const int q = blockIdx.x * 32 + threadIdx.x;
-    const int by = (blockIdx.y + 1) * tile_rows;
-    const int f = blockIdx.z;
-    if (q >= (g.wpr4 >> 2) || by >= g.BH) return;
-    const uint32_t* fb = fbits + (long long)f * g.h * g.wpr4;
-    const uint4 a4 = __ldg(reinterpret_cast<const uint4*>(fb + (long long)(2 * by) * g.wpr4) + q);
-    uint32_t Aw[4] = {a4.x, a4.y, a4.z, a4.w};
-    if ((Aw[0] | Aw[1] | Aw[2] | Aw[3]) == 0u) return;
-    Group gr;
-    load_group(gr, fb, g, by, q);
-    int* par = parent + (long long)f * g.BH * g.BW;
-    vertical_links(gr, fb, g, by, q, par);
+// pass 2: roots of one block row side by side (arbitrary order) in rootlist
+__global__ void __launch_bounds__(256)
+k_root_place(const Partial* __restrict__ parts, const int* __restrict__ pcount, int cap_parts, Geom g,
+             const int* __restrict__ parent, const uint32_t* __restrict__ rowbase,
+             uint32_t* __restrict__ rowfill, const int32_t* __restrict__ segoff, int* __restrict__ rootlist,
+             int cap_rows) {
+    const int n = min(*pcount, cap_parts);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const Partial p = parts[i];
+        if (!is_root_partial(p, parent + (long long)p.frame * g.BH * g.BW)) continue;
+        const long long row = (long long)p.frame * g.BH + p.root / g.BW;
+        const long long pos = (long long)segoff[p.frame] + rowbase[row] + atomicAdd(&rowfill[row], 1u);
+        if (pos < cap_rows) rootlist[pos] = p.root;
+    }
+}
+
+// pass 3: label = 1 + roots in earlier rows + smaller roots in the same row; parent[root] = -label
+__global__ void __launch_bounds__(256)
+k_root_rank(const Partial* __restrict__ parts, const int* __restrict__ pcount, int cap_parts, Geom g,
+            int* __restrict__ parent, const uint32_t* __restrict__ rowbase, const uint32_t* __restrict__ rowfill,
+            const int32_t* __restrict__ segoff, const int* __restrict__ rootlist, int cap_rows) {
+    const int n = min(*pcount, cap_parts);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const Partial p = parts[i];
+        int* par = parent + (long long)p.frame * g.BH * g.BW;
+        if (p.flags == 1) continue;
+        const int self = par[p.root];
+        if (self != p.root) continue;           // merged away (self >= 0) -- tags are written below, only by us
+        const long long row = (long long)p.frame * g.BH + p.root / g.BW;
+        const long long lo = (long long)segoff[p.frame] + rowbase[row];
+        const int cnt = (int)rowfill[row];
+        int rank = 0;
+        for (int j = 0; j < cnt; ++j)
+            if (lo + j < cap_rows && rootlist[lo + j] < p.root) ++rank;
+        par[p.root] = -(int)(rowbase[row] + rank + 1);
+    }
 }
 
 // every partial sum -> its component's row of the segment table
 __global__ void __launch_bounds__(256)
 k_props_final(const Partial* __restrict__ parts, const int* __restrict__ pcount, int cap_parts, Geom g,
-              const int* __restrict__ parent, const uint32_t* __restrict__ rowbase,
-              const int32_t* __restrict__ segoff, swb_segment* rows, int cap_rows) {
+              const int* __restrict__ parent, const int32_t* __restrict__ segoff, swb_segment* rows,
+              int cap_rows) {
     const int n = min(*pcount, cap_parts);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const Partial p = parts[i];
-        const int* par = parent + (long long)p.frame * g.BH * g.BW;
-        int x = p.root, v = par[x];
-        while (v >= 0) {
-            x = v;
-            v = par[x];
-        }
-        const int label = (int)rowbase[(long long)p.frame * g.BH + x / g.BW] - v;
+        const int label = label_of(parent + (long long)p.frame * g.BH * g.BW, p.root, nullptr, g.BW);
         const long long r = (long long)segoff[p.frame] + label - 1;
         if (r >= cap_rows) continue;
-        swb_segment* s = rows + r;
-        atomicAdd(&s->area, p.area);
-        atomicMin(&s->bbox[0], p.minr);
-        atomicMin(&s->bbox[1], p.minc);
-        atomicMax(&s->bbox[2], p.maxr + 1);
-        atomicMax(&s->bbox[3], p.maxc + 1);
-        atomicAdd(reinterpret_cast<unsigned long long*>(&s->sum_row), (unsigned long long)p.sr);
-        atomicAdd(reinterpret_cast<unsigned long long*>(&s->sum_col), (unsigned long long)p.sc);
+        add_to_row(rows + r, (uint32_t)p.area, p.minr, p.minc, p.maxr, p.maxc, p.sr, p.sc);
     }
 }
 
@@ -782,15 +798,16 @@ k_props_final(const Partial* __restrict__ parts, const int* __restrict__ pcount,
 // of one row and walks down RPT rows; stores are 16 bytes, contiguous per warp.
 template <typename LT, int PX>
 __global__ void __launch_bounds__(256)
-k_write_labels(const uint32_t* __restrict__ fbits, Geom g, const int* __restrict__ blocklabel,
-               LT* __restrict__ labels, int rows_per_thread) {
+k_write_labels(const uint32_t* __restrict__ fbits, Geom g, const int* __restrict__ parent,
+               const uint32_t* __restrict__ rowbase, LT* __restrict__ labels, int rows_per_thread) {
     const int f = blockIdx.z;
     const int gx = blockIdx.x * blockDim.x + threadIdx.x;   // pixel group within the row
     const int x = gx * PX;
     if (x >= g.mpitch) return;
     const int yb = blockIdx.y * rows_per_thread;
     const uint32_t* fb = fbits + (long long)f * g.h * g.wpr4;
-    const int* bl = blocklabel + (long long)f * g.BH * g.BW;
+    const int* par = parent + (long long)f * g.BH * g.BW;
+    const uint32_t* rbase = rowbase ? rowbase + (long long)f * g.BH : nullptr;
     LT* out = labels + (long long)f * g.h * g.mpitch;
     const int j = x >> 5, sh = x & 31;
     for (int yy = 0; yy < rows_per_thread; ++yy) {
@@ -801,11 +818,19 @@ k_write_labels(const uint32_t* __restrict__ fbits, Geom g, const int* __restrict
 #pragma unroll
         for (int i = 0; i < PX; ++i) v[i] = 0;
         if (bits) {
-            const int* blrow = bl + (long long)(y >> 1) * g.BW + (x >> 1);
+            const int b0 = (y >> 1) * g.BW + (x >> 1);
+            int last_p = 0x7FFFFFFF, last_lab = 0;
 #pragma unroll
             for (int i = 0; i < PX; i += 2) {
                 if ((bits >> i) & 3u) {
-                    const int lab = blrow[i >> 1];
+                    const int p0 = par[b0 + (i >> 1)];
+                    int lab;
+                    if (p0 == last_p) {
+                        lab = last_lab;
+                    } else {
+                        lab = label_of(par, b0 + (i >> 1), rbase, g.BW);
+                        last_p = p0; last_lab = lab;
+                    }
                     if ((bits >> i) & 1u) v[i] = (LT)lab;
                     if ((bits >> (i + 1)) & 1u) v[i + 1] = (LT)lab;
                 }
@@ -900,9 +925,11 @@ cudaError_t launch_ccl(cudaStream_t s, const uint32_t* fbits, int T, const Geom&
     dim3 gblock(bx, 256 / bx);
     dim3 ggrid((Q + bx - 1) / bx, (g.BH + gblock.y - 1) / gblock.y, T);
     const bool tiled = Q <= 32;      // a tile spans the full width: frames up to 4096 pixels wide
+    const uint32_t* rbase_for_labels = nullptr;
     int launches = 0;
+    cudaMemsetAsync(b.pcount, 0, 2 * sizeof(int), s);                  // pcount, overflow
     if (tiled) {
-        cudaMemsetAsync(b.pcount, 0, sizeof(int), s);
+        cudaMemsetAsync(b.rowcount, 0, (size_t)2 * T * g.BH * sizeof(uint32_t), s);   // rowcount, rowfill
         switch (bx) {
             case 1: launch_local<1>(s, fbits, T, g, b); break;
             case 2: launch_local<2>(s, fbits, T, g, b); break;
@@ -912,14 +939,17 @@ cudaError_t launch_ccl(cudaStream_t s, const uint32_t* fbits, int T, const Geom&
             default: launch_local<32>(s, fbits, T, g, b); break;
         }
         launches += 2;
+        mark();
+        k_root_count<<<296, 256, 0, s>>>(b.parts, b.pcount, b.cap_parts, g, b.parent, b.rowcount);
     } else {
         k_ccl_init<<<ggrid, gblock, 0, s>>>(fbits, g, b.parent);
         k_ccl_merge<<<ggrid, gblock, 0, s>>>(fbits, g, b.parent);
         launches += 2;
+        mark();
+        const long long n_rows_w = (long long)T * g.BH;
+        k_ccl_roots<<<(int)((n_rows_w * 32 + 255) / 256), 256, 0, s>>>(fbits, T, g, b.parent, b.rowcount);
+        rbase_for_labels = b.rowcount;
     }
-    mark();
-    const long long n_rows_w = (long long)T * g.BH;
-    k_ccl_roots<<<(int)((n_rows_w * 32 + 255) / 256), 256, 0, s>>>(fbits, T, g, b.parent, b.rowcount);
     k_ccl_scan<<<(T * 32 + 255) / 256, 256, 0, s>>>(T, g, b.rowcount, b.nseg);
     k_ccl_offsets<<<1, 1024, 0, s>>>(T, b.nseg, b.segoff, b.cap_rows, b.overflow);
     {
@@ -927,16 +957,18 @@ cudaError_t launch_ccl(cudaStream_t s, const uint32_t* fbits, int T, const Geom&
         k_seg_init<<<grid, 256, 0, s>>>(T, b.nseg, b.segoff, b.rows, b.cap_rows);
     }
     launches += 4;
-    mark();
     if (tiled) {
-        k_ccl_label<false><<<ggrid, gblock, 0, s>>>(fbits, g, b.parent, b.rowcount, b.segoff, b.blocklabel, b.rows,
-                                                    b.cap_rows);
-        k_props_final<<<296, 256, 0, s>>>(b.parts, b.pcount, b.cap_parts, g, b.parent, b.rowcount, b.segoff, b.rows,
-                                          b.cap_rows);
-        launches += 2;
+        uint32_t* rowfill = b.rowcount + (size_t)T * g.BH;
+        k_root_place<<<296, 256, 0, s>>>(b.parts, b.pcount, b.cap_parts, g, b.parent, b.rowcount, rowfill, b.segoff,
+                                         b.rootlist, b.cap_rows);
+        k_root_rank<<<296, 256, 0, s>>>(b.parts, b.pcount, b.cap_parts, g, b.parent, b.rowcount, rowfill, b.segoff,
+                                        b.rootlist, b.cap_rows);
+        mark();
+        k_props_final<<<296, 256, 0, s>>>(b.parts, b.pcount, b.cap_parts, g, b.parent, b.segoff, b.rows, b.cap_rows);
+        launches += 3;
     } else {
-        k_ccl_label<true><<<ggrid, gblock, 0, s>>>(fbits, g, b.parent, b.rowcount, b.segoff, b.blocklabel, b.rows,
-                                                   b.cap_rows);
+        mark();
+        k_ccl_props_wide<<<ggrid, gblock, 0, s>>>(fbits, g, b.parent, b.rowcount, b.segoff, b.rows, b.cap_rows);
         launches += 1;
     }
     mark();
@@ -944,10 +976,12 @@ cudaError_t launch_ccl(cudaStream_t s, const uint32_t* fbits, int T, const Geom&
         const int rpt = 8;
         if (label_elem_size == 4) {
             dim3 grid((g.mpitch / 4 + 255) / 256, (g.h + rpt - 1) / rpt, T);
-            k_write_labels<int32_t, 4><<<grid, 256, 0, s>>>(fbits, g, b.blocklabel, (int32_t*)labels, rpt);
+            k_write_labels<int32_t, 4><<<grid, 256, 0, s>>>(fbits, g, b.parent, rbase_for_labels, (int32_t*)labels,
+                                                            rpt);
         } else {
             dim3 grid((g.mpitch / 16 + 255) / 256, (g.h + rpt - 1) / rpt, T);
-            k_write_labels<uint8_t, 16><<<grid, 256, 0, s>>>(fbits, g, b.blocklabel, (uint8_t*)labels, rpt);
+            k_write_labels<uint8_t, 16><<<grid, 256, 0, s>>>(fbits, g, b.parent, rbase_for_labels, (uint8_t*)labels,
+                                                             rpt);
         }
         launches += 1;
     }

@@ -60,20 +60,22 @@ struct Partial {
     int area;
     int minr, minc, maxr, maxc;    // inclusive
     unsigned sr, sc;               // sums of row / column coordinates within the tile
-    int pad[3];
+    int flags;                     // 0 = one per tile-local component; 1 / 2 = per-run overflow partial
+                                   // (2: the run that starts at the root block)
+    int pad[2];
 };
 
 struct CclBuffers {
     int* parent;          // [T][BH][BW]
-    int* blocklabel;      // [T][BH][BW]
-    uint32_t* rowcount;   // [T][BH]  (becomes exclusive row base after the scan)
+    uint32_t* rowcount;   // [2][T][BH]: roots per block row (exclusive row base after the scan), then rowfill
     int32_t* nseg;        // [T] segments per frame
     int32_t* segoff;      // [T+1] exclusive prefix of nseg
     swb_segment* rows;    // [cap_rows]
     int cap_rows;
-    int32_t* overflow;    // device flag: 1 when total rows > cap_rows (or partials > cap_parts)
+    int32_t* overflow;    // = pcount + 1; device flag: 1 when total rows > cap_rows (or partials > cap_parts)
     Partial* parts;       // [cap_parts] tile-local regionprops partial sums
     int* pcount;          // number of partials appended
+    int* rootlist;        // [cap_rows] roots grouped by block row (tiled path ranking)
     int cap_parts;
 };
 cudaError_t launch_ccl(cudaStream_t s, const uint32_t* fbits, int T, const Geom& g,
