@@ -794,30 +794,47 @@ k_props_final(const Partial* __restrict__ parts, const int* __restrict__ pcount,
     }
 }
 
-// Dense label image.  A thread owns 4 (int32) or 16 (uint8) consecutive pixels
-// of one row and walks down RPT rows; stores are 16 bytes, contiguous per warp.
+// Dense label image.  A warp owns a span of 32 * PX pixels (PX = 4 int32 or 16 uint8 labels
+// per lane = one 16-byte store) over 8 rows.  The bit words of the span are loaded once,
+// coalesced (one word per lane per round), and handed to the lanes that need them with
+// shuffles, so the row loop has no dependent global load on the (dominant) background path.
 template <typename LT, int PX>
 __global__ void __launch_bounds__(256)
 k_write_labels(const uint32_t* __restrict__ fbits, Geom g, const int* __restrict__ parent,
-               const uint32_t* __restrict__ rowbase, LT* __restrict__ labels, int rows_per_thread) {
+               const uint32_t* __restrict__ rowbase, LT* __restrict__ labels) {
+    constexpr int WPS = PX;                 // words per span row (32 * PX pixels / 32)
+    constexpr int RPL = 32 / WPS;           // rows covered by one load round
+    constexpr int ROWS = 8;
+    constexpr int ROUNDS = ROWS / RPL;
+    const int lane = threadIdx.x & 31;
+    const int span = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int f = blockIdx.z;
-    const int gx = blockIdx.x * blockDim.x + threadIdx.x;   // pixel group within the row
-    const int x = gx * PX;
-    if (x >= g.mpitch) return;
-    const int yb = blockIdx.y * rows_per_thread;
+    const int yb = blockIdx.y * ROWS;
+    const int x = span * (32 * PX) + lane * PX;          // first pixel of this lane
+    if (span * (32 * PX) >= g.mpitch) return;            // warp-uniform
     const uint32_t* fb = fbits + (long long)f * g.h * g.wpr4;
+    uint32_t wreg[ROUNDS];
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+        const int y = yb + r * RPL + lane / WPS;
+        const int j = span * WPS + lane % WPS;
+        wreg[r] = (y < g.h && j < g.wpr4) ? __ldg(fb + (long long)y * g.wpr4 + j) : 0u;
+    }
     const int* par = parent + (long long)f * g.BH * g.BW;
     const uint32_t* rbase = rowbase ? rowbase + (long long)f * g.BH : nullptr;
-    LT* out = labels + (long long)f * g.h * g.mpitch;
-    const int j = x >> 5, sh = x & 31;
-    for (int yy = 0; yy < rows_per_thread; ++yy) {
-        const int y = yb + yy;
-        if (y >= g.h) break;
-        const uint32_t bits = (fb[(long long)y * g.wpr4 + j] >> sh) & ((PX == 32) ? 0xFFFFFFFFu : ((1u << PX) - 1u));
-        LT v[PX];
+    LT* out = labels + (long long)f * g.h * g.mpitch + x;
+    const int wsel = (lane * PX) >> 5, sh = (lane * PX) & 31;
 #pragma unroll
-        for (int i = 0; i < PX; ++i) v[i] = 0;
+    for (int r = 0; r < ROWS; ++r) {
+        const uint32_t word = __shfl_sync(0xFFFFFFFFu, wreg[r / RPL], (r % RPL) * WPS + wsel);
+        const int y = yb + r;
+        if (y >= g.h || x >= g.mpitch) continue;
+        const uint32_t bits = (word >> sh) & ((1u << PX) - 1u);
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
         if (bits) {
+            LT v[PX];
+#pragma unroll
+            for (int i = 0; i < PX; ++i) v[i] = 0;
             const int b0 = (y >> 1) * g.BW + (x >> 1);
             int last_p = 0x7FFFFFFF, last_lab = 0;
 #pragma unroll
@@ -835,19 +852,18 @@ k_write_labels(const uint32_t* __restrict__ fbits, Geom g, const int* __restrict
                     if ((bits >> (i + 1)) & 1u) v[i + 1] = (LT)lab;
                 }
             }
-        }
-        uint4 o;
-        if constexpr (sizeof(LT) == 4) {
-            o = make_uint4((uint32_t)v[0], (uint32_t)v[1], (uint32_t)v[2], (uint32_t)v[3]);
-        } else {
-            uint32_t w[4];
+            if constexpr (sizeof(LT) == 4) {
+                o = make_uint4((uint32_t)v[0], (uint32_t)v[1], (uint32_t)v[2], (uint32_t)v[3]);
+            } else {
+                uint32_t w[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                w[q] = (uint32_t)v[4 * q] | ((uint32_t)v[4 * q + 1] << 8) | ((uint32_t)v[4 * q + 2] << 16) |
-                       ((uint32_t)v[4 * q + 3] << 24);
-            o = make_uint4(w[0], w[1], w[2], w[3]);
+                for (int q = 0; q < 4; ++q)
+                    w[q] = (uint32_t)v[4 * q] | ((uint32_t)v[4 * q + 1] << 8) | ((uint32_t)v[4 * q + 2] << 16) |
+                           ((uint32_t)v[4 * q + 3] << 24);
+                o = make_uint4(w[0], w[1], w[2], w[3]);
+            }
         }
-        __stcs(reinterpret_cast<uint4*>(out + (long long)y * g.mpitch + x), o);
+        __stcs(reinterpret_cast<uint4*>(out + (long long)y * g.mpitch), o);
     }
 }
 
@@ -973,16 +989,17 @@ cudaError_t launch_ccl(cudaStream_t s, const uint32_t* fbits, int T, const Geom&
     }
     mark();
     if (labels != nullptr) {
-        const int rpt = 8;
-        if (label_elem_size == 4) {
-            dim3 grid((g.mpitch / 4 + 255) / 256, (g.h + rpt - 1) / rpt, T);
-            k_write_labels<int32_t, 4><<<grid, 256, 0, s>>>(fbits, g, b.parent, rbase_for_labels, (int32_t*)labels,
-                                                            rpt);
-        } else {
-            dim3 grid((g.mpitch / 16 + 255) / 256, (g.h + rpt - 1) / rpt, T);
-            k_write_labels<uint8_t, 16><<<grid, 256, 0, s>>>(fbits, g, b.parent, rbase_for_labels, (uint8_t*)labels,
-                                                             rpt);
-        }
+        // one warp per span of 128 (int32) / 512 (uint8) pixels x 8 rows; up to 8 warps per CTA
+        const int px_per_span = (label_elem_size == 4) ? 128 : 512;
+        const int nspans = (g.mpitch + px_per_span - 1) / px_per_span;
+        const int wpb = nspans < 8 ? nspans : 8;
+        dim3 grid((nspans + wpb - 1) / wpb, (g.h + 7) / 8, T);
+        if (label_elem_size == 4)
+            k_write_labels<int32_t, 4><<<grid, 32 * wpb, 0, s>>>(fbits, g, b.parent, rbase_for_labels,
+                                                                 (int32_t*)labels);
+        else
+            k_write_labels<uint8_t, 16><<<grid, 32 * wpb, 0, s>>>(fbits, g, b.parent, rbase_for_labels,
+                                                                  (uint8_t*)labels);
         launches += 1;
     }
     mark();

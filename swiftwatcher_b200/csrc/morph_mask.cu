@@ -9,152 +9,174 @@
 // inside the window, i.e. out-of-image pixels are ignored: they read as 1 for
 // an erosion and as 0 for a dilation.
 //
-// One CTA owns a 32-word x 64-row tile of one frame (+ halo), keeps it in
-// shared memory, runs each erosion/dilation as a horizontal pass (funnel
-// shifts across word boundaries) and a vertical pass, then writes the final
-// bit words and expands them to the {0,255} uint8 mask with 16-byte stores
-// that are contiguous across the warp.  It also realigns the "raw" bit columns
-// produced by K1 (origin X0a) to ROI-local columns (origin roi_x0).
+// Streaming design: a warp owns a slab of 32 consecutive bit words (lane = word;
+// lanes 1..30 produce output, lanes 0 and 31 are the horizontal halo) and marches
+// down a strip of rows.  Every erosion / dilation stage keeps the last 2R+1
+// horizontally processed rows of its input in registers (a delay line), so a row
+// of 1024 pixels goes through the whole open/close chain with a handful of
+// funnel shifts, LOP3s and two shuffles per stage, and nothing but the raw bit
+// words is ever re-read.  The kernel also realigns K1's "raw" bit columns
+// (origin X0a) to ROI-local columns (origin roi_x0), writes the final bit words
+// (rows padded to wpr4 words with zeros) and expands them to the {0,255} uint8
+// mask with 16-byte stores that are contiguous across the warp.
 #include "swb_internal.cuh"
 
 namespace swb {
 
 namespace {
 
-constexpr int TW = 32;         // tile width in 32-bit words (1024 pixels)
-constexpr int TH = 64;         // tile height in rows
-constexpr int HR_MAX = 8;      // max vertical halo: 4 ops x radius 2
-constexpr int SW = TW + 2;     // smem row: one halo word each side
-constexpr int SROWS = TH + 2 * HR_MAX;
+constexpr int SLAB = 30;   // output words per warp
+constexpr int SR = 32;     // output rows per warp
+constexpr int WPB = 4;     // warps per CTA
+
+// operation chains: 0 none, 1 open (E,D), 2 close (D,E), 3 open + close (E,D,D,E)
+__host__ __device__ constexpr int n_ops(int pat) { return pat == 0 ? 0 : (pat == 3 ? 4 : 2); }
+__host__ __device__ constexpr bool op_is_erode(int pat, int s) {
+    return pat == 1 ? (s == 0) : (pat == 2 ? (s == 1) : (s == 0 || s == 3));
+}
 
 __device__ __forceinline__ uint32_t colmask(int j, int w, int wpr) {
     if (j < 0 || j >= wpr) return 0u;
-    int rem = w - 32 * j;
+    const int rem = w - 32 * j;
     return rem >= 32 ? 0xFFFFFFFFu : ((1u << rem) - 1u);
 }
 
 template <int R>
 __device__ __forceinline__ uint32_t hop(uint32_t l, uint32_t c, uint32_t r, bool erode) {
-    // combine pixel x with x-R..x+R
-    uint32_t acc = c;
+    uint32_t acc = c;   // combine pixel x with x-R..x+R
 #pragma unroll
     for (int s = 1; s <= R; ++s) {
-        uint32_t right = __funnelshift_r(c, r, s);   // bit i = pixel i+s
-        uint32_t left = __funnelshift_l(l, c, s);    // bit i = pixel i-s
+        const uint32_t right = __funnelshift_r(c, r, s);   // bit i = pixel i+s
+        const uint32_t left = __funnelshift_l(l, c, s);    // bit i = pixel i-s
         acc = erode ? (acc & right & left) : (acc | right | left);
     }
     return acc;
 }
 
-template <int R>
-__global__ void __launch_bounds__(256)
-k_morph_mask(const uint32_t* __restrict__ raw_bits, Geom g, MorphCfg m, uint32_t* __restrict__ fbits,
+// 4 mask bits -> 4 bytes of 0x00 / 0xFF: put the bits on the byte sign positions
+// (disjoint shifted copies, no carries) and let PRMT replicate the sign bits.
+// (prmt.b32 directly: __byte_perm masks the replicate bit of the selector away.)
+__device__ __forceinline__ uint32_t expand4(uint32_t nibble) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(nibble * 0x10204080u), "r"(0u), "r"(0x0000BA98u));
+    return d;
+}
+
+template <int R, int PAT>
+__global__ void __launch_bounds__(32 * WPB)
+k_morph_mask(const uint32_t* __restrict__ raw_bits, Geom g, uint32_t* __restrict__ fbits,
              uint8_t* __restrict__ mask) {
-    __shared__ uint32_t bufA[SROWS][SW];
-    __shared__ uint32_t bufB[SROWS][SW];
-
+    constexpr int NOPS = n_ops(PAT);
+    constexpr int HR = NOPS * R;   // rows of vertical halo
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int slab = blockIdx.x;
     const int f = blockIdx.z;
-    const int tx0 = blockIdx.x * TW;
-    const int ty0 = blockIdx.y * TH;
-    const int HR = m.n_ops * R;                 // vertical halo actually needed
-    const int rows_ext = TH + 2 * HR;
-    const int tid = threadIdx.x;
-
+    const int y0 = (blockIdx.y * WPB + warp) * SR;
+    if (y0 >= g.h) return;                                   // warp-uniform
+    const int j = slab * SLAB + lane - 1;                    // this lane's word
+    const uint32_t Vcol = colmask(j, g.w, g.wpr);
+    const bool in_raw = (j >= 0 && j < g.wpr_raw);
+    const bool in_raw_next = (j + 1 >= 0 && j + 1 < g.wpr_raw);
     const uint32_t* raw_f = raw_bits + (long long)f * g.h * g.wpr_raw;
+    constexpr uint32_t fill0 = (NOPS > 0 && op_is_erode(PAT, 0)) ? 0xFFFFFFFFu : 0u;
 
-    // ---- load + realign + border fill for the first op -------------------------
-    const uint32_t fill0 = (m.n_ops > 0 && m.is_erode[0]) ? 0xFFFFFFFFu : 0u;
-    for (int i = tid; i < rows_ext * SW; i += blockDim.x) {
-        const int rr = i / SW, cc = i - rr * SW;
-        const int y = ty0 - HR + rr;
-        const int j = tx0 - 1 + cc;
-        uint32_t v = 0, V = 0;
-        if ((unsigned)y < (unsigned)g.h) {
-            V = colmask(j, g.w, g.wpr);
-            if (V) {
-                const uint32_t* rowp = raw_f + (long long)y * g.wpr_raw;
-                uint32_t lo = rowp[j];
-                uint32_t hi = (j + 1 < g.wpr_raw) ? rowp[j + 1] : 0u;
-                v = __funnelshift_r(lo, hi, g.dx) & V;
-            }
-        }
-        bufA[rr][cc] = v | (~V & fill0);
-    }
-    __syncthreads();
-
-    // ---- erosion / dilation chain -----------------------------------------------
-    for (int op = 0; op < m.n_ops; ++op) {
-        const bool erode = m.is_erode[op] != 0;
-        const uint32_t ident = erode ? 0xFFFFFFFFu : 0u;
-        const uint32_t fill_next = (op + 1 < m.n_ops && m.is_erode[op + 1]) ? 0xFFFFFFFFu : 0u;
-        // horizontal: A -> B
-        for (int i = tid; i < rows_ext * SW; i += blockDim.x) {
-            const int rr = i / SW, cc = i - rr * SW;
-            uint32_t l = cc > 0 ? bufA[rr][cc - 1] : ident;
-            uint32_t c = bufA[rr][cc];
-            uint32_t r = cc < SW - 1 ? bufA[rr][cc + 1] : ident;
-            bufB[rr][cc] = hop<R>(l, c, r, erode);
-        }
-        __syncthreads();
-        // vertical: B -> A, then re-apply the image border for the next op
-        for (int i = tid; i < rows_ext * SW; i += blockDim.x) {
-            const int rr = i / SW, cc = i - rr * SW;
-            uint32_t acc = bufB[rr][cc];
+    uint32_t win[NOPS > 0 ? NOPS : 1][2 * R + 1];
 #pragma unroll
-            for (int s = 1; s <= R; ++s) {
-                uint32_t up = rr - s >= 0 ? bufB[rr - s][cc] : ident;
-                uint32_t dn = rr + s < rows_ext ? bufB[rr + s][cc] : ident;
-                acc = erode ? (acc & up & dn) : (acc | up | dn);
-            }
-            const int y = ty0 - HR + rr;
-            const int j = tx0 - 1 + cc;
-            const uint32_t V = ((unsigned)y < (unsigned)g.h) ? colmask(j, g.w, g.wpr) : 0u;
-            bufA[rr][cc] = (acc & V) | (~V & fill_next);
-        }
-        __syncthreads();
-    }
+    for (int s = 0; s < (NOPS > 0 ? NOPS : 1); ++s)
+#pragma unroll
+        for (int i = 0; i < 2 * R + 1; ++i) win[s][i] = 0u;
 
-    // ---- outputs -------------------------------------------------------------------
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int r = warp; r < TH; r += (blockDim.x >> 5)) {
-        const int y = ty0 + r;
-        if (y >= g.h) break;
-        const uint32_t* srow = &bufA[HR + r][1];
-        // final bit words: lane = word
-        {
-            const int j = tx0 + lane;
-            if (j < g.wpr4) fbits[((long long)f * g.h + y) * g.wpr4 + j] = srow[lane];
+    const int y_end = min(y0 + SR, g.h);
+    for (int yin = y0 - HR; yin < y_end + HR; ++yin) {
+        // ---- raw row, realigned to ROI columns, border filled for the first op
+        const bool rowvalid = (unsigned)yin < (unsigned)g.h;
+        uint32_t v = 0u;
+        if (rowvalid) {                                      // warp-uniform
+            const uint32_t* rowp = raw_f + (long long)yin * g.wpr_raw;
+            const uint32_t lo = in_raw ? __ldg(rowp + j) : 0u;
+            uint32_t hi = __shfl_down_sync(0xFFFFFFFFu, lo, 1);
+            if (lane == 31) hi = in_raw_next ? __ldg(rowp + j + 1) : 0u;
+            v = __funnelshift_r(lo, hi, g.dx) & Vcol;
         }
+        const uint32_t V0 = rowvalid ? Vcol : 0u;
+        uint32_t cur = v | (~V0 & fill0);
+
+        // ---- erosion / dilation chain: stage s emits row yin - (s + 1) * R
+#pragma unroll
+        for (int s = 0; s < NOPS; ++s) {
+            const bool erode = op_is_erode(PAT, s);
+            const uint32_t ident = erode ? 0xFFFFFFFFu : 0u;
+            uint32_t l = __shfl_up_sync(0xFFFFFFFFu, cur, 1);
+            uint32_t r = __shfl_down_sync(0xFFFFFFFFu, cur, 1);
+            if (lane == 0) l = ident;
+            if (lane == 31) r = ident;
+            const uint32_t hrow = hop<R>(l, cur, r, erode);
+#pragma unroll
+            for (int i = 0; i < 2 * R; ++i) win[s][i] = win[s][i + 1];
+            win[s][2 * R] = hrow;
+            uint32_t acc = win[s][0];
+#pragma unroll
+            for (int i = 1; i < 2 * R + 1; ++i) acc = erode ? (acc & win[s][i]) : (acc | win[s][i]);
+            const int ys = yin - (s + 1) * R;
+            const uint32_t Vs = ((unsigned)ys < (unsigned)g.h) ? Vcol : 0u;
+            const uint32_t fill_next = (s + 1 < NOPS && op_is_erode(PAT, s + 1)) ? 0xFFFFFFFFu : 0u;
+            cur = (acc & Vs) | (~Vs & fill_next);
+        }
+
+        // ---- outputs for row yin - HR
+        const int yout = yin - HR;
+        if (yout < y0) continue;                             // warp-uniform (pipeline warm-up)
+        const long long orow = (long long)f * g.h + yout;
+        if (lane >= 1 && lane <= SLAB && j < g.wpr4) fbits[orow * g.wpr4 + j] = cur;
         if (mask != nullptr) {
-            uint8_t* mrow = mask + ((long long)f * g.h + y) * g.mpitch + (long long)tx0 * 32;
+            uint8_t* mrow = mask + orow * g.mpitch + (long long)slab * (SLAB * 32);
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-                const int wj = half * 16 + (lane >> 1);      // word within tile
-                if (tx0 + wj < g.wpr) {
-                    const uint32_t bits16 = (srow[wj] >> ((lane & 1) * 16)) & 0xFFFFu;
+                const int c = half * 32 + lane;              // 16-byte chunk of the slab's row
+                const int wi = c >> 1;                       // word within the slab
+                const uint32_t word = __shfl_sync(0xFFFFFFFFu, cur, wi < SLAB ? wi + 1 : 31);
+                if (wi < SLAB && slab * SLAB + wi < g.wpr) {
+                    const uint32_t b16 = (word >> ((c & 1) * 16)) & 0xFFFFu;
                     uint4 o;
-                    // nibble -> 4 bytes of 0x00 / 0xFF
-                    o.x = (((bits16 >> 0) & 0xFu) * 0x00204081u & 0x01010101u) * 0xFFu;
-                    o.y = (((bits16 >> 4) & 0xFu) * 0x00204081u & 0x01010101u) * 0xFFu;
-                    o.z = (((bits16 >> 8) & 0xFu) * 0x00204081u & 0x01010101u) * 0xFFu;
-                    o.w = (((bits16 >> 12) & 0xFu) * 0x00204081u & 0x01010101u) * 0xFFu;
-                    __stcs(reinterpret_cast<uint4*>(mrow + half * 512 + lane * 16), o);
+                    o.x = expand4(b16 & 0xFu);
+                    o.y = expand4((b16 >> 4) & 0xFu);
+                    o.z = expand4((b16 >> 8) & 0xFu);
+                    o.w = expand4(b16 >> 12);
+                    __stcs(reinterpret_cast<uint4*>(mrow + c * 16), o);
                 }
             }
         }
     }
 }
 
+template <int R, int PAT>
+cudaError_t launch_pat(cudaStream_t s, const uint32_t* raw_bits, int T, const Geom& g, uint32_t* fbits,
+                       uint8_t* mask) {
+    const int nslabs = (g.wpr4 + SLAB - 1) / SLAB;
+    const int nstrips = (g.h + SR - 1) / SR;
+    dim3 grid(nslabs, (nstrips + WPB - 1) / WPB, T);
+    k_morph_mask<R, PAT><<<grid, 32 * WPB, 0, s>>>(raw_bits, g, fbits, mask);
+    return cudaGetLastError();
+}
+
 }  // namespace
 
 cudaError_t launch_morph_mask(cudaStream_t s, const uint32_t* raw_bits, int T, const Geom& g,
                               const MorphCfg& m, uint32_t* fbits, uint8_t* mask, int* n_launches) {
-    dim3 grid((g.wpr + TW - 1) / TW, (g.h + TH - 1) / TH, T);
-    dim3 block(256);
     if (n_launches) *n_launches += 1;
-    if (m.radius == 2) k_morph_mask<2><<<grid, block, 0, s>>>(raw_bits, g, m, fbits, mask);
-    else k_morph_mask<1><<<grid, block, 0, s>>>(raw_bits, g, m, fbits, mask);
-    return cudaGetLastError();
+    int pat = 0;
+    if (m.n_ops == 4) pat = 3;
+    else if (m.n_ops == 2) pat = m.is_erode[0] ? 1 : 2;
+    if (pat == 0) return launch_pat<1, 0>(s, raw_bits, T, g, fbits, mask);
+    if (m.radius == 2) {
+        if (pat == 1) return launch_pat<2, 1>(s, raw_bits, T, g, fbits, mask);
+        if (pat == 2) return launch_pat<2, 2>(s, raw_bits, T, g, fbits, mask);
+        return launch_pat<2, 3>(s, raw_bits, T, g, fbits, mask);
+    }
+    if (pat == 1) return launch_pat<1, 1>(s, raw_bits, T, g, fbits, mask);
+    if (pat == 2) return launch_pat<1, 2>(s, raw_bits, T, g, fbits, mask);
+    return launch_pat<1, 3>(s, raw_bits, T, g, fbits, mask);
 }
 
 }  // namespace swb
