@@ -256,19 +256,265 @@ k_fg_bits(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint16_t* __re
     }
 }
 
+// ------------------------------------------------------------------------------------
+// v2: the same march through time, fed by the bulk-copy engine.
+//
+// One elected thread streams the CTA's 256 x 16-pixel slice of every frame into a
+// ring of shared-memory stages with cp.async.bulk (UBLKCP) completing on mbarriers;
+// all warps consume a stage with three conflict-free LDS.128 per thread, release it
+// with one mbarrier arrive per warp, and the producer refills a stage one step after
+// it was consumed.  Bytes in flight no longer cost registers, so the median/threshold
+// math overlaps the HBM latency at 2 CTAs per SM.
+//
+// Instruction diet (the v1 kernel was ALU-pipe bound, not HBM bound):
+//  * gray = two IDP.2A (16-bit weights x packed pixel bytes, no byte extraction):
+//    cv2's (3735 B + 19235 G + 9798 R + 2^14) >> 15 with every term doubled, so the
+//    result is byte 2 of the accumulator;
+//  * |x - median| = one VABSDIFF4 on the u16x2 lanes (high bytes are zero);
+//  * (d > thresh) = one VIADDMNMX.S16x2.RELU: max(min(d - thresh, 1), 0) -> 0/1 per lane,
+//    shifted into place and accumulated by one IMAD.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    int spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (++spins > (1 << 26)) __trap();   // never hang the GPU on a pipeline bug
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// 48 BGR bytes -> 8 u16x2 lanes of (gray[k], gray[k+8]) with IDP.2A
+__device__ __forceinline__ void bgr48_to_lanes_dp(const uint32_t (&w)[12], uint32_t (&out)[8]) {
+    constexpr uint32_t WB = 7470u, WG = 38470u, WR = 19596u, RND = 32768u;
+    uint32_t s[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int o = 3 * i, wi = o >> 2, r = o & 3;
+        uint32_t acc;
+        if (r == 0) {          // B G R x
+            acc = __dp2a_lo(WB | (WG << 16), w[wi], RND);
+            acc = __dp2a_hi(WR, w[wi], acc);
+        } else if (r == 1) {   // x B G R
+            acc = __dp2a_lo(WB << 16, w[wi], RND);
+            acc = __dp2a_hi(WG | (WR << 16), w[wi], acc);
+        } else if (r == 2) {   // x x B G | R
+            acc = __dp2a_hi(WB | (WG << 16), w[wi], RND);
+            acc = __dp2a_lo(WR, w[(wi + 1) % 12], acc);
+        } else {               // x x x B | G R
+            acc = __dp2a_hi(WB << 16, w[wi], RND);
+            acc = __dp2a_lo(WG | (WR << 16), w[(wi + 1) % 12], acc);
+        }
+        s[i] = acc;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) out[k] = __byte_perm(s[k], s[k + 8], 0x7632);
+}
+
+// (|x - m| > thresh) per u16 lane -> 16 bits (bit k = pixel k)
+__device__ __forceinline__ uint32_t fg_bits16_v2(const uint32_t (&cur)[8], const uint32_t (&med)[8],
+                                                 uint32_t neg_thresh_x2) {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t d = __vabsdiffu4(cur[k], med[k]);                          // lanes hold 0..255
+        const uint32_t f = __viaddmin_s16x2_relu(d, neg_thresh_x2, 0x00010001u);  // 1 where d > thresh
+        acc += f << k;
+    }
+    return (acc & 0xFFu) | ((acc >> 8) & 0xFF00u);
+}
+
+template <int N, int C, int S>
+__global__ void __launch_bounds__(256, (N <= 7) ? 2 : 1)
+k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint16_t* __restrict__ raw_bits) {
+    constexpr int TB = 16 * C;               // bytes per thread per frame
+    constexpr int STAGE_BYTES = 256 * TB;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + S * STAGE_BYTES);
+    uint64_t* empty = full + S;
+
+    const int tid = threadIdx.x;
+    const int gpr = wa >> 4;                 // 16-pixel groups per row
+    const int G = h * gpr;
+    const int g0 = blockIdx.x * 256;
+    const int g = g0 + tid;
+    const bool active = g < G;
+    const int row = active ? g / gpr : 0;
+    const int col = active ? g - row * gpr : 0;
+    const int t_start = blockIdx.y * Ts;
+    const int t_end = min(T, t_start + Ts);
+    const int n_out = t_end - t_start;
+    if (n_out <= 0) return;                  // block-uniform
+    const int n_total = n_out + N - 1;       // frames walked, starting at j_first
+    const int j_first = t_start - (N - 1);
+    // leading frames that come from the carried gray history instead of the pipeline
+    const int n_hist = (src.hist_valid && j_first < 0) ? min(-j_first, N - 1) : 0;
+    const int n_pipe = n_total - n_hist;
+    const int ngroups = min(256, G - g0);
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 8);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // producer: copy this CTA's slice of pipeline frame p into stage p % S
+    auto issue = [&](int p) {
+        int j = j_first + n_hist + p;
+        if (j < -src.n_inline_halo) j = -src.n_inline_halo;          // replicate the earliest frame
+        const uint8_t* fr = src.cur + (long long)j * src.frame_stride;
+        uint8_t* dst = smem + (p % S) * STAGE_BYTES;
+        uint64_t* bar = &full[p % S];
+        mbar_arrive_expect_tx(bar, (uint32_t)(ngroups * TB));
+        if (src.pitch == (long long)gpr * TB) {                     // rows are contiguous
+            bulk_g2s(dst, fr + (long long)g0 * TB, (uint32_t)(ngroups * TB), bar);
+        } else {
+            int r = g0 / gpr, c = g0 - r * gpr, rem = ngroups;
+            while (rem > 0) {
+                const int n = min(gpr - c, rem);
+                bulk_g2s(dst, fr + (long long)r * src.pitch + (long long)c * TB, (uint32_t)(n * TB), bar);
+                dst += n * TB;
+                rem -= n;
+                ++r;
+                c = 0;
+            }
+        }
+    };
+    if (tid == 0) {
+        const int pre = min(S, n_pipe);
+        for (int p = 0; p < pre; ++p) issue(p);
+    }
+
+    const uint32_t neg_th = ((uint32_t)(-thresh) & 0xFFFFu) * 0x00010001u;
+    const bool write_hist = (src.hist_out != nullptr) && (t_end == T) && active;
+    uint16_t* out = raw_bits + ((long long)t_start * h + row) * gpr + col;
+    const long long out_step = (long long)h * gpr;
+    const uint8_t* my_smem = smem + tid * TB;
+
+    uint32_t ring[N][8];
+    for (int base = 0; base < n_total; base += N) {
+#pragma unroll
+        for (int ph = 0; ph < N; ++ph) {
+            const int idx = base + ph;                 // frame j_first + idx goes to ring[ph]
+            if (idx < n_total) {                       // block-uniform
+                if (idx < n_hist) {
+                    if (active) {
+                        const uint4 v = __ldg(reinterpret_cast<const uint4*>(
+                            src.hist + ((long long)(j_first + idx + (N - 1)) * h + row) * wa + col * 16));
+                        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+                        gray16_to_lanes(w4, ring[ph]);
+                    }
+                } else {
+                    const int p = idx - n_hist;
+                    if (tid == 0 && p >= 1) {          // refill the stage consumed one step ago
+                        const int q = p - 1 + S;
+                        if (q < n_pipe) {
+                            mbar_wait(&empty[(p - 1) % S], (uint32_t)(((p - 1) / S) & 1));
+                            issue(q);
+                        }
+                    }
+                    mbar_wait(&full[p % S], (uint32_t)((p / S) & 1));
+                    const uint4* sp4 = reinterpret_cast<const uint4*>(my_smem + (p % S) * STAGE_BYTES);
+                    if constexpr (C == 3) {
+                        uint32_t w[12];
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            const uint4 v = sp4[i];
+                            w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+                        }
+                        bgr48_to_lanes_dp(w, ring[ph]);
+                    } else {
+                        const uint4 v = sp4[0];
+                        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+                        gray16_to_lanes(w4, ring[ph]);
+                    }
+                    __syncwarp();
+                    if ((tid & 31) == 0) mbar_arrive(&empty[p % S]);
+                }
+                if (idx >= N - 1 && active) {
+                    const int k = idx - (N - 1);       // output frame t_start + k
+                    uint32_t med[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        uint32_t v[N];
+#pragma unroll
+                        for (int s = 0; s < N; ++s) v[s] = ring[s][q];
+                        med[q] = median_lanes<N>(v);
+                    }
+                    out[(long long)k * out_step] = (uint16_t)fg_bits16_v2(ring[ph], med, neg_th);
+                    if (write_hist && idx == n_total - 1) {
+                        // last N-1 gray frames, oldest first: hist[s] = frame (T-1) - (N-2-s)
+#pragma unroll
+                        for (int s = 0; s < N - 1; ++s) {
+                            const int m = N - 2 - s;
+                            const int hs = ((ph - m) % N + N) % N;   // static
+                            *reinterpret_cast<uint4*>(src.hist_out + ((long long)s * h + row) * wa + col * 16) =
+                                lanes_to_gray16(ring[hs]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int N, int C>
+cudaError_t launch_v2(cudaStream_t s, const FrameSrc& src, int T, int Ts, const Geom& g, int thresh,
+                      uint16_t* raw_bits) {
+    constexpr int S = (C == 3) ? 4 : 8;
+    constexpr int SMEM = S * 256 * 16 * C + 2 * S * 8;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_fg_bits_v2<N, C, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const int G = g.h * (g.wa >> 4);
+    dim3 grid((G + 255) / 256, (T + Ts - 1) / Ts);
+    k_fg_bits_v2<N, C, S><<<grid, 256, SMEM, s>>>(src, T, Ts, g.h, g.wa, thresh, raw_bits);
+    return cudaGetLastError();
+}
+
 template <int N>
 cudaError_t launch_n(cudaStream_t s, const FrameSrc& src, int channels, int T, int Ts, const Geom& g,
                      int thresh, uint16_t* raw_bits, bool aligned) {
     const int G = g.h * (g.wa >> 4);
     dim3 grid((G + 255) / 256, (T + Ts - 1) / Ts);
     dim3 block(256);
-    if (channels == 3) {
-        if (aligned) k_fg_bits<N, 3, true><<<grid, block, 0, s>>>(src, T, Ts, g.h, g.wa, thresh, raw_bits);
-        else k_fg_bits<N, 3, false><<<grid, block, 0, s>>>(src, T, Ts, g.h, g.wa, thresh, raw_bits);
-    } else {
-        if (aligned) k_fg_bits<N, 1, true><<<grid, block, 0, s>>>(src, T, Ts, g.h, g.wa, thresh, raw_bits);
-        else k_fg_bits<N, 1, false><<<grid, block, 0, s>>>(src, T, Ts, g.h, g.wa, thresh, raw_bits);
+    if (aligned) {   // 16-byte aligned rows: bulk-copy pipeline (v2)
+        if (channels == 3) return launch_v2<N, 3>(s, src, T, Ts, g, thresh, raw_bits);
+        return launch_v2<N, 1>(s, src, T, Ts, g, thresh, raw_bits);
     }
+    // odd pitches / frame widths: guarded byte loads (v1)
+    if (channels == 3) k_fg_bits<N, 3, false><<<grid, block, 0, s>>>(src, T, Ts, g.h, g.wa, thresh, raw_bits);
+    else k_fg_bits<N, 1, false><<<grid, block, 0, s>>>(src, T, Ts, g.h, g.wa, thresh, raw_bits);
     return cudaGetLastError();
 }
 
