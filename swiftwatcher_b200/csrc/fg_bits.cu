@@ -121,6 +121,28 @@ __device__ __forceinline__ uint4 lanes_to_gray16(const uint32_t (&v)[8]) {
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// 16 gray values (lanes) -> the same values as 48 BGR bytes (v, v, v): the gray formula
+// maps them back to v exactly, so carried history rides the same pipeline as real frames.
+__device__ __forceinline__ void lanes_to_bgr48(const uint32_t (&v)[8], uint4 (&o)[3]) {
+    const uint4 g16 = lanes_to_gray16(v);
+    const uint32_t gw[4] = {g16.x, g16.y, g16.z, g16.w};
+    uint32_t w[12];
+#pragma unroll
+    for (int t = 0; t < 12; ++t) {
+        // output bytes 4t..4t+3 are gray pixels (4t)/3, (4t+1)/3, (4t+2)/3, (4t+3)/3
+        uint32_t word = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int px = (4 * t + b) / 3;
+            word |= ((gw[px >> 2] >> (8 * (px & 3))) & 0xFFu) << (8 * b);
+        }
+        w[t] = word;
+    }
+    o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    o[2] = make_uint4(w[8], w[9], w[10], w[11]);
+}
+
 template <int C, bool ALIGNED>
 struct RawPixels {
     uint32_t w[C == 3 ? 12 : 4];
@@ -198,11 +220,11 @@ k_fg_bits(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint16_t* __re
     auto load_frame = [&](int j, uint32_t (&dst)[8]) {
         // frame j relative to the first output frame of this submit
         if (j < 0 && src.hist_valid) {
+            // carried history: N-1 frames in the source format (gray stored as v,v,v), our own buffer
             const int slot = j + (N - 1);
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(
-                src.hist + ((long long)slot * h + row) * wa + col * 16));
-            uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-            gray16_to_lanes(w4, dst);
+            RawPixels<C, true> p;
+            load_raw<C, true>(p, src.hist + (((long long)slot * h + row) * gpr + col) * (16 * C), 16);
+            raw_to_lanes<C, true>(p, dst);
         } else {
             if (j < -src.n_inline_halo) j = -src.n_inline_halo;  // replicate earliest frame
             RawPixels<C, ALIGNED> p;
@@ -247,8 +269,16 @@ k_fg_bits(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint16_t* __re
                     for (int s = 0; s < N - 1; ++s) {
                         const int m = N - 2 - s;                  // frames back from the newest
                         const int hs = ((slot - m) % N + N) % N;  // static
-                        *reinterpret_cast<uint4*>(src.hist_out + ((long long)s * h + row) * wa + col * 16) =
-                            lanes_to_gray16(ring[hs]);
+                        uint8_t* hp = src.hist_out + (((long long)s * h + row) * gpr + col) * (16 * C);
+                        if constexpr (C == 3) {
+                            uint4 o[3];
+                            lanes_to_bgr48(ring[hs], o);
+                            reinterpret_cast<uint4*>(hp)[0] = o[0];
+                            reinterpret_cast<uint4*>(hp)[1] = o[1];
+                            reinterpret_cast<uint4*>(hp)[2] = o[2];
+                        } else {
+                            *reinterpret_cast<uint4*>(hp) = lanes_to_gray16(ring[hs]);
+                        }
                     }
                 }
             }
@@ -348,11 +378,14 @@ __device__ __forceinline__ uint32_t fg_bits16_v2(const uint32_t (&cur)[8], const
     return (acc & 0xFFu) | ((acc >> 8) & 0xFF00u);
 }
 
+constexpr int CONSUMERS = 256;               // 8 consumer warps: one 16-pixel group per thread
+constexpr int V2_THREADS = CONSUMERS + 32;   // + 1 producer warp
+
 template <int N, int C, int S>
-__global__ void __launch_bounds__(256, (N <= 7) ? 2 : 1)
+__global__ void __launch_bounds__(V2_THREADS, (N <= 7) ? 2 : 1)
 k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint16_t* __restrict__ raw_bits) {
     constexpr int TB = 16 * C;               // bytes per thread per frame
-    constexpr int STAGE_BYTES = 256 * TB;
+    constexpr int STAGE_BYTES = CONSUMERS * TB;
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + S * STAGE_BYTES);
     uint64_t* empty = full + S;
@@ -360,123 +393,134 @@ k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint16_t* _
     const int tid = threadIdx.x;
     const int gpr = wa >> 4;                 // 16-pixel groups per row
     const int G = h * gpr;
-    const int g0 = blockIdx.x * 256;
-    const int g = g0 + tid;
-    const bool active = g < G;
-    const int row = active ? g / gpr : 0;
-    const int col = active ? g - row * gpr : 0;
+    const int g0 = blockIdx.x * CONSUMERS;
     const int t_start = blockIdx.y * Ts;
     const int t_end = min(T, t_start + Ts);
     const int n_out = t_end - t_start;
     if (n_out <= 0) return;                  // block-uniform
-    const int n_total = n_out + N - 1;       // frames walked, starting at j_first
+    const int n_total = n_out + N - 1;       // frames walked: j_first .. t_end - 1
     const int j_first = t_start - (N - 1);
-    // leading frames that come from the carried gray history instead of the pipeline
-    const int n_hist = (src.hist_valid && j_first < 0) ? min(-j_first, N - 1) : 0;
-    const int n_pipe = n_total - n_hist;
-    const int ngroups = min(256, G - g0);
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 8);
+            mbar_init(&empty[s], CONSUMERS / 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    // producer: copy this CTA's slice of pipeline frame p into stage p % S
-    auto issue = [&](int p) {
-        int j = j_first + n_hist + p;
-        if (j < -src.n_inline_halo) j = -src.n_inline_halo;          // replicate the earliest frame
-        const uint8_t* fr = src.cur + (long long)j * src.frame_stride;
-        uint8_t* dst = smem + (p % S) * STAGE_BYTES;
-        uint64_t* bar = &full[p % S];
-        mbar_arrive_expect_tx(bar, (uint32_t)(ngroups * TB));
-        if (src.pitch == (long long)gpr * TB) {                     // rows are contiguous
-            bulk_g2s(dst, fr + (long long)g0 * TB, (uint32_t)(ngroups * TB), bar);
-        } else {
-            int r = g0 / gpr, c = g0 - r * gpr, rem = ngroups;
-            while (rem > 0) {
-                const int n = min(gpr - c, rem);
-                bulk_g2s(dst, fr + (long long)r * src.pitch + (long long)c * TB, (uint32_t)(n * TB), bar);
-                dst += n * TB;
-                rem -= n;
-                ++r;
-                c = 0;
+    if (tid >= CONSUMERS) {
+        // ===== producer warp: one elected lane streams this CTA's slice of every frame =====
+        if (tid != CONSUMERS) return;
+        const int ngroups = min(CONSUMERS, G - g0);
+        const uint32_t bytes = (uint32_t)(ngroups * TB);
+        for (int p = 0; p < n_total; ++p) {
+            const int st = p % S;
+            if (p >= S) mbar_wait(&empty[st], (uint32_t)((p / S - 1) & 1));
+            int j = j_first + p;
+            const uint8_t* fr;
+            long long pitch;
+            if (j < 0 && src.hist_valid) {                  // carried history, stored as frames
+                pitch = (long long)gpr * TB;
+                fr = src.hist + (long long)(j + (N - 1)) * h * pitch;
+            } else {
+                if (j < -src.n_inline_halo) j = -src.n_inline_halo;   // replicate the earliest frame
+                pitch = src.pitch;
+                fr = src.cur + (long long)j * src.frame_stride;
+            }
+            uint8_t* dst = smem + st * STAGE_BYTES;
+            mbar_arrive_expect_tx(&full[st], bytes);
+            if (pitch == (long long)gpr * TB) {             // rows are contiguous
+                bulk_g2s(dst, fr + (long long)g0 * TB, bytes, &full[st]);
+            } else {
+                int r = g0 / gpr, c = g0 - r * gpr, rem = ngroups;
+                while (rem > 0) {
+                    const int n = min(gpr - c, rem);
+                    bulk_g2s(dst, fr + (long long)r * pitch + (long long)c * TB, (uint32_t)(n * TB), &full[st]);
+                    dst += n * TB;
+                    rem -= n;
+                    ++r;
+                    c = 0;
+                }
             }
         }
-    };
-    if (tid == 0) {
-        const int pre = min(S, n_pipe);
-        for (int p = 0; p < pre; ++p) issue(p);
+        return;
     }
 
+    // ===== consumer warps =====
+    const int g = g0 + tid;
+    const bool active = g < G;
+    const int row = active ? g / gpr : 0;
+    const int col = active ? g - row * gpr : 0;
     const uint32_t neg_th = ((uint32_t)(-thresh) & 0xFFFFu) * 0x00010001u;
-    const bool write_hist = (src.hist_out != nullptr) && (t_end == T) && active;
     uint16_t* out = raw_bits + ((long long)t_start * h + row) * gpr + col;
     const long long out_step = (long long)h * gpr;
     const uint8_t* my_smem = smem + tid * TB;
+    const bool lane0 = (tid & 31) == 0;
 
     uint32_t ring[N][8];
-    for (int base = 0; base < n_total; base += N) {
+    // take pipeline frame p into ring[slot]
+    auto consume = [&](int p, uint32_t (&dst)[8]) {
+        const int st = p % S;
+        mbar_wait(&full[st], (uint32_t)((p / S) & 1));
+        const uint4* sp4 = reinterpret_cast<const uint4*>(my_smem + st * STAGE_BYTES);
+        if constexpr (C == 3) {
+            uint32_t w[12];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const uint4 v = sp4[i];
+                w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+            }
+            bgr48_to_lanes_dp(w, dst);
+        } else {
+            const uint4 v = sp4[0];
+            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+            gray16_to_lanes(w4, dst);
+        }
+        // release the stage only after the loaded words have been consumed (the converted
+        // lanes depend on every LDS), so the bulk engine can never overwrite data in flight
+        asm volatile("" ::"r"(dst[0]), "r"(dst[7]) : "memory");
+        __syncwarp();
+        if (lane0) mbar_arrive(&empty[st]);
+    };
+
+    // warm-up: the N-1 frames before the first output
+#pragma unroll
+    for (int s = 0; s < N - 1; ++s) consume(s, ring[s]);
+
+    for (int base = 0; base < n_out; base += N) {
 #pragma unroll
         for (int ph = 0; ph < N; ++ph) {
-            const int idx = base + ph;                 // frame j_first + idx goes to ring[ph]
-            if (idx < n_total) {                       // block-uniform
-                if (idx < n_hist) {
-                    if (active) {
-                        const uint4 v = __ldg(reinterpret_cast<const uint4*>(
-                            src.hist + ((long long)(j_first + idx + (N - 1)) * h + row) * wa + col * 16));
-                        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-                        gray16_to_lanes(w4, ring[ph]);
-                    }
-                } else {
-                    const int p = idx - n_hist;
-                    if (tid == 0 && p >= 1) {          // refill the stage consumed one step ago
-                        const int q = p - 1 + S;
-                        if (q < n_pipe) {
-                            mbar_wait(&empty[(p - 1) % S], (uint32_t)(((p - 1) / S) & 1));
-                            issue(q);
-                        }
-                    }
-                    mbar_wait(&full[p % S], (uint32_t)((p / S) & 1));
-                    const uint4* sp4 = reinterpret_cast<const uint4*>(my_smem + (p % S) * STAGE_BYTES);
-                    if constexpr (C == 3) {
-                        uint32_t w[12];
+            const int k = base + ph;                        // output frame t_start + k
+            if (k < n_out) {                                // block-uniform
+                const int slot = (N - 1 + ph) % N;          // static after unrolling
+                consume(k + N - 1, ring[slot]);
+                uint32_t med[8];
 #pragma unroll
-                        for (int i = 0; i < 3; ++i) {
-                            const uint4 v = sp4[i];
-                            w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
-                        }
-                        bgr48_to_lanes_dp(w, ring[ph]);
-                    } else {
-                        const uint4 v = sp4[0];
-                        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-                        gray16_to_lanes(w4, ring[ph]);
-                    }
-                    __syncwarp();
-                    if ((tid & 31) == 0) mbar_arrive(&empty[p % S]);
+                for (int q = 0; q < 8; ++q) {
+                    uint32_t v[N];
+#pragma unroll
+                    for (int s = 0; s < N; ++s) v[s] = ring[s][q];
+                    med[q] = median_lanes<N>(v);
                 }
-                if (idx >= N - 1 && active) {
-                    const int k = idx - (N - 1);       // output frame t_start + k
-                    uint32_t med[8];
+                if (active) *out = (uint16_t)fg_bits16_v2(ring[slot], med, neg_th);
+                out += out_step;
+                if (k == n_out - 1 && t_end == T && src.hist_out != nullptr && active) {
+                    // leave the last N-1 gray frames (oldest first) as frames for the next submit
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        uint32_t v[N];
-#pragma unroll
-                        for (int s = 0; s < N; ++s) v[s] = ring[s][q];
-                        med[q] = median_lanes<N>(v);
-                    }
-                    out[(long long)k * out_step] = (uint16_t)fg_bits16_v2(ring[ph], med, neg_th);
-                    if (write_hist && idx == n_total - 1) {
-                        // last N-1 gray frames, oldest first: hist[s] = frame (T-1) - (N-2-s)
-#pragma unroll
-                        for (int s = 0; s < N - 1; ++s) {
-                            const int m = N - 2 - s;
-                            const int hs = ((ph - m) % N + N) % N;   // static
-                            *reinterpret_cast<uint4*>(src.hist_out + ((long long)s * h + row) * wa + col * 16) =
-                                lanes_to_gray16(ring[hs]);
+                    for (int s = 0; s < N - 1; ++s) {
+                        const int m = N - 2 - s;                    // frames back from the newest
+                        const int hs = ((slot - m) % N + N) % N;    // static
+                        uint8_t* hp = src.hist_out + ((long long)s * h + row) * (long long)gpr * TB + col * TB;
+                        if constexpr (C == 3) {
+                            uint4 o[3];
+                            lanes_to_bgr48(ring[hs], o);
+                            reinterpret_cast<uint4*>(hp)[0] = o[0];
+                            reinterpret_cast<uint4*>(hp)[1] = o[1];
+                            reinterpret_cast<uint4*>(hp)[2] = o[2];
+                        } else {
+                            *reinterpret_cast<uint4*>(hp) = lanes_to_gray16(ring[hs]);
                         }
                     }
                 }
@@ -489,7 +533,7 @@ template <int N, int C>
 cudaError_t launch_v2(cudaStream_t s, const FrameSrc& src, int T, int Ts, const Geom& g, int thresh,
                       uint16_t* raw_bits) {
     constexpr int S = (C == 3) ? 4 : 8;
-    constexpr int SMEM = S * 256 * 16 * C + 2 * S * 8;
+    constexpr int SMEM = S * CONSUMERS * 16 * C + 2 * S * 8;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(k_fg_bits_v2<N, C, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -497,8 +541,8 @@ cudaError_t launch_v2(cudaStream_t s, const FrameSrc& src, int T, int Ts, const 
         configured = true;
     }
     const int G = g.h * (g.wa >> 4);
-    dim3 grid((G + 255) / 256, (T + Ts - 1) / Ts);
-    k_fg_bits_v2<N, C, S><<<grid, 256, SMEM, s>>>(src, T, Ts, g.h, g.wa, thresh, raw_bits);
+    dim3 grid((G + CONSUMERS - 1) / CONSUMERS, (T + Ts - 1) / Ts);
+    k_fg_bits_v2<N, C, S><<<grid, V2_THREADS, SMEM, s>>>(src, T, Ts, g.h, g.wa, thresh, raw_bits);
     return cudaGetLastError();
 }
 
