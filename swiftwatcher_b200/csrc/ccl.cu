@@ -22,9 +22,10 @@
 //
 // Tiled path (frames up to 4096 pixels wide; one CTA = full-width tile of 8..256
 // block rows held in shared memory):
-//   ccl_local     tile-local union-find in shared memory; writes parent[b] =
-//                 tile-local root for every block and one regionprops partial
-//                 sum per tile-local component (shared-memory atomics)
+//   ccl_local     the tile's runs are numbered in raster order (block-wide scan) and
+//                 listed in shared memory; union-find over run ids, one thread per
+//                 run; writes parent[b] = tile-local root for every block and one
+//                 regionprops partial sum per tile-local component (smem atomics)
 //   ccl_boundary  global unions between the first block row of a tile and the
 //                 last block row of the tile above (atomicMin union-find)
 // Wide path (wider frames): ccl_init + ccl_merge do everything globally and
@@ -336,27 +337,48 @@ __device__ __forceinline__ void emit_partial(Partial* parts, int idx, int f, int
     parts[idx] = p;
 }
 
-// BX = groups (of 4 words) per tile row, a power of two >= Q = wpr4 / 4; BY = 256 / BX block rows.
-// Tile-local block index: l = ty * ROWB + 16 * word + k (contiguous along a tile row), so the
-// left neighbour of a block is l - 1 and the block above it is l - ROWB.
+// BX = groups (of 4 words) per tile row, a power of two >= Q = wpr4 / 4; BY = 256 / BX block rows;
+// the tile always holds 1024 words (32 Ki pixels x 2 rows each).
+//
+// Sparse-to-dense: the tile's runs are numbered in raster order with a block-wide prefix sum
+// (at most 8 runs per word, 8192 per tile) and listed in shared memory; the union-find,
+// slot claiming and regionprops phases then run one THREAD PER RUN over that dense list, so
+// warps are full instead of having a lane or two busy.  Run ids grow with the block index of
+// the run start, so "link the larger id under the smaller" keeps the minimum block as root.
+struct LocalSmem {
+    static constexpr int MAXRUNS = 8192;
+    static constexpr int MAXR = 256;            // components with a shared-memory accumulator
+    static constexpr int AB_WORDS = 256 * 6;    // worst case BY * (4 * BX + 2) at BX = 1
+    static constexpr size_t bytes() {
+        return (size_t)2 * AB_WORDS * 4 + 1024 * 2 + (size_t)2 * MAXRUNS * 2 + MAXR * 30 + 64;
+    }
+};
+
 template <int BX>
 __global__ void __launch_bounds__(256)
 k_ccl_local(const uint32_t* __restrict__ fbits, Geom g, int* __restrict__ parent, Partial* __restrict__ parts,
             int* __restrict__ pcount, int cap_parts, int32_t* __restrict__ overflow) {
     constexpr int BY = 256 / BX;
-    constexpr int ROWB = BX * 64;            // blocks per tile row
-    constexpr int SW = BX * 4 + 2;           // words per tile row + one halo word each side
-    // tile-local components with a shared-memory accumulator: what fits in the 48 KB static limit
-    constexpr int MAXR = ((49152 - 32768 - 8 * BY * SW - 16) / 30) / 32 * 32;
-    __shared__ unsigned short sp[256 * 64];  // tile-local parents, used at run starts only (32 KB)
-    __shared__ uint32_t sP[BY * SW];         // A | B of every word
-    __shared__ uint32_t sB[BY * SW];         // bottom pixel row (B) of every word
-    __shared__ uint32_t st_area[MAXR], st_sr[MAXR], st_sc[MAXR];
-    __shared__ int st_minr[MAXR], st_minc[MAXR], st_maxr[MAXR], st_maxc[MAXR];
-    __shared__ unsigned short sroot[MAXR];
-    __shared__ int s_n, s_base;
+    constexpr int WR = BX * 4;               // words per tile row (power of two)
+    constexpr int SW = WR + 2;               // + one halo word each side
+    constexpr int MAXR = LocalSmem::MAXR;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint32_t* sA = reinterpret_cast<uint32_t*>(smem_raw);                 // [BY][SW] pixel row 2by
+    uint32_t* sB = sA + LocalSmem::AB_WORDS;                              // [BY][SW] pixel row 2by + 1
+    unsigned short* swpre = reinterpret_cast<unsigned short*>(sB + LocalSmem::AB_WORDS);   // [1024] runs before word
+    unsigned short* srun = swpre + 1024;                                  // [MAXRUNS] (word << 4) | first block
+    unsigned short* spar = srun + LocalSmem::MAXRUNS;                     // [MAXRUNS] parent run id / TAG | slot
+    uint32_t* st_area = reinterpret_cast<uint32_t*>(spar + LocalSmem::MAXRUNS);
+    uint32_t* st_sr = st_area + MAXR;
+    uint32_t* st_sc = st_sr + MAXR;
+    int* st_minr = reinterpret_cast<int*>(st_sc + MAXR);
+    int* st_minc = st_minr + MAXR;
+    int* st_maxr = st_minc + MAXR;
+    int* st_maxc = st_maxr + MAXR;
+    unsigned short* sroot = reinterpret_cast<unsigned short*>(st_maxc + MAXR);
+    int* s_misc = reinterpret_cast<int*>(sroot + MAXR);                   // [0..7] warp totals, [8] slots, [9] base
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx = tid % BX, ty = tid / BX;
     const int f = blockIdx.y;
     const int by0 = blockIdx.x * BY;
@@ -364,154 +386,181 @@ k_ccl_local(const uint32_t* __restrict__ fbits, Geom g, int* __restrict__ parent
     const int Q = g.wpr4 >> 2;
     const uint32_t* fb = fbits + (long long)f * g.h * g.wpr4;
 
+    // ---- phase A: load, publish the rows, number the runs in raster order
     Group gr;
 #pragma unroll
     for (int i = 0; i < 4; ++i) gr.A[i] = gr.B[i] = 0u;
     if (tx < Q && by < g.BH) load_group(gr, fb, g, by, tx);
-    const uint32_t any = gr.any();
     const int w0 = ty * SW + 1 + 4 * tx;     // smem index of this thread's word 0
+    uint32_t RS[4];
+    int cnt = 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        sP[w0 + i] = gr.A[i] | gr.B[i];
+        sA[w0 + i] = gr.A[i];
         sB[w0 + i] = gr.B[i];
+        RS[i] = run_starts(gr.A[i] | gr.B[i]);
+        cnt += __popc(RS[i]);
     }
-    if (tx == 0) { sP[ty * SW] = 0u; sB[ty * SW] = 0u; }
-    if (tx == BX - 1) { sP[ty * SW + SW - 1] = 0u; sB[ty * SW + SW - 1] = 0u; }
-    if (tid == 0) s_n = 0;
-
-    // ---- phase 1: every run start is its own parent
-    const int l0 = tid * 64;
-    RunIter it;
-    int i, k0;
-    uint32_t A, B;
-    if (any) {
-        it.init(gr);
-        while (it.next(gr, i, k0, A, B)) sp[l0 + i * 16 + k0] = (unsigned short)(l0 + i * 16 + k0);
-    }
-    if (!__syncthreads_or((int)any)) return;    // empty tile: nothing to write anywhere
-
-    // ---- phase 2: unions with the word to the left and with the block row above (same tile).
-    // Contacts are evaluated once per word (at its first run), unions dedup'd per run pair.
-    if (any) {
+    if (tx == 0) { sA[ty * SW] = 0u; sB[ty * SW] = 0u; }
+    if (tx == BX - 1) { sA[ty * SW + SW - 1] = 0u; sB[ty * SW + SW - 1] = 0u; }
+    int incl = cnt;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
-            const uint32_t Aw = gr.A[w];
-            const uint32_t P = Aw | gr.B[w];
-            if (!P) continue;
-            const int lw = l0 + w * 16;                  // tile-local index of block 0 of this word
-            if (P & 1u) {
-                const uint32_t Pl = sP[w0 + w - 1];
-                if (Pl >> 31) unite_s(sp, lw, lw - 16 + run_start_of(run_starts(Pl), 15));
-            }
-            if (ty == 0 || !Aw) continue;
-            const int wu = w0 + w - SW;                  // the word above
-            Contacts c = contacts(Aw, P, sB[wu - 1], sB[wu], sB[wu + 1]);
-            if ((c.UP | c.UL | c.UR) == 0u) continue;
-            const uint32_t RS = run_starts(P);
-            const uint32_t RSu = run_starts(sP[wu]);
-            const int lu = lw - ROWB;                    // block 0 of the word above
-            int last_a = -1, last_b = -1;
-            while (c.UP) {
-                const int k = (__ffs((int)c.UP) - 1) >> 1;
-                c.UP &= c.UP - 1;
-                const int a = lw + run_start_of(RS, k), b = lu + run_start_of(RSu, k);
-                if (a != last_a || b != last_b) unite_s(sp, a, b);
-                last_a = a; last_b = b;
-            }
-            while (c.UL) {
-                const int k = (__ffs((int)c.UL) - 1) >> 1;
-                c.UL &= c.UL - 1;
-                const int a = lw + run_start_of(RS, k);
-                const int b = (k > 0) ? lu + run_start_of(RSu, k - 1)
-                                      : lu - 16 + run_start_of(run_starts(sP[wu - 1]), 15);
-                if (a != last_a || b != last_b) unite_s(sp, a, b);
-                last_a = a; last_b = b;
-            }
-            while (c.UR) {
-                const int k = (__ffs((int)c.UR) - 1) >> 1;
-                c.UR &= c.UR - 1;
-                const int a = lw + run_start_of(RS, k);
-                const int b = (k < 15) ? lu + run_start_of(RSu, k + 1) : lu + 16;   // block 0 starts a run
-                if (a != last_a || b != last_b) unite_s(sp, a, b);
-                last_a = a; last_b = b;
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (lane == 31) s_misc[warp] = incl;
+    if (tid == 0) s_misc[8] = 0;
+    __syncthreads();
+    int base = incl - cnt, nruns = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        const int t = s_misc[w];
+        if (w < warp) base += t;
+        nruns += t;
+    }
+    if (nruns == 0) return;                  // empty tile (block-uniform): nothing to write anywhere
+    {
+        const int wi0 = ty * WR + 4 * tx;    // tile-raster word index
+        int r = base;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            swpre[wi0 + i] = (unsigned short)r;
+            uint32_t rs = RS[i];
+            while (rs) {
+                const int k0 = (__ffs((int)rs) - 1) >> 1;
+                rs &= rs - 1;
+                srun[r] = (unsigned short)(((wi0 + i) << 4) | k0);
+                spar[r] = (unsigned short)r;
+                ++r;
             }
         }
     }
     __syncthreads();
 
-    // ---- phase 3: roots claim an accumulator slot (entry becomes TAG | slot)
-    if (any) {
-        it.init(gr);
-        while (it.next(gr, i, k0, A, B)) {
-            const int l = l0 + i * 16 + k0;
-            if ((int)sp[l] == l) {
-                const int slot = atomicAdd(&s_n, 1);
-                if (slot < MAXR) {
-                    sroot[slot] = (unsigned short)l;
-                    st_area[slot] = 0u; st_sr[slot] = 0u; st_sc[slot] = 0u;
-                    st_minr[slot] = 0x7FFFFFFF; st_minc[slot] = 0x7FFFFFFF;
-                    st_maxr[slot] = -1; st_maxc[slot] = -1;
-                    sp[l] = (unsigned short)(TAG | (uint32_t)slot);
-                } else {
-                    sp[l] = (unsigned short)(TAG | NOSLOT);
-                }
-            }
+    // id of the run that contains (occupied) block k of the word at smem position sw / raster index wi
+    auto run_id = [&](int sw, int wi, int k) -> int {
+        const uint32_t rsu = run_starts(sA[sw] | sB[sw]);
+        return (int)swpre[wi] + __popc(rsu & ((2u << (2 * k)) - 1u)) - 1;
+    };
+
+    // ---- phase B: one thread per run: unions with the word to the left and the block row above
+    for (int r = tid; r < nruns; r += 256) {
+        const int d = (int)srun[r];
+        const int wi = d >> 4, k0 = d & 15;
+        const int rty = wi / WR, wx = wi % WR;
+        const int sw = rty * SW + 1 + wx;
+        const uint32_t A = sA[sw], B = sB[sw];
+        const uint32_t P = A | B;
+        if (k0 == 0 && (P & 1u)) {
+            const uint32_t Pl = sA[sw - 1] | sB[sw - 1];
+            if (Pl >> 31) unite_s(spar, r, run_id(sw - 1, wi - 1, 15));
+        }
+        if (rty == 0) continue;
+        const uint32_t m = run_mask(link_bits(P), k0);
+        const uint32_t Am = A & m;
+        if (!Am) continue;
+        const int su = sw - SW, wu = wi - WR;            // the word above
+        Contacts c = contacts(Am, P & m, sB[su - 1], sB[su], sB[su + 1]);
+        int last_b = -1;
+        while (c.UP) {
+            const int k = (__ffs((int)c.UP) - 1) >> 1;
+            c.UP &= c.UP - 1;
+            const int b = run_id(su, wu, k);
+            if (b != last_b) unite_s(spar, r, b);
+            last_b = b;
+        }
+        while (c.UL) {
+            const int k = (__ffs((int)c.UL) - 1) >> 1;
+            c.UL &= c.UL - 1;
+            const int b = (k > 0) ? run_id(su, wu, k - 1) : run_id(su - 1, wu - 1, 15);
+            if (b != last_b) unite_s(spar, r, b);
+            last_b = b;
+        }
+        while (c.UR) {
+            const int k = (__ffs((int)c.UR) - 1) >> 1;
+            c.UR &= c.UR - 1;
+            const int b = (k < 15) ? run_id(su, wu, k + 1) : run_id(su + 1, wu + 1, 0);
+            if (b != last_b) unite_s(spar, r, b);
+            last_b = b;
         }
     }
     __syncthreads();
 
-    // ---- phase 4: per run: root, global parent of every block, regionprops partial sums
-    if (any) {
-        int* par = parent + (long long)f * g.BH * g.BW + (long long)by * g.BW + tx * 64;
-        it.init(gr);
-        while (it.next(gr, i, k0, A, B)) {
-            // root of the run: walk to the tagged entry
-            int x = l0 + i * 16 + k0;
-            uint32_t p = sp[x];
-            while (!(p & TAG)) {
-                x = (int)p;
-                p = sp[x];
-            }
-            const uint32_t slot = p & NOSLOT;
-            const int rgid = (by0 + x / ROWB) * g.BW + (x % ROWB);    // tile-local -> global block id
-            const uint32_t P = A | B;
-            const uint32_t m = run_mask(link_bits(P), k0);
-            uint32_t O = occ_bits(P & m);
-            while (O) {
-                par[i * 16 + ((__ffs((int)O) - 1) >> 1)] = rgid;
-                O &= O - 1;
-            }
-            const RunStats s = run_stats(A & m, B & m, 2 * by, 32 * (4 * tx + i));
-            if (slot < (uint32_t)MAXR) {
-                atomicAdd(&st_area[slot], s.area);
-                atomicAdd(&st_sr[slot], s.sr);
-                atomicAdd(&st_sc[slot], s.sc);
-                atomicMin(&st_minr[slot], s.minr);
-                atomicMin(&st_minc[slot], s.minc);
-                atomicMax(&st_maxr[slot], s.maxr);
-                atomicMax(&st_maxc[slot], s.maxc);
-            } else {   // more than MAXR components in this tile: one partial per run, straight to global
-                const int idx = atomicAdd(pcount, 1);
-                const int own = (by0 + ty) * g.BW + tx * 64 + i * 16 + k0;
-                if (idx < cap_parts) emit_partial(parts, idx, f, rgid, s.area, s.minr, s.minc, s.maxr, s.maxc,
-                                                  s.sr, s.sc, own == rgid ? 2 : 1);
-                else *overflow = 1;
-            }
+    // ---- phase C: roots claim an accumulator slot (entry becomes TAG | slot)
+    for (int r = tid; r < nruns; r += 256) {
+        if ((int)spar[r] != r) continue;
+        const int slot = atomicAdd(&s_misc[8], 1);
+        if (slot < MAXR) {
+            sroot[slot] = (unsigned short)r;
+            st_area[slot] = 0u; st_sr[slot] = 0u; st_sc[slot] = 0u;
+            st_minr[slot] = 0x7FFFFFFF; st_minc[slot] = 0x7FFFFFFF;
+            st_maxr[slot] = -1; st_maxc[slot] = -1;
+            spar[r] = (unsigned short)(TAG | (uint32_t)slot);
+        } else {
+            spar[r] = (unsigned short)(TAG | NOSLOT);
         }
     }
     __syncthreads();
 
-    // ---- phase 5: one partial per tile-local component -> global list
-    const int n = min(s_n, MAXR);
-    if (tid == 0) s_base = atomicAdd(pcount, n);
+    // tile-local run id -> global block id of its first block
+    auto run_gid = [&](int r) -> int {
+        const int d = (int)srun[r];
+        const int wi = d >> 4;
+        return (by0 + wi / WR) * g.BW + (wi % WR) * 16 + (d & 15);
+    };
+
+    // ---- phase D: one thread per run: root, global parent of every block, regionprops partial sums
+    int* par_f = parent + (long long)f * g.BH * g.BW;
+    for (int r = tid; r < nruns; r += 256) {
+        int x = r;
+        uint32_t p = spar[x];
+        while (!(p & TAG)) {
+            x = (int)p;
+            p = spar[x];
+        }
+        const uint32_t slot = p & NOSLOT;
+        const int rgid = run_gid(x);
+        const int d = (int)srun[r];
+        const int wi = d >> 4, k0 = d & 15;
+        const int rty = wi / WR, wx = wi % WR;
+        const int sw = rty * SW + 1 + wx;
+        const uint32_t A = sA[sw], B = sB[sw];
+        const uint32_t P = A | B;
+        const uint32_t m = run_mask(link_bits(P), k0);
+        int* par = par_f + (long long)(by0 + rty) * g.BW + wx * 16;
+        uint32_t O = occ_bits(P & m);
+        while (O) {
+            par[(__ffs((int)O) - 1) >> 1] = rgid;
+            O &= O - 1;
+        }
+        const RunStats s = run_stats(A & m, B & m, 2 * (by0 + rty), 32 * wx);
+        if (slot < (uint32_t)MAXR) {
+            atomicAdd(&st_area[slot], s.area);
+            atomicAdd(&st_sr[slot], s.sr);
+            atomicAdd(&st_sc[slot], s.sc);
+            atomicMin(&st_minr[slot], s.minr);
+            atomicMin(&st_minc[slot], s.minc);
+            atomicMax(&st_maxr[slot], s.maxr);
+            atomicMax(&st_maxc[slot], s.maxc);
+        } else {   // more than MAXR components in this tile: one partial per run, straight to global
+            const int idx = atomicAdd(pcount, 1);
+            if (idx < cap_parts) emit_partial(parts, idx, f, rgid, s.area, s.minr, s.minc, s.maxr, s.maxc, s.sr,
+                                              s.sc, x == r ? 2 : 1);
+            else *overflow = 1;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase E: one partial per tile-local component -> global list
+    const int n = min(s_misc[8], MAXR);
+    if (tid == 0) s_misc[9] = atomicAdd(pcount, n);
     __syncthreads();
     for (int s = tid; s < n; s += 256) {
-        const int idx = s_base + s;
+        const int idx = s_misc[9] + s;
         if (idx < cap_parts) {
-            const int rl = (int)sroot[s];
-            const int rgid = (by0 + rl / ROWB) * g.BW + (rl % ROWB);
-            emit_partial(parts, idx, f, rgid, st_area[s], st_minr[s], st_minc[s], st_maxr[s], st_maxc[s], st_sr[s],
-                         st_sc[s], 0);
+            emit_partial(parts, idx, f, run_gid((int)sroot[s]), st_area[s], st_minr[s], st_minc[s], st_maxr[s],
+                         st_maxc[s], st_sr[s], st_sc[s], 0);
         } else {
             *overflow = 1;
         }
@@ -919,7 +968,13 @@ template <int BX>
 static void launch_local(cudaStream_t s, const uint32_t* fbits, int T, const Geom& g, const CclBuffers& b) {
     constexpr int BY = 256 / BX;
     dim3 grid((g.BH + BY - 1) / BY, T);
-    k_ccl_local<BX><<<grid, 256, 0, s>>>(fbits, g, b.parent, b.parts, b.pcount, b.cap_parts, b.overflow);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k_ccl_local<BX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LocalSmem::bytes());
+        configured = true;
+    }
+    k_ccl_local<BX><<<grid, 256, LocalSmem::bytes(), s>>>(fbits, g, b.parent, b.parts, b.pcount, b.cap_parts,
+                                                          b.overflow);
     const int n_boundaries = (g.BH + BY - 1) / BY - 1;
     if (n_boundaries > 0) {
         const int Q = g.wpr4 >> 2;
