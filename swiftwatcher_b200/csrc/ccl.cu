@@ -286,11 +286,11 @@ k_ccl_merge(const uint32_t* __restrict__ fbits, Geom g, int* parent) {
 }
 
 // Global unions between the first block row of every tile (tile_rows apart) and the
-// row above it.  grid = (ceil(Q / 32), n_boundaries, T), 32 threads.
-__global__ void __launch_bounds__(32)
+// row above it.  grid = (ceil(Q / 32), ceil(n_boundaries / 8), T), block = (32, 8).
+__global__ void __launch_bounds__(256)
 k_ccl_boundary(const uint32_t* __restrict__ fbits, Geom g, int tile_rows, int* parent) {
     const int q = blockIdx.x * 32 + threadIdx.x;
-    const int by = (blockIdx.y + 1) * tile_rows;
+    const int by = (blockIdx.y * 8 + threadIdx.y + 1) * tile_rows;
     const int f = blockIdx.z;
     if (q >= (g.wpr4 >> 2) || by >= g.BH) return;
     const uint32_t* fb = fbits + (long long)f * g.h * g.wpr4;
@@ -978,8 +978,8 @@ static void launch_local(cudaStream_t s, const uint32_t* fbits, int T, const Geo
     const int n_boundaries = (g.BH + BY - 1) / BY - 1;
     if (n_boundaries > 0) {
         const int Q = g.wpr4 >> 2;
-        dim3 bgrid((Q + 31) / 32, n_boundaries, T);
-        k_ccl_boundary<<<bgrid, 32, 0, s>>>(fbits, g, BY, b.parent);
+        dim3 bgrid((Q + 31) / 32, (n_boundaries + 7) / 8, T);
+        k_ccl_boundary<<<bgrid, dim3(32, 8), 0, s>>>(fbits, g, BY, b.parent);
     }
 }
 

@@ -74,6 +74,59 @@ __device__ __forceinline__ uint32_t median_lanes(const uint32_t (&v)[N]) {
     }
 }
 
+// ---- pipe-balanced medians for the v2 kernel -----------------------------------------
+// K1 is bound by the ALU pipe (VIMNMX, LOP3, PRMT ...), while the FMA pipe idles.  The
+// median of three is x + y + z - min3 - max3: two VIMNMX3 on the ALU pipe and four adds
+// that are forced onto the FMA pipe as IMAD (multiplier `one` is a kernel argument equal
+// to 1, so ptxas cannot turn the IMAD back into an ALU-pipe IADD3).  u16x2 lanes never
+// carry or borrow here (sums <= 765, and sum >= min + max per lane).
+struct FmaAdd {
+    uint32_t one, mone;
+    __device__ __forceinline__ uint32_t add(uint32_t a, uint32_t b) const {
+        uint32_t d;
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b));
+        return d;
+    }
+    __device__ __forceinline__ uint32_t sub(uint32_t a, uint32_t b) const {   // a - b
+        uint32_t d;
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(b), "r"(mone), "r"(a));
+        return d;
+    }
+    __device__ __forceinline__ uint32_t med3(uint32_t x, uint32_t y, uint32_t z) const {
+        const uint32_t s = add(add(x, y), z);
+        return sub(sub(s, __vimin3_u16x2(x, y, z)), __vimax3_u16x2(x, y, z));
+    }
+};
+
+template <int N>
+__device__ __forceinline__ uint32_t median_lanes_fma(const uint32_t (&v)[N], const FmaAdd& f) {
+    if constexpr (N == 3) {
+        return f.med3(v[0], v[1], v[2]);
+    } else if constexpr (N == 5) {
+        // pairs: min on the ALU pipe, max = a + b - min on the FMA pipe
+        const uint32_t mn1 = vmin2(v[0], v[1]), mx1 = f.sub(f.add(v[0], v[1]), mn1);
+        const uint32_t mn2 = vmin2(v[2], v[3]), mx2 = f.sub(f.add(v[2], v[3]), mn2);
+        return f.med3(v[4], vmax2(mn1, mn2), vmin2(mx1, mx2));
+    } else if constexpr (N == 9) {
+        // three sorted triples (min3, max3, middle by sum), then med3(max of mins, med of
+        // middles, min of maxes)
+        uint32_t lo[3], hi[3], mid[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const uint32_t a = v[3 * c], b = v[3 * c + 1], d = v[3 * c + 2];
+            lo[c] = __vimin3_u16x2(a, b, d);
+            hi[c] = __vimax3_u16x2(a, b, d);
+            mid[c] = f.sub(f.sub(f.add(f.add(a, b), d), lo[c]), hi[c]);
+        }
+        const uint32_t L = __vimax3_u16x2(lo[0], lo[1], lo[2]);
+        const uint32_t H = __vimin3_u16x2(hi[0], hi[1], hi[2]);
+        const uint32_t M = f.med3(mid[0], mid[1], mid[2]);
+        return f.med3(L, M, H);
+    } else {
+        return median_lanes<N>(v);
+    }
+}
+
 // cv2 4.13 BGR2GRAY: (3735 B + 19235 G + 9798 R + 2^14) >> 15, evaluated with all
 // terms doubled so that the result is byte 2 of the sum (sum < 2^24).
 __device__ __forceinline__ uint32_t gray_sum(uint32_t b, uint32_t g, uint32_t r) {
@@ -338,12 +391,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  : "memory");
 }
 
-// 48 BGR bytes -> 8 u16x2 lanes of (gray[k], gray[k+8]) with IDP.2A
-__device__ __forceinline__ void bgr48_to_lanes_dp(const uint32_t (&w)[12], uint32_t (&out)[8]) {
+// 2L BGR pixels (6L bytes, 3L/2 words) -> L u16x2 lanes of (gray[k], gray[k+L]) with IDP.2A
+template <int L>
+__device__ __forceinline__ void bgr_to_lanes_dp(const uint32_t (&w)[3 * L / 2], uint32_t (&out)[L]) {
     constexpr uint32_t WB = 7470u, WG = 38470u, WR = 19596u, RND = 32768u;
-    uint32_t s[16];
+    constexpr int NW = 3 * L / 2;
+    uint32_t s[2 * L];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
+    for (int i = 0; i < 2 * L; ++i) {
         const int o = 3 * i, wi = o >> 2, r = o & 3;
         uint32_t acc;
         if (r == 0) {          // B G R x
@@ -354,44 +409,109 @@ __device__ __forceinline__ void bgr48_to_lanes_dp(const uint32_t (&w)[12], uint3
             acc = __dp2a_hi(WG | (WR << 16), w[wi], acc);
         } else if (r == 2) {   // x x B G | R
             acc = __dp2a_hi(WB | (WG << 16), w[wi], RND);
-            acc = __dp2a_lo(WR, w[(wi + 1) % 12], acc);
+            acc = __dp2a_lo(WR, w[(wi + 1) % NW], acc);
         } else {               // x x x B | G R
             acc = __dp2a_hi(WB << 16, w[wi], RND);
-            acc = __dp2a_lo(WG | (WR << 16), w[(wi + 1) % 12], acc);
+            acc = __dp2a_lo(WG | (WR << 16), w[(wi + 1) % NW], acc);
         }
         s[i] = acc;
     }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) out[k] = __byte_perm(s[k], s[k + 8], 0x7632);
+    for (int k = 0; k < L; ++k) out[k] = __byte_perm(s[k], s[k + L], 0x7632);
 }
 
-// (|x - m| > thresh) per u16 lane -> 16 bits (bit k = pixel k)
-__device__ __forceinline__ uint32_t fg_bits16_v2(const uint32_t (&cur)[8], const uint32_t (&med)[8],
-                                                 uint32_t neg_thresh_x2) {
+// 2L gray bytes (L/2 words) -> lanes
+template <int L>
+__device__ __forceinline__ void gray_to_lanes(const uint32_t (&w)[L / 2], uint32_t (&out)[L]) {
+#pragma unroll
+    for (int k = 0; k < L; ++k) {
+        const uint32_t lo = (w[k >> 2] >> (8 * (k & 3))) & 0xFFu;
+        const uint32_t hi = (w[(k + L) >> 2] >> (8 * ((k + L) & 3))) & 0xFFu;
+        out[k] = lo | (hi << 16);
+    }
+}
+
+// lanes -> 2L gray bytes
+template <int L>
+__device__ __forceinline__ void lanes_to_gray(const uint32_t (&v)[L], uint32_t (&w)[L / 2]) {
+#pragma unroll
+    for (int t = 0; t < L / 2; ++t) {
+        uint32_t word = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int px = 4 * t + b;
+            const uint32_t val = (px < L) ? (v[px] & 0xFFu) : ((v[px - L] >> 16) & 0xFFu);
+            word |= val << (8 * b);
+        }
+        w[t] = word;
+    }
+}
+
+// lanes -> the same gray values as 6L BGR bytes (v, v, v): the gray formula maps them back to
+// v exactly, so carried history rides the same pipeline as real frames
+template <int L>
+__device__ __forceinline__ void lanes_to_bgr(const uint32_t (&v)[L], uint32_t (&w)[3 * L / 2]) {
+    uint32_t gw[L / 2];
+    lanes_to_gray<L>(v, gw);
+#pragma unroll
+    for (int t = 0; t < 3 * L / 2; ++t) {
+        uint32_t word = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int px = (4 * t + b) / 3;
+            word |= ((gw[px >> 2] >> (8 * (px & 3))) & 0xFFu) << (8 * b);
+        }
+        w[t] = word;
+    }
+}
+
+// (|x - m| > thresh) per u16 lane -> 2L bits (bit k = pixel k)
+template <int L>
+__device__ __forceinline__ uint32_t fg_bits_v2(const uint32_t (&cur)[L], const uint32_t (&med)[L],
+                                               uint32_t neg_thresh_x2) {
     uint32_t acc = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < L; ++k) {
         const uint32_t d = __vabsdiffu4(cur[k], med[k]);                          // lanes hold 0..255
         const uint32_t f = __viaddmin_s16x2_relu(d, neg_thresh_x2, 0x00010001u);  // 1 where d > thresh
         acc += f << k;
     }
-    return (acc & 0xFFu) | ((acc >> 8) & 0xFF00u);
+    constexpr uint32_t M = (1u << L) - 1u;
+    return (acc & M) | ((acc >> (16 - L)) & (M << L));
 }
 
-constexpr int CONSUMERS = 256;               // 8 consumer warps: one 16-pixel group per thread
+// Temporal sub-chunk length: long enough that the N-1 warm-up frames are a few
+// percent of the work, short enough that the grid has several waves of CTAs.
+int pick_ts(int T, int n_col_blocks, int median_n) {
+    const int target_ctas = 148 * 2 * 4;
+    int ts = T;
+    while (ts > 32 && (long long)n_col_blocks * ((T + ts - 1) / ts) < target_ctas) ts = (ts + 1) / 2;
+    const int min_ts = 16 * (median_n - 1) > 0 ? 16 * (median_n - 1) : 1;  // <= ~6% warm-up
+    if (ts < min_ts) ts = min_ts;
+    if (ts > T) ts = T;
+    if (ts < 1) ts = 1;
+    return ts;
+}
+
+constexpr int CONSUMERS = 256;               // 8 consumer warps: one pixel group per thread
 constexpr int V2_THREADS = CONSUMERS + 32;   // + 1 producer warp
 
-template <int N, int C, int S>
-__global__ void __launch_bounds__(V2_THREADS, (N <= 7) ? 2 : 1)
-k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint16_t* __restrict__ raw_bits) {
-    constexpr int TB = 16 * C;               // bytes per thread per frame
+// L = u16x2 registers per ring slot: a thread owns 2L adjacent pixels (16 for N <= 5; 8 for the
+// longer windows, whose ring would not fit the register file at two CTAs per SM).
+template <int N, int C, int S, int L>
+__global__ void __launch_bounds__(V2_THREADS, 2)
+k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t one,
+             uint8_t* __restrict__ raw_bits) {
+    constexpr int PPT = 2 * L;               // pixels per thread
+    constexpr int TB = PPT * C;              // bytes per thread per frame
     constexpr int STAGE_BYTES = CONSUMERS * TB;
+    constexpr int NWORDS = TB / 4;
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + S * STAGE_BYTES);
     uint64_t* empty = full + S;
 
     const int tid = threadIdx.x;
-    const int gpr = wa >> 4;                 // 16-pixel groups per row
+    const int gpr = wa / PPT;                // pixel groups per row
     const int G = h * gpr;
     const int g0 = blockIdx.x * CONSUMERS;
     const int t_start = blockIdx.y * Ts;
@@ -412,6 +532,7 @@ k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint16_t* _
 
     if (tid >= CONSUMERS) {
         // ===== producer warp: one elected lane streams this CTA's slice of every frame =====
+        // (groups per row and per CTA are multiples of 4, so every copy is 16-byte granular)
         if (tid != CONSUMERS) return;
         const int ngroups = min(CONSUMERS, G - g0);
         const uint32_t bytes = (uint32_t)(ngroups * TB);
@@ -454,33 +575,41 @@ k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint16_t* _
     const int row = active ? g / gpr : 0;
     const int col = active ? g - row * gpr : 0;
     const uint32_t neg_th = ((uint32_t)(-thresh) & 0xFFFFu) * 0x00010001u;
-    uint16_t* out = raw_bits + ((long long)t_start * h + row) * gpr + col;
-    const long long out_step = (long long)h * gpr;
+    FmaAdd fa;
+    fa.one = one;
+    fa.mone = 0u - one;
+    // raw bits: one bit per pixel, PPT / 8 bytes per thread per frame
+    uint8_t* out = raw_bits + (((long long)t_start * h + row) * gpr + col) * (PPT / 8);
+    const long long out_step = (long long)h * gpr * (PPT / 8);
     const uint8_t* my_smem = smem + tid * TB;
     const bool lane0 = (tid & 31) == 0;
 
-    uint32_t ring[N][8];
-    // take pipeline frame p into ring[slot]
-    auto consume = [&](int p, uint32_t (&dst)[8]) {
+    uint32_t ring[N][L];
+    // take pipeline frame p into a ring slot
+    auto consume = [&](int p, uint32_t (&dst)[L]) {
         const int st = p % S;
         mbar_wait(&full[st], (uint32_t)((p / S) & 1));
-        const uint4* sp4 = reinterpret_cast<const uint4*>(my_smem + st * STAGE_BYTES);
-        if constexpr (C == 3) {
-            uint32_t w[12];
+        uint32_t w[NWORDS];
+        if constexpr (TB % 16 == 0) {
+            const uint4* sp4 = reinterpret_cast<const uint4*>(my_smem + st * STAGE_BYTES);
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
+            for (int i = 0; i < TB / 16; ++i) {
                 const uint4 v = sp4[i];
                 w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
             }
-            bgr48_to_lanes_dp(w, dst);
         } else {
-            const uint4 v = sp4[0];
-            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-            gray16_to_lanes(w4, dst);
+            const uint2* sp2 = reinterpret_cast<const uint2*>(my_smem + st * STAGE_BYTES);
+#pragma unroll
+            for (int i = 0; i < TB / 8; ++i) {
+                const uint2 v = sp2[i];
+                w[2 * i] = v.x; w[2 * i + 1] = v.y;
+            }
         }
+        if constexpr (C == 3) bgr_to_lanes_dp<L>(w, dst);
+        else gray_to_lanes<L>(w, dst);
         // release the stage only after the loaded words have been consumed (the converted
         // lanes depend on every LDS), so the bulk engine can never overwrite data in flight
-        asm volatile("" ::"r"(dst[0]), "r"(dst[7]) : "memory");
+        asm volatile("" ::"r"(dst[0]), "r"(dst[L - 1]) : "memory");
         __syncwarp();
         if (lane0) mbar_arrive(&empty[st]);
     };
@@ -496,15 +625,19 @@ k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint16_t* _
             if (k < n_out) {                                // block-uniform
                 const int slot = (N - 1 + ph) % N;          // static after unrolling
                 consume(k + N - 1, ring[slot]);
-                uint32_t med[8];
+                uint32_t med[L];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
+                for (int q = 0; q < L; ++q) {
                     uint32_t v[N];
 #pragma unroll
                     for (int s = 0; s < N; ++s) v[s] = ring[s][q];
-                    med[q] = median_lanes<N>(v);
+                    med[q] = median_lanes_fma<N>(v, fa);
                 }
-                if (active) *out = (uint16_t)fg_bits16_v2(ring[slot], med, neg_th);
+                const uint32_t bits = fg_bits_v2<L>(ring[slot], med, neg_th);
+                if (active) {
+                    if constexpr (PPT == 16) *reinterpret_cast<uint16_t*>(out) = (uint16_t)bits;
+                    else *out = (uint8_t)bits;
+                }
                 out += out_step;
                 if (k == n_out - 1 && t_end == T && src.hist_out != nullptr && active) {
                     // leave the last N-1 gray frames (oldest first) as frames for the next submit
@@ -512,16 +645,13 @@ k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint16_t* _
                     for (int s = 0; s < N - 1; ++s) {
                         const int m = N - 2 - s;                    // frames back from the newest
                         const int hs = ((slot - m) % N + N) % N;    // static
-                        uint8_t* hp = src.hist_out + ((long long)s * h + row) * (long long)gpr * TB + col * TB;
-                        if constexpr (C == 3) {
-                            uint4 o[3];
-                            lanes_to_bgr48(ring[hs], o);
-                            reinterpret_cast<uint4*>(hp)[0] = o[0];
-                            reinterpret_cast<uint4*>(hp)[1] = o[1];
-                            reinterpret_cast<uint4*>(hp)[2] = o[2];
-                        } else {
-                            *reinterpret_cast<uint4*>(hp) = lanes_to_gray16(ring[hs]);
-                        }
+                        uint32_t hw[NWORDS];
+                        if constexpr (C == 3) lanes_to_bgr<L>(ring[hs], hw);
+                        else lanes_to_gray<L>(ring[hs], hw);
+                        uint32_t* hp = reinterpret_cast<uint32_t*>(
+                            src.hist_out + (((long long)s * h + row) * gpr + col) * TB);
+#pragma unroll
+                        for (int i = 0; i < NWORDS; ++i) hp[i] = hw[i];
                     }
                 }
             }
@@ -530,32 +660,38 @@ k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint16_t* _
 }
 
 template <int N, int C>
-cudaError_t launch_v2(cudaStream_t s, const FrameSrc& src, int T, int Ts, const Geom& g, int thresh,
+cudaError_t launch_v2(cudaStream_t s, const FrameSrc& src, int T, const Geom& g, int thresh,
                       uint16_t* raw_bits) {
-    constexpr int S = (C == 3) ? 4 : 8;
-    constexpr int SMEM = S * CONSUMERS * 16 * C + 2 * S * 8;
+    constexpr int L = (N <= 5) ? 8 : 4;
+    constexpr int TB = 2 * L * C;
+    constexpr int S = (TB >= 48) ? 4 : 8;
+    constexpr int SMEM = S * CONSUMERS * TB + 2 * S * 8;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_fg_bits_v2<N, C, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        cudaError_t e = cudaFuncSetAttribute(k_fg_bits_v2<N, C, S, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    const int G = g.h * (g.wa >> 4);
-    dim3 grid((G + CONSUMERS - 1) / CONSUMERS, (T + Ts - 1) / Ts);
-    k_fg_bits_v2<N, C, S><<<grid, V2_THREADS, SMEM, s>>>(src, T, Ts, g.h, g.wa, thresh, raw_bits);
+    const int G = g.h * (g.wa / (2 * L));
+    const int n_col_blocks = (G + CONSUMERS - 1) / CONSUMERS;
+    const int Ts = pick_ts(T, n_col_blocks, N);
+    dim3 grid(n_col_blocks, (T + Ts - 1) / Ts);
+    k_fg_bits_v2<N, C, S, L><<<grid, V2_THREADS, SMEM, s>>>(src, T, Ts, g.h, g.wa, thresh, 1u,
+                                                           reinterpret_cast<uint8_t*>(raw_bits));
     return cudaGetLastError();
 }
 
 template <int N>
-cudaError_t launch_n(cudaStream_t s, const FrameSrc& src, int channels, int T, int Ts, const Geom& g,
+cudaError_t launch_n(cudaStream_t s, const FrameSrc& src, int channels, int T, const Geom& g,
                      int thresh, uint16_t* raw_bits, bool aligned) {
+    if (aligned) {   // 16-byte aligned rows: bulk-copy pipeline (v2)
+        if (channels == 3) return launch_v2<N, 3>(s, src, T, g, thresh, raw_bits);
+        return launch_v2<N, 1>(s, src, T, g, thresh, raw_bits);
+    }
     const int G = g.h * (g.wa >> 4);
+    const int Ts = pick_ts(T, (G + 255) / 256, N);
     dim3 grid((G + 255) / 256, (T + Ts - 1) / Ts);
     dim3 block(256);
-    if (aligned) {   // 16-byte aligned rows: bulk-copy pipeline (v2)
-        if (channels == 3) return launch_v2<N, 3>(s, src, T, Ts, g, thresh, raw_bits);
-        return launch_v2<N, 1>(s, src, T, Ts, g, thresh, raw_bits);
-    }
     // odd pitches / frame widths: guarded byte loads (v1)
     if (channels == 3) k_fg_bits<N, 3, false><<<grid, block, 0, s>>>(src, T, Ts, g.h, g.wa, thresh, raw_bits);
     else k_fg_bits<N, 1, false><<<grid, block, 0, s>>>(src, T, Ts, g.h, g.wa, thresh, raw_bits);
@@ -564,30 +700,15 @@ cudaError_t launch_n(cudaStream_t s, const FrameSrc& src, int channels, int T, i
 
 }  // namespace
 
-// Temporal sub-chunk length: long enough that the N-1 warm-up frames are a few
-// percent of the work, short enough that the grid has several waves of CTAs.
-static int pick_ts(int T, int n_col_blocks, int median_n) {
-    const int target_ctas = 148 * 2 * 4;
-    int ts = T;
-    while (ts > 32 && (long long)n_col_blocks * ((T + ts - 1) / ts) < target_ctas) ts = (ts + 1) / 2;
-    const int min_ts = 16 * (median_n - 1) > 0 ? 16 * (median_n - 1) : 1;  // <= ~6% warm-up
-    if (ts < min_ts) ts = min_ts;
-    if (ts > T) ts = T;
-    if (ts < 1) ts = 1;
-    return ts;
-}
-
 cudaError_t launch_fg_bits(cudaStream_t s, const FrameSrc& src, int channels, int median_n, int T,
                            const Geom& g, int thresh, uint16_t* raw_bits, bool aligned, int* n_launches) {
-    const int G = g.h * (g.wa >> 4);
-    const int Ts = pick_ts(T, (G + 255) / 256, median_n);
     if (n_launches) *n_launches += 1;
     switch (median_n) {
-        case 1: return launch_n<1>(s, src, channels, T, Ts, g, thresh, raw_bits, aligned);
-        case 3: return launch_n<3>(s, src, channels, T, Ts, g, thresh, raw_bits, aligned);
-        case 5: return launch_n<5>(s, src, channels, T, Ts, g, thresh, raw_bits, aligned);
-        case 7: return launch_n<7>(s, src, channels, T, Ts, g, thresh, raw_bits, aligned);
-        case 9: return launch_n<9>(s, src, channels, T, Ts, g, thresh, raw_bits, aligned);
+        case 1: return launch_n<1>(s, src, channels, T, g, thresh, raw_bits, aligned);
+        case 3: return launch_n<3>(s, src, channels, T, g, thresh, raw_bits, aligned);
+        case 5: return launch_n<5>(s, src, channels, T, g, thresh, raw_bits, aligned);
+        case 7: return launch_n<7>(s, src, channels, T, g, thresh, raw_bits, aligned);
+        case 9: return launch_n<9>(s, src, channels, T, g, thresh, raw_bits, aligned);
         default: return cudaErrorInvalidValue;
     }
 }
