@@ -301,8 +301,8 @@ int swb_create(const swb_config* cfg, swb_ctx** out) {
     CUB(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
     if (nh > 0) {
-        CUB(dalloc(&ctx->hist[0], (size_t)nh * g.h * g.wa * c.channels));
-        CUB(dalloc(&ctx->hist[1], (size_t)nh * g.h * g.wa * c.channels));
+        CUB(dalloc(&ctx->hist[0], (size_t)nh * g.h * g.wa));
+        CUB(dalloc(&ctx->hist[1], (size_t)nh * g.h * g.wa));
     }
     CUB(dalloc(&ctx->raw_bits, (size_t)T * g.h * g.wpr_raw * 2 + 8));
     CUB(dalloc(&ctx->fbits, (size_t)T * g.h * g.wpr4));

@@ -116,7 +116,7 @@ __device__ __forceinline__ uint32_t median_lanes_fma(const uint32_t (&v)[N], con
             const uint32_t a = v[3 * c], b = v[3 * c + 1], d = v[3 * c + 2];
             lo[c] = __vimin3_u16x2(a, b, d);
             hi[c] = __vimax3_u16x2(a, b, d);
-            mid[c] = f.sub(f.sub(f.add(f.add(a, b), d), lo[c]), hi[c]);
+            mid[c] = a + b + d - lo[c] - hi[c];      // two IADD3 (fewer instructions; ALU has room here)
         }
         const uint32_t L = __vimax3_u16x2(lo[0], lo[1], lo[2]);
         const uint32_t H = __vimin3_u16x2(hi[0], hi[1], hi[2]);
@@ -172,28 +172,6 @@ __device__ __forceinline__ uint4 lanes_to_gray16(const uint32_t (&v)[8]) {
         w[q + 2] = __byte_perm(hi01, hi23, 0x5410);
     }
     return make_uint4(w[0], w[1], w[2], w[3]);
-}
-
-// 16 gray values (lanes) -> the same values as 48 BGR bytes (v, v, v): the gray formula
-// maps them back to v exactly, so carried history rides the same pipeline as real frames.
-__device__ __forceinline__ void lanes_to_bgr48(const uint32_t (&v)[8], uint4 (&o)[3]) {
-    const uint4 g16 = lanes_to_gray16(v);
-    const uint32_t gw[4] = {g16.x, g16.y, g16.z, g16.w};
-    uint32_t w[12];
-#pragma unroll
-    for (int t = 0; t < 12; ++t) {
-        // output bytes 4t..4t+3 are gray pixels (4t)/3, (4t+1)/3, (4t+2)/3, (4t+3)/3
-        uint32_t word = 0;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int px = (4 * t + b) / 3;
-            word |= ((gw[px >> 2] >> (8 * (px & 3))) & 0xFFu) << (8 * b);
-        }
-        w[t] = word;
-    }
-    o[0] = make_uint4(w[0], w[1], w[2], w[3]);
-    o[1] = make_uint4(w[4], w[5], w[6], w[7]);
-    o[2] = make_uint4(w[8], w[9], w[10], w[11]);
 }
 
 template <int C, bool ALIGNED>
@@ -273,11 +251,11 @@ k_fg_bits(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint16_t* __re
     auto load_frame = [&](int j, uint32_t (&dst)[8]) {
         // frame j relative to the first output frame of this submit
         if (j < 0 && src.hist_valid) {
-            // carried history: N-1 frames in the source format (gray stored as v,v,v), our own buffer
+            // carried history: N-1 compact gray frames [h][wa] in our own buffer
             const int slot = j + (N - 1);
-            RawPixels<C, true> p;
-            load_raw<C, true>(p, src.hist + (((long long)slot * h + row) * gpr + col) * (16 * C), 16);
-            raw_to_lanes<C, true>(p, dst);
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(src.hist + ((long long)slot * h + row) * wa + col * 16));
+            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+            gray16_to_lanes(w4, dst);
         } else {
             if (j < -src.n_inline_halo) j = -src.n_inline_halo;  // replicate earliest frame
             RawPixels<C, ALIGNED> p;
@@ -322,16 +300,8 @@ k_fg_bits(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint16_t* __re
                     for (int s = 0; s < N - 1; ++s) {
                         const int m = N - 2 - s;                  // frames back from the newest
                         const int hs = ((slot - m) % N + N) % N;  // static
-                        uint8_t* hp = src.hist_out + (((long long)s * h + row) * gpr + col) * (16 * C);
-                        if constexpr (C == 3) {
-                            uint4 o[3];
-                            lanes_to_bgr48(ring[hs], o);
-                            reinterpret_cast<uint4*>(hp)[0] = o[0];
-                            reinterpret_cast<uint4*>(hp)[1] = o[1];
-                            reinterpret_cast<uint4*>(hp)[2] = o[2];
-                        } else {
-                            *reinterpret_cast<uint4*>(hp) = lanes_to_gray16(ring[hs]);
-                        }
+                        *reinterpret_cast<uint4*>(src.hist_out + ((long long)s * h + row) * wa + col * 16) =
+                            lanes_to_gray16(ring[hs]);
                     }
                 }
             }
@@ -447,24 +417,6 @@ __device__ __forceinline__ void lanes_to_gray(const uint32_t (&v)[L], uint32_t (
     }
 }
 
-// lanes -> the same gray values as 6L BGR bytes (v, v, v): the gray formula maps them back to
-// v exactly, so carried history rides the same pipeline as real frames
-template <int L>
-__device__ __forceinline__ void lanes_to_bgr(const uint32_t (&v)[L], uint32_t (&w)[3 * L / 2]) {
-    uint32_t gw[L / 2];
-    lanes_to_gray<L>(v, gw);
-#pragma unroll
-    for (int t = 0; t < 3 * L / 2; ++t) {
-        uint32_t word = 0;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int px = (4 * t + b) / 3;
-            word |= ((gw[px >> 2] >> (8 * (px & 3))) & 0xFFu) << (8 * b);
-        }
-        w[t] = word;
-    }
-}
-
 // (|x - m| > thresh) per u16 lane -> 2L bits (bit k = pixel k)
 template <int L>
 __device__ __forceinline__ uint32_t fg_bits_v2(const uint32_t (&cur)[L], const uint32_t (&med)[L],
@@ -542,15 +494,16 @@ k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t on
             int j = j_first + p;
             const uint8_t* fr;
             long long pitch;
-            if (j < 0 && src.hist_valid) {                  // carried history, stored as frames
-                pitch = (long long)gpr * TB;
-                fr = src.hist + (long long)(j + (N - 1)) * h * pitch;
-            } else {
-                if (j < -src.n_inline_halo) j = -src.n_inline_halo;   // replicate the earliest frame
-                pitch = src.pitch;
-                fr = src.cur + (long long)j * src.frame_stride;
-            }
             uint8_t* dst = smem + st * STAGE_BYTES;
+            if (j < 0 && src.hist_valid) {                  // carried history: compact gray frames
+                const uint8_t* hf = src.hist + (long long)(j + (N - 1)) * h * wa;
+                mbar_arrive_expect_tx(&full[st], (uint32_t)(ngroups * PPT));
+                bulk_g2s(dst, hf + (long long)g0 * PPT, (uint32_t)(ngroups * PPT), &full[st]);
+                continue;
+            }
+            if (j < -src.n_inline_halo) j = -src.n_inline_halo;   // replicate the earliest frame
+            pitch = src.pitch;
+            fr = src.cur + (long long)j * src.frame_stride;
             mbar_arrive_expect_tx(&full[st], bytes);
             if (pitch == (long long)gpr * TB) {             // rows are contiguous
                 bulk_g2s(dst, fr + (long long)g0 * TB, bytes, &full[st]);
@@ -585,10 +538,22 @@ k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t on
     const bool lane0 = (tid & 31) == 0;
 
     uint32_t ring[N][L];
-    // take pipeline frame p into a ring slot
-    auto consume = [&](int p, uint32_t (&dst)[L]) {
+    // take pipeline frame p into a ring slot; `maybe_hist`: the stage may hold a carried
+    // gray frame (only the warm-up frames of the first temporal sub-chunk can)
+    auto consume = [&](int p, uint32_t (&dst)[L], bool maybe_hist) {
         const int st = p % S;
         mbar_wait(&full[st], (uint32_t)((p / S) & 1));
+        if (C == 3 && maybe_hist && src.hist_valid && j_first + p < 0) {   // block-uniform
+            uint32_t gw[L / 2];
+            const uint32_t* sg = reinterpret_cast<const uint32_t*>(smem + st * STAGE_BYTES + tid * PPT);
+#pragma unroll
+            for (int i = 0; i < L / 2; ++i) gw[i] = sg[i];
+            gray_to_lanes<L>(gw, dst);
+            asm volatile("" ::"r"(dst[0]), "r"(dst[L - 1]) : "memory");
+            __syncwarp();
+            if (lane0) mbar_arrive(&empty[st]);
+            return;
+        }
         uint32_t w[NWORDS];
         if constexpr (TB % 16 == 0) {
             const uint4* sp4 = reinterpret_cast<const uint4*>(my_smem + st * STAGE_BYTES);
@@ -616,7 +581,7 @@ k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t on
 
     // warm-up: the N-1 frames before the first output
 #pragma unroll
-    for (int s = 0; s < N - 1; ++s) consume(s, ring[s]);
+    for (int s = 0; s < N - 1; ++s) consume(s, ring[s], true);
 
     for (int base = 0; base < n_out; base += N) {
 #pragma unroll
@@ -624,7 +589,7 @@ k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t on
             const int k = base + ph;                        // output frame t_start + k
             if (k < n_out) {                                // block-uniform
                 const int slot = (N - 1 + ph) % N;          // static after unrolling
-                consume(k + N - 1, ring[slot]);
+                consume(k + N - 1, ring[slot], false);
                 uint32_t med[L];
 #pragma unroll
                 for (int q = 0; q < L; ++q) {
@@ -645,13 +610,12 @@ k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t on
                     for (int s = 0; s < N - 1; ++s) {
                         const int m = N - 2 - s;                    // frames back from the newest
                         const int hs = ((slot - m) % N + N) % N;    // static
-                        uint32_t hw[NWORDS];
-                        if constexpr (C == 3) lanes_to_bgr<L>(ring[hs], hw);
-                        else lanes_to_gray<L>(ring[hs], hw);
+                        uint32_t hw[L / 2];
+                        lanes_to_gray<L>(ring[hs], hw);
                         uint32_t* hp = reinterpret_cast<uint32_t*>(
-                            src.hist_out + (((long long)s * h + row) * gpr + col) * TB);
+                            src.hist_out + (((long long)s * h + row) * gpr + col) * PPT);
 #pragma unroll
-                        for (int i = 0; i < NWORDS; ++i) hp[i] = hw[i];
+                        for (int i = 0; i < L / 2; ++i) hp[i] = hw[i];
                     }
                 }
             }

@@ -88,17 +88,26 @@ k_morph_mask(const uint32_t* __restrict__ raw_bits, Geom g, uint32_t* __restrict
         for (int i = 0; i < 2 * R + 1; ++i) win[s][i] = 0u;
 
     const int y_end = min(y0 + SR, g.h);
-    for (int yin = y0 - HR; yin < y_end + HR; ++yin) {
-        // ---- raw row, realigned to ROI columns, border filled for the first op
-        const bool rowvalid = (unsigned)yin < (unsigned)g.h;
-        uint32_t v = 0u;
-        if (rowvalid) {                                      // warp-uniform
-            const uint32_t* rowp = raw_f + (long long)yin * g.wpr_raw;
-            const uint32_t lo = in_raw ? __ldg(rowp + j) : 0u;
-            uint32_t hi = __shfl_down_sync(0xFFFFFFFFu, lo, 1);
-            if (lane == 31) hi = in_raw_next ? __ldg(rowp + j + 1) : 0u;
-            v = __funnelshift_r(lo, hi, g.dx) & Vcol;
+    // raw words of row y (this lane's word; lane 31 also fetches the word after it), 0 outside the image
+    auto fetch = [&](int y, uint32_t& lo, uint32_t& edge) {
+        lo = 0u;
+        edge = 0u;
+        if ((unsigned)y < (unsigned)g.h) {
+            const uint32_t* rowp = raw_f + (long long)y * g.wpr_raw;
+            if (in_raw) lo = __ldg(rowp + j);
+            if (lane == 31 && in_raw_next) edge = __ldg(rowp + j + 1);
         }
+    };
+    uint32_t lo_n, edge_n;
+    fetch(y0 - HR, lo_n, edge_n);
+    for (int yin = y0 - HR; yin < y_end + HR; ++yin) {
+        // ---- raw row (prefetched one row ahead), realigned to ROI columns, border filled for the first op
+        const bool rowvalid = (unsigned)yin < (unsigned)g.h;
+        const uint32_t lo = lo_n, edge = edge_n;
+        fetch(yin + 1, lo_n, edge_n);
+        uint32_t hi = __shfl_down_sync(0xFFFFFFFFu, lo, 1);
+        if (lane == 31) hi = edge;
+        const uint32_t v = rowvalid ? (__funnelshift_r(lo, hi, g.dx) & Vcol) : 0u;
         const uint32_t V0 = rowvalid ? Vcol : 0u;
         uint32_t cur = v | (~V0 & fill0);
 

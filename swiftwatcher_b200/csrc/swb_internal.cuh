@@ -36,8 +36,7 @@ struct FrameSrc {
     long long pitch;           // bytes between rows
     int n_inline_halo;         // frames -n_inline_halo..-1 are readable at cur + j*stride
     int hist_valid;            // frames j < 0 come from `hist` instead
-    const uint8_t* hist;       // [N-1][h][wa * channels]: carried history as compact frames in the
-                               // source format (gray values stored as B=G=R=v); slot s = frame s-(N-1)
+    const uint8_t* hist;       // [N-1][h][wa] gray: carried history as compact gray frames; slot s = frame s-(N-1)
     uint8_t* hist_out;         // where to leave the last N-1 frames of this submit (or null)
     int avail_w;               // pixels readable from raw column 0 in a row (guarded path)
 };
