@@ -438,7 +438,7 @@ int pick_ts(int T, int n_col_blocks, int median_n) {
     const int target_ctas = 148 * 2 * 4;
     int ts = T;
     while (ts > 32 && (long long)n_col_blocks * ((T + ts - 1) / ts) < target_ctas) ts = (ts + 1) / 2;
-    const int min_ts = 16 * (median_n - 1) > 0 ? 16 * (median_n - 1) : 1;  // <= ~6% warm-up
+    const int min_ts = 8 * (median_n - 1) > 0 ? 8 * (median_n - 1) : 1;   // <= 12.5% warm-up
     if (ts < min_ts) ts = min_ts;
     if (ts > T) ts = T;
     if (ts < 1) ts = 1;

@@ -11,7 +11,7 @@
 //
 // Streaming design: a warp owns a slab of 32 consecutive bit words (lane = word;
 // lanes 1..30 produce output, lanes 0 and 31 are the horizontal halo) and marches
-// down a strip of rows.  Every erosion / dilation stage keeps the last 2R+1
+// down a strip of 32 (64 for the deepest chain) rows.  Every erosion / dilation stage keeps the last 2R+1
 // horizontally processed rows of its input in registers (a delay line), so a row
 // of 1024 pixels goes through the whole open/close chain with a handful of
 // funnel shifts, LOP3s and two shuffles per stage, and nothing but the raw bit
@@ -26,11 +26,12 @@ namespace swb {
 namespace {
 
 constexpr int SLAB = 30;   // output words per warp
-constexpr int SR = 32;     // output rows per warp
 constexpr int WPB = 4;     // warps per CTA
 
 // operation chains: 0 none, 1 open (E,D), 2 close (D,E), 3 open + close (E,D,D,E)
 __host__ __device__ constexpr int n_ops(int pat) { return pat == 0 ? 0 : (pat == 3 ? 4 : 2); }
+// output rows per warp: longer strips when the vertical halo is deep
+__host__ __device__ constexpr int strip_rows(int r, int pat) { return n_ops(pat) * r >= 8 ? 64 : 32; }
 __host__ __device__ constexpr bool op_is_erode(int pat, int s) {
     return pat == 1 ? (s == 0) : (pat == 2 ? (s == 1) : (s == 0 || s == 3));
 }
@@ -68,6 +69,7 @@ k_morph_mask(const uint32_t* __restrict__ raw_bits, Geom g, uint32_t* __restrict
              uint8_t* __restrict__ mask) {
     constexpr int NOPS = n_ops(PAT);
     constexpr int HR = NOPS * R;   // rows of vertical halo
+    constexpr int SR = strip_rows(R, PAT);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int slab = blockIdx.x;
@@ -163,6 +165,7 @@ template <int R, int PAT>
 cudaError_t launch_pat(cudaStream_t s, const uint32_t* raw_bits, int T, const Geom& g, uint32_t* fbits,
                        uint8_t* mask) {
     const int nslabs = (g.wpr4 + SLAB - 1) / SLAB;
+    constexpr int SR = strip_rows(R, PAT);
     const int nstrips = (g.h + SR - 1) / SR;
     dim3 grid(nslabs, (nstrips + WPB - 1) / WPB, T);
     k_morph_mask<R, PAT><<<grid, 32 * WPB, 0, s>>>(raw_bits, g, fbits, mask);
