@@ -401,19 +401,16 @@ __device__ __forceinline__ void gray_to_lanes(const uint32_t (&w)[L / 2], uint32
     }
 }
 
-// lanes -> 2L gray bytes
+// lanes -> 2L gray bytes (word t = pixels 4t..4t+3; pixel k < L is the low half of lane k,
+// pixel k >= L the high half of lane k - L): three PRMT per word
 template <int L>
 __device__ __forceinline__ void lanes_to_gray(const uint32_t (&v)[L], uint32_t (&w)[L / 2]) {
 #pragma unroll
-    for (int t = 0; t < L / 2; ++t) {
-        uint32_t word = 0;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int px = 4 * t + b;
-            const uint32_t val = (px < L) ? (v[px] & 0xFFu) : ((v[px - L] >> 16) & 0xFFu);
-            word |= val << (8 * b);
-        }
-        w[t] = word;
+    for (int t = 0; t < L / 4; ++t) {
+        const uint32_t p01 = __byte_perm(v[4 * t + 0], v[4 * t + 1], 0x6240);   // (a.lo, b.lo, a.hi, b.hi)
+        const uint32_t p23 = __byte_perm(v[4 * t + 2], v[4 * t + 3], 0x6240);
+        w[t] = __byte_perm(p01, p23, 0x5410);
+        w[t + L / 4] = __byte_perm(p01, p23, 0x7632);
     }
 }
 
@@ -432,14 +429,46 @@ __device__ __forceinline__ uint32_t fg_bits_v2(const uint32_t (&cur)[L], const u
     return (acc & M) | ((acc >> (16 - L)) & (M << L));
 }
 
+// ---- shared-core sliding medians -------------------------------------------------------
+// Consecutive windows share most of their frames, so K outputs are produced per loop
+// iteration from one partially sorted "core" plus a few extras (all on packed u16x2 lanes):
+//  * N = 5, K = 2: windows {t-4..t} and {t-3..t+1} share {t-3..t}.  With the core kept as two
+//    sorted pairs, its two middle values s2 <= s3 cost 4 min/max, and the median of five is
+//    clamp(extra, s2, s3).  The pair (t-1, t) is the old pair of the next iteration.
+//    5 min/max per output instead of 14.
+//  * N = 9, K = 3: windows of outputs t, t+1, t+2 share {t-6..t-1} = two time-aligned triples
+//    that are sorted once (and reused by the next iteration).  Their merged middle four
+//    m2..m5 cost 10 min/max; every window adds three extras, sorted (y1 <= y2 <= y3), and the
+//    fifth smallest of the nine is the fourth smallest of {m2..m5} U {y1..y3}
+//    = min(m5, max(m4, y1), max(m3, y2), max(m2, y3)).  ~15 min/max per output instead of 26.
+// a + b - min(a, b) stands in for max(a, b) where that moves work from the ALU pipe to the
+// FMA pipe (lanes never carry: per-lane sums stay below 2^16 and above each term).
+template <int N>
+__host__ __device__ constexpr int group_k() { return N == 5 ? 2 : (N == 9 ? 3 : 1); }
+
+struct Sorted3 { uint32_t lo, mid, hi; };
+__device__ __forceinline__ Sorted3 sort3_lanes(uint32_t a, uint32_t b, uint32_t c, const FmaAdd& f) {
+    Sorted3 s;
+    s.lo = __vimin3_u16x2(a, b, c);
+    s.hi = __vimax3_u16x2(a, b, c);
+    s.mid = f.sub(f.sub(f.add(f.add(a, b), c), s.lo), s.hi);
+    return s;
+}
+// fourth smallest of sorted (m2 <= m3 <= m4 <= m5) U sorted (y.lo <= y.mid <= y.hi)
+__device__ __forceinline__ uint32_t select4of7(uint32_t m2, uint32_t m3, uint32_t m4, uint32_t m5, const Sorted3& y) {
+    return vmin2(m5, __vimin3_u16x2(vmax2(m4, y.lo), vmax2(m3, y.mid), vmax2(m2, y.hi)));
+}
+
 // Temporal sub-chunk length: long enough that the N-1 warm-up frames are a few
-// percent of the work, short enough that the grid has several waves of CTAs.
+// percent of the work, short enough that the grid has several waves of CTAs; a
+// multiple of 6 so that only the last sub-chunk of a submit has a partial group.
 int pick_ts(int T, int n_col_blocks, int median_n) {
     const int target_ctas = 148 * 2 * 4;
     int ts = T;
     while (ts > 32 && (long long)n_col_blocks * ((T + ts - 1) / ts) < target_ctas) ts = (ts + 1) / 2;
     const int min_ts = 8 * (median_n - 1) > 0 ? 8 * (median_n - 1) : 1;   // <= 12.5% warm-up
     if (ts < min_ts) ts = min_ts;
+    ts = (ts + 5) / 6 * 6;
     if (ts > T) ts = T;
     if (ts < 1) ts = 1;
     return ts;
@@ -458,6 +487,7 @@ k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t on
     constexpr int TB = PPT * C;              // bytes per thread per frame
     constexpr int STAGE_BYTES = CONSUMERS * TB;
     constexpr int NWORDS = TB / 4;
+    constexpr int K = group_k<N>();          // outputs per loop iteration
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + S * STAGE_BYTES);
     uint64_t* empty = full + S;
@@ -470,7 +500,8 @@ k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t on
     const int t_end = min(T, t_start + Ts);
     const int n_out = t_end - t_start;
     if (n_out <= 0) return;                  // block-uniform
-    const int n_total = n_out + N - 1;       // frames walked: j_first .. t_end - 1
+    const int n_iter = (n_out + K - 1) / K;
+    const int n_total = K * n_iter + N - 1;  // frames walked: j_first .. (a partial last group re-reads frame T-1)
     const int j_first = t_start - (N - 1);
 
     if (tid == 0) {
@@ -491,7 +522,7 @@ k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t on
         for (int p = 0; p < n_total; ++p) {
             const int st = p % S;
             if (p >= S) mbar_wait(&empty[st], (uint32_t)((p / S - 1) & 1));
-            int j = j_first + p;
+            int j = min(j_first + p, T - 1);
             const uint8_t* fr;
             long long pitch;
             uint8_t* dst = smem + st * STAGE_BYTES;
@@ -536,9 +567,12 @@ k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t on
     const long long out_step = (long long)h * gpr * (PPT / 8);
     const uint8_t* my_smem = smem + tid * TB;
     const bool lane0 = (tid & 31) == 0;
+    // the last N-1 gray frames of the submit (pipeline frames hist_from .. hist_to) are left
+    // for the next submit as they pass through (only the last temporal sub-chunk sees them)
+    const int hist_to = (T - 1) - j_first;
+    const int hist_from = (src.hist_out != nullptr && t_end == T) ? hist_to - (N - 2) : 0x7FFFFFFF;
 
-    uint32_t ring[N][L];
-    // take pipeline frame p into a ring slot; `maybe_hist`: the stage may hold a carried
+    // take pipeline frame p as packed gray lanes; `maybe_hist`: the stage may hold a carried
     // gray frame (only the warm-up frames of the first temporal sub-chunk can)
     auto consume = [&](int p, uint32_t (&dst)[L], bool maybe_hist) {
         const int st = p % S;
@@ -549,74 +583,190 @@ k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t on
 #pragma unroll
             for (int i = 0; i < L / 2; ++i) gw[i] = sg[i];
             gray_to_lanes<L>(gw, dst);
-            asm volatile("" ::"r"(dst[0]), "r"(dst[L - 1]) : "memory");
-            __syncwarp();
-            if (lane0) mbar_arrive(&empty[st]);
-            return;
-        }
-        uint32_t w[NWORDS];
-        if constexpr (TB % 16 == 0) {
-            const uint4* sp4 = reinterpret_cast<const uint4*>(my_smem + st * STAGE_BYTES);
-#pragma unroll
-            for (int i = 0; i < TB / 16; ++i) {
-                const uint4 v = sp4[i];
-                w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
-            }
         } else {
-            const uint2* sp2 = reinterpret_cast<const uint2*>(my_smem + st * STAGE_BYTES);
+            uint32_t w[NWORDS];
+            if constexpr (TB % 16 == 0) {
+                const uint4* sp4 = reinterpret_cast<const uint4*>(my_smem + st * STAGE_BYTES);
 #pragma unroll
-            for (int i = 0; i < TB / 8; ++i) {
-                const uint2 v = sp2[i];
-                w[2 * i] = v.x; w[2 * i + 1] = v.y;
+                for (int i = 0; i < TB / 16; ++i) {
+                    const uint4 v = sp4[i];
+                    w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+                }
+            } else {
+                const uint2* sp2 = reinterpret_cast<const uint2*>(my_smem + st * STAGE_BYTES);
+#pragma unroll
+                for (int i = 0; i < TB / 8; ++i) {
+                    const uint2 v = sp2[i];
+                    w[2 * i] = v.x; w[2 * i + 1] = v.y;
+                }
             }
+            if constexpr (C == 3) bgr_to_lanes_dp<L>(w, dst);
+            else gray_to_lanes<L>(w, dst);
         }
-        if constexpr (C == 3) bgr_to_lanes_dp<L>(w, dst);
-        else gray_to_lanes<L>(w, dst);
         // release the stage only after the loaded words have been consumed (the converted
         // lanes depend on every LDS), so the bulk engine can never overwrite data in flight
         asm volatile("" ::"r"(dst[0]), "r"(dst[L - 1]) : "memory");
         __syncwarp();
         if (lane0) mbar_arrive(&empty[st]);
+        if (p >= hist_from && p <= hist_to && active) {     // rare: at most N-1 frames per submit
+            uint32_t hw[L / 2];
+            lanes_to_gray<L>(dst, hw);
+            uint32_t* hp = reinterpret_cast<uint32_t*>(
+                src.hist_out + (((long long)(p - hist_from) * h + row) * gpr + col) * PPT);
+#pragma unroll
+            for (int i = 0; i < L / 2; ++i) hp[i] = hw[i];
+        }
+    };
+    // foreground flag of one lane (two pixels): 1 per u16 half where |x - median| > thresh
+    auto fg_flag = [&](uint32_t x, uint32_t med) -> uint32_t {
+        return __viaddmin_s16x2_relu(__vabsdiffu4(x, med), neg_th, 0x00010001u);
+    };
+    // store the bits of output k (frame t_start + k); acc = sum over lanes q of flag << q
+    auto emit_acc = [&](int k, uint32_t acc) {
+        constexpr uint32_t M = (1u << L) - 1u;
+        const uint32_t bits = (acc & M) | ((acc >> (16 - L)) & (M << L));
+        if (active && k < n_out) {
+            uint8_t* o = out + (long long)k * out_step;
+            if constexpr (PPT == 16) *reinterpret_cast<uint16_t*>(o) = (uint16_t)bits;
+            else *o = (uint8_t)bits;
+        }
     };
 
-    // warm-up: the N-1 frames before the first output
+    if constexpr (N == 5) {
+        // ---- two outputs per iteration (see "shared-core sliding medians") ----
+        // iteration m: outputs t, t+1 (t = t_start + 2m; frame t is pipeline frame 2m + 4)
+        uint32_t ev[2][L];        // raw even pipeline frames: ev[m & 1] = frame t-4, ev[(m+1) & 1] = frame t-2
+        uint32_t odd[L];          // raw frame t-1
+        uint32_t plo[L], phi[L];  // sorted pair (t-3, t-2)
+        {
+            uint32_t a[L];
+            consume(0, ev[0], true);
+            consume(1, a, true);
+            consume(2, ev[1], true);
+            consume(3, odd, true);
 #pragma unroll
-    for (int s = 0; s < N - 1; ++s) consume(s, ring[s], true);
-
-    for (int base = 0; base < n_out; base += N) {
+            for (int q = 0; q < L; ++q) {
+                plo[q] = vmin2(a[q], ev[1][q]);
+                phi[q] = vmax2(a[q], ev[1][q]);
+            }
+        }
+        for (int m0 = 0; m0 < n_iter; m0 += 2) {
 #pragma unroll
-        for (int ph = 0; ph < N; ++ph) {
-            const int k = base + ph;                        // output frame t_start + k
-            if (k < n_out) {                                // block-uniform
-                const int slot = (N - 1 + ph) % N;          // static after unrolling
-                consume(k + N - 1, ring[slot], false);
-                uint32_t med[L];
+            for (int u = 0; u < 2; ++u) {
+                const int m = m0 + u;
+                if (m >= n_iter) break;                         // block-uniform; no state is live after the loop
+                uint32_t x0[L], x1[L], s2[L], s3[L];
+                consume(2 * m + 4, x0, false);
+                uint32_t acc0 = 0u, acc1 = 0u;
 #pragma unroll
                 for (int q = 0; q < L; ++q) {
-                    uint32_t v[N];
-#pragma unroll
-                    for (int s = 0; s < N; ++s) v[s] = ring[s][q];
-                    med[q] = median_lanes_fma<N>(v, fa);
+                    const uint32_t qlo = vmin2(odd[q], x0[q]);
+                    const uint32_t qhi = fa.sub(fa.add(odd[q], x0[q]), qlo);
+                    const uint32_t a = vmax2(plo[q], qlo), b = vmin2(phi[q], qhi);
+                    s2[q] = vmin2(a, b);
+                    s3[q] = fa.sub(fa.add(a, b), s2[q]);
+                    acc0 += fg_flag(x0[q], vmax2(s2[q], vmin2(ev[u][q], s3[q]))) << q;
+                    plo[q] = qlo;
+                    phi[q] = qhi;
+                    ev[u][q] = x0[q];
                 }
-                const uint32_t bits = fg_bits_v2<L>(ring[slot], med, neg_th);
-                if (active) {
-                    if constexpr (PPT == 16) *reinterpret_cast<uint16_t*>(out) = (uint16_t)bits;
-                    else *out = (uint8_t)bits;
+                emit_acc(2 * m, acc0);
+                consume(2 * m + 5, x1, false);
+#pragma unroll
+                for (int q = 0; q < L; ++q) {
+                    acc1 += fg_flag(x1[q], vmax2(s2[q], vmin2(x1[q], s3[q]))) << q;
+                    odd[q] = x1[q];
                 }
-                out += out_step;
-                if (k == n_out - 1 && t_end == T && src.hist_out != nullptr && active) {
-                    // leave the last N-1 gray frames (oldest first) as frames for the next submit
+                emit_acc(2 * m + 1, acc1);
+            }
+        }
+    } else if constexpr (N == 9) {
+        // ---- three outputs per iteration ----
+        // iteration m: outputs t, t+1, t+2 (t = t_start + 3m; frame t is pipeline frame 3m + 8).
+        // Triples are aligned to t_start: {t-9,t-8,t-7}, A = {t-6,t-5,t-4}, B = {t-3,t-2,t-1}.
+        uint32_t rw[3][L];        // raw last two frames of the triples, packed u8x4 (first | second << 8): rw[m % 3] = (t-8, t-7)
+        uint32_t st[2][3][L];     // sorted triples: st[m & 1] = A, st[(m + 1) & 1] = B
+        {
+            uint32_t a[L], b[L], c[L];
+            consume(0, a, true);
+            consume(1, b, true);
 #pragma unroll
-                    for (int s = 0; s < N - 1; ++s) {
-                        const int m = N - 2 - s;                    // frames back from the newest
-                        const int hs = ((slot - m) % N + N) % N;    // static
-                        uint32_t hw[L / 2];
-                        lanes_to_gray<L>(ring[hs], hw);
-                        uint32_t* hp = reinterpret_cast<uint32_t*>(
-                            src.hist_out + (((long long)s * h + row) * gpr + col) * PPT);
+            for (int q = 0; q < L; ++q) rw[0][q] = a[q] | (b[q] << 8);
 #pragma unroll
-                        for (int i = 0; i < L / 2; ++i) hp[i] = hw[i];
+            for (int i = 0; i < 2; ++i) {
+                consume(2 + 3 * i, a, true);
+                consume(3 + 3 * i, b, true);
+                consume(4 + 3 * i, c, true);
+#pragma unroll
+                for (int q = 0; q < L; ++q) {
+                    const Sorted3 s = sort3_lanes(a[q], b[q], c[q], fa);
+                    st[i][0][q] = s.lo; st[i][1][q] = s.mid; st[i][2][q] = s.hi;
+                    rw[1 + i][q] = b[q] | (c[q] << 8);
+                }
+            }
+        }
+        for (int m0 = 0; m0 < n_iter; m0 += 6) {
+#pragma unroll
+            for (int u = 0; u < 6; ++u) {
+                const int m = m0 + u;
+                if (m >= n_iter) break;                         // block-uniform; no state is live after the loop
+                const int ia = u & 1, ib = ia ^ 1, ie = u % 3;  // static after unrolling
+                uint32_t x0[L], x1[L], x2[L];
+                consume(3 * m + 8, x0, false);
+                consume(3 * m + 9, x1, false);
+                consume(3 * m + 10, x2, false);
+                uint32_t acc0 = 0u, acc1 = 0u, acc2 = 0u;
+#pragma unroll
+                for (int q = 0; q < L; ++q) {
+                    // middle four of A U B
+                    const uint32_t pp = vmax2(st[ia][0][q], st[ib][0][q]);
+                    const uint32_t qq = vmin2(st[ia][2][q], st[ib][2][q]);
+                    const uint32_t uu = vmin2(st[ia][1][q], st[ib][1][q]);
+                    const uint32_t vv = fa.sub(fa.add(st[ia][1][q], st[ib][1][q]), uu);
+                    const uint32_t m2 = vmin2(pp, uu), m5 = vmax2(qq, vv);
+                    const uint32_t gg = vmax2(pp, uu), hh = vmin2(qq, vv);
+                    const uint32_t m3 = vmin2(gg, hh);
+                    const uint32_t m4 = fa.sub(fa.add(gg, hh), m3);
+                    const uint32_t e0 = rw[ie][q] & 0x00FF00FFu, e1 = (rw[ie][q] >> 8) & 0x00FF00FFu;
+                    Sorted3 y = sort3_lanes(e0, e1, x0[q], fa);             // extras of window t
+                    acc0 += fg_flag(x0[q], select4of7(m2, m3, m4, m5, y)) << q;
+                    y = sort3_lanes(e1, x0[q], x1[q], fa);                  // extras of window t+1
+                    acc1 += fg_flag(x1[q], select4of7(m2, m3, m4, m5, y)) << q;
+                    y = sort3_lanes(x0[q], x1[q], x2[q], fa);               // extras of window t+2 = the new triple
+                    acc2 += fg_flag(x2[q], select4of7(m2, m3, m4, m5, y)) << q;
+                    st[ia][0][q] = y.lo; st[ia][1][q] = y.mid; st[ia][2][q] = y.hi;   // A is dead: the next B
+                    rw[ie][q] = fa.add(x1[q], x2[q] << 8);
+                }
+                emit_acc(3 * m, acc0);
+                emit_acc(3 * m + 1, acc1);
+                emit_acc(3 * m + 2, acc2);
+            }
+        }
+    } else {
+        // ---- generic ring: one output per step, time loop unrolled by N ----
+        uint32_t ring[N][L];
+#pragma unroll
+        for (int s = 0; s < N - 1; ++s) consume(s, ring[s], true);
+        for (int base = 0; base < n_out; base += N) {
+#pragma unroll
+            for (int ph = 0; ph < N; ++ph) {
+                const int k = base + ph;                        // output frame t_start + k
+                if (k >= n_out) break;                          // block-uniform
+                {
+                    const int slot = (N - 1 + ph) % N;          // static after unrolling
+                    consume(k + N - 1, ring[slot], false);
+                    uint32_t med[L];
+#pragma unroll
+                    for (int q = 0; q < L; ++q) {
+                        uint32_t v[N];
+#pragma unroll
+                        for (int s = 0; s < N; ++s) v[s] = ring[s][q];
+                        med[q] = median_lanes_fma<N>(v, fa);
                     }
+                    uint32_t acc = 0u;
+#pragma unroll
+                    for (int q = 0; q < L; ++q) acc += fg_flag(ring[slot][q], med[q]) << q;
+                    emit_acc(k, acc);
                 }
             }
         }

@@ -318,6 +318,47 @@ def test_carried_history_across_submits():
         assert np.array_equal(ctx.labels()[3], fresh[3]["labels"])
 
 
+@pytest.mark.parametrize("n,sizes", [(9, (1, 2, 3, 11, 4, 9, 7)), (5, (3, 1, 1, 6, 2, 7)), (3, (1, 1, 5)), (7, (2, 9, 3))])
+def test_carried_history_all_windows(n, sizes):
+    """SWB_HALO_CARRY with submits shorter and longer than the window, for every median
+    kernel variant (grouped N = 5 / 9 loops have partial last groups here)."""
+    total = sum(sizes)
+    frames = synth.synth_video(31, 0, 0, total, 40, 96, 25)
+    region = [(0, 0), (96, 40)]
+    par = rp.PathParams(region, n, 15, 3, True, False, "i32")
+    want = rp.run_path(frames, par)
+    with swb.FilterContext(frames.shape[1:], region, median_n=n, label_mode="i32", max_frames=max(sizes)) as ctx:
+        t = 0
+        for k in sizes:
+            ctx.submit(np.ascontiguousarray(frames[t:t + k]))     # n_halo = CARRY
+            masks = ctx.masks()
+            for i in range(k):
+                assert np.array_equal(masks[i], want[t + i]["mask"]), (t, i)
+            t += k
+
+
+@pytest.mark.parametrize("n,T", [(5, 67), (9, 71), (9, 150), (5, 97)])
+def test_many_temporal_subchunks(n, T):
+    """Small frames with many frames per submit: K1 splits the submit into temporal sub-chunks
+    (multiples of 6 frames) whose last one is a partial group; every frame must still match."""
+    frames = synth.synth_video(32, 0, 0, T, 36, 64, 12)
+    region = [(0, 0), (64, 36)]
+    par = rp.PathParams(region, n, 15, 3, True, False, "i32")
+    want = rp.run_path(frames, par)
+    with swb.FilterContext(frames.shape[1:], region, median_n=n, label_mode="i32", max_frames=T) as ctx:
+        ctx.submit(frames, n_halo=0)
+        masks = ctx.masks()
+        for i in range(T):
+            assert np.array_equal(masks[i], want[i]["mask"]), i
+        # and the history left behind continues the stream
+        more = synth.synth_video(32, 0, T, 5, 36, 64, 12)
+        want2 = rp.run_path(np.concatenate([frames, more]), par)
+        ctx.submit(more)
+        masks = ctx.masks()
+        for i in range(5):
+            assert np.array_equal(masks[i], want2[T + i]["mask"]), i
+
+
 def test_device_resident_input_zero_copy():
     import torch
     frames = synth.synth_video(28, 0, 0, 10, 72, 160, 30)
