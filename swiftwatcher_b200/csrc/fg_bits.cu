@@ -16,6 +16,8 @@
 //
 // Work unit = (256-thread column group, temporal sub-chunk of Ts frames); each
 // sub-chunk re-reads its N-1 preceding frames as warm-up.
+#include <cstdlib>
+
 #include "swb_internal.cuh"
 
 namespace swb {
@@ -479,8 +481,8 @@ constexpr int V2_THREADS = CONSUMERS + 32;   // + 1 producer warp
 
 // L = u16x2 registers per ring slot: a thread owns 2L adjacent pixels (16 for N <= 5; 8 for the
 // longer windows, whose ring would not fit the register file at two CTAs per SM).
-template <int N, int C, int S, int L>
-__global__ void __launch_bounds__(V2_THREADS, 2)
+template <int N, int C, int S, int L, int OCC>
+__global__ void __launch_bounds__(V2_THREADS, OCC)
 k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t one,
              uint8_t* __restrict__ raw_bits) {
     constexpr int PPT = 2 * L;               // pixels per thread
@@ -684,14 +686,17 @@ k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t on
         // ---- three outputs per iteration ----
         // iteration m: outputs t, t+1, t+2 (t = t_start + 3m; frame t is pipeline frame 3m + 8).
         // Triples are aligned to t_start: {t-9,t-8,t-7}, A = {t-6,t-5,t-4}, B = {t-3,t-2,t-1}.
-        uint32_t rw[3][L];        // raw last two frames of the triples, packed u8x4 (first | second << 8): rw[m % 3] = (t-8, t-7)
+        // The raw last two frames of each triple are needed again three iterations later (as the
+        // extras t-8, t-7): they wait in a thread-private shared-memory ring, packed u8x4
+        // (first | second << 8), slot m % 3 -- read at the top of iteration m, rewritten at its end.
+        static_assert(L == 4, "one 16-byte ring entry per thread");
+        uint4* rw_ring = reinterpret_cast<uint4*>(smem + S * STAGE_BYTES + 2 * S * 8) + tid;   // [3][CONSUMERS]
         uint32_t st[2][3][L];     // sorted triples: st[m & 1] = A, st[(m + 1) & 1] = B
         {
             uint32_t a[L], b[L], c[L];
             consume(0, a, true);
             consume(1, b, true);
-#pragma unroll
-            for (int q = 0; q < L; ++q) rw[0][q] = a[q] | (b[q] << 8);
+            rw_ring[0] = make_uint4(a[0] | (b[0] << 8), a[1] | (b[1] << 8), a[2] | (b[2] << 8), a[3] | (b[3] << 8));
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 consume(2 + 3 * i, a, true);
@@ -701,20 +706,27 @@ k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t on
                 for (int q = 0; q < L; ++q) {
                     const Sorted3 s = sort3_lanes(a[q], b[q], c[q], fa);
                     st[i][0][q] = s.lo; st[i][1][q] = s.mid; st[i][2][q] = s.hi;
-                    rw[1 + i][q] = b[q] | (c[q] << 8);
                 }
+                rw_ring[(1 + i) * CONSUMERS] =
+                    make_uint4(b[0] | (c[0] << 8), b[1] | (c[1] << 8), b[2] | (c[2] << 8), b[3] | (c[3] << 8));
             }
         }
-        for (int m0 = 0; m0 < n_iter; m0 += 6) {
+        int slot = 0;                                           // m % 3
+        for (int m0 = 0; m0 < n_iter; m0 += 2) {
 #pragma unroll
-            for (int u = 0; u < 6; ++u) {
+            for (int u = 0; u < 2; ++u) {
                 const int m = m0 + u;
                 if (m >= n_iter) break;                         // block-uniform; no state is live after the loop
-                const int ia = u & 1, ib = ia ^ 1, ie = u % 3;  // static after unrolling
+                const int ia = u, ib = u ^ 1;                   // static after unrolling
                 uint32_t x0[L], x1[L], x2[L];
                 consume(3 * m + 8, x0, false);
                 consume(3 * m + 9, x1, false);
                 consume(3 * m + 10, x2, false);
+                uint4* rwp = rw_ring + slot * CONSUMERS;
+                slot = (slot == 2) ? 0 : slot + 1;
+                const uint4 e4 = *rwp;
+                const uint32_t ep[L] = {e4.x, e4.y, e4.z, e4.w};
+                uint32_t np[L];
                 uint32_t acc0 = 0u, acc1 = 0u, acc2 = 0u;
 #pragma unroll
                 for (int q = 0; q < L; ++q) {
@@ -727,7 +739,7 @@ k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t on
                     const uint32_t gg = vmax2(pp, uu), hh = vmin2(qq, vv);
                     const uint32_t m3 = vmin2(gg, hh);
                     const uint32_t m4 = fa.sub(fa.add(gg, hh), m3);
-                    const uint32_t e0 = rw[ie][q] & 0x00FF00FFu, e1 = (rw[ie][q] >> 8) & 0x00FF00FFu;
+                    const uint32_t e0 = ep[q] & 0x00FF00FFu, e1 = (ep[q] >> 8) & 0x00FF00FFu;
                     Sorted3 y = sort3_lanes(e0, e1, x0[q], fa);             // extras of window t
                     acc0 += fg_flag(x0[q], select4of7(m2, m3, m4, m5, y)) << q;
                     y = sort3_lanes(e1, x0[q], x1[q], fa);                  // extras of window t+1
@@ -735,8 +747,9 @@ k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t on
                     y = sort3_lanes(x0[q], x1[q], x2[q], fa);               // extras of window t+2 = the new triple
                     acc2 += fg_flag(x2[q], select4of7(m2, m3, m4, m5, y)) << q;
                     st[ia][0][q] = y.lo; st[ia][1][q] = y.mid; st[ia][2][q] = y.hi;   // A is dead: the next B
-                    rw[ie][q] = fa.add(x1[q], x2[q] << 8);
+                    np[q] = fa.add(x1[q], x2[q] << 8);
                 }
+                *rwp = make_uint4(np[0], np[1], np[2], np[3]);
                 emit_acc(3 * m, acc0);
                 emit_acc(3 * m + 1, acc1);
                 emit_acc(3 * m + 2, acc2);
@@ -773,16 +786,16 @@ k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t on
     }
 }
 
-template <int N, int C>
-cudaError_t launch_v2(cudaStream_t s, const FrameSrc& src, int T, const Geom& g, int thresh,
-                      uint16_t* raw_bits) {
+template <int N, int C, int OCC>
+cudaError_t launch_v2_occ(cudaStream_t s, const FrameSrc& src, int T, const Geom& g, int thresh,
+                          uint16_t* raw_bits) {
     constexpr int L = (N <= 5) ? 8 : 4;
     constexpr int TB = 2 * L * C;
     constexpr int S = (TB >= 48) ? 4 : 8;
-    constexpr int SMEM = S * CONSUMERS * TB + 2 * S * 8;
+    constexpr int SMEM = S * CONSUMERS * TB + 2 * S * 8 + (N == 9 ? 3 * CONSUMERS * 16 : 0);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_fg_bits_v2<N, C, S, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        cudaError_t e = cudaFuncSetAttribute(k_fg_bits_v2<N, C, S, L, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) return e;
         configured = true;
     }
@@ -790,9 +803,20 @@ cudaError_t launch_v2(cudaStream_t s, const FrameSrc& src, int T, const Geom& g,
     const int n_col_blocks = (G + CONSUMERS - 1) / CONSUMERS;
     const int Ts = pick_ts(T, n_col_blocks, N);
     dim3 grid(n_col_blocks, (T + Ts - 1) / Ts);
-    k_fg_bits_v2<N, C, S, L><<<grid, V2_THREADS, SMEM, s>>>(src, T, Ts, g.h, g.wa, thresh, 1u,
-                                                           reinterpret_cast<uint8_t*>(raw_bits));
+    k_fg_bits_v2<N, C, S, L, OCC><<<grid, V2_THREADS, SMEM, s>>>(src, T, Ts, g.h, g.wa, thresh, 1u,
+                                                                reinterpret_cast<uint8_t*>(raw_bits));
     return cudaGetLastError();
+}
+
+template <int N, int C>
+cudaError_t launch_v2(cudaStream_t s, const FrameSrc& src, int T, const Geom& g, int thresh,
+                      uint16_t* raw_bits) {
+    if constexpr (N == 9) {
+        // the N = 9 loop fits 72 registers: three CTAs (24 consumer warps) per SM
+        static const bool occ2 = [] { const char* e = getenv("SWB_K1_N9_OCC"); return e && e[0] == '2'; }();
+        if (!occ2) return launch_v2_occ<N, C, 3>(s, src, T, g, thresh, raw_bits);
+    }
+    return launch_v2_occ<N, C, 2>(s, src, T, g, thresh, raw_bits);
 }
 
 template <int N>
