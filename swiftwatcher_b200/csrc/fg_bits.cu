@@ -574,11 +574,11 @@ k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t on
     const int hist_to = (T - 1) - j_first;
     const int hist_from = (src.hist_out != nullptr && t_end == T) ? hist_to - (N - 2) : 0x7FFFFFFF;
 
-    // take pipeline frame p as packed gray lanes; `maybe_hist`: the stage may hold a carried
-    // gray frame (only the warm-up frames of the first temporal sub-chunk can)
-    auto consume = [&](int p, uint32_t (&dst)[L], bool maybe_hist) {
-        const int st = p % S;
-        mbar_wait(&full[st], (uint32_t)((p / S) & 1));
+    // take pipeline frame p (held by stage st, barrier phase parity `par`) as packed gray lanes;
+    // `maybe_hist`: the stage may hold a carried gray frame (only the warm-up frames of the first
+    // temporal sub-chunk can).  In the grouped loops st is a compile-time constant after unrolling.
+    auto consume_at = [&](int st, uint32_t par, int p, uint32_t (&dst)[L], bool maybe_hist) {
+        mbar_wait(&full[st], par);
         if (C == 3 && maybe_hist && src.hist_valid && j_first + p < 0) {   // block-uniform
             uint32_t gw[L / 2];
             const uint32_t* sg = reinterpret_cast<const uint32_t*>(smem + st * STAGE_BYTES + tid * PPT);
@@ -610,15 +610,22 @@ k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t on
         asm volatile("" ::"r"(dst[0]), "r"(dst[L - 1]) : "memory");
         __syncwarp();
         if (lane0) mbar_arrive(&empty[st]);
-        if (p >= hist_from && p <= hist_to && active) {     // rare: at most N-1 frames per submit
+    };
+    auto consume = [&](int p, uint32_t (&dst)[L], bool maybe_hist) {
+        consume_at(p % S, (uint32_t)((p / S) & 1), p, dst, maybe_hist);
+    };
+    // leave pipeline frame p for the next submit if it is one of the last N-1 frames (rare)
+    auto keep_for_next = [&](int p, const uint32_t (&v)[L]) {
+        if (p >= hist_from && p <= hist_to && active) {
             uint32_t hw[L / 2];
-            lanes_to_gray<L>(dst, hw);
+            lanes_to_gray<L>(v, hw);
             uint32_t* hp = reinterpret_cast<uint32_t*>(
                 src.hist_out + (((long long)(p - hist_from) * h + row) * gpr + col) * PPT);
 #pragma unroll
             for (int i = 0; i < L / 2; ++i) hp[i] = hw[i];
         }
     };
+    const bool short_tail = hist_from < N - 1;   // warm-up frames are among the last N-1 (n_out < N-1)
     // foreground flag of one lane (two pixels): 1 per u16 half where |x - median| > thresh
     auto fg_flag = [&](uint32_t x, uint32_t med) -> uint32_t {
         return __viaddmin_s16x2_relu(__vabsdiffu4(x, med), neg_th, 0x00010001u);
@@ -640,12 +647,19 @@ k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t on
         uint32_t ev[2][L];        // raw even pipeline frames: ev[m & 1] = frame t-4, ev[(m+1) & 1] = frame t-2
         uint32_t odd[L];          // raw frame t-1
         uint32_t plo[L], phi[L];  // sorted pair (t-3, t-2)
+        static_assert(S == 4, "N = 5: four frames per unrolled loop body = four stages");
         {
             uint32_t a[L];
             consume(0, ev[0], true);
             consume(1, a, true);
             consume(2, ev[1], true);
             consume(3, odd, true);
+            if (short_tail) {
+                keep_for_next(0, ev[0]);
+                keep_for_next(1, a);
+                keep_for_next(2, ev[1]);
+                keep_for_next(3, odd);
+            }
 #pragma unroll
             for (int q = 0; q < L; ++q) {
                 plo[q] = vmin2(a[q], ev[1][q]);
@@ -653,12 +667,13 @@ k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t on
             }
         }
         for (int m0 = 0; m0 < n_iter; m0 += 2) {
+            const uint32_t par = (uint32_t)(((m0 >> 1) + 1) & 1);   // frames 4 + 2 m0 + i: stage i, round 1 + m0 / 2
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const int m = m0 + u;
                 if (m >= n_iter) break;                         // block-uniform; no state is live after the loop
                 uint32_t x0[L], x1[L], s2[L], s3[L];
-                consume(2 * m + 4, x0, false);
+                consume_at(2 * u, par, 2 * m + 4, x0, false);
                 uint32_t acc0 = 0u, acc1 = 0u;
 #pragma unroll
                 for (int q = 0; q < L; ++q) {
@@ -673,13 +688,17 @@ k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t on
                     ev[u][q] = x0[q];
                 }
                 emit_acc(2 * m, acc0);
-                consume(2 * m + 5, x1, false);
+                consume_at(2 * u + 1, par, 2 * m + 5, x1, false);
 #pragma unroll
                 for (int q = 0; q < L; ++q) {
                     acc1 += fg_flag(x1[q], vmax2(s2[q], vmin2(x1[q], s3[q]))) << q;
                     odd[q] = x1[q];
                 }
                 emit_acc(2 * m + 1, acc1);
+                if (2 * m + 5 >= hist_from) {                   // block-uniform, last frames of the submit only
+                    keep_for_next(2 * m + 4, ev[u]);
+                    keep_for_next(2 * m + 5, x1);
+                }
             }
         }
     } else if constexpr (N == 9) {
@@ -692,16 +711,19 @@ k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t on
         static_assert(L == 4, "one 16-byte ring entry per thread");
         uint4* rw_ring = reinterpret_cast<uint4*>(smem + S * STAGE_BYTES + 2 * S * 8) + tid;   // [3][CONSUMERS]
         uint32_t st[2][3][L];     // sorted triples: st[m & 1] = A, st[(m + 1) & 1] = B
+        static_assert(S == 6, "N = 9: six frames per unrolled loop body = six stages");
         {
             uint32_t a[L], b[L], c[L];
             consume(0, a, true);
             consume(1, b, true);
+            if (short_tail) { keep_for_next(0, a); keep_for_next(1, b); }
             rw_ring[0] = make_uint4(a[0] | (b[0] << 8), a[1] | (b[1] << 8), a[2] | (b[2] << 8), a[3] | (b[3] << 8));
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 consume(2 + 3 * i, a, true);
                 consume(3 + 3 * i, b, true);
                 consume(4 + 3 * i, c, true);
+                if (short_tail) { keep_for_next(2 + 3 * i, a); keep_for_next(3 + 3 * i, b); keep_for_next(4 + 3 * i, c); }
 #pragma unroll
                 for (int q = 0; q < L; ++q) {
                     const Sorted3 s = sort3_lanes(a[q], b[q], c[q], fa);
@@ -713,15 +735,21 @@ k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t on
         }
         int slot = 0;                                           // m % 3
         for (int m0 = 0; m0 < n_iter; m0 += 2) {
+            const uint32_t jp = (uint32_t)((m0 >> 1) & 1);      // frame 8 + 3 m0 + i: stage (8 + i) % 6, round m0 / 2 + (8 + i) / 6
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const int m = m0 + u;
                 if (m >= n_iter) break;                         // block-uniform; no state is live after the loop
                 const int ia = u, ib = u ^ 1;                   // static after unrolling
                 uint32_t x0[L], x1[L], x2[L];
-                consume(3 * m + 8, x0, false);
-                consume(3 * m + 9, x1, false);
-                consume(3 * m + 10, x2, false);
+                consume_at((8 + 3 * u) % 6, jp ^ (uint32_t)(((8 + 3 * u) / 6) & 1), 3 * m + 8, x0, false);
+                consume_at((9 + 3 * u) % 6, jp ^ (uint32_t)(((9 + 3 * u) / 6) & 1), 3 * m + 9, x1, false);
+                consume_at((10 + 3 * u) % 6, jp ^ (uint32_t)(((10 + 3 * u) / 6) & 1), 3 * m + 10, x2, false);
+                if (3 * m + 10 >= hist_from) {                  // block-uniform, last frames of the submit only
+                    keep_for_next(3 * m + 8, x0);
+                    keep_for_next(3 * m + 9, x1);
+                    keep_for_next(3 * m + 10, x2);
+                }
                 uint4* rwp = rw_ring + slot * CONSUMERS;
                 slot = (slot == 2) ? 0 : slot + 1;
                 const uint4 e4 = *rwp;
@@ -759,7 +787,10 @@ k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t on
         // ---- generic ring: one output per step, time loop unrolled by N ----
         uint32_t ring[N][L];
 #pragma unroll
-        for (int s = 0; s < N - 1; ++s) consume(s, ring[s], true);
+        for (int s = 0; s < N - 1; ++s) {
+            consume(s, ring[s], true);
+            if (short_tail) keep_for_next(s, ring[s]);
+        }
         for (int base = 0; base < n_out; base += N) {
 #pragma unroll
             for (int ph = 0; ph < N; ++ph) {
@@ -768,6 +799,7 @@ k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t on
                 {
                     const int slot = (N - 1 + ph) % N;          // static after unrolling
                     consume(k + N - 1, ring[slot], false);
+                    if (k + N - 1 >= hist_from) keep_for_next(k + N - 1, ring[slot]);
                     uint32_t med[L];
 #pragma unroll
                     for (int q = 0; q < L; ++q) {
@@ -791,7 +823,7 @@ cudaError_t launch_v2_occ(cudaStream_t s, const FrameSrc& src, int T, const Geom
                           uint16_t* raw_bits) {
     constexpr int L = (N <= 5) ? 8 : 4;
     constexpr int TB = 2 * L * C;
-    constexpr int S = (TB >= 48) ? 4 : 8;
+    constexpr int S = (N == 5) ? 4 : (N == 9 ? 6 : 8);   // grouped loops: stages = frames per unrolled body
     constexpr int SMEM = S * CONSUMERS * TB + 2 * S * 8 + (N == 9 ? 3 * CONSUMERS * 16 : 0);
     static bool configured = false;
     if (!configured) {
