@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -18,6 +19,7 @@ namespace {
 thread_local std::string g_error;
 
 constexpr int N_TIMERS = 6;
+constexpr int MAX_SUB = 4;   // sub-batches of one submit (see swb_submit)
 const char* const TIMER_NAMES[N_TIMERS] = {"fg_bits",   "morph_mask", "ccl_merge",
                                            "ccl_rank",  "ccl_label",  "write_labels"};
 // ccl_merge = local + boundary (or init + merge); ccl_rank = root ranking + scans + seg_init;
@@ -34,6 +36,12 @@ struct swb_ctx {
     int cap_rows;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    // host submits: sub-batches of frames are filtered on `worker` while later frames are still being copied
+    cudaStream_t worker = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_h2d[MAX_SUB] = {};
+    bool pipeline = true;
+    long long sub_min_px = 64ll << 20;   // least work (pixels) per sub-batch
     // device buffers
     uint8_t* in_buf = nullptr;      // host-mode staging: [N-1 + max_frames][h][in_pitch]
     size_t in_buf_bytes = 0;
@@ -149,6 +157,11 @@ void free_ctx_buffers(swb_ctx* c) {
     if (c->h_overflow) cudaFreeHost(c->h_overflow);
     for (auto& e : c->ev)
         if (e) cudaEventDestroy(e);
+    for (auto& e : c->ev_h2d)
+        if (e) cudaEventDestroy(e);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->worker) cudaStreamDestroy(c->worker);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
 }
 
@@ -162,8 +175,8 @@ int alloc_ccl(swb_ctx* ctx, CclBuffers& b, const Geom& g, int T, int cap_rows) {
     b.cap_rows = cap_rows;
     b.cap_parts = 2 * cap_rows + 4096;
     CU(ctx, dalloc(&b.parts, (size_t)b.cap_parts));
-    CU(ctx, dalloc(&b.pcount, 2));
-    b.overflow = b.pcount + 1;
+    CU(ctx, dalloc(&b.pcount, MAX_SUB + 1));     // one partial counter per sub-batch, then the overflow flag
+    b.overflow = b.pcount + MAX_SUB;
     CU(ctx, dalloc(&b.rootlist, (size_t)cap_rows));
     return SWB_OK;
 }
@@ -300,6 +313,16 @@ int swb_create(const swb_config* cfg, swb_ctx** out) {
     } while (0)
     CUB(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
+    CUB(cudaStreamCreateWithFlags(&ctx->worker, cudaStreamNonBlocking));
+    CUB(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    for (auto& e : ctx->ev_h2d) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    {
+        const char* e = getenv("SWB_PIPELINE");
+        ctx->pipeline = !(e && e[0] == '0');
+        const char* m = getenv("SWB_SUB_MIN_PX");    // test hook: small frames never reach the default
+        if (m && atoll(m) > 0) ctx->sub_min_px = atoll(m);
+    }
     if (nh > 0) {
         CUB(dalloc(&ctx->hist[0], (size_t)nh * g.h * g.wa));
         CUB(dalloc(&ctx->hist[1], (size_t)nh * g.h * g.wa));
@@ -359,9 +382,30 @@ int swb_submit(swb_ctx* ctx, const uint8_t* frames, int32_t n_frames, int32_t n_
     const int n_total = inline_halo + n_frames;
     const int C = c.channels;
 
+    // ---- sub-batches (host frames only).  The PCIe copy of a large submit takes ~30x longer than
+    // filtering it, so the submit is cut into up to MAX_SUB sub-batches of frames: the copies stay
+    // in order on the caller's stream and sub-batch b is filtered on the worker stream as soon as
+    // its frames have landed, while b+1 is still in flight.  Frames are independent given their N-1
+    // predecessors (read in place), so the only coupling is the running offset into the segment
+    // table (CclChain).  Results are identical to one batch.  (Device-resident submits stay one
+    // batch: running two sub-batches side by side on two streams measured 4-8 % slower, the
+    // bandwidth-bound kernels only get in each other's way.)
+    const bool from_host = (mem_kind == SWB_MEM_HOST);
+    int tsub = n_frames, nsub = 1;
+    if (from_host && ctx->pipeline && !ctx->timing) {
+        const long long px = (long long)g.h * g.wa;
+        const long long min_frames = (ctx->sub_min_px + px - 1) / px;   // >= 64 Mpx of work per sub-batch
+        long long ts = std::max<long long>({(n_frames + MAX_SUB - 1) / MAX_SUB, min_frames, N - 1, 6});
+        ts = (ts + 5) / 6 * 6;
+        if (ts < n_frames) {
+            tsub = (int)ts;
+            nsub = (n_frames + tsub - 1) / tsub;
+        }
+    }
+
     FrameSrc src{};
     bool aligned;
-    if (mem_kind == SWB_MEM_HOST) {
+    if (from_host) {
         // stage only the (32-pixel aligned) ROI columns / rows of every frame
         const long long in_pitch = (long long)g.wa * C;
         const long long in_stride = in_pitch * g.h;
@@ -371,25 +415,6 @@ int swb_submit(swb_ctx* ctx, const uint8_t* frames, int32_t n_frames, int32_t n_
             ctx->in_buf_bytes = need;
             ctx->in_pitch = in_pitch;
             ctx->in_stride = in_stride;
-        }
-        const int copy_px = std::min(g.wa, c.frame_w - ctx->X0a);
-        const uint8_t* sbase = frames + (long long)c.roi_y0 * c.frame_pitch + (long long)ctx->X0a * C;
-        if (copy_px == c.frame_w && g.h == c.frame_h && c.frame_pitch == in_pitch && c.frame_stride == in_stride) {
-            CU(ctx, cudaMemcpyAsync(ctx->in_buf, frames, (size_t)in_stride * n_total, cudaMemcpyHostToDevice, s));
-        } else if (c.frame_stride % c.frame_pitch == 0) {
-            cudaMemcpy3DParms p;
-            memset(&p, 0, sizeof(p));
-            p.srcPtr = make_cudaPitchedPtr(const_cast<uint8_t*>(sbase), (size_t)c.frame_pitch,
-                                           (size_t)c.frame_pitch, (size_t)(c.frame_stride / c.frame_pitch));
-            p.dstPtr = make_cudaPitchedPtr(ctx->in_buf, (size_t)in_pitch, (size_t)in_pitch, (size_t)g.h);
-            p.extent = make_cudaExtent((size_t)copy_px * C, (size_t)g.h, (size_t)n_total);
-            p.kind = cudaMemcpyHostToDevice;
-            CU(ctx, cudaMemcpy3DAsync(&p, s));
-        } else {
-            for (int f = 0; f < n_total; ++f)
-                CU(ctx, cudaMemcpy2DAsync(ctx->in_buf + (long long)f * in_stride, (size_t)in_pitch,
-                                          sbase + (long long)f * c.frame_stride, (size_t)c.frame_pitch,
-                                          (size_t)copy_px * C, (size_t)g.h, cudaMemcpyHostToDevice, s));
         }
         src.cur = ctx->in_buf + (long long)inline_halo * in_stride;
         src.frame_stride = in_stride;
@@ -417,16 +442,92 @@ int swb_submit(swb_ctx* ctx, const uint8_t* frames, int32_t n_frames, int32_t n_
     src.hist = ctx->hist[ctx->hist_cur];
     src.hist_out = (N > 1) ? ctx->hist[ctx->hist_cur ^ 1] : nullptr;
 
+    // host frames [a, a + n) of this call (halo frames included) -> staging buffer
+    auto stage_in = [&](int a, int n, cudaStream_t st) -> cudaError_t {
+        const int copy_px = std::min(g.wa, c.frame_w - ctx->X0a);
+        const uint8_t* sbase = frames + (long long)c.roi_y0 * c.frame_pitch + (long long)ctx->X0a * C +
+                               (long long)a * c.frame_stride;
+        uint8_t* dbase = ctx->in_buf + (long long)a * ctx->in_stride;
+        if (copy_px == c.frame_w && g.h == c.frame_h && c.frame_pitch == ctx->in_pitch && c.frame_stride == ctx->in_stride)
+            return cudaMemcpyAsync(dbase, frames + (long long)a * c.frame_stride, (size_t)ctx->in_stride * n,
+                                   cudaMemcpyHostToDevice, st);
+        if (c.frame_stride % c.frame_pitch == 0) {
+            cudaMemcpy3DParms p;
+            memset(&p, 0, sizeof(p));
+            p.srcPtr = make_cudaPitchedPtr(const_cast<uint8_t*>(sbase), (size_t)c.frame_pitch,
+                                           (size_t)c.frame_pitch, (size_t)(c.frame_stride / c.frame_pitch));
+            p.dstPtr = make_cudaPitchedPtr(dbase, (size_t)ctx->in_pitch, (size_t)ctx->in_pitch, (size_t)g.h);
+            p.extent = make_cudaExtent((size_t)copy_px * C, (size_t)g.h, (size_t)n);
+            p.kind = cudaMemcpyHostToDevice;
+            return cudaMemcpy3DAsync(&p, st);
+        }
+        for (int f = 0; f < n; ++f) {
+            cudaError_t e = cudaMemcpy2DAsync(dbase + (long long)f * ctx->in_stride, (size_t)ctx->in_pitch,
+                                              sbase + (long long)f * c.frame_stride, (size_t)c.frame_pitch,
+                                              (size_t)copy_px * C, (size_t)g.h, cudaMemcpyHostToDevice, st);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    };
+
     int launches = 0;
-    if (ctx->timing) CU(ctx, cudaEventRecord(ctx->ev[0], s));
-    CU(ctx, launch_fg_bits(s, src, C, N, n_frames, g, c.threshold, ctx->raw_bits, aligned, &launches));
-    if (ctx->timing) CU(ctx, cudaEventRecord(ctx->ev[1], s));
-    CU(ctx, launch_morph_mask(s, reinterpret_cast<const uint32_t*>(ctx->raw_bits), n_frames, g, ctx->morph,
-                              ctx->fbits, ctx->mask, &launches));
-    if (ctx->timing) CU(ctx, cudaEventRecord(ctx->ev[2], s));
-    CU(ctx, launch_ccl(s, ctx->fbits, n_frames, g, ctx->ccl, ctx->labels, ctx->label_elem, &launches,
-                       ctx->timing ? &ctx->ev[3] : nullptr, 4));
-    ctx->ev_valid = ctx->timing;
+    if (nsub == 1) {
+        if (from_host) CU(ctx, stage_in(0, n_total, s));
+        if (ctx->timing) CU(ctx, cudaEventRecord(ctx->ev[0], s));
+        CU(ctx, launch_fg_bits(s, src, C, N, n_frames, g, c.threshold, ctx->raw_bits, aligned, &launches));
+        if (ctx->timing) CU(ctx, cudaEventRecord(ctx->ev[1], s));
+        CU(ctx, launch_morph_mask(s, reinterpret_cast<const uint32_t*>(ctx->raw_bits), n_frames, g, ctx->morph,
+                                  ctx->fbits, ctx->mask, &launches));
+        if (ctx->timing) CU(ctx, cudaEventRecord(ctx->ev[2], s));
+        CU(ctx, launch_ccl(s, ctx->fbits, n_frames, g, ctx->ccl, ctx->labels, ctx->label_elem, &launches,
+                           ctx->timing ? &ctx->ev[3] : nullptr, 4));
+        ctx->ev_valid = ctx->timing;
+    } else {
+        cudaStream_t sw = ctx->worker;
+        CU(ctx, cudaMemsetAsync(ctx->ccl.overflow, 0, sizeof(int32_t), s));
+        CU(ctx, cudaEventRecord(ctx->ev_fork, s));
+        CU(ctx, cudaStreamWaitEvent(sw, ctx->ev_fork, 0));
+        const int cap_parts_sub = ctx->ccl.cap_parts / nsub;
+        for (int b = 0; b < nsub; ++b) {
+            const int f0 = b * tsub;
+            const int nb = std::min(tsub, n_frames - f0);
+            const int a = (b == 0) ? 0 : inline_halo + f0;
+            CU(ctx, stage_in(a, inline_halo + f0 + nb - a, s));
+            CU(ctx, cudaEventRecord(ctx->ev_h2d[b], s));
+            CU(ctx, cudaStreamWaitEvent(sw, ctx->ev_h2d[b], 0));
+            FrameSrc sb = src;
+            if (b > 0) {                    // the N-1 frames before f0 are in place (tsub >= N-1)
+                sb.cur = src.cur + (long long)f0 * src.frame_stride;
+                sb.n_inline_halo = N - 1;
+                sb.hist_valid = 0;
+            }
+            if (b < nsub - 1) sb.hist_out = nullptr;
+            uint16_t* raw_b = ctx->raw_bits + (size_t)f0 * g.h * g.wpr_raw * 2;
+            uint32_t* fbits_b = ctx->fbits + (size_t)f0 * g.h * g.wpr4;
+            uint8_t* mask_b = ctx->mask ? ctx->mask + (size_t)f0 * g.h * g.mpitch : nullptr;
+            void* labels_b = ctx->labels
+                                 ? static_cast<uint8_t*>(ctx->labels) + (size_t)f0 * g.h * g.mpitch * ctx->label_elem
+                                 : nullptr;
+            CclBuffers cb = ctx->ccl;
+            cb.parent += (size_t)f0 * g.BH * g.BW;
+            cb.rowcount += (size_t)2 * f0 * g.BH;
+            cb.nseg += f0;
+            cb.segoff += f0;
+            cb.parts += (size_t)b * cap_parts_sub;
+            cb.cap_parts = cap_parts_sub;
+            cb.pcount += b;
+            CclChain chain;
+            chain.frame_base = f0;
+            chain.segoff_base = (b > 0) ? ctx->ccl.segoff + f0 : nullptr;   // left there by sub-batch b-1
+            CU(ctx, launch_fg_bits(sw, sb, C, N, nb, g, c.threshold, raw_b, aligned, &launches));
+            CU(ctx, launch_morph_mask(sw, reinterpret_cast<const uint32_t*>(raw_b), nb, g, ctx->morph, fbits_b, mask_b,
+                                      &launches));
+            CU(ctx, launch_ccl(sw, fbits_b, nb, g, cb, labels_b, ctx->label_elem, &launches, nullptr, 0, &chain));
+        }
+        CU(ctx, cudaEventRecord(ctx->ev_join, sw));
+        CU(ctx, cudaStreamWaitEvent(s, ctx->ev_join, 0));
+        ctx->ev_valid = false;
+    }
     ctx->launches += launches;
     if (N > 1) {
         ctx->hist_cur ^= 1;

@@ -656,12 +656,12 @@ k_ccl_scan(int T, Geom g, uint32_t* __restrict__ rowcount, int32_t* __restrict__
 
 // one CTA: exclusive scan of nseg over frames
 __global__ void __launch_bounds__(1024)
-k_ccl_offsets(int T, const int32_t* __restrict__ nseg, int32_t* __restrict__ segoff, int cap_rows,
+k_ccl_offsets(int T, const int32_t* __restrict__ nseg, int32_t* segoff, const int32_t* base, int cap_rows,
               int32_t* __restrict__ overflow) {
     __shared__ int32_t warp_tot[32];
     __shared__ int32_t carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) carry = 0;
+    if (tid == 0) carry = base ? *base : 0;   // sub-batches of one submit chain their offsets (base == segoff of the previous one + its T)
     __syncthreads();
     for (int f0 = 0; f0 < T; f0 += 1024) {
         const int f = f0 + tid;
@@ -698,7 +698,7 @@ k_ccl_offsets(int T, const int32_t* __restrict__ nseg, int32_t* __restrict__ seg
 }
 
 __global__ void __launch_bounds__(256)
-k_seg_init(int T, const int32_t* __restrict__ nseg, const int32_t* __restrict__ segoff,
+k_seg_init(int T, int frame_base, const int32_t* __restrict__ nseg, const int32_t* __restrict__ segoff,
            swb_segment* __restrict__ rows, int cap_rows) {
     const int f = blockIdx.y;
     const int n = nseg[f];
@@ -706,7 +706,7 @@ k_seg_init(int T, const int32_t* __restrict__ nseg, const int32_t* __restrict__ 
         const long long r = (long long)segoff[f] + i;
         if (r >= cap_rows) return;
         swb_segment s;
-        s.frame = f;
+        s.frame = frame_base + f;
         s.label = i + 1;
         s.area = 0;
         s.bbox[0] = 0x7FFFFFFF;
@@ -984,7 +984,8 @@ static void launch_local(cudaStream_t s, const uint32_t* fbits, int T, const Geo
 }
 
 cudaError_t launch_ccl(cudaStream_t s, const uint32_t* fbits, int T, const Geom& g, const CclBuffers& b,
-                       void* labels, int label_elem_size, int* n_launches, cudaEvent_t* ev, int n_ev) {
+                       void* labels, int label_elem_size, int* n_launches, cudaEvent_t* ev, int n_ev,
+                       const CclChain* chain) {
     int evi = 0;
     auto mark = [&]() {
         if (ev && evi < n_ev) cudaEventRecord(ev[evi++], s);
@@ -996,9 +997,10 @@ cudaError_t launch_ccl(cudaStream_t s, const uint32_t* fbits, int T, const Geom&
     dim3 gblock(bx, 256 / bx);
     dim3 ggrid((Q + bx - 1) / bx, (g.BH + gblock.y - 1) / gblock.y, T);
     const bool tiled = Q <= 32;      // a tile spans the full width: frames up to 4096 pixels wide
-    const uint32_t* rbase_for_labels = nullptr;
+    const uint32_t* rbase_for_labels = tiled ? nullptr : b.rowcount;
     int launches = 0;
-    cudaMemsetAsync(b.pcount, 0, 2 * sizeof(int), s);                  // pcount, overflow
+    cudaMemsetAsync(b.pcount, 0, sizeof(int), s);
+    if (!chain) cudaMemsetAsync(b.overflow, 0, sizeof(int32_t), s);    // a chained submit clears it once, before its first sub-batch
     if (tiled) {
         cudaMemsetAsync(b.rowcount, 0, (size_t)2 * T * g.BH * sizeof(uint32_t), s);   // rowcount, rowfill
         switch (bx) {
@@ -1019,13 +1021,12 @@ cudaError_t launch_ccl(cudaStream_t s, const uint32_t* fbits, int T, const Geom&
         mark();
         const long long n_rows_w = (long long)T * g.BH;
         k_ccl_roots<<<(int)((n_rows_w * 32 + 255) / 256), 256, 0, s>>>(fbits, T, g, b.parent, b.rowcount);
-        rbase_for_labels = b.rowcount;
     }
     k_ccl_scan<<<(T * 32 + 255) / 256, 256, 0, s>>>(T, g, b.rowcount, b.nseg);
-    k_ccl_offsets<<<1, 1024, 0, s>>>(T, b.nseg, b.segoff, b.cap_rows, b.overflow);
+    k_ccl_offsets<<<1, 1024, 0, s>>>(T, b.nseg, b.segoff, chain ? chain->segoff_base : nullptr, b.cap_rows, b.overflow);
     {
         dim3 grid(4, T);
-        k_seg_init<<<grid, 256, 0, s>>>(T, b.nseg, b.segoff, b.rows, b.cap_rows);
+        k_seg_init<<<grid, 256, 0, s>>>(T, chain ? chain->frame_base : 0, b.nseg, b.segoff, b.rows, b.cap_rows);
     }
     launches += 4;
     if (tiled) {

@@ -72,15 +72,23 @@ struct CclBuffers {
     int32_t* segoff;      // [T+1] exclusive prefix of nseg
     swb_segment* rows;    // [cap_rows]
     int cap_rows;
-    int32_t* overflow;    // = pcount + 1; device flag: 1 when total rows > cap_rows (or partials > cap_parts)
+    int32_t* overflow;    // device flag: 1 when total rows > cap_rows (or partials > cap_parts)
     Partial* parts;       // [cap_parts] tile-local regionprops partial sums
     int* pcount;          // number of partials appended
     int* rootlist;        // [cap_rows] roots grouped by block row (tiled path ranking)
     int cap_parts;
 };
+// A submit from host memory is cut into sub-batches of frames (each starts as soon as its
+// frames have landed on the device); their segment-table offsets are chained: sub-batch k
+// starts where k-1 ended (*segoff_base).  Sub-batches run in order on one stream.
+struct CclChain {
+    int frame_base;                     // first frame of the sub-batch within the submit
+    const int32_t* segoff_base;         // device: offset of the sub-batch's first table row (null = 0)
+};
 cudaError_t launch_ccl(cudaStream_t s, const uint32_t* fbits, int T, const Geom& g,
                        const CclBuffers& b, void* labels, int label_elem_size,
-                       int* n_launches, cudaEvent_t* stage_events, int n_stage_events);
+                       int* n_launches, cudaEvent_t* stage_events, int n_stage_events,
+                       const CclChain* chain = nullptr);
 
 cudaError_t launch_pack_bits(cudaStream_t s, const uint8_t* img, int h, int w, uint32_t* fbits,
                              int wpr4);

@@ -359,6 +359,40 @@ def test_many_temporal_subchunks(n, T):
             assert np.array_equal(masks[i], want2[T + i]["mask"]), i
 
 
+@pytest.mark.parametrize("n,T,se,close,mode", [(9, 71, 5, True, "i32"), (5, 50, 3, False, "u8"), (5, 26, 3, False, "i32"),
+                                               (3, 31, 3, True, "i32")])
+def test_sub_batches_equal_one_batch(monkeypatch, n, T, se, close, mode):
+    """A host submit cut into sub-batches that are filtered while later frames are still being
+    copied (forced here with the SWB_SUB_MIN_PX test hook; real frames reach it at >= 64 Mpx per
+    sub-batch) gives exactly the oracle's masks, labels and table, the same as the one-batch
+    device-resident submit, and leaves the right history behind."""
+    import torch
+    monkeypatch.setenv("SWB_SUB_MIN_PX", "1")
+    frames = synth.synth_video(33, 0, 0, T + 6, 44, 100, 25)
+    region = [(3, 2), (99, 43)]
+    par = rp.PathParams(region, n, 15, se, True, close, mode)
+    want = rp.run_path(frames, par)
+    with swb.FilterContext(frames.shape[1:], region, median_n=n, morph_size=se, do_close=close, label_mode=mode,
+                           max_frames=T) as ctx:
+        check_against_oracle(frames[:T], region, n=n, se=se, do_close=close, mode=mode, ctx=ctx, n_halo=0)
+        ctx.submit(np.ascontiguousarray(frames[T:]))            # CARRY: history written by the last sub-batch
+        labels = ctx.labels()
+        for i in range(6):
+            assert np.array_equal(labels[i], want[T + i]["labels"]), i
+        dev = torch.from_numpy(frames).cuda()
+        ctx.reset()
+        ctx.submit(dev[:T], n_halo=0)
+        rows_d, counts_d = ctx.collect()
+        labels_d = ctx.labels()
+    monkeypatch.setenv("SWB_PIPELINE", "0")                     # one batch on one stream
+    with swb.FilterContext(frames.shape[1:], region, median_n=n, morph_size=se, do_close=close, label_mode=mode,
+                           max_frames=T) as ctx:
+        ctx.submit(frames[:T], n_halo=0)
+        rows_1, counts_1 = ctx.collect()
+        assert np.array_equal(rows_1, rows_d) and np.array_equal(counts_1, counts_d)
+        assert np.array_equal(ctx.labels(), labels_d)
+
+
 def test_device_resident_input_zero_copy():
     import torch
     frames = synth.synth_video(28, 0, 0, 10, 72, 160, 30)
