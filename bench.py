@@ -38,6 +38,10 @@ CONFIGS = {
                                       do_close=False, birds=300, chunk=512),
     # BASELINE.json configs[4] filtering part (dense swarm, ~500 segments/frame)
     "1080p_dense_n5_open3": dict(H=1080, W=1920, roi=None, N=5, se=3, do_close=False, birds=2500, chunk=256),
+    # BASELINE.json configs[4]: filter + label + batched segment classification (SqueezeNet1.0 as in the
+    # reference, random-init weights: model.pt is not redistributable), ~500 segments per frame
+    "1080p_swarm500_classify": dict(H=1080, W=1920, roi=None, N=5, se=3, do_close=False, birds=500, chunk=16,
+                                    classify=True),
 }
 DEFAULT_CONFIG = "1080p_full_n5_open3"
 SEED = 2
@@ -141,8 +145,27 @@ def cpu_baseline_sample(cfg, n_frames, threads=None):
     halo = cfg["N"] - 1
     frames = synth.synth_video(SEED, 0, 1000, halo + n_frames, H, W, cfg["birds"])
     par = rp.PathParams(roi, cfg["N"], 15, cfg["se"], True, cfg["do_close"], "u8")
+    ref_clf = None
+    if cfg.get("classify"):
+        # the reference's per-segment classifier loop (segment_classification.py:27-45) on the host
+        import torch
+        from oracle import reference_classifier as rc
+        from swiftwatcher_b200.segment_classification import setup_model
+        torch.manual_seed(SEED)
+        ref_clf = rc.RefSegmentClassifier(setup_model(2, "cpu").state_dict(), "cpu")
     t0 = time.perf_counter()
     out = rp.run_path(frames[halo:], par, history=list(frames[:halo]), want_images=True)
+    if ref_clf is not None:
+        class _Seg:
+            pass
+        for o in out:
+            segs_o = []
+            for im in o["crops"]:
+                if im.size:
+                    sg = _Seg()
+                    sg.segment_image, sg.label = im, 0
+                    segs_o.append(sg)
+            ref_clf(segs_o)
     dt = time.perf_counter() - t0
     segs = sum(len(o["props"]) for o in out)
     return n_frames / dt, dt, segs, cv2.getNumThreads()
@@ -156,6 +179,8 @@ def run_reference(args, cfg, name):
     if rank != 0:
         return
     sample = max(2, min(8, int(24 // max(args.steps, 1)) or 2)) if cfg["H"] >= 1080 and cfg["roi"] is None else 64
+    if cfg.get("classify"):
+        sample = 1
     for _ in range(min(args.warmup, 1)):
         cpu_baseline_sample(cfg, 2)
     t_total, n_total, segs, threads = 0.0, 0, 0, 0
@@ -246,8 +271,25 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    clf = None
+    if cfg.get("classify"):
+        from swiftwatcher_b200.segment_classification import SegmentClassifier, setup_model
+        torch.manual_seed(SEED)
+        clf = SegmentClassifier(setup_model(2, "cpu").state_dict(), device="cuda:%d" % local_rank, batch_size=2048)
+    stats = {"segments": 0, "kept": 0}
+
+    def run_step(context, frames):
+        """One pass of the hot path over one chunk (+ the classifier where the config has it)."""
+        context.submit(frames, n_halo=halo)
+        if clf is not None:
+            rows_s, _ = context.collect()
+            with torch.cuda.stream(stream):
+                keep = clf.classify_submit(context, len(rows_s))
+                stats["kept"] += int(keep.sum().item())      # device -> host read of the result
+            stats["segments"] += len(rows_s)
+
     for i in range(args.warmup):
-        ctx.submit(bufs[i % n_buf], n_halo=halo)
+        run_step(ctx, bufs[i % n_buf])
     ctx.sync()
     rows, counts = ctx.collect()
     segs_per_frame = float(counts.mean())
@@ -260,7 +302,7 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for i in range(args.steps):
-        ctx.submit(bufs[i % n_buf], n_halo=halo)
+        run_step(ctx, bufs[i % n_buf])
     ev1.record(stream)
     barrier()
     clocks = sampler.stop()
@@ -293,6 +335,21 @@ def main():
                 "algorithmic_bytes_per_launch": alg[dom] * T,
                 "path_achieved": round(alg["path"] * fps / world / 1e9, 1),
                 "path_frac": round(alg["path"] * fps / world / 1e9 / peak, 4), "kernels": kernels}
+    if clf is not None:
+        # the classifier (cuDNN convolutions, library code) dominates this config: time it alone
+        crops = torch.randint(0, 256, (4096, 24, 24, 3), dtype=torch.uint8, device="cuda")
+        with torch.cuda.stream(stream):
+            clf.predict(crops[:2048])
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record(stream)
+            clf.predict(crops)
+            c1.record(stream)
+        torch.cuda.synchronize()
+        roofline["classifier"] = {"crops_per_s": round(4096 / (c0.elapsed_time(c1) * 1e-3), 1),
+                                  "segments_per_frame": round(segs_per_frame, 1),
+                                  "note": "torchvision SqueezeNet1.0 as in the reference (float32, cuDNN, library code), "
+                                          "[B,3,224,224] inputs built from device-gathered 24x24 crops; the hot-path "
+                                          "kernels in `kernels` are the filtering + labelling part of the step"}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
@@ -309,15 +366,16 @@ def main():
         host = torch.empty((halo + T, H, W, 3), dtype=torch.uint8, pin_memory=True)
         host.copy_(bufs[0])
         torch.cuda.synchronize()
-        ctx_h.submit(host, n_halo=halo)
+        ctx_h.set_stream(stream.cuda_stream)
+        run_step(ctx_h, host)
         rows_h, counts_h = ctx_h.collect()
         d2h = 0
         barrier()
         t0 = time.perf_counter()
         for i in range(args.e2e_steps):
-            ctx_h.submit(host, n_halo=halo)
+            run_step(ctx_h, host)
             rows_h, counts_h = ctx_h.collect()
-            d2h = rows_h.nbytes + counts_h.nbytes + 4 * (T + 1)
+            d2h = rows_h.nbytes + counts_h.nbytes + 4 * (T + 1) + (8 if clf is not None else 0)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if world > 1:
@@ -332,7 +390,8 @@ def main():
             h2d = (halo + T) * rh * min(wa, W - x0a) * 3
         e2e = {"value": world * args.e2e_steps * T / dt, "unit": "frames/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps,
-               "note": "pinned host frames -> swb_submit (H2D) -> swb_collect (D2H segment table); PCIe-bound"}
+               "note": "pinned host frames -> swb_submit (H2D) -> swb_collect (D2H segment table)"
+                       + (" -> device crops -> classifier -> kept count (D2H)" if clf is not None else "; PCIe-bound")}
         ctx_h.close()
         del host
 
@@ -342,6 +401,8 @@ def main():
         n_cpu = args.cpu_frames or (16 if roi is None and H >= 1080 else 300)
         if H > 1080:
             n_cpu = args.cpu_frames or 4
+        if cfg.get("classify"):
+            n_cpu = args.cpu_frames or 2
         cpu_fps, cpu_dt, _, threads = cpu_baseline_sample(cfg, n_cpu)
         cpu = {"value": cpu_fps, "unit": "frames/s", "cores": threads, "kind": "port",
                "sample": "%d frames of %s (%.1f s) through oracle/reference_path.py: the reference's cv2/scipy calls "
@@ -350,7 +411,8 @@ def main():
 
     if rank == 0:
         line = {
-            "metric": "frames/sec (filter + label hot path)", "value": fps, "unit": "frames/s",
+            "metric": "frames/sec (filter + label hot path%s)" % (" + segment classification" if clf is not None else ""),
+            "value": fps, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": args.config, "frame": [H, W, 3], "roi": roi, "median_n": N,
@@ -358,7 +420,9 @@ def main():
                        "labels": args.label_mode, "frames_per_step": T, "halo_frames": halo,
                        "resident_chunks": n_buf, "segments_per_frame": round(segs_per_frame, 1),
                        "l2": "inputs (%.1f GB/step) >> 126 MB L2; no flush" % ((halo + T) * frame_bytes / 1e9),
-                       "partition": "temporal chunks, %d-frame halo, no collective" % halo},
+                       "partition": "temporal chunks, %d-frame halo, no collective" % halo,
+                       **({"classifier": "squeezenet1_0 (2 classes), random-init weights, float32, eval mode"}
+                          if clf is not None else {})},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks,
         }

@@ -1,0 +1,151 @@
+"""Oracle for the segment classifier — TEST INFRASTRUCTURE ONLY.
+
+Restates ``swiftwatcher/segment_classification.py`` one segment at a time, exactly as the
+reference does it: the five torchvision transforms through PIL (:16-23), one forward pass
+on a [1, 3, 224, 224] tensor per segment (:30-36), ``torch.max(score, 1)`` (:37), keep
+class 1 (:39-40), relabel the kept segments 1..k (:42-43).
+
+Two things cannot be taken over literally (both recorded in DESIGN.md):
+* ``models.squeezenet1_0(pretrained=True)`` (:51) needs a download; every parameter is
+  overwritten by ``load_state_dict`` (:15), so ``weights=None`` builds the same module;
+* the reference never calls ``model.eval()``, so Dropout(0.5) is live and its output is
+  random; ``eval_mode=True`` (default) is the deterministic function the product is
+  compared against, ``eval_mode=False`` reproduces the reference's stochastic behaviour.
+
+Pinning: ``reference_module()`` imports the reference's own, unmodified
+``segment_classification.py`` from /root/reference (with the constructor's download
+disabled) so that the tests can check this restatement and the product against the real
+class and the real ``model.pt`` wherever /root/reference exists (the build container).
+"""
+
+import importlib
+import sys
+
+import torch
+from torch import nn
+from torchvision import models, transforms
+
+
+def setup_model(num_classes, device):
+    """segment_classification.py:48-67."""
+    model = models.squeezenet1_0(weights=None)
+    for param in model.parameters():
+        param.requires_grad = False
+    model.classifier[1] = nn.Conv2d(512, num_classes, kernel_size=1)
+    model.num_classes = num_classes
+    return model.to(device)
+
+
+class RefSegmentClassifier:
+    """segment_classification.py:13-45, per-segment loop."""
+
+    def __init__(self, state_dict, device, eval_mode=True):
+        self.device = torch.device(device)
+        self.model = setup_model(2, self.device)
+        self.model.load_state_dict(state_dict)
+        if eval_mode:
+            self.model.eval()
+        self.transforms = [
+            transforms.ToPILImage(),
+            transforms.Resize((24, 24)),
+            transforms.Pad((224 - 24) // 2),
+            transforms.ToTensor(),
+            transforms.Normalize([0.485, 0.456, 0.406], [0.229, 0.224, 0.225]),
+        ]
+
+    def transform(self, image):
+        x = image
+        for t in self.transforms:
+            x = t(x)
+        return x
+
+    @torch.no_grad()
+    def score(self, segment_image):
+        return self.model(self.transform(segment_image).unsqueeze(0).to(self.device))
+
+    @torch.no_grad()
+    def __call__(self, segments):
+        keep = []
+        for segment in segments:
+            score = self.score(segment.segment_image)
+            _, y_pred = torch.max(score, 1)
+            if y_pred == 1:
+                keep.append(segment)
+        for i, segment in enumerate(keep):
+            segment.label = i + 1
+        return keep
+
+
+def random_state_dict(seed):
+    """Seeded random-init weights of the reference architecture (there is no network for
+    checkpoints on the GPU box; model.pt itself is not redistributed).  The bias of the
+    class-0 output is centred on a fixed set of noise crops so that the two classes both
+    occur (with plain random weights the constant padding decides every crop the same way)."""
+    g = torch.Generator().manual_seed(seed)
+    model = setup_model(2, "cpu")
+    sd = model.state_dict()
+    for k, v in sd.items():
+        if v.dtype.is_floating_point:
+            fan = v[0].numel() if v.dim() > 1 else 16
+            sd[k] = (torch.randn(v.shape, generator=g) * (2.0 / max(fan, 1)) ** 0.5).to(v.dtype)
+    model.load_state_dict(sd)
+    model.eval()
+    crops = torch.randint(0, 256, (48, 3, 24, 24), generator=g).float().div(255)
+    x = torch.zeros((48, 3, 224, 224))
+    x[:, :, 100:124, 100:124] = crops
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    with torch.no_grad():
+        feat = model.features((x - mean) / std)
+        # both outputs on the linear side of the final ReLU, then bisection on the class-0
+        # bias until the median margin over the noise crops is zero
+        conv = model.classifier[1]
+        conv.bias[1] = 16.0 - float((conv(feat) - conv.bias.view(1, 2, 1, 1))[:, 1].min())
+        lo, hi = float(conv.bias[1]) - 256.0, float(conv.bias[1]) + 256.0
+        for _ in range(40):
+            mid = 0.5 * (lo + hi)
+            model.classifier[1].bias[0] = mid
+            s = torch.flatten(model.classifier(feat), 1)
+            if float((s[:, 1] - s[:, 0]).median()) > 0:
+                lo = mid
+            else:
+                hi = mid
+    sd["classifier.1.bias"] = model.classifier[1].bias.detach().clone()
+    return sd
+
+
+def reference_module(root="/root/reference"):
+    """The reference's own segment_classification module, imported unmodified
+    (torchvision's constructor is told not to download)."""
+    real = models.squeezenet1_0
+
+    def no_download(pretrained=False, **kw):
+        kw.pop("weights", None)
+        return real(weights=None, **kw)
+
+    models.squeezenet1_0 = no_download
+    sys.path.insert(0, root)
+    try:
+        sys.modules.pop("swiftwatcher.segment_classification", None)
+        mod = importlib.import_module("swiftwatcher.segment_classification")
+    finally:
+        sys.path.remove(root)
+    mod._restore = lambda: setattr(models, "squeezenet1_0", real)
+    return mod
+
+
+def build_reference_classifier(mod, model_path):
+    """``mod.SegmentClassifier(model_path)`` on this machine: model.pt holds CUDA tensors
+    and the reference's bare ``torch.load`` (:15) cannot map them on a CPU-only host, so
+    ``torch.load`` is given ``map_location=mod.device`` for the duration of the call."""
+    real_load = torch.load
+
+    def load(f, *a, **kw):
+        kw.setdefault("map_location", mod.device)
+        return real_load(f, *a, **kw)
+
+    torch.load = load
+    try:
+        return mod.SegmentClassifier(model_path)
+    finally:
+        torch.load = real_load

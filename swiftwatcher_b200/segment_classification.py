@@ -1,0 +1,152 @@
+"""SegmentClassifier — the reference's segment classifier fed batched crops.
+
+Mirror of ``swiftwatcher/segment_classification.py``: same
+class name, constructor argument and call semantics (``classifier(segments)``
+returns the segments predicted as class 1, relabelled 1..k, :27-45).  The model
+is the reference's own (torchvision SqueezeNet1.0 with a 2-class 1x1 classifier
+conv, :48-67, weights from the user's ``model.pt``) and it stays a PyTorch
+module — BASELINE.json keeps the classifier as it is.  What changes is how it
+is fed:
+
+* the reference runs one forward pass per segment on a [1, 3, 224, 224] tensor
+  built by five torchvision transforms through PIL (:16-23, :30-36);
+* here all crops of a frame (or of a whole submit) are preprocessed as one
+  tensor with the same arithmetic (uint8 -> float32 / 255, zero pad 100 px,
+  ``(x - mean) / std``: bit-identical to ToTensor + Pad + Normalize) and go
+  through the model in large batches; crops can come straight from the device
+  (``FilterContext.gather_crops``: 24x24 tiles cut from the BGR frames by a CUDA
+  kernel) without touching the host.
+
+Deliberate differences:
+* ``model.eval()`` — the reference never calls it, so its Dropout(0.5) is live
+  and its predictions are random from run to run;
+* ``squeezenet1_0(weights=None)`` — the reference's ``pretrained=True`` needs a
+  download and every tensor is overwritten by ``model.pt`` anyway (52/52 keys);
+* crops that are not 24x24 (segments larger than 24 px, or cut by the frame
+  border) go through the reference's PIL resize, one by one, as before.
+"""
+
+import numpy as np
+import torch
+from torch import nn
+from torchvision import models, transforms
+
+CROP = 24
+PAD = (224 - CROP) // 2
+_MEAN = (0.485, 0.456, 0.406)
+_STD = (0.229, 0.224, 0.225)
+
+
+def setup_model(num_classes, device):
+    """segment_classification.py:48-67 (architecture only; no download)."""
+    model = models.squeezenet1_0(weights=None)
+    for param in model.parameters():
+        param.requires_grad = False
+    model.classifier[1] = nn.Conv2d(512, num_classes, kernel_size=1)
+    model.num_classes = num_classes
+    return model.to(device)
+
+
+class SegmentClassifier:
+    def __init__(self, model_path, device=None, batch_size=2048, channels_last=True):
+        if device is None:   # the reference's module-level choice (:10)
+            device = torch.device("cuda:0" if torch.cuda.is_available() else "cpu")
+        self.device = torch.device(device)
+        self.model = setup_model(2, self.device)
+        state = model_path if isinstance(model_path, dict) else torch.load(model_path, map_location=self.device)
+        self.model.load_state_dict(state)
+        self.model.eval()
+        for p in self.model.parameters():
+            p.requires_grad = False
+        self.channels_last = channels_last and self.device.type == "cuda"
+        if self.channels_last:
+            self.model = self.model.to(memory_format=torch.channels_last)
+        self.batch_size = int(batch_size)
+        self._mean = torch.tensor(_MEAN, dtype=torch.float32, device=self.device).view(1, 3, 1, 1)
+        self._std = torch.tensor(_STD, dtype=torch.float32, device=self.device).view(1, 3, 1, 1)
+        # the reference's per-image transform chain, for crops that need the PIL resize
+        self.transforms = [
+            transforms.ToPILImage(),
+            transforms.Resize((CROP, CROP)),
+            transforms.Pad(PAD),
+            transforms.ToTensor(),
+            transforms.Normalize(list(_MEAN), list(_STD)),
+        ]
+
+    # -- preprocessing -----------------------------------------------------------
+    def preprocess(self, crops):
+        """[B, 24, 24, 3] uint8 (numpy or torch, any device) -> [B, 3, 224, 224]
+        float32 on the model's device; same values as ToPILImage -> Resize(24)
+        (identity) -> Pad(100) -> ToTensor -> Normalize applied to each crop."""
+        x = torch.as_tensor(crops)
+        if x.dim() != 4 or tuple(x.shape[1:]) != (CROP, CROP, 3) or x.dtype != torch.uint8:
+            raise ValueError("crops must be [B, %d, %d, 3] uint8" % (CROP, CROP))
+        x = x.to(self.device, non_blocking=True).permute(0, 3, 1, 2).to(torch.float32).div(255)
+        out = torch.zeros((x.shape[0], 3, 224, 224), dtype=torch.float32, device=self.device)
+        out[:, :, PAD:PAD + CROP, PAD:PAD + CROP] = x
+        out.sub_(self._mean).div_(self._std)
+        if self.channels_last:
+            out = out.contiguous(memory_format=torch.channels_last)
+        return out
+
+    def _transform_one(self, image):
+        x = np.ascontiguousarray(image)
+        for t in self.transforms:
+            x = t(x)
+        return x
+
+    # -- scoring -----------------------------------------------------------------
+    @torch.no_grad()
+    def scores(self, crops):
+        """Class scores [B, 2] (float32, on the model's device) for 24x24 crops."""
+        n = int(crops.shape[0])
+        out = torch.empty((n, 2), dtype=torch.float32, device=self.device)
+        for a in range(0, n, self.batch_size):
+            b = min(n, a + self.batch_size)
+            out[a:b] = self.model(self.preprocess(crops[a:b]))
+        return out
+
+    @torch.no_grad()
+    def predict(self, crops):
+        """argmax class per crop (torch.max(score, 1), :37-38) as a bool 'keep' mask."""
+        if int(crops.shape[0]) == 0:
+            return torch.zeros((0,), dtype=torch.bool, device=self.device)
+        _, y = torch.max(self.scores(crops), 1)
+        return y == 1
+
+    @torch.no_grad()
+    def __call__(self, segments):
+        """segment_classification.py:27-45 with one batched forward pass."""
+        segments = list(segments)
+        keep = np.zeros(len(segments), dtype=bool)
+        exact, odd = [], []
+        for i, s in enumerate(segments):
+            im = s.segment_image
+            (exact if tuple(im.shape) == (CROP, CROP, 3) else odd).append(i)
+        if exact:
+            crops = np.stack([segments[i].segment_image for i in exact])
+            keep[exact] = self.predict(crops).cpu().numpy()
+        for i in odd:   # resized through PIL exactly as the reference does
+            im = segments[i].segment_image
+            if im.size == 0:
+                raise ValueError("segment %d has an empty segment_image (bbox outside the frame)" % i)
+            x = self._transform_one(im).unsqueeze(0).to(self.device)
+            _, y = torch.max(self.model(x), 1)
+            keep[i] = bool(y.item() == 1)
+        kept = [s for s, k in zip(segments, keep) if k]
+        for i, s in enumerate(kept):
+            s.label = i + 1
+        return kept
+
+    # -- device-resident path -------------------------------------------------------
+    @torch.no_grad()
+    def classify_submit(self, ctx, n_rows):
+        """Keep mask [n_rows] (bool, device) for the segment table of ``ctx``'s last
+        submit: crops are gathered on the device from the BGR frames
+        (``swb_gather_crops``) and never visit the host.  Needs device-resident
+        full frames (device submit, or host submit of a full-frame ROI)."""
+        if n_rows == 0:
+            return torch.zeros((0,), dtype=torch.bool, device=self.device)
+        crops = torch.empty((n_rows, CROP, CROP, 3), dtype=torch.uint8, device=self.device)
+        ctx.gather_crops(n_rows, CROP, out=crops)
+        return self.predict(crops)

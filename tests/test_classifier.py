@@ -1,0 +1,154 @@
+"""Segment classifier fed batched crops against the oracle's
+per-segment restatement of swiftwatcher/segment_classification.py, and — where
+/root/reference exists — against the reference's own class with the real model.pt."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import reference_classifier as rc
+from oracle import reference_path as rp
+from oracle import synth
+
+REF = "/root/reference"
+TOL = 1e-4   # float32 scores: batched vs one-by-one forward passes (different conv algorithms)
+
+
+class Seg:
+    def __init__(self, image, label):
+        self.segment_image = image
+        self.label = label
+
+
+def make_segments(rng, n, odd=()):
+    segs = []
+    for i in range(n):
+        shape = odd[i] if i < len(odd) else (24, 24)
+        segs.append(Seg(rng.integers(0, 256, size=shape + (3,), dtype=np.uint8), 100 + i))
+    return segs
+
+
+def test_preprocess_equals_the_transform_chain_bit_for_bit():
+    from swiftwatcher_b200.segment_classification import SegmentClassifier
+    sd = rc.random_state_dict(1)
+    clf = SegmentClassifier(sd, device="cpu")
+    ref = rc.RefSegmentClassifier(sd, "cpu")
+    rng = np.random.default_rng(0)
+    crops = rng.integers(0, 256, size=(9, 24, 24, 3), dtype=np.uint8)
+    crops[0] = 0
+    crops[1] = 255
+    got = clf.preprocess(crops)
+    for i in range(len(crops)):
+        assert torch.equal(got[i], ref.transform(crops[i])), i
+
+
+def test_batched_call_equals_per_segment_loop_cpu():
+    from swiftwatcher_b200.segment_classification import SegmentClassifier
+    sd = rc.random_state_dict(2)
+    rng = np.random.default_rng(1)
+    odd = [(30, 24), (24, 41), (11, 24)]          # go through the PIL resize, as in the reference
+    a = make_segments(rng, 40, odd)
+    b = [Seg(s.segment_image.copy(), s.label) for s in a]
+    clf = SegmentClassifier(sd, device="cpu", batch_size=16)
+    ref = rc.RefSegmentClassifier(sd, "cpu")
+    kept = clf(a)
+    want = ref(b)
+    assert [id(s) for s in kept] == [id(a[b.index(w)]) for w in want]
+    assert [s.label for s in kept] == list(range(1, len(kept) + 1))
+    assert 0 < len(kept) < len(a)                 # the seeded weights split the crops
+    exact = np.stack([s.segment_image for s in a[3:]])
+    got = clf.scores(exact)
+    exp = torch.cat([ref.score(s.segment_image) for s in a[3:]])
+    assert torch.allclose(got, exp, rtol=TOL, atol=TOL)
+    assert clf(a[:0]) == []
+
+
+def test_empty_crop_is_an_error():
+    from swiftwatcher_b200.segment_classification import SegmentClassifier
+    clf = SegmentClassifier(rc.random_state_dict(3), device="cpu")
+    with pytest.raises(ValueError):
+        clf([Seg(np.zeros((0, 24, 3), dtype=np.uint8), 1)])
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "swiftwatcher", "model.pt")),
+                    reason="the reference (and its model.pt) only exists in the build container")
+def test_against_the_reference_class_and_model_pt():
+    """The reference's own SegmentClassifier (unmodified module, real weights, eval mode
+    for determinism) keeps exactly the segments the batched classifier keeps."""
+    from swiftwatcher_b200.segment_classification import SegmentClassifier
+    mod = rc.reference_module(REF)
+    try:
+        path = os.path.join(REF, "swiftwatcher", "model.pt")
+        their = rc.build_reference_classifier(mod, path)
+        their.model.eval()
+        dev = str(mod.device)
+        ours = SegmentClassifier(path, device=dev, batch_size=32)
+        oracle = rc.RefSegmentClassifier(torch.load(path, map_location=dev), dev)
+        # bird-like crops from the synthetic generator + noise crops
+        frames = synth.synth_video(5, 0, 0, 6, 120, 200, 40)
+        par = rp.PathParams([(0, 0), (200, 120)], 5, 15, 3, True, False, "u8")
+        out = rp.run_path(frames, par, want_images=True)
+        images = [im for o in out for im in o.get("crops", []) if im.shape == (24, 24, 3)][:40]
+        rng = np.random.default_rng(2)
+        images += [rng.integers(0, 256, size=(24, 24, 3), dtype=np.uint8) for _ in range(24)]
+        a = [Seg(im, 7) for im in images]
+        b = [Seg(im, 7) for im in images]
+        c = [Seg(im, 7) for im in images]
+        kept_theirs = their(a)
+        kept_ours = ours(b)
+        kept_oracle = oracle(c)
+        assert [a.index(s) for s in kept_theirs] == [b.index(s) for s in kept_ours] == [c.index(s) for s in kept_oracle]
+        assert [s.label for s in kept_ours] == list(range(1, len(kept_ours) + 1))
+        got = ours.scores(np.stack(images))
+        exp = torch.cat([oracle.score(im) for im in images])
+        assert torch.allclose(got, exp, rtol=TOL, atol=TOL)
+    finally:
+        mod._restore()
+
+
+@pytest.mark.gpu
+def test_gpu_batched_scores_and_device_crops():
+    import swiftwatcher_b200 as swb
+    from swiftwatcher_b200 import image_filtering as img
+    from swiftwatcher_b200.segment_classification import SegmentClassifier
+    # full float32 convolutions on both sides (torch's default lets cuDNN use TF32, whose
+    # rounding noise is larger than the margins of the random-weight model)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sd = rc.random_state_dict(4)
+    clf = SegmentClassifier(sd, device="cuda:0", batch_size=64)
+    ref = rc.RefSegmentClassifier({k: v.cuda() for k, v in sd.items()}, "cuda:0")
+    frames = synth.synth_video(6, 0, 0, 8, 160, 256, 60)
+    region = [(0, 0), (256, 160)]
+    dev = torch.from_numpy(frames).cuda()
+    with swb.FilterContext(frames.shape[1:], region, label_mode="i32", max_frames=8) as ctx:
+        ctx.submit(dev, n_halo=0)
+        rows, counts = ctx.collect()
+        n = len(rows)
+        assert n > 20
+        crops = torch.empty((n, 24, 24, 3), dtype=torch.uint8, device="cuda")
+        ctx.gather_crops(n, 24, out=crops)
+        keep_dev = clf.classify_submit(ctx, n).cpu().numpy()
+    # host crops with the reference's slicing; interior segments up to 24 px give the same 24x24 tile
+    props = swb.props_from_rows(rows)
+    same = []
+    for i, (p, r) in enumerate(zip(props, rows)):
+        im = img.extract_segment_images([p], frames[r["frame"]], (24, 24), region)[0]
+        if im.shape == (24, 24, 3):
+            assert np.array_equal(im, crops[i].cpu().numpy()), i
+            same.append(i)
+    assert len(same) > 10
+    got = clf.scores(crops[same])
+    exp = torch.cat([ref.score(crops[i].cpu().numpy()) for i in same])
+    assert torch.allclose(got, exp, rtol=TOL, atol=TOL)          # batch 64 vs batch 1
+    margin = (exp[:, 1] - exp[:, 0]).abs().cpu().numpy()
+    pred_ref = (exp[:, 1] > exp[:, 0]).cpu().numpy()
+    decided = margin > 10 * TOL
+    assert decided.sum() > 5 and 0 < pred_ref[decided].sum() < decided.sum()
+    assert np.array_equal(keep_dev[same][decided], pred_ref[decided])
+    segs = [Seg(crops[i].cpu().numpy(), 9) for i in same]
+    kept = clf(segs)
+    kept_idx = np.zeros(len(segs), dtype=bool)
+    kept_idx[[segs.index(s) for s in kept]] = True
+    assert np.array_equal(kept_idx[decided], keep_dev[same][decided])
