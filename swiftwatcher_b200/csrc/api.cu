@@ -152,6 +152,7 @@ void free_ctx_buffers(swb_ctx* c) {
     cudaFree(c->ccl.rows);
     cudaFree(c->ccl.parts);
     cudaFree(c->ccl.pcount);
+    cudaFree(c->ccl.big_tiles);
     cudaFree(c->ccl.rootlist);
     if (c->h_segoff) cudaFreeHost(c->h_segoff);
     if (c->h_overflow) cudaFreeHost(c->h_overflow);
@@ -175,8 +176,9 @@ int alloc_ccl(swb_ctx* ctx, CclBuffers& b, const Geom& g, int T, int cap_rows) {
     b.cap_rows = cap_rows;
     b.cap_parts = 2 * cap_rows + 4096;
     CU(ctx, dalloc(&b.parts, (size_t)b.cap_parts));
-    CU(ctx, dalloc(&b.pcount, MAX_SUB + 1));     // one partial counter per sub-batch, then the overflow flag
-    b.overflow = b.pcount + MAX_SUB;
+    CU(ctx, dalloc(&b.pcount, 2 * MAX_SUB + 1)); // {partials, listed tiles} per sub-batch, then the overflow flag
+    b.overflow = b.pcount + 2 * MAX_SUB;
+    CU(ctx, dalloc(&b.big_tiles, (size_t)T * ((g.BH + 7) / 8)));   // tiles are at least 8 block rows tall
     CU(ctx, dalloc(&b.rootlist, (size_t)cap_rows));
     return SWB_OK;
 }
@@ -515,7 +517,8 @@ int swb_submit(swb_ctx* ctx, const uint8_t* frames, int32_t n_frames, int32_t n_
             cb.segoff += f0;
             cb.parts += (size_t)b * cap_parts_sub;
             cb.cap_parts = cap_parts_sub;
-            cb.pcount += b;
+            cb.pcount += 2 * b;
+            cb.big_tiles += (size_t)f0 * ((g.BH + 7) / 8);
             CclChain chain;
             chain.frame_base = f0;
             chain.segoff_base = (b > 0) ? ctx->ccl.segoff + f0 : nullptr;   // left there by sub-batch b-1
@@ -802,8 +805,9 @@ int swb_stage_cc_label(int32_t device, const uint8_t* in, int32_t h, int32_t w, 
         b.cap_rows = cap;
         b.cap_parts = 2 * cap + 4096;
         CU(nullptr, t.alloc(&b.parts, (size_t)b.cap_parts));
-        CU(nullptr, t.alloc(&b.pcount, 2));
-        b.overflow = b.pcount + 1;
+        CU(nullptr, t.alloc(&b.pcount, 3));
+        b.overflow = b.pcount + 2;
+        CU(nullptr, t.alloc(&b.big_tiles, (size_t)(g.BH + 7) / 8));
         CU(nullptr, t.alloc(&b.rootlist, (size_t)cap));
     }
     CU(nullptr, cudaMemcpy(d_in, in, n, cudaMemcpyHostToDevice));

@@ -39,6 +39,8 @@
 //   seg_init      initialise the table rows (frame, label, empty bbox)
 //   props_final   adds every partial sum to its component's table row
 //   write_labels  dense int32 / uint8 label image: bits + parent walk to the tagged root
+#include <algorithm>
+
 #include "swb_internal.cuh"
 
 namespace swb {
@@ -345,19 +347,27 @@ __device__ __forceinline__ void emit_partial(Partial* parts, int idx, int f, int
 // slot claiming and regionprops phases then run one THREAD PER RUN over that dense list, so
 // warps are full instead of having a lane or two busy.  Run ids grow with the block index of
 // the run start, so "link the larger id under the smaller" keeps the minimum block as root.
+//
+// Two sizes of the run list: the common kernel holds up to RUNS_FAST runs (28 KB of shared
+// memory, eight CTAs per SM -- the tile is latency-bound on a few threads' union chains, so
+// resident tiles per SM are what buys throughput); a tile with more runs (dense noise) puts
+// itself on a list and is redone by the RUNS_MAX variant (8 runs per word, the worst case).
 struct LocalSmem {
-    static constexpr int MAXRUNS = 8192;
+    static constexpr int RUNS_FAST = 1536;
+    static constexpr int RUNS_MAX = 8192;
     static constexpr int MAXR = 256;            // components with a shared-memory accumulator
     static constexpr int AB_WORDS = 256 * 6;    // worst case BY * (4 * BX + 2) at BX = 1
-    static constexpr size_t bytes() {
-        return (size_t)2 * AB_WORDS * 4 + 1024 * 2 + (size_t)2 * MAXRUNS * 2 + MAXR * 30 + 64;
+    static constexpr size_t bytes(int maxruns) {
+        return (size_t)2 * AB_WORDS * 4 + 1024 * 2 + (size_t)2 * maxruns * 2 + MAXR * 30 + 64;
     }
 };
 
-template <int BX>
-__global__ void __launch_bounds__(256)
-k_ccl_local(const uint32_t* __restrict__ fbits, Geom g, int* __restrict__ parent, Partial* __restrict__ parts,
-            int* __restrict__ pcount, int cap_parts, int32_t* __restrict__ overflow) {
+// One tile (frame f, block rows tile * BY ...).  Returns false (block-uniform, nothing written)
+// when the tile has more than MAXRUNS runs.
+template <int BX, int MAXRUNS>
+__device__ __forceinline__ bool ccl_local_tile(const uint32_t* __restrict__ fbits, const Geom& g, int* __restrict__ parent,
+                                               Partial* __restrict__ parts, int* __restrict__ pcount, int cap_parts,
+                                               int32_t* __restrict__ overflow, int f, int tile) {
     constexpr int BY = 256 / BX;
     constexpr int WR = BX * 4;               // words per tile row (power of two)
     constexpr int SW = WR + 2;               // + one halo word each side
@@ -367,8 +377,8 @@ k_ccl_local(const uint32_t* __restrict__ fbits, Geom g, int* __restrict__ parent
     uint32_t* sB = sA + LocalSmem::AB_WORDS;                              // [BY][SW] pixel row 2by + 1
     unsigned short* swpre = reinterpret_cast<unsigned short*>(sB + LocalSmem::AB_WORDS);   // [1024] runs before word
     unsigned short* srun = swpre + 1024;                                  // [MAXRUNS] (word << 4) | first block
-    unsigned short* spar = srun + LocalSmem::MAXRUNS;                     // [MAXRUNS] parent run id / TAG | slot
-    uint32_t* st_area = reinterpret_cast<uint32_t*>(spar + LocalSmem::MAXRUNS);
+    unsigned short* spar = srun + MAXRUNS;                                // [MAXRUNS] parent run id / TAG | slot
+    uint32_t* st_area = reinterpret_cast<uint32_t*>(spar + MAXRUNS);
     uint32_t* st_sr = st_area + MAXR;
     uint32_t* st_sc = st_sr + MAXR;
     int* st_minr = reinterpret_cast<int*>(st_sc + MAXR);
@@ -380,8 +390,7 @@ k_ccl_local(const uint32_t* __restrict__ fbits, Geom g, int* __restrict__ parent
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx = tid % BX, ty = tid / BX;
-    const int f = blockIdx.y;
-    const int by0 = blockIdx.x * BY;
+    const int by0 = tile * BY;
     const int by = by0 + ty;
     const int Q = g.wpr4 >> 2;
     const uint32_t* fb = fbits + (long long)f * g.h * g.wpr4;
@@ -419,7 +428,8 @@ k_ccl_local(const uint32_t* __restrict__ fbits, Geom g, int* __restrict__ parent
         if (w < warp) base += t;
         nruns += t;
     }
-    if (nruns == 0) return;                  // empty tile (block-uniform): nothing to write anywhere
+    if (nruns == 0) return true;             // empty tile (block-uniform): nothing to write anywhere
+    if (nruns > MAXRUNS) return false;       // block-uniform: left to the RUNS_MAX variant
     {
         const int wi0 = ty * WR + 4 * tx;    // tile-raster word index
         int r = base;
@@ -564,6 +574,34 @@ k_ccl_local(const uint32_t* __restrict__ fbits, Geom g, int* __restrict__ parent
         } else {
             *overflow = 1;
         }
+    }
+    return true;
+}
+
+// grid = (tiles per frame, T): every tile; tiles with too many runs go on the list
+template <int BX>
+__global__ void __launch_bounds__(256)
+k_ccl_local(const uint32_t* __restrict__ fbits, Geom g, int* __restrict__ parent, Partial* __restrict__ parts,
+            int* __restrict__ pcount, int cap_parts, int32_t* __restrict__ overflow, int* __restrict__ big_tiles,
+            int* __restrict__ big_count) {
+    if (!ccl_local_tile<BX, LocalSmem::RUNS_FAST>(fbits, g, parent, parts, pcount, cap_parts, overflow,
+                                                  (int)blockIdx.y, (int)blockIdx.x)) {
+        if (threadIdx.x == 0) big_tiles[atomicAdd(big_count, 1)] = (int)(blockIdx.y * gridDim.x + blockIdx.x);
+    }
+}
+
+// the listed tiles, with room for the worst case (usually none: the CTAs find an empty list and leave)
+template <int BX>
+__global__ void __launch_bounds__(256)
+k_ccl_local_big(const uint32_t* __restrict__ fbits, Geom g, int* __restrict__ parent, Partial* __restrict__ parts,
+                int* __restrict__ pcount, int cap_parts, int32_t* __restrict__ overflow,
+                const int* __restrict__ big_tiles, const int* __restrict__ big_count, int tiles_per_frame) {
+    const int n = *big_count;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const int t = big_tiles[i];
+        ccl_local_tile<BX, LocalSmem::RUNS_MAX>(fbits, g, parent, parts, pcount, cap_parts, overflow,
+                                                t / tiles_per_frame, t % tiles_per_frame);
+        __syncthreads();                     // shared memory is reused by the next tile
     }
 }
 
@@ -967,15 +1005,23 @@ k_gather_crops(const uint8_t* __restrict__ frames, long long frame_stride, long 
 template <int BX>
 static void launch_local(cudaStream_t s, const uint32_t* fbits, int T, const Geom& g, const CclBuffers& b) {
     constexpr int BY = 256 / BX;
-    dim3 grid((g.BH + BY - 1) / BY, T);
+    const int tiles = (g.BH + BY - 1) / BY;
+    dim3 grid(tiles, T);
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(k_ccl_local<BX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LocalSmem::bytes());
+        cudaFuncSetAttribute(k_ccl_local<BX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)LocalSmem::bytes(LocalSmem::RUNS_FAST));
+        cudaFuncSetAttribute(k_ccl_local_big<BX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)LocalSmem::bytes(LocalSmem::RUNS_MAX));
         configured = true;
     }
-    k_ccl_local<BX><<<grid, 256, LocalSmem::bytes(), s>>>(fbits, g, b.parent, b.parts, b.pcount, b.cap_parts,
-                                                          b.overflow);
-    const int n_boundaries = (g.BH + BY - 1) / BY - 1;
+    int* big_count = b.pcount + 1;
+    k_ccl_local<BX><<<grid, 256, LocalSmem::bytes(LocalSmem::RUNS_FAST), s>>>(
+        fbits, g, b.parent, b.parts, b.pcount, b.cap_parts, b.overflow, b.big_tiles, big_count);
+    const int big_grid = (int)std::min<long long>((long long)tiles * T, 148 * 4);
+    k_ccl_local_big<BX><<<big_grid, 256, LocalSmem::bytes(LocalSmem::RUNS_MAX), s>>>(
+        fbits, g, b.parent, b.parts, b.pcount, b.cap_parts, b.overflow, b.big_tiles, big_count, tiles);
+    const int n_boundaries = tiles - 1;
     if (n_boundaries > 0) {
         const int Q = g.wpr4 >> 2;
         dim3 bgrid((Q + 31) / 32, (n_boundaries + 7) / 8, T);
@@ -999,7 +1045,7 @@ cudaError_t launch_ccl(cudaStream_t s, const uint32_t* fbits, int T, const Geom&
     const bool tiled = Q <= 32;      // a tile spans the full width: frames up to 4096 pixels wide
     const uint32_t* rbase_for_labels = tiled ? nullptr : b.rowcount;
     int launches = 0;
-    cudaMemsetAsync(b.pcount, 0, sizeof(int), s);
+    cudaMemsetAsync(b.pcount, 0, 2 * sizeof(int), s);                  // partial counter, listed-tile counter
     if (!chain) cudaMemsetAsync(b.overflow, 0, sizeof(int32_t), s);    // a chained submit clears it once, before its first sub-batch
     if (tiled) {
         cudaMemsetAsync(b.rowcount, 0, (size_t)2 * T * g.BH * sizeof(uint32_t), s);   // rowcount, rowfill
@@ -1011,7 +1057,7 @@ cudaError_t launch_ccl(cudaStream_t s, const uint32_t* fbits, int T, const Geom&
             case 16: launch_local<16>(s, fbits, T, g, b); break;
             default: launch_local<32>(s, fbits, T, g, b); break;
         }
-        launches += 2;
+        launches += 3;
         mark();
         k_root_count<<<296, 256, 0, s>>>(b.parts, b.pcount, b.cap_parts, g, b.parent, b.rowcount);
     } else {

@@ -74,7 +74,8 @@ struct CclBuffers {
     int cap_rows;
     int32_t* overflow;    // device flag: 1 when total rows > cap_rows (or partials > cap_parts)
     Partial* parts;       // [cap_parts] tile-local regionprops partial sums
-    int* pcount;          // number of partials appended
+    int* pcount;          // [2]: number of partials appended; number of listed (dense) tiles
+    int* big_tiles;       // [T * tiles per frame] tiles with more runs than the common labelling kernel holds
     int* rootlist;        // [cap_rows] roots grouped by block row (tiled path ranking)
     int cap_parts;
 };
