@@ -218,20 +218,8 @@ __device__ __forceinline__ Contacts contacts(uint32_t A, uint32_t P, uint32_t Bp
 
 // Unions between the blocks of group (by, q) and the block row above: only the
 // bottom pixel row (2by - 1) of that row matters.
-__device__ void vertical_links(const Group& gr, const uint32_t* fb, const Geom& g, int by, int q, int* par) {
-    const uint32_t* up = fb + (long long)(2 * by - 1) * g.wpr4 + 4 * q;
-    const uint4 u4 = __ldg(reinterpret_cast<const uint4*>(up));
-    uint32_t U[6];
-    U[1] = u4.x; U[2] = u4.y; U[3] = u4.z; U[4] = u4.w;
-    if ((U[1] | U[2] | U[3] | U[4]) == 0u) {
-        // only the diagonal neighbours outside the group can still touch
-        U[0] = (q > 0 && (gr.A[0] & 1u)) ? up[-1] : 0u;
-        U[5] = (4 * q + 4 < g.wpr4 && (gr.A[3] >> 31)) ? up[4] : 0u;
-        if ((U[0] | U[5]) == 0u) return;
-    } else {
-        U[0] = q > 0 ? up[-1] : 0u;
-        U[5] = 4 * q + 4 < g.wpr4 ? up[4] : 0u;
-    }
+// U[1..4] = the pixel row above the group (2by - 1), U[0] / U[5] = its neighbour words
+__device__ void vertical_links_with(const Group& gr, const uint32_t (&U)[6], const Geom& g, int by, int q, int* par) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const uint32_t A = gr.A[i];
@@ -255,6 +243,23 @@ __device__ void vertical_links(const Group& gr, const uint32_t* fb, const Geom& 
             unite(par, base + k, upbase + k + 1);
         }
     }
+}
+
+__device__ void vertical_links(const Group& gr, const uint32_t* fb, const Geom& g, int by, int q, int* par) {
+    const uint32_t* up = fb + (long long)(2 * by - 1) * g.wpr4 + 4 * q;
+    const uint4 u4 = __ldg(reinterpret_cast<const uint4*>(up));
+    uint32_t U[6];
+    U[1] = u4.x; U[2] = u4.y; U[3] = u4.z; U[4] = u4.w;
+    if ((U[1] | U[2] | U[3] | U[4]) == 0u) {
+        // only the diagonal neighbours outside the group can still touch
+        U[0] = (q > 0 && (gr.A[0] & 1u)) ? up[-1] : 0u;
+        U[5] = (4 * q + 4 < g.wpr4 && (gr.A[3] >> 31)) ? up[4] : 0u;
+        if ((U[0] | U[5]) == 0u) return;
+    } else {
+        U[0] = q > 0 ? up[-1] : 0u;
+        U[5] = 4 * q + 4 < g.wpr4 ? up[4] : 0u;
+    }
+    vertical_links_with(gr, U, g, by, q, par);
 }
 
 __global__ void __launch_bounds__(256)
@@ -296,12 +301,19 @@ k_ccl_boundary(const uint32_t* __restrict__ fbits, Geom g, int tile_rows, int* p
     const int f = blockIdx.z;
     if (q >= (g.wpr4 >> 2) || by >= g.BH) return;
     const uint32_t* fb = fbits + (long long)f * g.h * g.wpr4;
-    const uint4 a4 = __ldg(reinterpret_cast<const uint4*>(fb + (long long)(2 * by) * g.wpr4) + q);
-    if ((a4.x | a4.y | a4.z | a4.w) == 0u) return;
+    // every word this thread can need, in one round of independent loads (the kernel is pure latency)
     Group gr;
     load_group(gr, fb, g, by, q);
+    const uint32_t* up = fb + (long long)(2 * by - 1) * g.wpr4 + 4 * q;
+    const uint4 u4 = __ldg(reinterpret_cast<const uint4*>(up));
+    uint32_t U[6];
+    U[0] = q > 0 ? __ldg(up - 1) : 0u;
+    U[5] = 4 * q + 4 < g.wpr4 ? __ldg(up + 4) : 0u;
+    U[1] = u4.x; U[2] = u4.y; U[3] = u4.z; U[4] = u4.w;
+    if ((gr.A[0] | gr.A[1] | gr.A[2] | gr.A[3]) == 0u) return;
+    if ((U[0] | U[1] | U[2] | U[3] | U[4] | U[5]) == 0u) return;
     int* par = parent + (long long)f * g.BH * g.BW;
-    vertical_links(gr, fb, g, by, q, par);
+    vertical_links_with(gr, U, g, by, q, par);
 }
 
 // ------------------------------------------------------------------------------------
@@ -845,10 +857,12 @@ k_root_place(const Partial* __restrict__ parts, const int* __restrict__ pcount, 
 }
 
 // pass 3: label = 1 + roots in earlier rows + smaller roots in the same row; parent[root] = -label
+// ... and the root's thread initialises its row of the segment table (frame, label, empty sums)
 __global__ void __launch_bounds__(256)
 k_root_rank(const Partial* __restrict__ parts, const int* __restrict__ pcount, int cap_parts, Geom g,
             int* __restrict__ parent, const uint32_t* __restrict__ rowbase, const uint32_t* __restrict__ rowfill,
-            const int32_t* __restrict__ segoff, const int* __restrict__ rootlist, int cap_rows) {
+            const int32_t* __restrict__ segoff, const int* __restrict__ rootlist, int cap_rows, int frame_base,
+            swb_segment* __restrict__ rows) {
     const int n = min(*pcount, cap_parts);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const Partial p = parts[i];
@@ -862,7 +876,23 @@ k_root_rank(const Partial* __restrict__ parts, const int* __restrict__ pcount, i
         int rank = 0;
         for (int j = 0; j < cnt; ++j)
             if (lo + j < cap_rows && rootlist[lo + j] < p.root) ++rank;
-        par[p.root] = -(int)(rowbase[row] + rank + 1);
+        const int label = (int)(rowbase[row] + rank + 1);
+        par[p.root] = -label;
+        const long long r = (long long)segoff[p.frame] + label - 1;
+        if (r < cap_rows) {
+            swb_segment s;
+            s.frame = frame_base + p.frame;
+            s.label = label;
+            s.area = 0;
+            s.bbox[0] = 0x7FFFFFFF;
+            s.bbox[1] = 0x7FFFFFFF;
+            s.bbox[2] = 0;
+            s.bbox[3] = 0;
+            s.reserved = 0;
+            s.sum_row = 0;
+            s.sum_col = 0;
+            rows[r] = s;
+        }
     }
 }
 
@@ -1070,17 +1100,18 @@ cudaError_t launch_ccl(cudaStream_t s, const uint32_t* fbits, int T, const Geom&
     }
     k_ccl_scan<<<(T * 32 + 255) / 256, 256, 0, s>>>(T, g, b.rowcount, b.nseg);
     k_ccl_offsets<<<1, 1024, 0, s>>>(T, b.nseg, b.segoff, chain ? chain->segoff_base : nullptr, b.cap_rows, b.overflow);
-    {
+    if (!tiled) {
         dim3 grid(4, T);
         k_seg_init<<<grid, 256, 0, s>>>(T, chain ? chain->frame_base : 0, b.nseg, b.segoff, b.rows, b.cap_rows);
+        launches += 1;
     }
-    launches += 4;
+    launches += 3;
     if (tiled) {
         uint32_t* rowfill = b.rowcount + (size_t)T * g.BH;
         k_root_place<<<296, 256, 0, s>>>(b.parts, b.pcount, b.cap_parts, g, b.parent, b.rowcount, rowfill, b.segoff,
                                          b.rootlist, b.cap_rows);
         k_root_rank<<<296, 256, 0, s>>>(b.parts, b.pcount, b.cap_parts, g, b.parent, b.rowcount, rowfill, b.segoff,
-                                        b.rootlist, b.cap_rows);
+                                        b.rootlist, b.cap_rows, chain ? chain->frame_base : 0, b.rows);
         mark();
         k_props_final<<<296, 256, 0, s>>>(b.parts, b.pcount, b.cap_parts, g, b.parent, b.segoff, b.rows, b.cap_rows);
         launches += 3;
