@@ -398,9 +398,9 @@ def main():
     # ---- the reference's CPU path on this box's host cores (rank 0, N=1 only)
     cpu = None
     if not args.no_cpu and world == 1:
-        n_cpu = args.cpu_frames or (16 if roi is None and H >= 1080 else 300)
+        n_cpu = args.cpu_frames or (64 if roi is None and H >= 1080 else 300)
         if H > 1080:
-            n_cpu = args.cpu_frames or 4
+            n_cpu = args.cpu_frames or 12
         if cfg.get("classify"):
             n_cpu = args.cpu_frames or 2
         cpu_fps, cpu_dt, _, threads = cpu_baseline_sample(cfg, n_cpu)
