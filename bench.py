@@ -43,6 +43,9 @@ CONFIGS = {
     "1080p_swarm500_classify": dict(H=1080, W=1920, roi=None, N=5, se=3, do_close=False, birds=500, chunk=16,
                                     classify=True),
 }
+# BASELINE.json configs[3]: 16 videos, each with its own chimney ROI, processed concurrently
+CONFIGS["16x1080p_rois_n5_open3"] = dict(H=1080, W=1920, roi=None, N=5, se=3, do_close=False, birds=300, chunk=256,
+                                         videos=16)
 DEFAULT_CONFIG = "1080p_full_n5_open3"
 SEED = 2
 
@@ -206,6 +209,178 @@ def run_reference(args, cfg, name):
     print(json.dumps(line))
 
 
+def video_roi(v, H, W):
+    """ROI of video v: a 2:1 rectangle (generate_crop_region, image_filtering.py:48-51) between
+    200x100 and 640x320, placed by an integer hash so that every run sees the same rectangles."""
+    hsh = (v * 2654435761 + 0x9E3779B9) & 0xFFFFFFFF
+    w = 200 + 8 * (hsh % 56)                       # 200 .. 640, multiples of 8
+    h = w // 2
+    x0 = (hsh >> 8) % (W - w)
+    y0 = (hsh >> 20) % (H - h)
+    return [(int(x0), int(y0)), (int(x0 + w), int(y0 + h))]
+
+
+def run_multi_video(args, cfg, name):
+    """configs[3]: whole videos are dealt round-robin to the GPUs (no temporal split, no
+    collective); on each GPU every video has its own context and CUDA stream, so the small ROI
+    kernels of different videos overlap.  A step = one chunk of every video of this rank."""
+    import torch
+    import torch.distributed as dist
+    import swiftwatcher_b200 as swb
+    from swiftwatcher_b200.pipeline import synth_frames
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    H, W, N, T = cfg["H"], cfg["W"], cfg["N"], cfg["chunk"]
+    halo = N - 1
+    mine = [v for v in range(cfg["videos"]) if v % world == rank]
+    main_stream = torch.cuda.Stream()
+    vids = []
+    for v in mine:
+        roi = video_roi(v, H, W)
+        x = torch.empty((halo + T, H, W, 3), dtype=torch.uint8, device="cuda")
+        synth_frames(SEED, v, 1000 - halo, halo + T, H, W, cfg["birds"], device=local_rank, out=x)
+        ctx = swb.FilterContext((H, W, 3), roi, median_n=N, threshold=15, morph_size=cfg["se"], do_open=True,
+                                do_close=cfg["do_close"], label_mode=args.label_mode, max_frames=T,
+                                max_segments=T * 1024, device=local_rank)
+        st = torch.cuda.Stream()
+        ctx.set_stream(st.cuda_stream)
+        vids.append(dict(v=v, roi=roi, frames=x, ctx=ctx, stream=st, done=torch.cuda.Event()))
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(fork):
+        for d in vids:
+            d["stream"].wait_event(fork)
+            d["ctx"].submit(d["frames"], n_halo=halo)
+
+    for _ in range(args.warmup):
+        fork = torch.cuda.Event()
+        fork.record(main_stream)
+        step(fork)
+    torch.cuda.synchronize()
+    segs = sum(float(d["ctx"].collect()[1].mean()) for d in vids) / max(len(vids), 1)
+
+    sampler = ClockSampler(local_rank)
+    launches0 = sum(d["ctx"].launch_count() for d in vids)
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(main_stream)
+    for _ in range(args.steps):
+        step(ev0)
+    for d in vids:
+        d["done"].record(d["stream"])
+        main_stream.wait_event(d["done"])
+    ev1.record(main_stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    launches = sum(d["ctx"].launch_count() for d in vids) - launches0
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    frames_total = cfg["videos"] * T * args.steps
+    fps = frames_total / (ms * 1e-3)
+    peak, peak_src = measured_peak()
+    px = [(video_roi(v, H, W)[1][0] - video_roi(v, H, W)[0][0]) * (video_roi(v, H, W)[1][1] - video_roi(v, H, W)[0][1])
+          for v in range(cfg["videos"])]
+    alg_per_step = 8 * sum(px) * T                      # all videos, one chunk each
+    path_gbs = alg_per_step * args.steps / (ms * 1e-3) / 1e9 / world
+    # one video alone on one stream, for comparison (what concurrency buys)
+    solo = None
+    if vids:
+        d = vids[0]
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(d["stream"])
+        for _ in range(args.steps):
+            d["ctx"].submit(d["frames"], n_halo=halo)
+        b.record(d["stream"])
+        torch.cuda.synchronize()
+        solo = T * args.steps / (a.elapsed_time(b) * 1e-3)
+
+    # end to end: pinned host frames of every video, ROI staged by swb_submit, tables read back
+    e2e = None
+    if not args.no_e2e:
+        Te = min(T, 64)
+        hosts = []
+        for d in vids:
+            hbuf = torch.empty((halo + Te, H, W, 3), dtype=torch.uint8, pin_memory=True)
+            hbuf.copy_(d["frames"][:halo + Te])
+            hosts.append(hbuf)
+        torch.cuda.synchronize()
+        h2d = d2h = 0
+        for rep_i in range(args.e2e_steps + 1):
+            if rep_i == 1:
+                barrier()
+                t0 = time.perf_counter()
+                h2d = d2h = 0
+            for d, hbuf in zip(vids, hosts):
+                d["ctx"].submit(hbuf, n_halo=halo)
+            for d in vids:
+                rows_h, counts_h = d["ctx"].collect()
+                d2h += rows_h.nbytes + counts_h.nbytes + 4 * (Te + 1)
+                (x0, y0), (x1, y1) = d["roi"]
+                x0a = x0 & ~31
+                wa = ((x1 + 31) & ~31) - x0a
+                h2d += (halo + Te) * (y1 - y0) * min(wa, W - x0a) * 3
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        e2e = {"value": cfg["videos"] * Te * args.e2e_steps / dt, "unit": "frames/s",
+               "h2d_bytes_per_step": h2d // max(args.e2e_steps, 1), "d2h_bytes_per_step": d2h // max(args.e2e_steps, 1),
+               "steps": args.e2e_steps, "frames_per_video_per_step": Te,
+               "note": "pinned host frames of every video -> swb_submit (ROI staged over PCIe) -> swb_collect"}
+        del hosts
+
+    cpu = None
+    if not args.no_cpu and world == 1:
+        c1 = dict(cfg)
+        c1["roi"] = video_roi(0, H, W)
+        n_cpu = args.cpu_frames or 200
+        cpu_fps, cpu_dt, _, threads = cpu_baseline_sample(c1, n_cpu)
+        cpu = {"value": cpu_fps, "unit": "frames/s", "cores": threads, "kind": "port",
+               "sample": "%d frames of video 0 (ROI %r, %.1f s) through oracle/reference_path.py; the reference "
+                         "processes its videos one after another" % (n_cpu, c1["roi"], cpu_dt)}
+    if rank == 0:
+        line = {
+            "metric": "frames/sec (filter + label hot path)", "value": fps, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": name, "frame": [H, W, 3], "videos": cfg["videos"],
+                       "videos_per_gpu": len(mine), "rois": [video_roi(v, H, W) for v in range(cfg["videos"])],
+                       "median_n": N, "threshold": 15, "morph": cfg["se"], "labels": args.label_mode,
+                       "frames_per_video_per_step": T, "segments_per_frame": round(segs, 1),
+                       "l2": "full 1080p frames of all videos resident (%.1f GB on this GPU) >> 126 MB L2; no flush"
+                             % (len(mine) * (halo + T) * H * W * 3 / 1e9),
+                       "partition": "whole videos round-robin over GPUs, one context + stream per video, no collective"},
+            "roofline": {"bound": "hbm", "kernel": "whole path (launch/latency bound at ROI size)",
+                         "achieved": round(path_gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(path_gbs / peak, 4),
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_per_step,
+                         "single_video_fps_alone": solo},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line))
+    for d in vids:
+        d["ctx"].close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -226,7 +401,12 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     if args.impl == "reference":
+        if cfg.get("videos"):
+            cfg["roi"] = video_roi(0, cfg["H"], cfg["W"])
         run_reference(args, cfg, args.config)
+        return
+    if cfg.get("videos"):
+        run_multi_video(args, cfg, args.config)
         return
 
     import torch
