@@ -173,6 +173,12 @@ int swb_stage_cc_label(int32_t device, const uint8_t* in, int32_t h, int32_t w,
 int swb_stage_regionprops(int32_t device, const void* labels, int32_t elem_size,
                           int32_t h, int32_t w, swb_segment* rows, int32_t cap, int32_t* n_rows);
 
+/* Page-locked host memory for frame ingest (io_video.py:11-165 decodes frames into host
+ * arrays; frames decoded into these buffers reach the device by DMA at full PCIe speed
+ * and asynchronously).  Portable across devices.  Needs a CUDA device like everything else. */
+int swb_host_alloc(void** ptr, uint64_t bytes);
+int swb_host_free(void* ptr);
+
 /* Synthetic video (bench / tests): frames t0..t0+n-1 of the seeded generator,
  * bit-identical to oracle/synth.py.  dst: [n][h][w][3] uint8. */
 int swb_synth_frames(int32_t device, uint8_t* dst, int32_t mem_kind, uint32_t seed, uint32_t video,

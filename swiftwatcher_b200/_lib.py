@@ -69,6 +69,8 @@ SYMBOLS = {
     "swb_stage_grey_morph": (C.c_int, [_I32, _P, _I32, _I32, _I32, _I32, _I32, _P]),
     "swb_stage_cc_label": (C.c_int, [_I32, _P, _I32, _I32, _P, _P, C.POINTER(_I32)]),
     "swb_stage_regionprops": (C.c_int, [_I32, _P, _I32, _I32, _I32, _P, _I32, C.POINTER(_I32)]),
+    "swb_host_alloc": (C.c_int, [C.POINTER(_P), C.c_uint64]),
+    "swb_host_free": (C.c_int, [_P]),
     "swb_synth_frames": (C.c_int, [_I32, _P, _I32, _U32, _U32, _I32, _I32, _I32, _I32, _I32]),
 }
 
@@ -122,3 +124,31 @@ def ptr(a):
     if hasattr(a, "data_ptr"):
         return C.c_void_p(a.data_ptr())
     raise TypeError("cannot take the address of %r" % type(a))
+
+
+class _PinnedOwner:
+    """Owns one swb_host_alloc allocation; freed when the last numpy view goes away."""
+
+    def __init__(self, nbytes):
+        self.ptr = _P()
+        check(load().swb_host_alloc(C.byref(self.ptr), nbytes))
+        self.nbytes = nbytes
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                load().swb_host_free(self.ptr)
+                self.ptr = _P()
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.uint8):
+    """numpy array in page-locked host memory (swb_host_alloc): the host side of the
+    frame ingest — decode into it, submit it, and the copy to the device is a DMA."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    owner = _PinnedOwner(max(n, 1))
+    buf = (C.c_uint8 * max(n, 1)).from_address(owner.ptr.value)
+    buf._owner = owner                      # keeps the allocation alive as long as any view exists
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)

@@ -860,6 +860,24 @@ int swb_stage_regionprops(int32_t device, const void* labels, int32_t elem_size,
     return SWB_OK;
 }
 
+int swb_host_alloc(void** ptr, uint64_t bytes) {
+    if (!ptr || bytes == 0) return fail(nullptr, SWB_ERR_INVALID, "bad argument");
+    *ptr = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0)
+        return fail(nullptr, SWB_ERR_CUDA, "no CUDA device available; libswb200 has no CPU path");
+    cudaError_t e = cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) return fail(nullptr, SWB_ERR_CUDA, "cudaHostAlloc(%llu): %s", (unsigned long long)bytes, cudaGetErrorString(e));
+    return SWB_OK;
+}
+
+int swb_host_free(void* ptr) {
+    if (!ptr) return SWB_OK;
+    cudaError_t e = cudaFreeHost(ptr);
+    if (e != cudaSuccess) return fail(nullptr, SWB_ERR_CUDA, "cudaFreeHost: %s", cudaGetErrorString(e));
+    return SWB_OK;
+}
+
 int swb_synth_frames(int32_t device, uint8_t* dst, int32_t mem_kind, uint32_t seed, uint32_t video, int32_t t0,
                      int32_t n, int32_t h, int32_t w, int32_t n_birds) {
     if (!dst || n <= 0 || h <= 0 || w <= 0 || n_birds < 0 || n > 65535) return fail(nullptr, SWB_ERR_INVALID, "bad argument");

@@ -1037,13 +1037,12 @@ static void launch_local(cudaStream_t s, const uint32_t* fbits, int T, const Geo
     constexpr int BY = 256 / BX;
     const int tiles = (g.BH + BY - 1) / BY;
     dim3 grid(tiles, T);
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    if (once.need()) {
         cudaFuncSetAttribute(k_ccl_local<BX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)LocalSmem::bytes(LocalSmem::RUNS_FAST));
         cudaFuncSetAttribute(k_ccl_local_big<BX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)LocalSmem::bytes(LocalSmem::RUNS_MAX));
-        configured = true;
     }
     int* big_count = b.pcount + 1;
     k_ccl_local<BX><<<grid, 256, LocalSmem::bytes(LocalSmem::RUNS_FAST), s>>>(

@@ -825,11 +825,10 @@ cudaError_t launch_v2_occ(cudaStream_t s, const FrameSrc& src, int T, const Geom
     constexpr int TB = 2 * L * C;
     constexpr int S = (N == 5) ? 4 : (N == 9 ? 6 : 8);   // grouped loops: stages = frames per unrolled body
     constexpr int SMEM = S * CONSUMERS * TB + 2 * S * 8 + (N == 9 ? 3 * CONSUMERS * 16 : 0);
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    if (once.need()) {
         cudaError_t e = cudaFuncSetAttribute(k_fg_bits_v2<N, C, S, L, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     const int G = g.h * (g.wa / (2 * L));
     const int n_col_blocks = (G + CONSUMERS - 1) / CONSUMERS;

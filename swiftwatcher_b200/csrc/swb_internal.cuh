@@ -98,6 +98,20 @@ cudaError_t launch_gather_crops_n(cudaStream_t s, const uint8_t* frames, long lo
                                   int roi_x0, int roi_y0, const swb_segment* rows, int n_rows,
                                   int crop, uint8_t* dst);
 
+// cudaFuncSetAttribute is per device: remember which devices a kernel's dynamic shared-memory
+// limit has been raised on (one process may drive several GPUs, one context each).
+struct PerDeviceOnce {
+    unsigned long long done = 0;   // bit d: configured on device d (d < 64)
+    bool need() {
+        int d = 0;
+        cudaGetDevice(&d);
+        const unsigned long long bit = 1ull << (d & 63);
+        if (done & bit) return false;
+        done |= bit;
+        return true;
+    }
+};
+
 // single-stage kernels (stages.cu)
 cudaError_t launch_stage_gray(cudaStream_t s, const uint8_t* bgr, int h, int w, uint8_t* out);
 cudaError_t launch_stage_median(cudaStream_t s, const uint8_t* stack, int n, int h, int w, uint8_t* out);

@@ -25,6 +25,7 @@ from collections import OrderedDict, deque
 import numpy as np
 
 from . import image_filtering as img
+from ._lib import pinned_empty
 from .pipeline import FilterContext, props_from_rows
 
 
@@ -81,6 +82,21 @@ class FrameQueue(deque):
                             device=device)
         self._ctx = None
         self._ctx_key = None
+        self._pinned = [None, None]
+        self._pinned_cur = 0
+
+    def pinned_batch(self, frame_shape, n=None):
+        """A fresh [n, H, W(, 3)] uint8 batch in page-locked host memory (swb_host_alloc), oldest
+        frame first: readers decode straight into its rows (``reader.get_n_frames(n, out=batch)``)
+        and ``segment_queue`` submits it without another copy.  Two buffers alternate, so the
+        frames of the previous batch (e.g. the tracker's cached frame) stay intact."""
+        n = self.maxlen if n is None else n
+        shape = (self.maxlen,) + tuple(frame_shape)
+        self._pinned_cur ^= 1
+        k = self._pinned_cur
+        if self._pinned[k] is None or self._pinned[k].shape != shape:
+            self._pinned[k] = pinned_empty(shape)
+        return self._pinned[k][:n]
 
     def is_empty(self):
         return len(self) == 0
@@ -140,7 +156,20 @@ class FrameQueue(deque):
             return
         frames = self.get_queue()                 # index 0 = newest
         ctx = self._context(frames[0].shape, crop_region)
-        batch = np.ascontiguousarray(np.stack(frames[::-1]))   # oldest first
+        # oldest first, in pinned memory; frames that were decoded into the current batch are in place
+        def address(a):
+            return a.__array_interface__["data"][0]
+        cur = self._pinned[self._pinned_cur]
+        ordered = frames[::-1]
+        in_place = (cur is not None and len(ordered) <= len(cur) and tuple(cur.shape[1:]) == tuple(ordered[0].shape)
+                    and all(isinstance(f, np.ndarray) and f.dtype == np.uint8 and f.flags["C_CONTIGUOUS"]
+                            and address(f) == address(cur[i]) for i, f in enumerate(ordered)))
+        if in_place:
+            batch = cur[:len(ordered)]
+        else:
+            batch = self.pinned_batch(ordered[0].shape, len(ordered))
+            for i, f in enumerate(ordered):
+                np.copyto(batch[i], f)
         ctx.submit(batch)                          # history carried across batches
         rows, counts = ctx.collect()
         masks = ctx.masks()
