@@ -527,9 +527,11 @@ def main():
         torch.cuda.synchronize()
         roofline["classifier"] = {"crops_per_s": round(4096 / (c0.elapsed_time(c1) * 1e-3), 1),
                                   "segments_per_frame": round(segs_per_frame, 1),
-                                  "note": "torchvision SqueezeNet1.0 as in the reference (float32, cuDNN, library code), "
-                                          "[B,3,224,224] inputs built from device-gathered 24x24 crops; the hot-path "
-                                          "kernels in `kernels` are the filtering + labelling part of the step"}
+                                  "note": "torchvision SqueezeNet1.0 weights and layers as in the reference (float32, "
+                                          "cuDNN, library code), evaluated on the window of positions the device-gathered "
+                                          "24x24 crop can influence + cached blank-canvas activations (WindowedSqueezeNet: "
+                                          "same scores as the padded 224x224 forward pass to 1e-4); the hot-path kernels "
+                                          "in `kernels` are the filtering + labelling part of the step"}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:

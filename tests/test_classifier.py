@@ -64,6 +64,25 @@ def test_batched_call_equals_per_segment_loop_cpu():
     assert clf(a[:0]) == []
 
 
+def test_windowed_evaluation_equals_the_full_forward_pass():
+    """WindowedSqueezeNet computes each layer only where the 24x24 crop can matter and takes
+    the rest from the blank canvas: same scores as model(x) on the padded 224x224 canvas."""
+    from swiftwatcher_b200.segment_classification import SegmentClassifier
+    rng = np.random.default_rng(5)
+    crops = rng.integers(0, 256, size=(12, 24, 24, 3), dtype=np.uint8)
+    crops[0] = 0
+    crops[1] = 255
+    states = [rc.random_state_dict(6)]
+    if os.path.exists(os.path.join(REF, "swiftwatcher", "model.pt")):
+        states.append(torch.load(os.path.join(REF, "swiftwatcher", "model.pt"), map_location="cpu"))
+    for sd in states:
+        full = SegmentClassifier(sd, device="cpu", windowed=False)
+        win = SegmentClassifier(sd, device="cpu", windowed=True)
+        a, b = full.scores(crops), win.scores(crops)
+        assert torch.allclose(a, b, rtol=TOL, atol=TOL), (a - b).abs().max()
+        assert a.abs().max() > 0.1                     # not a dead network
+
+
 def test_empty_crop_is_an_error():
     from swiftwatcher_b200.segment_classification import SegmentClassifier
     clf = SegmentClassifier(rc.random_state_dict(3), device="cpu")
@@ -147,6 +166,10 @@ def test_gpu_batched_scores_and_device_crops():
     decided = margin > 10 * TOL
     assert decided.sum() > 5 and 0 < pred_ref[decided].sum() < decided.sum()
     assert np.array_equal(keep_dev[same][decided], pred_ref[decided])
+    full = SegmentClassifier(sd, device="cuda:0", batch_size=64, windowed=False)
+    assert clf.windowed is not None and full.windowed is None
+    assert torch.allclose(full.scores(crops[same]), exp, rtol=TOL, atol=TOL)   # plain batched forward pass
+    assert torch.allclose(full.scores(crops[same]), got, rtol=TOL, atol=TOL)   # == windowed evaluation
     segs = [Seg(crops[i].cpu().numpy(), 9) for i in same]
     kept = clf(segs)
     kept_idx = np.zeros(len(segs), dtype=bool)
