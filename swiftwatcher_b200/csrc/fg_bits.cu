@@ -516,39 +516,45 @@ k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t on
     __syncthreads();
 
     if (tid >= CONSUMERS) {
-        // ===== producer warp: one elected lane streams this CTA's slice of every frame =====
+        // ===== producer warp: streams this CTA's slice of every frame =====
         // (groups per row and per CTA are multiples of 4, so every copy is 16-byte granular)
-        if (tid != CONSUMERS) return;
+        const int lane = tid - CONSUMERS;
         const int ngroups = min(CONSUMERS, G - g0);
         const uint32_t bytes = (uint32_t)(ngroups * TB);
+        const bool contiguous = (src.pitch == (long long)gpr * TB);
+        if (contiguous && lane != 0) return;          // one bulk copy per frame: one lane is enough
+        // Rows of a cropped ROI are not adjacent in memory: the slice is one copy per row segment.
+        // The lanes of the warp issue them side by side (lane i takes segments i, i + 32, ...):
+        // a single lane issuing 12+ small copies per frame was slower than the eight consumer warps.
+        const int r0 = g0 / gpr, c0 = g0 - r0 * gpr;
+        const int len0 = min(gpr - c0, ngroups);      // first segment (the rest of row r0)
+        const int nseg = contiguous ? 1 : 1 + (ngroups - len0 + gpr - 1) / gpr;
         for (int p = 0; p < n_total; ++p) {
             const int st = p % S;
             if (p >= S) mbar_wait(&empty[st], (uint32_t)((p / S - 1) & 1));
             int j = min(j_first + p, T - 1);
-            const uint8_t* fr;
-            long long pitch;
             uint8_t* dst = smem + st * STAGE_BYTES;
             if (j < 0 && src.hist_valid) {                  // carried history: compact gray frames
-                const uint8_t* hf = src.hist + (long long)(j + (N - 1)) * h * wa;
-                mbar_arrive_expect_tx(&full[st], (uint32_t)(ngroups * PPT));
-                bulk_g2s(dst, hf + (long long)g0 * PPT, (uint32_t)(ngroups * PPT), &full[st]);
+                if (lane == 0) {
+                    const uint8_t* hf = src.hist + (long long)(j + (N - 1)) * h * wa;
+                    mbar_arrive_expect_tx(&full[st], (uint32_t)(ngroups * PPT));
+                    bulk_g2s(dst, hf + (long long)g0 * PPT, (uint32_t)(ngroups * PPT), &full[st]);
+                }
                 continue;
             }
             if (j < -src.n_inline_halo) j = -src.n_inline_halo;   // replicate the earliest frame
-            pitch = src.pitch;
-            fr = src.cur + (long long)j * src.frame_stride;
-            mbar_arrive_expect_tx(&full[st], bytes);
-            if (pitch == (long long)gpr * TB) {             // rows are contiguous
+            const uint8_t* fr = src.cur + (long long)j * src.frame_stride;
+            if (contiguous) {
+                mbar_arrive_expect_tx(&full[st], bytes);
                 bulk_g2s(dst, fr + (long long)g0 * TB, bytes, &full[st]);
             } else {
-                int r = g0 / gpr, c = g0 - r * gpr, rem = ngroups;
-                while (rem > 0) {
-                    const int n = min(gpr - c, rem);
-                    bulk_g2s(dst, fr + (long long)r * pitch + (long long)c * TB, (uint32_t)(n * TB), &full[st]);
-                    dst += n * TB;
-                    rem -= n;
-                    ++r;
-                    c = 0;
+                if (lane == 0) mbar_arrive_expect_tx(&full[st], bytes);
+                __syncwarp();                               // the expectation is posted before any copy can complete
+                for (int i = lane; i < nseg; i += 32) {
+                    const int off = (i == 0) ? 0 : len0 + (i - 1) * gpr;      // first group of the segment within the slice
+                    const int n = (i == 0) ? len0 : min(gpr, ngroups - off);
+                    bulk_g2s(dst + off * TB, fr + (long long)(r0 + i) * src.pitch + (long long)(i == 0 ? c0 : 0) * TB,
+                             (uint32_t)(n * TB), &full[st]);
                 }
             }
         }
