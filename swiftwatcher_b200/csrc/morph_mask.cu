@@ -63,12 +63,138 @@ __device__ __forceinline__ uint32_t expand4(uint32_t nibble) {
     return d;
 }
 
+// One warp, one strip of rows.  INTERIOR: every row the strip touches (its own rows and the
+// vertical halo of every stage) lies inside the image, so no row needs the border fill and
+// the per-row validity tests disappear; DX0: the raw bit columns are already ROI-aligned
+// (full-frame ROI), so there is no realignment shift and no extra edge word.
+// The row loop is unrolled by the window height 2R+1: a stage's window is "the last 2R+1
+// horizontally filtered rows", AND / OR do not care about their order, so row r simply
+// overwrites slot r mod (2R+1) — a static register after unrolling, no rotation moves.
+template <int R, int PAT, bool INTERIOR, bool DX0>
+__device__ __forceinline__ void morph_strip(const uint32_t* __restrict__ raw_f, const Geom& g, uint32_t* __restrict__ fbits,
+                                            uint8_t* __restrict__ mask, int f, int slab, int lane, int y0) {
+    constexpr int NOPS = n_ops(PAT);
+    constexpr int NW = NOPS > 0 ? NOPS : 1;
+    constexpr int HR = NOPS * R;   // rows of vertical halo
+    constexpr int SR = strip_rows(R, PAT);
+    constexpr int W = 2 * R + 1;
+    const int j = slab * SLAB + lane - 1;                    // this lane's word
+    const uint32_t Vcol = colmask(j, g.w, g.wpr);
+    const bool in_raw = (j >= 0 && j < g.wpr_raw);
+    const bool in_raw_next = (j + 1 >= 0 && j + 1 < g.wpr_raw);
+    constexpr uint32_t fill0 = (NOPS > 0 && op_is_erode(PAT, 0)) ? 0xFFFFFFFFu : 0u;
+    // what a stage's output reads as outside the image columns: the identity of the next stage
+    uint32_t fillc[NW];
+#pragma unroll
+    for (int s = 0; s < NW; ++s)
+        fillc[s] = (s + 1 < NOPS && op_is_erode(PAT, s + 1)) ? ~Vcol : 0u;
+
+    uint32_t win[NW][W];
+#pragma unroll
+    for (int s = 0; s < NW; ++s)
+#pragma unroll
+        for (int i = 0; i < W; ++i) win[s][i] = 0u;
+
+    const int y_end = min(y0 + SR, g.h);
+    const int y_stop = y_end + HR;
+    // mask output: lane -> two 16-byte chunks of the slab's row
+    const bool st_bits = lane >= 1 && lane <= SLAB && j < g.wpr4;
+    bool st_mask[2];
+    int src_lane[2];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int wi = (half * 32 + lane) >> 1;              // word within the slab
+        st_mask[half] = mask != nullptr && wi < SLAB && slab * SLAB + wi < g.wpr;
+        src_lane[half] = wi < SLAB ? wi + 1 : 31;
+    }
+    // raw words of row y (this lane's word; lane 31 also fetches the word after it), 0 outside the image
+    auto fetch = [&](int y, uint32_t& lo, uint32_t& edge) {
+        lo = 0u;
+        edge = 0u;
+        if (INTERIOR || (unsigned)y < (unsigned)g.h) {
+            const uint32_t* rowp = raw_f + (long long)y * g.wpr_raw;
+            if (in_raw) lo = __ldg(rowp + j);
+            if (!DX0 && lane == 31 && in_raw_next) edge = __ldg(rowp + j + 1);
+        }
+    };
+    uint32_t lo_n, edge_n;
+    fetch(y0 - HR, lo_n, edge_n);
+    const long long orow0 = (long long)f * g.h;
+    for (int base = y0 - HR; base < y_stop; base += W) {
+#pragma unroll
+        for (int u = 0; u < W; ++u) {
+            const int yin = base + u;
+            if (yin >= y_stop) break;                        // warp-uniform
+            // ---- raw row (prefetched one row ahead), realigned to ROI columns, border filled for the first op
+            const uint32_t lo = lo_n, edge = edge_n;
+            if (INTERIOR || yin + 1 < y_stop) fetch(yin + 1, lo_n, edge_n);
+            uint32_t v;
+            if constexpr (DX0) {
+                v = lo;
+            } else {
+                uint32_t hi = __shfl_down_sync(0xFFFFFFFFu, lo, 1);
+                if (lane == 31) hi = edge;
+                v = __funnelshift_r(lo, hi, g.dx);
+            }
+            uint32_t cur;
+            if constexpr (INTERIOR) {
+                cur = (v & Vcol) | (~Vcol & fill0);
+            } else {
+                const uint32_t V0 = ((unsigned)yin < (unsigned)g.h) ? Vcol : 0u;
+                cur = (v & V0) | (~V0 & fill0);
+            }
+            // ---- erosion / dilation chain: stage s emits row yin - (s + 1) * R
+#pragma unroll
+            for (int s = 0; s < NOPS; ++s) {
+                const bool erode = op_is_erode(PAT, s);
+                // lanes 0 / 31 have no neighbour on one side: whatever they read only spoils the far R
+                // bits of the halo word per stage, which no output word ever looks at
+                const uint32_t l = __shfl_up_sync(0xFFFFFFFFu, cur, 1);
+                const uint32_t r = __shfl_down_sync(0xFFFFFFFFu, cur, 1);
+                win[s][u] = hop<R>(l, cur, r, erode);
+                uint32_t acc = win[s][0];
+#pragma unroll
+                for (int i = 1; i < W; ++i) acc = erode ? (acc & win[s][i]) : (acc | win[s][i]);
+                if constexpr (INTERIOR) {
+                    cur = (acc & Vcol) | fillc[s];
+                } else {
+                    const int ys = yin - (s + 1) * R;
+                    const bool rv = (unsigned)ys < (unsigned)g.h;
+                    const uint32_t fill_next = (s + 1 < NOPS && op_is_erode(PAT, s + 1)) ? 0xFFFFFFFFu : 0u;
+                    cur = rv ? ((acc & Vcol) | fillc[s]) : fill_next;
+                }
+            }
+            // ---- outputs for row yin - HR
+            const int yout = yin - HR;
+            if (yout < y0) continue;                             // warp-uniform (pipeline warm-up)
+            const long long orow = orow0 + yout;
+            if (st_bits) fbits[orow * g.wpr4 + j] = cur;
+            if (mask != nullptr) {
+                uint8_t* mrow = mask + orow * g.mpitch + (long long)slab * (SLAB * 32);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int c = half * 32 + lane;              // 16-byte chunk of the slab's row
+                    const uint32_t word = __shfl_sync(0xFFFFFFFFu, cur, src_lane[half]);
+                    if (st_mask[half]) {
+                        const uint32_t b16 = (word >> ((c & 1) * 16)) & 0xFFFFu;
+                        uint4 o;
+                        o.x = expand4(b16 & 0xFu);
+                        o.y = expand4((b16 >> 4) & 0xFu);
+                        o.z = expand4((b16 >> 8) & 0xFu);
+                        o.w = expand4(b16 >> 12);
+                        __stcs(reinterpret_cast<uint4*>(mrow + c * 16), o);
+                    }
+                }
+            }
+        }
+    }
+}
+
 template <int R, int PAT>
 __global__ void __launch_bounds__(32 * WPB)
 k_morph_mask(const uint32_t* __restrict__ raw_bits, Geom g, uint32_t* __restrict__ fbits,
              uint8_t* __restrict__ mask) {
-    constexpr int NOPS = n_ops(PAT);
-    constexpr int HR = NOPS * R;   // rows of vertical halo
+    constexpr int HR = n_ops(PAT) * R;
     constexpr int SR = strip_rows(R, PAT);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -76,88 +202,14 @@ k_morph_mask(const uint32_t* __restrict__ raw_bits, Geom g, uint32_t* __restrict
     const int f = blockIdx.z;
     const int y0 = (blockIdx.y * WPB + warp) * SR;
     if (y0 >= g.h) return;                                   // warp-uniform
-    const int j = slab * SLAB + lane - 1;                    // this lane's word
-    const uint32_t Vcol = colmask(j, g.w, g.wpr);
-    const bool in_raw = (j >= 0 && j < g.wpr_raw);
-    const bool in_raw_next = (j + 1 >= 0 && j + 1 < g.wpr_raw);
     const uint32_t* raw_f = raw_bits + (long long)f * g.h * g.wpr_raw;
-    constexpr uint32_t fill0 = (NOPS > 0 && op_is_erode(PAT, 0)) ? 0xFFFFFFFFu : 0u;
-
-    uint32_t win[NOPS > 0 ? NOPS : 1][2 * R + 1];
-#pragma unroll
-    for (int s = 0; s < (NOPS > 0 ? NOPS : 1); ++s)
-#pragma unroll
-        for (int i = 0; i < 2 * R + 1; ++i) win[s][i] = 0u;
-
-    const int y_end = min(y0 + SR, g.h);
-    // raw words of row y (this lane's word; lane 31 also fetches the word after it), 0 outside the image
-    auto fetch = [&](int y, uint32_t& lo, uint32_t& edge) {
-        lo = 0u;
-        edge = 0u;
-        if ((unsigned)y < (unsigned)g.h) {
-            const uint32_t* rowp = raw_f + (long long)y * g.wpr_raw;
-            if (in_raw) lo = __ldg(rowp + j);
-            if (lane == 31 && in_raw_next) edge = __ldg(rowp + j + 1);
-        }
-    };
-    uint32_t lo_n, edge_n;
-    fetch(y0 - HR, lo_n, edge_n);
-    for (int yin = y0 - HR; yin < y_end + HR; ++yin) {
-        // ---- raw row (prefetched one row ahead), realigned to ROI columns, border filled for the first op
-        const bool rowvalid = (unsigned)yin < (unsigned)g.h;
-        const uint32_t lo = lo_n, edge = edge_n;
-        fetch(yin + 1, lo_n, edge_n);
-        uint32_t hi = __shfl_down_sync(0xFFFFFFFFu, lo, 1);
-        if (lane == 31) hi = edge;
-        const uint32_t v = rowvalid ? (__funnelshift_r(lo, hi, g.dx) & Vcol) : 0u;
-        const uint32_t V0 = rowvalid ? Vcol : 0u;
-        uint32_t cur = v | (~V0 & fill0);
-
-        // ---- erosion / dilation chain: stage s emits row yin - (s + 1) * R
-#pragma unroll
-        for (int s = 0; s < NOPS; ++s) {
-            const bool erode = op_is_erode(PAT, s);
-            const uint32_t ident = erode ? 0xFFFFFFFFu : 0u;
-            uint32_t l = __shfl_up_sync(0xFFFFFFFFu, cur, 1);
-            uint32_t r = __shfl_down_sync(0xFFFFFFFFu, cur, 1);
-            if (lane == 0) l = ident;
-            if (lane == 31) r = ident;
-            const uint32_t hrow = hop<R>(l, cur, r, erode);
-#pragma unroll
-            for (int i = 0; i < 2 * R; ++i) win[s][i] = win[s][i + 1];
-            win[s][2 * R] = hrow;
-            uint32_t acc = win[s][0];
-#pragma unroll
-            for (int i = 1; i < 2 * R + 1; ++i) acc = erode ? (acc & win[s][i]) : (acc | win[s][i]);
-            const int ys = yin - (s + 1) * R;
-            const uint32_t Vs = ((unsigned)ys < (unsigned)g.h) ? Vcol : 0u;
-            const uint32_t fill_next = (s + 1 < NOPS && op_is_erode(PAT, s + 1)) ? 0xFFFFFFFFu : 0u;
-            cur = (acc & Vs) | (~Vs & fill_next);
-        }
-
-        // ---- outputs for row yin - HR
-        const int yout = yin - HR;
-        if (yout < y0) continue;                             // warp-uniform (pipeline warm-up)
-        const long long orow = (long long)f * g.h + yout;
-        if (lane >= 1 && lane <= SLAB && j < g.wpr4) fbits[orow * g.wpr4 + j] = cur;
-        if (mask != nullptr) {
-            uint8_t* mrow = mask + orow * g.mpitch + (long long)slab * (SLAB * 32);
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int c = half * 32 + lane;              // 16-byte chunk of the slab's row
-                const int wi = c >> 1;                       // word within the slab
-                const uint32_t word = __shfl_sync(0xFFFFFFFFu, cur, wi < SLAB ? wi + 1 : 31);
-                if (wi < SLAB && slab * SLAB + wi < g.wpr) {
-                    const uint32_t b16 = (word >> ((c & 1) * 16)) & 0xFFFFu;
-                    uint4 o;
-                    o.x = expand4(b16 & 0xFu);
-                    o.y = expand4((b16 >> 4) & 0xFu);
-                    o.z = expand4((b16 >> 8) & 0xFu);
-                    o.w = expand4(b16 >> 12);
-                    __stcs(reinterpret_cast<uint4*>(mrow + c * 16), o);
-                }
-            }
-        }
+    const bool interior = (y0 - HR >= 0) && (y0 + SR + HR <= g.h);   // warp-uniform
+    if (g.dx == 0) {
+        if (interior) morph_strip<R, PAT, true, true>(raw_f, g, fbits, mask, f, slab, lane, y0);
+        else morph_strip<R, PAT, false, true>(raw_f, g, fbits, mask, f, slab, lane, y0);
+    } else {
+        if (interior) morph_strip<R, PAT, true, false>(raw_f, g, fbits, mask, f, slab, lane, y0);
+        else morph_strip<R, PAT, false, false>(raw_f, g, fbits, mask, f, slab, lane, y0);
     }
 }
 
