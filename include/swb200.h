@@ -59,8 +59,18 @@ typedef struct swb_config {
     int32_t out_flags;       /* SWB_OUT_MASK | SWB_OUT_LABELS                                */
     int32_t max_frames;      /* max output frames per submit                                 */
     int32_t max_segments;    /* max segment rows per submit (0 = 1024 per frame)             */
-    int32_t reserved[3];
+    int32_t bg_model;        /* SWB_BG_MEDIAN (rolling median, BASELINE.json) or SWB_BG_RPCA */
+    int32_t reserved[2];
 } swb_config;
+
+/* Background models.  SWB_BG_RPCA is the reference's own localisation (rpca + bilateral_blur,
+ * image_filtering.py:220-307, data_structures.py:191-196): every submit is one batch of
+ * n_frames <= 32 frames (the reference's queue holds 21) that is decomposed on its own — no
+ * temporal history, n_halo is ignored, median_n is unused — then bilateralFilter(7, 15, 1),
+ * threshold, opening and labelling as usual.  swb_submit synchronises in this mode (the
+ * stopping test of the IALM iteration runs on the host). */
+#define SWB_BG_MEDIAN 0
+#define SWB_BG_RPCA   1
 
 /* One row of the per-frame segment table: what skimage.measure.regionprops
  * (image_filtering.py:332-335) exposes and swiftwatcher consumes.
@@ -172,6 +182,19 @@ int swb_stage_cc_label(int32_t device, const uint8_t* in, int32_t h, int32_t w,
  * label image (elem_size 1 or 4).  Rows ordered by label. */
 int swb_stage_regionprops(int32_t device, const void* labels, int32_t elem_size,
                           int32_t h, int32_t w, swb_segment* rows, int32_t cap, int32_t* n_rows);
+
+/* rpca, image_filtering.py:220-253, on a stack of n gray frames [n][h][w] (column k of the
+ * reference's matrix = frame k, i.e. pass the frames in the order the reference would):
+ * out[k] = clip(-E, 0, 255) as uint8; iters = IALM iterations taken (may be NULL). */
+int swb_stage_rpca(int32_t device, const uint8_t* frames, int32_t n, int32_t h, int32_t w,
+                   uint8_t* out, int32_t* iters);
+/* bilateral_blur, image_filtering.py:304-307 = cv2.bilateralFilter(frame, d, sigma_color,
+ * sigma_space) for an 8-bit single-channel image, d <= 7. */
+int swb_stage_bilateral(int32_t device, const uint8_t* in, int32_t h, int32_t w, int32_t d,
+                        double sigma_color, double sigma_space, uint8_t* out);
+/* SWB_BG_RPCA only: the "RPCA" images (clip(-E, 0, 255), uint8, ROI-sized) of frames
+ * [t0, t0 + n) of the last submit. */
+int swb_get_rpca(swb_ctx* ctx, int32_t t0, int32_t n, uint8_t* dst, int32_t mem_kind);
 
 /* Page-locked host memory for frame ingest (io_video.py:11-165 decodes frames into host
  * arrays; frames decoded into these buffers reach the device by DMA at full PCIe speed

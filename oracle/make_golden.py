@@ -177,11 +177,55 @@ def path_case(ref, rp, synth, name, c):
     print(name, "segments/frame (i32):", counts32)
 
 
-def main():
+RPCA_CASES = {
+    # the reference's real pipeline (rpca + bilateral) on one 21-frame batch, and a short batch
+    "rpca_roi_batch21": dict(seed=7, video=0, H=96, W=160, birds=40, T=21, roi=[(16, 8), (144, 88)]),
+    "rpca_full_batch8": dict(seed=8, video=1, H=54, W=100, birds=25, T=8, roi=[(0, 0), (100, 54)]),
+}
+
+
+def rpca_case(ref, rp, synth, name, c):
+    """data_structures.py:171-217 with the reference's own functions, one batch, oldest first on disk."""
+    frames = synth.synth_video(c["seed"], c["video"], 0, c["T"], c["H"], c["W"], c["birds"])
+    roi = c["roi"]
+    grays = [ref.convert_grayscale(ref.crop_frame(f, roi)) for f in frames]
+    sparse_newest_first = ref.rpca(grays[::-1])                     # the queue holds the newest frame at index 0
+    mine, iters = rp.rpca(grays[::-1], want_iters=True)
+    assert all(np.array_equal(a, b) for a, b in zip(sparse_newest_first, mine)), name
+    sparse = sparse_newest_first[::-1]
+    bil, masks, lab8, tabs, counts = [], [], [], [], []
+    for sp in sparse:
+        b = ref.bilateral_blur(sp, 7, 15, 1)
+        assert np.array_equal(b, rp.bilateral_blur(sp, 7, 15, 1))
+        x = ref.grayscale_opening(ref.thresh_to_zero(b, 15), (3, 3))
+        l8 = ref.cc_labeling(x, 4)
+        p8 = ref.get_segment_properties(l8)
+        bil.append(b); masks.append(np.packbits(x > 0, axis=1, bitorder="little")); lab8.append(l8)
+        tabs.append(rp.props_table(p8)); counts.append(len(p8))
+    got = rp.run_path_rpca(frames, rp.PathParams(roi, 1, 15, 3, True, False, "u8"))
+    for t in range(c["T"]):
+        assert np.array_equal(got[t]["labels"], lab8[t]) and np.array_equal(got[t]["rpca"], sparse[t]), (name, t)
+    # how far the scalar definition of the bilateral filter is from the (SIMD) library on these images
+    bs = sum(int((rp.bilateral_scalar(sp) != b).sum()) for sp, b in zip(sparse, bil))
+    out = dict(cfg=np.array([c["seed"], c["video"], c["H"], c["W"], c["birds"], c["T"], roi[0][0], roi[0][1],
+                             roi[1][0], roi[1][1], iters]),
+               gray=np.stack(grays), rpca=np.stack(sparse), bilateral=np.stack(bil), masks_packed=np.stack(masks),
+               labels_u8=np.stack(lab8), counts_u8=np.array(counts),
+               props_u8=np.concatenate(tabs) if sum(counts) else np.zeros((0, 8)))
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(name, "IALM iterations:", iters, "segments/frame:", counts, "scalar-vs-cv2 bilateral px:", bs)
+
+
+def main(only=None):
     os.makedirs(GOLD, exist_ok=True)
     ref = import_reference()
     from oracle import reference_path as rp
     from oracle import synth
+    if only in (None, "rpca"):
+        for name, c in RPCA_CASES.items():
+            rpca_case(ref, rp, synth, name, c)
+    if only == "rpca":
+        return
     stage_kats(ref, rp)
     for name, c in PATH_CASES.items():
         path_case(ref, rp, synth, name, c)
@@ -190,4 +234,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1] if len(sys.argv) > 1 else None)

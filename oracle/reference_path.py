@@ -323,3 +323,109 @@ def props_table(props):
     for i, p in enumerate(props):
         tab[i] = (p.label, p.area, *p.bbox, *p.centroid)
     return tab
+
+
+# ----------------------------------------------------------------------------
+# The reference's own background model: rpca + bilateral_blur
+# ----------------------------------------------------------------------------
+def inexact_augmented_lagrange_multiplier(X, lmbda=0.01, tol=0.001, maxiter=100):
+    """image_filtering.py:256-301, statement for statement (numpy + LAPACK svd).
+    Returns (A, E, iterations)."""
+    from numpy.linalg import norm, svd
+    Y = X
+    norm_two = norm(Y.ravel(), 2)
+    norm_inf = norm(Y.ravel(), np.inf) / lmbda
+    dual_norm = np.max([norm_two, norm_inf])
+    Y = Y / dual_norm
+    A = np.zeros(Y.shape)
+    E = np.zeros(Y.shape)
+    dnorm = norm(X, 'fro')
+    mu = 1.25 / norm_two
+    rho = 1.5
+    itr = 0
+    while True:
+        Eraw = X - A + (1 / mu) * Y
+        Eupdate = np.maximum(Eraw - lmbda / mu, 0) + np.minimum(Eraw + lmbda / mu, 0)
+        U, S, V = svd(X - Eupdate + (1 / mu) * Y, full_matrices=False)
+        svp = (S > 1 / mu).shape[0]          # == n: every singular value is shifted, none dropped (:285)
+        A = np.dot(np.dot(U[:, :svp], np.diag(S[:svp] - 1 / mu)), V[:svp, :])
+        E = Eupdate
+        Z = X - A - E
+        Y = Y + mu * Z
+        mu = np.min([mu * rho, mu * 1e7])
+        itr += 1
+        if ((norm(Z, 'fro') / dnorm) < tol) or (itr >= maxiter):
+            break
+    return A, E, itr
+
+
+def rpca(frame_list, want_iters=False):
+    """image_filtering.py:220-253: list of gray frames -> list of uint8 "sparse" images
+    (what is darker than the low-rank background)."""
+    img_matrix = np.array(frame_list)
+    col_matrix = np.transpose(img_matrix.reshape(img_matrix.shape[0], img_matrix.shape[1] * img_matrix.shape[2]))
+    _, s_columns, itr = inexact_augmented_lagrange_multiplier(col_matrix)
+    s_columns = np.negative(s_columns)
+    s_columns = np.clip(s_columns, 0, 255).astype(np.uint8)
+    out = [np.reshape(s_columns[:, i], (img_matrix.shape[1], img_matrix.shape[2]))
+           for i in range(img_matrix.shape[0])]
+    return (out, itr) if want_iters else out
+
+
+def bilateral_blur(frame, d, sigmaColor, sigmaSpace):
+    """image_filtering.py:304-307 (the reference's own cv2 call)."""
+    return cv2.bilateralFilter(frame, d, sigmaColor, sigmaSpace).astype(np.uint8)
+
+
+def bilateral_scalar(img, d=7, sigma_color=15.0, sigma_space=1.0):
+    """OpenCV's scalar definition of bilateralFilter for 8-bit single-channel images, restated
+    (library-independent): taps with sqrt(i^2 + j^2) <= d // 2 visited i-outer / j-inner (centre
+    included), float32 weights (float)exp(.), BORDER_REFLECT_101, float32 accumulation in tap
+    order, cvRound(sum / wsum).  Equals cv2 with setUseOptimized(False) bit for bit; cv2's SIMD
+    body differs from it on about one pixel per million (exact .5 ties)."""
+    radius = max(d // 2, 1)
+    gc, gs = -0.5 / (sigma_color * sigma_color), -0.5 / (sigma_space * sigma_space)
+    cw = np.array([np.float32(math.exp(i * i * gc)) for i in range(256)], dtype=np.float32)
+    t = cv2.copyMakeBorder(img, radius, radius, radius, radius, cv2.BORDER_REFLECT_101)
+    h, w = img.shape
+    c = img.astype(np.int32)
+    s = np.zeros((h, w), np.float32)
+    ws = np.zeros((h, w), np.float32)
+    for i in range(-radius, radius + 1):
+        for j in range(-radius, radius + 1):
+            r = math.sqrt(i * i + j * j)
+            if r > radius:
+                continue
+            sw = np.float32(math.exp(r * r * gs))
+            v = t[radius + i:radius + i + h, radius + j:radius + j + w]
+            wk = (sw * cw[np.abs(v.astype(np.int32) - c)]).astype(np.float32)
+            ws = (ws + wk).astype(np.float32)
+            s = (s + (v.astype(np.float32) * wk).astype(np.float32)).astype(np.float32)
+    return np.rint((s / ws).astype(np.float32)).astype(np.uint8)
+
+
+def run_path_rpca(frames_bgr, params, want_images=False):
+    """FrameQueue.preprocess_queue + segment_queue as the reference really runs them
+    (data_structures.py:171-217) on ONE batch of frames given oldest first: crop, gray,
+    rpca over the batch with the newest frame as column 0 (appendleft, :134,:160), bilateral
+    (7, 15, 1), thresh_to_zero, opening, labelling, regionprops.  One dict per frame, oldest first."""
+    grays = [convert_grayscale(crop_frame(f, params.crop_region)) for f in frames_bgr]
+    sparse = rpca(grays[::-1])[::-1]
+    out = []
+    for t, sp in enumerate(sparse):
+        bl = bilateral_blur(sp, 7, 15, 1)
+        th = thresh_to_zero(bl, params.thresh)
+        filt = th
+        if params.do_open:
+            filt = grayscale_opening(filt, (params.se, params.se))
+        if params.do_close:
+            filt = grayscale_closing(filt, (params.se, params.se))
+        labels = label_frame(filt, params)
+        props = get_segment_properties(labels)
+        rec = {"mask": ((filt > 0).astype(np.uint8) * 255), "labels": labels, "props": props,
+               "rpca": sp, "bilateral": bl}
+        if want_images:
+            rec["filtered"] = filt
+            rec["crops"] = extract_segment_images(props, frames_bgr[t], params.min_seg_size, params.crop_region)
+        out.append(rec)
+    return out

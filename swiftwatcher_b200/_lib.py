@@ -18,6 +18,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 LABELS_I32, LABELS_U8 = 0, 1
 HALO_CARRY = -1
 OUT_MASK, OUT_LABELS = 1, 2
+BG_MEDIAN, BG_RPCA = 0, 1
 
 
 class SwbConfig(C.Structure):
@@ -28,7 +29,7 @@ class SwbConfig(C.Structure):
         ("median_n", C.c_int32), ("threshold", C.c_int32), ("morph_size", C.c_int32),
         ("do_open", C.c_int32), ("do_close", C.c_int32), ("label_mode", C.c_int32),
         ("out_flags", C.c_int32), ("max_frames", C.c_int32), ("max_segments", C.c_int32),
-        ("reserved", C.c_int32 * 3),
+        ("bg_model", C.c_int32), ("reserved", C.c_int32 * 2),
     ]
 
 
@@ -69,6 +70,9 @@ SYMBOLS = {
     "swb_stage_grey_morph": (C.c_int, [_I32, _P, _I32, _I32, _I32, _I32, _I32, _P]),
     "swb_stage_cc_label": (C.c_int, [_I32, _P, _I32, _I32, _P, _P, C.POINTER(_I32)]),
     "swb_stage_regionprops": (C.c_int, [_I32, _P, _I32, _I32, _I32, _P, _I32, C.POINTER(_I32)]),
+    "swb_stage_rpca": (C.c_int, [_I32, _P, _I32, _I32, _I32, _P, C.POINTER(_I32)]),
+    "swb_stage_bilateral": (C.c_int, [_I32, _P, _I32, _I32, _I32, C.c_double, C.c_double, _P]),
+    "swb_get_rpca": (C.c_int, [_P, _I32, _I32, _P, _I32]),
     "swb_host_alloc": (C.c_int, [C.POINTER(_P), C.c_uint64]),
     "swb_host_free": (C.c_int, [_P]),
     "swb_synth_frames": (C.c_int, [_I32, _P, _I32, _U32, _U32, _I32, _I32, _I32, _I32, _I32]),

@@ -54,6 +54,12 @@ struct swb_ctx {
     uint8_t* mask = nullptr;
     void* labels = nullptr;
     CclBuffers ccl{};
+    // RPCA background model (SWB_BG_RPCA)
+    RpcaWork rpca{};
+    uint8_t* rp_gray = nullptr;     // [n][h*w] cropped gray stack, newest frame first (the reference's column order)
+    uint8_t* rp_sparse = nullptr;   // [n][h*w] clip(-E, 0, 255)
+    BilateralLut* d_lut = nullptr;
+    int rp_iters = 0;
     // host staging (pinned)
     int32_t* h_segoff = nullptr;
     int32_t* h_overflow = nullptr;
@@ -154,6 +160,10 @@ void free_ctx_buffers(swb_ctx* c) {
     cudaFree(c->ccl.pcount);
     cudaFree(c->ccl.big_tiles);
     cudaFree(c->ccl.rootlist);
+    rpca_free(c->rpca);
+    cudaFree(c->rp_gray);
+    cudaFree(c->rp_sparse);
+    cudaFree(c->d_lut);
     if (c->h_segoff) cudaFreeHost(c->h_segoff);
     if (c->h_overflow) cudaFreeHost(c->h_overflow);
     for (auto& e : c->ev)
@@ -282,6 +292,9 @@ int swb_create(const swb_config* cfg, swb_ctx** out) {
     if (c.label_mode != SWB_LABELS_I32 && c.label_mode != SWB_LABELS_U8)
         return fail(nullptr, SWB_ERR_INVALID, "bad label_mode %d", c.label_mode);
     if (c.max_frames <= 0 || c.max_frames > 32768) return fail(nullptr, SWB_ERR_INVALID, "max_frames must be in 1..32768");
+    if (c.bg_model != SWB_BG_MEDIAN && c.bg_model != SWB_BG_RPCA) return fail(nullptr, SWB_ERR_INVALID, "bad bg_model %d", c.bg_model);
+    if (c.bg_model == SWB_BG_RPCA && c.max_frames > 32)
+        return fail(nullptr, SWB_ERR_INVALID, "bg_model RPCA decomposes one batch per submit: max_frames must be <= 32 (got %d)", c.max_frames);
     if (c.max_segments <= 0) c.max_segments = 1024 * c.max_frames;
 
     swb_ctx* ctx = new swb_ctx();
@@ -336,6 +349,16 @@ int swb_create(const swb_config* cfg, swb_ctx** out) {
         CUB(cudaMalloc(&ctx->labels, (size_t)T * g.h * g.mpitch * ctx->label_elem));
     rc = alloc_ccl(ctx, ctx->ccl, g, T, ctx->cap_rows);
     if (rc != SWB_OK) return bail(rc);
+    if (c.bg_model == SWB_BG_RPCA) {
+        const long long P = (long long)g.h * g.w;
+        CUB(rpca_alloc(ctx->rpca, P, T));
+        CUB(dalloc(&ctx->rp_gray, (size_t)P * T));
+        CUB(dalloc(&ctx->rp_sparse, (size_t)P * T));
+        CUB(cudaMalloc(reinterpret_cast<void**>(&ctx->d_lut), sizeof(BilateralLut)));
+        BilateralLut lut;
+        bilateral_lut(7, 15.0, 1.0, lut);            // data_structures.py:194: bilateral_blur(frame, 7, 15, 1)
+        CUB(cudaMemcpy(ctx->d_lut, &lut, sizeof(lut), cudaMemcpyHostToDevice));
+    }
     CUB(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_segoff), ((size_t)T + 1) * sizeof(int32_t)));
     CUB(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_overflow), sizeof(int32_t)));
     for (auto& e : ctx->ev) CUB(cudaEventCreate(&e));
@@ -394,7 +417,9 @@ int swb_submit(swb_ctx* ctx, const uint8_t* frames, int32_t n_frames, int32_t n_
     // bandwidth-bound kernels only get in each other's way.)
     const bool from_host = (mem_kind == SWB_MEM_HOST);
     int tsub = n_frames, nsub = 1;
-    if (from_host && ctx->pipeline && !ctx->timing) {
+    if (c.bg_model == SWB_BG_RPCA && n_frames > ctx->rpca.nmax)
+        return fail(ctx, SWB_ERR_CAPACITY, "RPCA batch of %d frames exceeds max_frames", n_frames);
+    if (from_host && ctx->pipeline && !ctx->timing && c.bg_model == SWB_BG_MEDIAN) {
         const long long px = (long long)g.h * g.wa;
         const long long min_frames = (ctx->sub_min_px + px - 1) / px;   // >= 64 Mpx of work per sub-batch
         long long ts = std::max<long long>({(n_frames + MAX_SUB - 1) / MAX_SUB, min_frames, N - 1, 6});
@@ -476,9 +501,25 @@ int swb_submit(swb_ctx* ctx, const uint8_t* frames, int32_t n_frames, int32_t n_
     if (nsub == 1) {
         if (from_host) CU(ctx, stage_in(0, n_total, s));
         if (ctx->timing) CU(ctx, cudaEventRecord(ctx->ev[0], s));
-        CU(ctx, launch_fg_bits(s, src, C, N, n_frames, g, c.threshold, ctx->raw_bits, aligned, &launches));
+        Geom gm = g;                                  // geometry of the morphology input bits
+        if (c.bg_model == SWB_BG_RPCA) {
+            // crop + gray (newest frame first, the reference's column order, data_structures.py:134,160) ->
+            // IALM -> bilateral + threshold -> one bit per pixel, ROI-local columns
+            const uint8_t* f0 = src.cur + (long long)g.dx * C;      // src.cur is 32-px aligned: step to the ROI column
+            CU(ctx, launch_crop_gray(s, f0, src.frame_stride, src.pitch, C, 0, 0, g.h, g.w, n_frames, 1, ctx->rp_gray));
+            CU(ctx, rpca_run(s, ctx->rp_gray, n_frames, (long long)g.h * g.w, ctx->rpca, ctx->rp_sparse, &ctx->rp_iters,
+                             &launches));
+            gm.dx = 0;
+            gm.wpr_raw = g.wpr;
+            gm.wa = g.wpr * 32;
+            CU(ctx, launch_bilateral(s, ctx->rp_sparse, n_frames, g.h, g.w, ctx->d_lut, 1, nullptr, c.threshold,
+                                     reinterpret_cast<uint32_t*>(ctx->raw_bits), gm.wpr_raw));
+            launches += 2;
+        } else {
+            CU(ctx, launch_fg_bits(s, src, C, N, n_frames, g, c.threshold, ctx->raw_bits, aligned, &launches));
+        }
         if (ctx->timing) CU(ctx, cudaEventRecord(ctx->ev[1], s));
-        CU(ctx, launch_morph_mask(s, reinterpret_cast<const uint32_t*>(ctx->raw_bits), n_frames, g, ctx->morph,
+        CU(ctx, launch_morph_mask(s, reinterpret_cast<const uint32_t*>(ctx->raw_bits), n_frames, gm, ctx->morph,
                                   ctx->fbits, ctx->mask, &launches));
         if (ctx->timing) CU(ctx, cudaEventRecord(ctx->ev[2], s));
         CU(ctx, launch_ccl(s, ctx->fbits, n_frames, g, ctx->ccl, ctx->labels, ctx->label_elem, &launches,
@@ -532,7 +573,7 @@ int swb_submit(swb_ctx* ctx, const uint8_t* frames, int32_t n_frames, int32_t n_
         ctx->ev_valid = false;
     }
     ctx->launches += launches;
-    if (N > 1) {
+    if (N > 1 && c.bg_model == SWB_BG_MEDIAN) {
         ctx->hist_cur ^= 1;
         ctx->hist_has = true;
     }
@@ -857,6 +898,64 @@ int swb_stage_regionprops(int32_t device, const void* labels, int32_t elem_size,
         rows[k++] = s;
     }
     if (n_rows) *n_rows = k;
+    return SWB_OK;
+}
+
+int swb_get_rpca(swb_ctx* ctx, int32_t t0, int32_t n, uint8_t* dst, int32_t mem_kind) {
+    if (!ctx || !dst) return fail(ctx, SWB_ERR_INVALID, "null argument");
+    if (ctx->cfg.bg_model != SWB_BG_RPCA) return fail(ctx, SWB_ERR_STATE, "the context does not use bg_model SWB_BG_RPCA");
+    if (!ctx->pending) return fail(ctx, SWB_ERR_STATE, "no submit to read from");
+    if (t0 < 0 || n < 0 || t0 + n > ctx->last_T) return fail(ctx, SWB_ERR_INVALID, "bad frame range");
+    CU(ctx, cudaSetDevice(ctx->cfg.device));
+    const size_t P = (size_t)ctx->g.h * ctx->g.w;
+    // the stack is newest first: frame t is image last_T - 1 - t
+    for (int t = t0; t < t0 + n; ++t)
+        CU(ctx, cudaMemcpyAsync(dst + (size_t)(t - t0) * P, ctx->rp_sparse + (size_t)(ctx->last_T - 1 - t) * P, P,
+                                mem_kind == SWB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SWB_OK;
+}
+
+int swb_stage_rpca(int32_t device, const uint8_t* frames, int32_t n, int32_t h, int32_t w, uint8_t* out, int32_t* iters) {
+    if (!frames || !out || n < 1 || n > 32 || h <= 0 || w <= 0) return fail(nullptr, SWB_ERR_INVALID, "bad argument (1 <= n <= 32)");
+    STAGE_PROLOGUE();
+    const long long P = (long long)h * w;
+    DevTmp t;
+    uint8_t *d_in, *d_out;
+    CU(nullptr, t.alloc(&d_in, (size_t)P * n));
+    CU(nullptr, t.alloc(&d_out, (size_t)P * n));
+    RpcaWork wk;
+    cudaError_t e = rpca_alloc(wk, P, n);
+    if (e != cudaSuccess) { rpca_free(wk); return fail(nullptr, SWB_ERR_CUDA, "rpca_alloc: %s", cudaGetErrorString(e)); }
+    int it = 0;
+    e = cudaMemcpy(d_in, frames, (size_t)P * n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = rpca_run(0, d_in, n, P, wk, d_out, &it, nullptr);
+    if (e == cudaSuccess) e = cudaMemcpy(out, d_out, (size_t)P * n, cudaMemcpyDeviceToHost);
+    rpca_free(wk);
+    if (e != cudaSuccess) return fail(nullptr, SWB_ERR_CUDA, "swb_stage_rpca: %s", cudaGetErrorString(e));
+    if (iters) *iters = it;
+    return SWB_OK;
+}
+
+int swb_stage_bilateral(int32_t device, const uint8_t* in, int32_t h, int32_t w, int32_t d, double sigma_color,
+                        double sigma_space, uint8_t* out) {
+    if (!in || !out || h <= 0 || w <= 0) return fail(nullptr, SWB_ERR_INVALID, "bad argument");
+    if (d < 1 || d > 7 || !(sigma_color > 0) || !(sigma_space > 0))
+        return fail(nullptr, SWB_ERR_INVALID, "bilateral: 1 <= d <= 7 and positive sigmas (the reference uses 7, 15, 1)");
+    STAGE_PROLOGUE();
+    DevTmp t;
+    uint8_t *d_in, *d_out;
+    BilateralLut* d_lut;
+    const size_t n = (size_t)h * w;
+    CU(nullptr, t.alloc(&d_in, n));
+    CU(nullptr, t.alloc(&d_out, n));
+    CU(nullptr, t.alloc(&d_lut, 1));
+    BilateralLut lut;
+    bilateral_lut(d, sigma_color, sigma_space, lut);
+    CU(nullptr, cudaMemcpy(d_lut, &lut, sizeof(lut), cudaMemcpyHostToDevice));
+    CU(nullptr, cudaMemcpy(d_in, in, n, cudaMemcpyHostToDevice));
+    CU(nullptr, launch_bilateral(0, d_in, 1, h, w, d_lut, 0, d_out, 0, nullptr, 0));
+    CU(nullptr, cudaMemcpy(out, d_out, n, cudaMemcpyDeviceToHost));
     return SWB_OK;
 }
 

@@ -1,0 +1,474 @@
+// RPCA background model — the reference's own localisation step.
+//
+// rpca (image_filtering.py:220-253) stacks the n gray frames of a batch as the columns of
+// a (P x n) matrix X (P = h*w pixels, n = 21) and splits it into low rank + sparse with the
+// inexact augmented Lagrange multiplier method (:256-301); the "RPCA" image of a frame is
+// clip(-E, 0, 255) truncated to uint8 (:243-245: what is darker than the background).
+//
+// Each IALM iteration is, per pixel row p (all float64, same operation order as the numpy code):
+//     Eraw = (X - A) + (1/mu) Y                E = shrink(Eraw, lambda/mu)        (:282-283)
+//     M    = (X - E) + (1/mu) Y                                                   (:284)
+//     A'   = U diag(S - 1/mu) V^T  with  U S V^T = svd(M)   (svp == n always)     (:284-290)
+//     Z    = (X - A') - E;   Y += mu Z;   mu *= rho;   stop when |Z|_F / |X|_F < tol
+// M is tall and skinny, so the thin SVD goes through the n x n Gram matrix: G = M^T M =
+// V diag(S^2) V^T and A' = M W with W = V diag((S - 1/mu) / S) V^T — two streaming passes over
+// X, A, Y per iteration plus a 21 x 21 symmetric eigenproblem (cyclic Jacobi on the host):
+//   pass 1  k_rpca_gram   M -> per-CTA partial Gram sums (fixed order: deterministic)
+//   pass 2  k_rpca_apply  recomputes E, M; A' = M W; Z; Y; |Z|^2 partials; the uint8 image of E
+// Bandwidth-bound float64 streaming (about 50 bytes per matrix element per iteration); the
+// Gram products and the 441 multiply-adds per pixel row of A' = M W run from shared memory.
+//
+// Parity: the reference's LAPACK SVD and this Gram / Jacobi route differ in the last bits of A;
+// the uint8 image only changes where -E lies within ~1e-12 of an integer.  On the golden batches
+// it is bit-identical (tests/golden/rpca_*.npz, produced by the reference's own rpca()).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "swb_internal.cuh"
+
+namespace swb {
+
+namespace {
+
+constexpr int RP_THREADS = 256;
+constexpr int RP_NMAX = 32;
+
+__device__ __forceinline__ double shrink(double v, double thr) {
+    // np.maximum(v - thr, 0) + np.minimum(v + thr, 0)
+    return fmax(v - thr, 0.0) + fmin(v + thr, 0.0);
+}
+
+// sum of squares (exact, integers) and maximum of the gray stack
+__global__ void __launch_bounds__(RP_THREADS)
+k_rpca_norms(const uint8_t* __restrict__ x, long long total, unsigned long long* __restrict__ sumsq,
+             unsigned int* __restrict__ vmax) {
+    unsigned long long s = 0;
+    unsigned int m = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const unsigned int v = x[i];
+        s += (unsigned long long)(v * v);
+        m = max(m, v);
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        s += __shfl_down_sync(0xFFFFFFFFu, s, d);
+        m = max(m, __shfl_down_sync(0xFFFFFFFFu, m, d));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(sumsq, s);          // integer sums: order does not matter
+        atomicMax(vmax, m);
+    }
+}
+
+__global__ void __launch_bounds__(RP_THREADS)
+k_rpca_init(const uint8_t* __restrict__ x, long long total, double dual_norm, double* __restrict__ A,
+            double* __restrict__ Y) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        A[i] = 0.0;
+        Y[i] = (double)x[i] / dual_norm;
+    }
+}
+
+// pass 1: partial Gram matrices.  A CTA walks tiles of RP_THREADS pixel rows: thread t computes
+// M[p0 + t][0..n) into shared memory (padded rows: conflict-free column reads), then thread q
+// accumulates the pair (i, j) = pairs[q] over the tile.  gpart[cta][q], q < n(n+1)/2.
+__global__ void __launch_bounds__(RP_THREADS)
+k_rpca_gram(const uint8_t* __restrict__ X, const double* __restrict__ A, const double* __restrict__ Y, int n,
+            long long P, double inv_mu, double thr, double* __restrict__ gpart) {
+    extern __shared__ double sm[];                 // [n][RP_THREADS + 1]
+    constexpr int LD = RP_THREADS + 1;
+    const int t = threadIdx.x;
+    const int npairs = n * (n + 1) / 2;
+    double acc[3] = {0.0, 0.0, 0.0};               // up to 3 pairs per thread (n <= 32: 528 pairs)
+    int pi[3], pj[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        int q = t + k * RP_THREADS;
+        pi[k] = pj[k] = -1;
+        if (q < npairs) {                          // row-major upper triangle: q -> (i, j), j >= i
+            int i = 0;
+            while (q >= n - i) { q -= n - i; ++i; }
+            pi[k] = i;
+            pj[k] = i + q;
+        }
+    }
+    const long long ntiles = (P + RP_THREADS - 1) / RP_THREADS;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long p = tile * RP_THREADS + t;
+        for (int i = 0; i < n; ++i) {
+            double m = 0.0;
+            if (p < P) {
+                const long long idx = (long long)i * P + p;
+                const double x = (double)X[idx];
+                const double t2 = __dmul_rn(inv_mu, Y[idx]);           // numpy rounds the product, then the sum
+                const double e = shrink(__dadd_rn(x - A[idx], t2), thr);
+                m = __dadd_rn(x - e, t2);
+            }
+            sm[i * LD + t] = m;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (pi[k] < 0) continue;
+            const double* a = sm + pi[k] * LD;
+            const double* b = sm + pj[k] * LD;
+            double s = 0.0;
+#pragma unroll 8
+            for (int r = 0; r < RP_THREADS; ++r) s = fma(a[r], b[r], s);
+            acc[k] += s;
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        if (pi[k] >= 0) gpart[(long long)blockIdx.x * npairs + t + k * RP_THREADS] = acc[k];
+}
+
+// fixed-order sum of the per-CTA partials -> packed upper triangle
+__global__ void k_rpca_gram_reduce(const double* __restrict__ gpart, int nctas, int npairs, double* __restrict__ G) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= npairs) return;
+    double s = 0.0;
+    for (int c = 0; c < nctas; ++c) s += gpart[(long long)c * npairs + q];
+    G[q] = s;
+}
+
+// pass 2: A' = M W, Z, Y, |Z|^2, uint8 image of E.  Thread = pixel row; M and E of the row sit in
+// shared memory columns (stride blockDim: conflict-free), W is read as a broadcast.
+__global__ void __launch_bounds__(RP_THREADS)
+k_rpca_apply(const uint8_t* __restrict__ X, const double* __restrict__ A, double* __restrict__ Anew,
+             double* __restrict__ Y, int n, long long P, double inv_mu, double thr, double mu,
+             const double* __restrict__ Wg, double* __restrict__ zpart, uint8_t* __restrict__ out) {
+    extern __shared__ double sm[];
+    double* sW = sm;                               // [n][n]
+    double* sM = sW + n * n;                       // [n][RP_THREADS]
+    double* sE = sM + n * RP_THREADS;              // [n][RP_THREADS]
+    const int t = threadIdx.x;
+    for (int i = t; i < n * n; i += RP_THREADS) sW[i] = Wg[i];
+    __syncthreads();
+    double zz = 0.0;
+    const long long ntiles = (P + RP_THREADS - 1) / RP_THREADS;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long p = tile * RP_THREADS + t;
+        if (p < P) {
+            for (int i = 0; i < n; ++i) {
+                const long long idx = (long long)i * P + p;
+                const double x = (double)X[idx];
+                const double t2 = __dmul_rn(inv_mu, Y[idx]);           // numpy rounds the product, then the sum
+                const double e = shrink(__dadd_rn(x - A[idx], t2), thr);
+                sE[i * RP_THREADS + t] = e;
+                sM[i * RP_THREADS + t] = __dadd_rn(x - e, t2);
+                // clip(-E, 0, 255).astype(uint8): truncation
+                const double ne = fmin(fmax(-e, 0.0), 255.0);
+                out[idx] = (uint8_t)ne;
+            }
+            for (int j = 0; j < n; ++j) {
+                double a = 0.0;
+                for (int i = 0; i < n; ++i) a = fma(sM[i * RP_THREADS + t], sW[i * n + j], a);
+                const long long idx = (long long)j * P + p;
+                const double z = ((double)X[idx] - a) - sE[j * RP_THREADS + t];
+                Anew[idx] = a;
+                Y[idx] = __dadd_rn(Y[idx], __dmul_rn(mu, z));
+                zz = fma(z, z, zz);
+            }
+        }
+    }
+    // per-CTA |Z|^2 in a fixed order
+    __shared__ double red[RP_THREADS / 32];
+    for (int d = 16; d > 0; d >>= 1) zz += __shfl_down_sync(0xFFFFFFFFu, zz, d);
+    __syncthreads();
+    if ((t & 31) == 0) red[t >> 5] = zz;
+    __syncthreads();
+    if (t == 0) {
+        double s = 0.0;
+        for (int w = 0; w < RP_THREADS / 32; ++w) s += red[w];
+        zpart[blockIdx.x] = s;
+    }
+}
+
+// crop + gray into the compact [n][h*w] stack (convert_grayscale, image_filtering.py:188-196;
+// crop_frame :199-203); column order = `order[k]` picks the source frame of column k
+__global__ void __launch_bounds__(RP_THREADS)
+k_crop_gray(const uint8_t* __restrict__ frames, long long frame_stride, long long pitch, int channels, int x0,
+            int y0, int h, int w, int n, int newest_first, uint8_t* __restrict__ out) {
+    const long long P = (long long)h * w;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P * n; i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i / P);
+        const long long p = i - (long long)k * P;
+        const int y = (int)(p / w), x = (int)(p - (long long)y * w);
+        const int f = newest_first ? n - 1 - k : k;
+        const uint8_t* px = frames + (long long)f * frame_stride + (long long)(y0 + y) * pitch + (long long)(x0 + x) * channels;
+        uint8_t v;
+        if (channels == 3) v = (uint8_t)((3735u * px[0] + 19235u * px[1] + 9798u * px[2] + 16384u) >> 15);
+        else v = px[0];
+        out[i] = v;
+    }
+}
+
+// symmetric eigenproblem, cyclic Jacobi (n <= 32): a = V diag(d) V^T, a is destroyed
+void jacobi_eigh(int n, std::vector<double>& a, std::vector<double>& d, std::vector<double>& v) {
+    v.assign((size_t)n * n, 0.0);
+    for (int i = 0; i < n; ++i) v[(size_t)i * n + i] = 1.0;
+    for (int sweep = 0; sweep < 100; ++sweep) {
+        double off = 0.0, diag = 0.0;
+        for (int i = 0; i < n; ++i) {
+            diag += a[(size_t)i * n + i] * a[(size_t)i * n + i];
+            for (int j = i + 1; j < n; ++j) off += a[(size_t)i * n + j] * a[(size_t)i * n + j];
+        }
+        if (off <= 1e-34 * diag || off == 0.0) break;   // off-diagonal mass below eps^2 of the diagonal
+        for (int p = 0; p < n - 1; ++p) {
+            for (int q = p + 1; q < n; ++q) {
+                const double apq = a[(size_t)p * n + q];
+                if (apq == 0.0) continue;
+                const double app = a[(size_t)p * n + p], aqq = a[(size_t)q * n + q];
+                const double theta = (aqq - app) / (2.0 * apq);
+                const double tt = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+                const double c = 1.0 / std::sqrt(tt * tt + 1.0), s = tt * c;
+                for (int k = 0; k < n; ++k) {          // rotate rows / columns p, q of a
+                    const double akp = a[(size_t)k * n + p], akq = a[(size_t)k * n + q];
+                    a[(size_t)k * n + p] = c * akp - s * akq;
+                    a[(size_t)k * n + q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < n; ++k) {
+                    const double apk = a[(size_t)p * n + k], aqk = a[(size_t)q * n + k];
+                    a[(size_t)p * n + k] = c * apk - s * aqk;
+                    a[(size_t)q * n + k] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < n; ++k) {
+                    const double vkp = v[(size_t)k * n + p], vkq = v[(size_t)k * n + q];
+                    v[(size_t)k * n + p] = c * vkp - s * vkq;
+                    v[(size_t)k * n + q] = s * vkp + c * vkq;
+                }
+            }
+        }
+    }
+    d.resize(n);
+    for (int i = 0; i < n; ++i) d[i] = a[(size_t)i * n + i];
+}
+
+}  // namespace
+
+cudaError_t rpca_alloc(RpcaWork& w, long long P, int nmax) {
+    memset(&w, 0, sizeof(w));
+    if (nmax > RP_NMAX) return cudaErrorInvalidValue;
+    w.P = P;
+    w.nmax = nmax;
+    w.nctas = 148 * 4;
+    const size_t elems = (size_t)P * nmax;
+    cudaError_t e;
+    if ((e = cudaMalloc(&w.A0, elems * sizeof(double))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&w.A1, elems * sizeof(double))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&w.Y, elems * sizeof(double))) != cudaSuccess) return e;
+    const int npairs = nmax * (nmax + 1) / 2;
+    if ((e = cudaMalloc(&w.gpart, (size_t)w.nctas * npairs * sizeof(double))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&w.G, (size_t)npairs * sizeof(double))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&w.W, (size_t)nmax * nmax * sizeof(double))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&w.zpart, (size_t)w.nctas * sizeof(double))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&w.sumsq, 16)) != cudaSuccess) return e;
+    if ((e = cudaMallocHost(&w.h_buf, (size_t)(npairs + nmax * nmax + w.nctas + 4) * sizeof(double))) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+void rpca_free(RpcaWork& w) {
+    cudaFree(w.A0);
+    cudaFree(w.A1);
+    cudaFree(w.Y);
+    cudaFree(w.gpart);
+    cudaFree(w.G);
+    cudaFree(w.W);
+    cudaFree(w.zpart);
+    cudaFree(w.sumsq);
+    if (w.h_buf) cudaFreeHost(w.h_buf);
+    memset(&w, 0, sizeof(w));
+}
+
+cudaError_t launch_crop_gray(cudaStream_t s, const uint8_t* frames, long long frame_stride, long long pitch,
+                             int channels, int x0, int y0, int h, int w, int n, int newest_first, uint8_t* out) {
+    const long long total = (long long)h * w * n;
+    const int grid = (int)std::min<long long>((total + RP_THREADS - 1) / RP_THREADS, 148 * 16);
+    k_crop_gray<<<grid, RP_THREADS, 0, s>>>(frames, frame_stride, pitch, channels, x0, y0, h, w, n, newest_first, out);
+    return cudaGetLastError();
+}
+
+// inexact_augmented_lagrange_multiplier (image_filtering.py:256-301) on the device.
+// X: [n][P] uint8 (column k of the reference's matrix = X[k]); out: [n][P] uint8 = clip(-E, 0, 255).
+// Synchronises the stream every iteration (the stopping test and the 21 x 21 eigenproblem run on the host).
+cudaError_t rpca_run(cudaStream_t s, const uint8_t* X, int n, long long P, RpcaWork& w, uint8_t* out, int* iters,
+                     int* n_launches) {
+    if (n < 1 || n > w.nmax || P > w.P) return cudaErrorInvalidValue;
+    const double lmbda = 0.01, tol = 0.001, rho = 1.5;
+    const int maxiter = 100;
+    const long long total = (long long)n * P;
+    const int npairs = n * (n + 1) / 2;
+    const int nctas = (int)std::min<long long>(w.nctas, (P + RP_THREADS - 1) / RP_THREADS);
+    double* hG = w.h_buf;
+    double* hW = hG + w.nmax * (w.nmax + 1) / 2;
+    double* hZ = hW + w.nmax * w.nmax;
+    unsigned long long* hS = reinterpret_cast<unsigned long long*>(hZ + w.nctas);
+    cudaError_t e;
+    int launches = 0;
+
+    static PerDeviceOnce once;
+    const int smem_gram = RP_NMAX * (RP_THREADS + 1) * (int)sizeof(double);
+    const int smem_apply = (RP_NMAX * RP_NMAX + 2 * RP_NMAX * RP_THREADS) * (int)sizeof(double);
+    if (once.need()) {
+        cudaFuncSetAttribute(k_rpca_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_gram);
+        cudaFuncSetAttribute(k_rpca_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_apply);
+    }
+
+    cudaMemsetAsync(w.sumsq, 0, 16, s);
+    k_rpca_norms<<<nctas, RP_THREADS, 0, s>>>(X, total, w.sumsq, reinterpret_cast<unsigned int*>(w.sumsq + 1));
+    cudaMemcpyAsync(hS, w.sumsq, 16, cudaMemcpyDeviceToHost, s);
+    if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+    const double norm_two = std::sqrt((double)hS[0]);                 // norm(Y.ravel(), 2) == norm(X, 'fro')
+    const double norm_inf = (double)(unsigned int)hS[1] / lmbda;
+    if (norm_two == 0.0) {                                            // all-black batch: E == 0
+        cudaMemsetAsync(out, 0, (size_t)total, s);
+        if (iters) *iters = 0;
+        if (n_launches) *n_launches += 1;
+        return cudaGetLastError();
+    }
+    const double dual_norm = std::max(norm_two, norm_inf);
+    const double dnorm = norm_two;
+    double mu = 1.25 / norm_two;
+    k_rpca_init<<<nctas, RP_THREADS, 0, s>>>(X, total, dual_norm, w.A0, w.Y);
+    launches += 2;
+
+    double* Aold = w.A0;
+    double* Anew = w.A1;
+    std::vector<double> g((size_t)n * n), d, v;
+    int itr = 0;
+    while (true) {
+        const double inv_mu = 1 / mu;
+        const double thr = lmbda / mu;
+        k_rpca_gram<<<nctas, RP_THREADS, n * (RP_THREADS + 1) * sizeof(double), s>>>(X, Aold, w.Y, n, P, inv_mu, thr, w.gpart);
+        k_rpca_gram_reduce<<<(npairs + 127) / 128, 128, 0, s>>>(w.gpart, nctas, npairs, w.G);
+        cudaMemcpyAsync(hG, w.G, (size_t)npairs * sizeof(double), cudaMemcpyDeviceToHost, s);
+        if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+        for (int i = 0, q = 0; i < n; ++i)
+            for (int j = i; j < n; ++j, ++q) g[(size_t)i * n + j] = g[(size_t)j * n + i] = hG[q];
+        jacobi_eigh(n, g, d, v);
+        // W = V diag((S - 1/mu) / S) V^T  (svp == n: every singular value is shifted, none is dropped)
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) {
+                double acc = 0.0;
+                for (int k = 0; k < n; ++k) {
+                    const double sv = d[k] > 0.0 ? std::sqrt(d[k]) : 0.0;
+                    if (sv <= 0.0) continue;       // exactly dependent columns: U is undefined there (see header)
+                    acc += v[(size_t)i * n + k] * ((sv - inv_mu) / sv) * v[(size_t)j * n + k];
+                }
+                hW[(size_t)i * n + j] = acc;
+            }
+        cudaMemcpyAsync(w.W, hW, (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice, s);
+        k_rpca_apply<<<nctas, RP_THREADS, (size_t)(n * n + 2 * n * RP_THREADS) * sizeof(double), s>>>(
+            X, Aold, Anew, w.Y, n, P, inv_mu, thr, mu, w.W, w.zpart, out);
+        cudaMemcpyAsync(hZ, w.zpart, (size_t)nctas * sizeof(double), cudaMemcpyDeviceToHost, s);
+        launches += 3;
+        if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+        double zz = 0.0;
+        for (int c = 0; c < nctas; ++c) zz += hZ[c];
+        std::swap(Aold, Anew);
+        mu = std::min(mu * rho, mu * 1e7);
+        ++itr;
+        if (std::sqrt(zz) / dnorm < tol || itr >= maxiter) break;
+    }
+    if (iters) *iters = itr;
+    if (n_launches) *n_launches += launches;
+    return cudaGetLastError();
+}
+
+
+// ------------------------------------------------------------------------------------------
+// bilateral_blur = cv2.bilateralFilter(frame, 7, 15, 1) (image_filtering.py:304-307,
+// data_structures.py:194).  OpenCV's definition for 8-bit single-channel images
+// (modules/imgproc bilateral_filter, 4.x): radius = d / 2; the taps are the offsets with
+// sqrt(i^2 + j^2) <= radius visited i-outer / j-inner (29 for d = 7, centre included);
+// space weight = (float)exp(-r^2 / (2 sigma_space^2)), colour weight = (float)exp(-dv^2 /
+// (2 sigma_color^2)) from a 256-entry table; BORDER_REFLECT_101; float32 accumulation of
+// w and v * w in tap order; result = cvRound(sum / wsum).  The tables are built on the host with
+// the same double-precision exp.  This is bit-identical to cv2 with setUseOptimized(False);
+// OpenCV's SIMD body differs from its own scalar code on about one pixel per million (exact .5
+// ties of the float quotient), so against the optimised build parity is "equal up to 1 grey level
+// on <= 2 ppm of the pixels" (tests).
+// ------------------------------------------------------------------------------------------
+void bilateral_lut(int d, double sigma_color, double sigma_space, BilateralLut& lut) {
+    int radius = d / 2;
+    if (radius < 1) radius = 1;
+    if (radius > 3) radius = 3;                    // 64-tap table: d <= 7 (the reference uses 7)
+    const double gc = -0.5 / (sigma_color * sigma_color), gs = -0.5 / (sigma_space * sigma_space);
+    for (int i = 0; i < 256; ++i) lut.color[i] = (float)std::exp((double)i * i * gc);
+    int k = 0;
+    for (int i = -radius; i <= radius; ++i)
+        for (int j = -radius; j <= radius; ++j) {
+            const double r = std::sqrt((double)i * i + (double)j * j);
+            if (r > radius) continue;
+            lut.space[k] = (float)std::exp(r * r * gs);
+            lut.dy[k] = i;
+            lut.dx[k] = j;
+            ++k;
+        }
+    lut.ntaps = k;
+    lut.radius = radius;
+}
+
+namespace {
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i;
+    return i;
+}
+
+// thread = pixel; a warp covers 32 consecutive pixels of a row so that the thresholded result
+// is one ballot per word
+__global__ void __launch_bounds__(256)
+k_bilateral(const uint8_t* __restrict__ in, int n, int h, int w, const BilateralLut* __restrict__ lutp, int reverse,
+            uint8_t* __restrict__ out, int thresh, uint32_t* __restrict__ bits, int wpr_bits) {
+    __shared__ BilateralLut lut;
+    for (int i = threadIdx.x; i < (int)(sizeof(BilateralLut) / 4); i += blockDim.x)
+        reinterpret_cast<uint32_t*>(&lut)[i] = reinterpret_cast<const uint32_t*>(lutp)[i];
+    __syncthreads();
+    const int wpr = (w + 31) / 32;
+    const int lane = threadIdx.x & 31;
+    const long long nwords = (long long)n * h * wpr;
+    for (long long word = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; word < nwords;
+         word += ((long long)gridDim.x * blockDim.x) >> 5) {
+        const int f = (int)(word / ((long long)h * wpr));
+        const long long rem = word - (long long)f * h * wpr;
+        const int y = (int)(rem / wpr), x = (int)(rem - (long long)y * wpr) * 32 + lane;
+        const uint8_t* img = in + (long long)(reverse ? n - 1 - f : f) * h * w;
+        int res = 0;
+        if (x < w) {
+            const int c = img[(long long)y * w + x];
+            float sum = 0.f, wsum = 0.f;
+            for (int k = 0; k < lut.ntaps; ++k) {
+                const int yy = reflect101(y + lut.dy[k], h), xx = reflect101(x + lut.dx[k], w);
+                const int v = img[(long long)yy * w + xx];
+                const float wk = __fmul_rn(lut.space[k], lut.color[abs(v - c)]);
+                wsum = __fadd_rn(wsum, wk);
+                sum = __fadd_rn(sum, __fmul_rn((float)v, wk));
+            }
+            res = __float2int_rn(__fdiv_rn(sum, wsum));
+            res = min(max(res, 0), 255);
+            if (out) out[((long long)f * h + y) * w + x] = (uint8_t)res;
+        }
+        if (bits) {
+            const uint32_t b = __ballot_sync(0xFFFFFFFFu, res > thresh);
+            if (lane == 0 && x / 32 < wpr_bits) bits[((long long)f * h + y) * wpr_bits + x / 32] = b;
+        }
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_bilateral(cudaStream_t s, const uint8_t* in, int n, int h, int w, const BilateralLut* d_lut,
+                             int reverse, uint8_t* out, int thresh, uint32_t* bits, int wpr_bits) {
+    const long long nwords = (long long)n * h * ((w + 31) / 32);
+    const int grid = (int)std::min<long long>((nwords * 32 + 255) / 256, 148 * 32);
+    k_bilateral<<<grid, 256, 0, s>>>(in, n, h, w, d_lut, reverse, out, thresh, bits, wpr_bits);
+    return cudaGetLastError();
+}
+
+}  // namespace swb

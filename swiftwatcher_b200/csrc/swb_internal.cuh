@@ -112,6 +112,35 @@ struct PerDeviceOnce {
     }
 };
 
+// ---- RPCA background model (rpca.cu): the reference's own localisation, SURVEY.md §8f #4 ----
+struct RpcaWork {
+    double *A0, *A1, *Y;            // [n][P] low-rank iterate (ping-pong) and the Lagrange multiplier
+    double *gpart, *G, *W, *zpart;  // per-CTA Gram partials, packed Gram matrix, W = V f(S) V^T, |Z|^2 partials
+    unsigned long long* sumsq;      // [2]: sum of squares, maximum of the gray stack
+    double* h_buf;                  // pinned host staging (G, W, |Z|^2 partials, norms)
+    long long P;
+    int nmax, nctas;
+};
+cudaError_t rpca_alloc(RpcaWork& w, long long P, int nmax);
+void rpca_free(RpcaWork& w);
+cudaError_t rpca_run(cudaStream_t s, const uint8_t* X, int n, long long P, RpcaWork& w, uint8_t* out, int* iters,
+                     int* n_launches);
+cudaError_t launch_crop_gray(cudaStream_t s, const uint8_t* frames, long long frame_stride, long long pitch,
+                             int channels, int x0, int y0, int h, int w, int n, int newest_first, uint8_t* out);
+// bilateral_blur (image_filtering.py:304-307 = cv2.bilateralFilter, 8-bit, one channel) for a stack of
+// frames; `out` (uint8 images) and / or `bits` (the thresholded result as 1 bit per pixel, rows of
+// wpr_bits words: the input of the morphology kernel) may be null.  frame_map: frame f reads image
+// (reverse ? n - 1 - f : f) of the stack.
+struct BilateralLut {
+    float color[256];
+    float space[64];
+    int dy[64], dx[64];
+    int ntaps, radius;
+};
+void bilateral_lut(int d, double sigma_color, double sigma_space, BilateralLut& lut);
+cudaError_t launch_bilateral(cudaStream_t s, const uint8_t* in, int n, int h, int w, const BilateralLut* d_lut,
+                             int reverse, uint8_t* out, int thresh, uint32_t* bits, int wpr_bits);
+
 // single-stage kernels (stages.cu)
 cudaError_t launch_stage_gray(cudaStream_t s, const uint8_t* bgr, int h, int w, uint8_t* out);
 cudaError_t launch_stage_median(cudaStream_t s, const uint8_t* stack, int n, int h, int w, uint8_t* out);

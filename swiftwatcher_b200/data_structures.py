@@ -73,13 +73,13 @@ class FrameQueue(deque):
     """data_structures.py:116-217 with the batch handed to the GPU."""
 
     def __init__(self, queue_size=21, median_n=5, threshold=15, morph_size=3,
-                 do_close=False, label_mode="u8", device=0):
+                 do_close=False, label_mode="u8", device=0, bg_model="median"):
         deque.__init__(self, maxlen=queue_size)
         self.frames_read = 0
         self.frames_processed = 0
         self._params = dict(median_n=median_n, threshold=threshold, morph_size=morph_size,
                             do_open=True, do_close=do_close, label_mode=label_mode,
-                            device=device)
+                            device=device, bg_model=bg_model)
         self._ctx = None
         self._ctx_key = None
         self._pinned = [None, None]
@@ -175,6 +175,9 @@ class FrameQueue(deque):
         masks = ctx.masks()
         labels = ctx.labels()
         n = len(frames)
+        if ctx.bg_model == "rpca":                 # the reference's own intermediate (data_structures.py:191-192)
+            sparse = ctx.rpca_images()
+            self.store_processed_queue([sparse[n - 1 - pos] for pos in range(n)], "RPCA")
         self.store_processed_queue([masks[n - 1 - pos] for pos in range(n)], "mask")
         self.store_processed_queue([labels[n - 1 - pos] for pos in range(n)], "cc_labeling")
         offs = np.concatenate([[0], np.cumsum(counts)])

@@ -106,6 +106,30 @@ def grayscale_closing(frame, SE):
     return _morph(frame, SE, 1)
 
 
+def rpca(frame_list):
+    """image_filtering.py:220-253 — robust PCA (IALM) over a batch of gray frames: list of uint8
+    "sparse" images, what is darker than the low-rank background.  Columns are taken in list
+    order, as in the reference (its queue holds the newest frame first).  float64 on the GPU, SVD
+    through the n x n Gram matrix (csrc/rpca.cu); at most 32 frames."""
+    stack = np.ascontiguousarray(np.array(frame_list))
+    if stack.ndim != 3 or stack.dtype != np.uint8:
+        raise ValueError("frame_list must hold 2-D uint8 frames of one shape")
+    out = np.empty_like(stack)
+    check(_lib.load().swb_stage_rpca(_DEVICE, ptr(stack), stack.shape[0], stack.shape[1], stack.shape[2],
+                                     ptr(out), None))
+    return [out[i] for i in range(stack.shape[0])]
+
+
+def bilateral_blur(frame, d, sigmaColor, sigmaSpace):
+    """image_filtering.py:304-307 — cv2.bilateralFilter for an 8-bit single-channel frame
+    (OpenCV's scalar definition, see csrc/rpca.cu; the reference calls it with (7, 15, 1))."""
+    a = _u8(frame, 2)
+    out = np.empty_like(a)
+    check(_lib.load().swb_stage_bilateral(_DEVICE, ptr(a), a.shape[0], a.shape[1], int(d), float(sigmaColor),
+                                          float(sigmaSpace), ptr(out)))
+    return out
+
+
 def cc_labeling(frame, connectivity):
     """image_filtering.py:325-329 — the reference passes ``connectivity``
     into cv2's ``labels`` slot, so labelling is always 8-connected; labels use

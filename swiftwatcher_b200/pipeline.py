@@ -11,7 +11,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import (HALO_CARRY, LABELS_I32, LABELS_U8, MEM_DEVICE, MEM_HOST, OUT_LABELS,
+from ._lib import (BG_MEDIAN, BG_RPCA, HALO_CARRY, LABELS_I32, LABELS_U8, MEM_DEVICE, MEM_HOST, OUT_LABELS,
                    OUT_MASK, SEGMENT_DTYPE, SwbConfig, check, ptr)
 
 
@@ -57,10 +57,12 @@ class FilterContext:
     def __init__(self, frame_shape, crop_region=None, median_n=5, threshold=15,
                  morph_size=3, do_open=True, do_close=False, label_mode="u8",
                  max_frames=21, max_segments=0, device=0, want_mask=True,
-                 want_labels=True, frame_pitch=0, frame_stride=0):
+                 want_labels=True, frame_pitch=0, frame_stride=0, bg_model="median"):
         """frame_shape: (H, W, 3) BGR or (H, W) gray.  crop_region: the
         reference's ``[(x0, y0), (x1, y1)]`` (image_filtering.py:199-203);
-        None = whole frame."""
+        None = whole frame.  bg_model: "median" (rolling temporal median, BASELINE.json) or
+        "rpca" (the reference's own rpca + bilateral_blur, image_filtering.py:220-307: every
+        submit is one batch of <= 32 frames decomposed on its own)."""
         self._lib = _lib.load()
         h, w = int(frame_shape[0]), int(frame_shape[1])
         ch = int(frame_shape[2]) if len(frame_shape) == 3 else 1
@@ -79,6 +81,10 @@ class FilterContext:
         cfg.out_flags = (OUT_MASK if want_mask else 0) | (OUT_LABELS if want_labels else 0)
         cfg.max_frames = max_frames
         cfg.max_segments = max_segments
+        if bg_model not in ("median", "rpca"):
+            raise ValueError("bg_model must be 'median' or 'rpca'")
+        cfg.bg_model = BG_RPCA if bg_model == "rpca" else BG_MEDIAN
+        self.bg_model = bg_model
         self.cfg = cfg
         self.frame_shape = (h, w, ch) if ch == 3 else (h, w)
         self.frame_bytes = (frame_stride or (frame_pitch or w * ch) * h)
@@ -179,6 +185,13 @@ class FilterContext:
         n = self._n_last - t0 if n is None else n
         out = np.empty((n, self.roi_h, self.roi_w), dtype=self.label_dtype)
         check(self._lib.swb_get_labels(self._ctx, t0, n, ptr(out), MEM_HOST), self._ctx)
+        return out
+
+    def rpca_images(self, t0=0, n=None):
+        """bg_model="rpca": the uint8 "RPCA" images (clip(-E, 0, 255)) of the last submit."""
+        n = self._n_last - t0 if n is None else n
+        out = np.empty((n, self.roi_h, self.roi_w), dtype=np.uint8)
+        check(self._lib.swb_get_rpca(self._ctx, t0, n, ptr(out), MEM_HOST), self._ctx)
         return out
 
     def mask_bits(self, t0=0, n=None):
