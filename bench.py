@@ -43,6 +43,11 @@ CONFIGS = {
     "1080p_swarm500_classify": dict(H=1080, W=1920, roi=None, N=5, se=3, do_close=False, birds=500, chunk=16,
                                     classify=True),
 }
+# the reference's own background model (rpca + bilateral) on its own batch size (21 frames)
+CONFIGS["1080p_roi320x160_rpca21"] = dict(H=1080, W=1920, roi=[(800, 400), (1120, 560)], N=1, se=3, do_close=False,
+                                          birds=300, chunk=21, bg_model="rpca")
+CONFIGS["1080p_full_rpca21"] = dict(H=1080, W=1920, roi=None, N=1, se=3, do_close=False, birds=300, chunk=21,
+                                    bg_model="rpca")
 # BASELINE.json configs[3]: 16 videos, each with its own chimney ROI, processed concurrently
 CONFIGS["16x1080p_rois_n5_open3"] = dict(H=1080, W=1920, roi=None, N=5, se=3, do_close=False, birds=300, chunk=256,
                                          videos=16)
@@ -157,7 +162,10 @@ def cpu_baseline_sample(cfg, n_frames, threads=None):
         torch.manual_seed(SEED)
         ref_clf = rc.RefSegmentClassifier(setup_model(2, "cpu").state_dict(), "cpu")
     t0 = time.perf_counter()
-    out = rp.run_path(frames[halo:], par, history=list(frames[:halo]), want_images=True)
+    if cfg.get("bg_model") == "rpca":
+        out = rp.run_path_rpca(frames[halo:], par, want_images=True)   # the reference as written: IALM + bilateral
+    else:
+        out = rp.run_path(frames[halo:], par, history=list(frames[:halo]), want_images=True)
     if ref_clf is not None:
         class _Seg:
             pass
@@ -184,6 +192,8 @@ def run_reference(args, cfg, name):
     sample = max(2, min(8, int(24 // max(args.steps, 1)) or 2)) if cfg["H"] >= 1080 and cfg["roi"] is None else 64
     if cfg.get("classify"):
         sample = 1
+    if cfg.get("bg_model") == "rpca":
+        sample = cfg["chunk"]
     for _ in range(min(args.warmup, 1)):
         cpu_baseline_sample(cfg, 2)
     t_total, n_total, segs, threads = 0.0, 0, 0, 0
@@ -442,7 +452,7 @@ def main():
 
     ctx = swb.FilterContext((H, W, 3), roi, median_n=N, threshold=15, morph_size=cfg["se"], do_open=True,
                             do_close=cfg["do_close"], label_mode=args.label_mode, max_frames=T,
-                            max_segments=T * 4096, device=local_rank)
+                            max_segments=T * 4096, device=local_rank, bg_model=cfg.get("bg_model", "median"))
     stream = torch.cuda.Stream()          # a real (non-default) stream: the library launches on it and the
     ctx.set_stream(stream.cuda_stream)    # CUDA events below are recorded on it
 
@@ -544,7 +554,7 @@ def main():
     if not args.no_e2e:
         ctx_h = swb.FilterContext((H, W, 3), roi, median_n=N, threshold=15, morph_size=cfg["se"], do_open=True,
                                   do_close=cfg["do_close"], label_mode=args.label_mode, max_frames=T,
-                                  max_segments=T * 4096, device=local_rank)
+                                  max_segments=T * 4096, device=local_rank, bg_model=cfg.get("bg_model", "median"))
         host = torch.empty((halo + T, H, W, 3), dtype=torch.uint8, pin_memory=True)
         host.copy_(bufs[0])
         torch.cuda.synchronize()
@@ -585,11 +595,22 @@ def main():
             n_cpu = args.cpu_frames or 12
         if cfg.get("classify"):
             n_cpu = args.cpu_frames or 2
-        cpu_fps, cpu_dt, _, threads = cpu_baseline_sample(cfg, n_cpu)
-        cpu = {"value": cpu_fps, "unit": "frames/s", "cores": threads, "kind": "port",
-               "sample": "%d frames of %s (%.1f s) through oracle/reference_path.py: the reference's cv2/scipy calls "
-                         "+ np.median/absdiff; cv2 pool of %d threads, numpy/scipy stages single-threaded; "
-                         "host has %d CPUs" % (n_cpu, args.config, cpu_dt, threads, os.cpu_count())}
+        if cfg.get("bg_model") == "rpca":
+            n_cpu = T                              # one batch: the decomposition cannot be sampled
+            if roi is None and not args.cpu_frames:
+                n_cpu = 0                          # ~86 s per 21-frame 1080p batch: only with --cpu-frames
+        if n_cpu > 0:
+            cpu_fps, cpu_dt, _, threads = cpu_baseline_sample(cfg, n_cpu)
+            cpu = {"value": cpu_fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                   "sample": "%d frames of %s (%.1f s) through oracle/reference_path.py: the reference's cv2/scipy calls "
+                             "+ %s; cv2 pool of %d threads, numpy/scipy stages single-threaded; host has %d CPUs"
+                             % (n_cpu, args.config, cpu_dt,
+                                "its IALM rpca (numpy/LAPACK svd)" if cfg.get("bg_model") == "rpca" else "np.median/absdiff",
+                                threads, os.cpu_count())}
+        else:
+            cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "port",
+                   "sample": "skipped by default (SURVEY.md measured 86 s per 21-frame 1080p batch = 0.24 frames/s for "
+                             "the reference as written); pass --cpu-frames 21 to time it here"}
 
     if rank == 0:
         line = {

@@ -127,12 +127,15 @@ k_rpca_gram(const uint8_t* __restrict__ X, const double* __restrict__ A, const d
 }
 
 // fixed-order sum of the per-CTA partials -> packed upper triangle
+// (one warp per pair: lane l sums CTAs l, l + 32, ...; then a shuffle tree — the same order every run)
 __global__ void k_rpca_gram_reduce(const double* __restrict__ gpart, int nctas, int npairs, double* __restrict__ G) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (q >= npairs) return;
     double s = 0.0;
-    for (int c = 0; c < nctas; ++c) s += gpart[(long long)c * npairs + q];
-    G[q] = s;
+    for (int c = lane; c < nctas; c += 32) s += gpart[(long long)c * npairs + q];
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_down_sync(0xFFFFFFFFu, s, d);
+    if (lane == 0) G[q] = s;
 }
 
 // pass 2: A' = M W, Z, Y, |Z|^2, uint8 image of E.  Thread = pixel row; M and E of the row sit in
@@ -179,6 +182,68 @@ k_rpca_apply(const uint8_t* __restrict__ X, const double* __restrict__ A, double
     __shared__ double red[RP_THREADS / 32];
     for (int d = 16; d > 0; d >>= 1) zz += __shfl_down_sync(0xFFFFFFFFu, zz, d);
     __syncthreads();
+    if ((t & 31) == 0) red[t >> 5] = zz;
+    __syncthreads();
+    if (t == 0) {
+        double s = 0.0;
+        for (int w = 0; w < RP_THREADS / 32; ++w) s += red[w];
+        zpart[blockIdx.x] = s;
+    }
+}
+
+// pass 2 for a compile-time batch size (the reference's queue holds 21 frames): the row's E and
+// the accumulators of A' = M W stay in registers, W rows are read from shared memory as double2
+// broadcasts (one load per two multiply-adds instead of two loads per multiply-add).
+template <int N>
+__global__ void __launch_bounds__(RP_THREADS, 2)
+k_rpca_apply_n(const uint8_t* __restrict__ X, const double* __restrict__ A, double* __restrict__ Anew,
+               double* __restrict__ Y, long long P, double inv_mu, double thr, double mu,
+               const double* __restrict__ Wg, double* __restrict__ zpart, uint8_t* __restrict__ out) {
+    constexpr int NP = (N + 1) & ~1;               // W rows padded to an even length
+    __shared__ __align__(16) double sW[N * NP];
+    extern __shared__ double sE[];                 // [N][RP_THREADS]: the row's E (registers hold the accumulators)
+    const int t = threadIdx.x;
+    for (int i = t; i < N * NP; i += RP_THREADS) {
+        const int r = i / NP, c = i - r * NP;
+        sW[i] = c < N ? Wg[r * N + c] : 0.0;
+    }
+    __syncthreads();
+    double zz = 0.0;
+    const long long ntiles = (P + RP_THREADS - 1) / RP_THREADS;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long p = tile * RP_THREADS + t;
+        if (p >= P) continue;
+        double acc[NP];
+#pragma unroll
+        for (int j = 0; j < NP; ++j) acc[j] = 0.0;
+#pragma unroll 3
+        for (int i = 0; i < N; ++i) {
+            const long long idx = (long long)i * P + p;
+            const double x = (double)X[idx];
+            const double t2 = __dmul_rn(inv_mu, Y[idx]);
+            const double e = shrink(__dadd_rn(x - A[idx], t2), thr);
+            sE[i * RP_THREADS + t] = e;
+            const double m = __dadd_rn(x - e, t2);
+            out[idx] = (uint8_t)fmin(fmax(-e, 0.0), 255.0);
+            const double2* wr = reinterpret_cast<const double2*>(sW + i * NP);
+#pragma unroll
+            for (int j = 0; j < NP / 2; ++j) {
+                const double2 w2 = wr[j];
+                acc[2 * j] = fma(m, w2.x, acc[2 * j]);
+                acc[2 * j + 1] = fma(m, w2.y, acc[2 * j + 1]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            const long long idx = (long long)j * P + p;
+            const double z = ((double)X[idx] - acc[j]) - sE[j * RP_THREADS + t];
+            Anew[idx] = acc[j];
+            Y[idx] = __dadd_rn(Y[idx], __dmul_rn(mu, z));
+            zz = fma(z, z, zz);
+        }
+    }
+    __shared__ double red[RP_THREADS / 32];
+    for (int d = 16; d > 0; d >>= 1) zz += __shfl_down_sync(0xFFFFFFFFu, zz, d);
     if ((t & 31) == 0) red[t >> 5] = zz;
     __syncthreads();
     if (t == 0) {
@@ -316,6 +381,8 @@ cudaError_t rpca_run(cudaStream_t s, const uint8_t* X, int n, long long P, RpcaW
     if (once.need()) {
         cudaFuncSetAttribute(k_rpca_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_gram);
         cudaFuncSetAttribute(k_rpca_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_apply);
+        cudaFuncSetAttribute(k_rpca_apply_n<21>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             21 * RP_THREADS * (int)sizeof(double));
     }
 
     cudaMemsetAsync(w.sumsq, 0, 16, s);
@@ -344,7 +411,7 @@ cudaError_t rpca_run(cudaStream_t s, const uint8_t* X, int n, long long P, RpcaW
         const double inv_mu = 1 / mu;
         const double thr = lmbda / mu;
         k_rpca_gram<<<nctas, RP_THREADS, n * (RP_THREADS + 1) * sizeof(double), s>>>(X, Aold, w.Y, n, P, inv_mu, thr, w.gpart);
-        k_rpca_gram_reduce<<<(npairs + 127) / 128, 128, 0, s>>>(w.gpart, nctas, npairs, w.G);
+        k_rpca_gram_reduce<<<(npairs * 32 + 127) / 128, 128, 0, s>>>(w.gpart, nctas, npairs, w.G);
         cudaMemcpyAsync(hG, w.G, (size_t)npairs * sizeof(double), cudaMemcpyDeviceToHost, s);
         if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
         for (int i = 0, q = 0; i < n; ++i)
@@ -362,8 +429,12 @@ cudaError_t rpca_run(cudaStream_t s, const uint8_t* X, int n, long long P, RpcaW
                 hW[(size_t)i * n + j] = acc;
             }
         cudaMemcpyAsync(w.W, hW, (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice, s);
-        k_rpca_apply<<<nctas, RP_THREADS, (size_t)(n * n + 2 * n * RP_THREADS) * sizeof(double), s>>>(
-            X, Aold, Anew, w.Y, n, P, inv_mu, thr, mu, w.W, w.zpart, out);
+        if (n == 21)
+            k_rpca_apply_n<21><<<nctas, RP_THREADS, 21 * RP_THREADS * sizeof(double), s>>>(X, Aold, Anew, w.Y, P, inv_mu, thr, mu,
+                                                                                           w.W, w.zpart, out);
+        else
+            k_rpca_apply<<<nctas, RP_THREADS, (size_t)(n * n + 2 * n * RP_THREADS) * sizeof(double), s>>>(
+                X, Aold, Anew, w.Y, n, P, inv_mu, thr, mu, w.W, w.zpart, out);
         cudaMemcpyAsync(hZ, w.zpart, (size_t)nctas * sizeof(double), cudaMemcpyDeviceToHost, s);
         launches += 3;
         if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
