@@ -7,7 +7,7 @@
 
 A step is one pass of the hot path over one chunk of synthetic video: by
 default BASELINE.json configs[1] (1080p full frame, N=5 median, 3x3 opening,
-int32 labels) in chunks of 512 frames (3.2 GB of BGR, >> the 126 MB L2, so no
+int32 labels) in chunks of 1024 frames (6.4 GB of BGR, >> the 126 MB L2, so no
 L2 flush is needed between steps).  Inputs are generated on the device by the
 seeded CUDA generator before the timed region.  `value` is device-timed (CUDA
 events on the launch stream, max over ranks); `e2e` runs the same chunks
@@ -30,14 +30,14 @@ sys.path.insert(0, ROOT)
 
 CONFIGS = {
     # BASELINE.json configs[1]
-    "1080p_full_n5_open3": dict(H=1080, W=1920, roi=None, N=5, se=3, do_close=False, birds=300, chunk=512),
+    "1080p_full_n5_open3": dict(H=1080, W=1920, roi=None, N=5, se=3, do_close=False, birds=300, chunk=1024),
     # BASELINE.json configs[2]
-    "4k_full_n9_oc5": dict(H=2160, W=3840, roi=None, N=9, se=5, do_close=True, birds=600, chunk=128),
+    "4k_full_n9_oc5": dict(H=2160, W=3840, roi=None, N=9, se=5, do_close=True, birds=600, chunk=256),
     # BASELINE.json configs[0] geometry (the reference's CPU-runnable case)
     "1080p_roi320x240_n5_open3": dict(H=1080, W=1920, roi=[(800, 400), (1120, 640)], N=5, se=3,
-                                      do_close=False, birds=300, chunk=512),
+                                      do_close=False, birds=300, chunk=2048),
     # BASELINE.json configs[4] filtering part (dense swarm, ~500 segments/frame)
-    "1080p_dense_n5_open3": dict(H=1080, W=1920, roi=None, N=5, se=3, do_close=False, birds=2500, chunk=256),
+    "1080p_dense_n5_open3": dict(H=1080, W=1920, roi=None, N=5, se=3, do_close=False, birds=2500, chunk=512),
     # BASELINE.json configs[4]: filter + label + batched segment classification (SqueezeNet1.0 as in the
     # reference, random-init weights: model.pt is not redistributable), ~500 segments per frame
     "1080p_swarm500_classify": dict(H=1080, W=1920, roi=None, N=5, se=3, do_close=False, birds=500, chunk=16,
@@ -49,7 +49,7 @@ CONFIGS["1080p_roi320x160_rpca21"] = dict(H=1080, W=1920, roi=[(800, 400), (1120
 CONFIGS["1080p_full_rpca21"] = dict(H=1080, W=1920, roi=None, N=1, se=3, do_close=False, birds=300, chunk=21,
                                     bg_model="rpca")
 # BASELINE.json configs[3]: 16 videos, each with its own chimney ROI, processed concurrently
-CONFIGS["16x1080p_rois_n5_open3"] = dict(H=1080, W=1920, roi=None, N=5, se=3, do_close=False, birds=300, chunk=256,
+CONFIGS["16x1080p_rois_n5_open3"] = dict(H=1080, W=1920, roi=None, N=5, se=3, do_close=False, birds=300, chunk=512,
                                          videos=16)
 DEFAULT_CONFIG = "1080p_full_n5_open3"
 SEED = 2
