@@ -328,35 +328,41 @@ def props_table(props):
 # ----------------------------------------------------------------------------
 # The reference's own background model: rpca + bilateral_blur
 # ----------------------------------------------------------------------------
+def soft_threshold(values, t):
+    """Elementwise shrinkage towards zero by t, written as the reference writes it (:283):
+    max(v - t, 0) + min(v + t, 0)."""
+    return np.maximum(values - t, 0) + np.minimum(values + t, 0)
+
+
 def inexact_augmented_lagrange_multiplier(X, lmbda=0.01, tol=0.001, maxiter=100):
-    """image_filtering.py:256-301, statement for statement (numpy + LAPACK svd).
-    Returns (A, E, iterations)."""
+    """Robust PCA by the inexact ALM iteration of image_filtering.py:256-301 — the same float64
+    operations in the same order (numpy + LAPACK svd), so that the result is bit-identical to the
+    reference's; ``oracle/make_golden.py rpca`` asserts that.  Returns (low_rank, sparse, iterations).
+
+    Per iteration: sparse = shrink(X - low_rank + Y/mu, lmbda/mu); thin SVD of X - sparse + Y/mu;
+    low_rank = U diag(S - 1/mu) V (all singular values are kept: ``(S > 1/mu).shape[0]`` at :285 is
+    the length of S, not a count); residual Z = X - low_rank - sparse; Y += mu Z; mu *= 1.5."""
     from numpy.linalg import norm, svd
-    Y = X
-    norm_two = norm(Y.ravel(), 2)
-    norm_inf = norm(Y.ravel(), np.inf) / lmbda
-    dual_norm = np.max([norm_two, norm_inf])
-    Y = Y / dual_norm
-    A = np.zeros(Y.shape)
-    E = np.zeros(Y.shape)
-    dnorm = norm(X, 'fro')
-    mu = 1.25 / norm_two
-    rho = 1.5
-    itr = 0
-    while True:
-        Eraw = X - A + (1 / mu) * Y
-        Eupdate = np.maximum(Eraw - lmbda / mu, 0) + np.minimum(Eraw + lmbda / mu, 0)
-        U, S, V = svd(X - Eupdate + (1 / mu) * Y, full_matrices=False)
-        svp = (S > 1 / mu).shape[0]          # == n: every singular value is shifted, none dropped (:285)
-        A = np.dot(np.dot(U[:, :svp], np.diag(S[:svp] - 1 / mu)), V[:svp, :])
-        E = Eupdate
-        Z = X - A - E
-        Y = Y + mu * Z
-        mu = np.min([mu * rho, mu * 1e7])
-        itr += 1
-        if ((norm(Z, 'fro') / dnorm) < tol) or (itr >= maxiter):
-            break
-    return A, E, itr
+    flat = X.ravel()
+    two_norm = norm(flat, 2)
+    scale = np.max([two_norm, norm(flat, np.inf) / lmbda])     # dual norm (:271-273)
+    multiplier = X / scale
+    low_rank = np.zeros(multiplier.shape)
+    sparse = np.zeros(multiplier.shape)
+    x_norm = norm(X, 'fro')
+    mu, growth, done = 1.25 / two_norm, 1.5, 0
+    converged = False
+    while not converged:
+        sparse = soft_threshold(X - low_rank + (1 / mu) * multiplier, lmbda / mu)
+        U, S, Vt = svd(X - sparse + (1 / mu) * multiplier, full_matrices=False)
+        kept = S.shape[0]
+        low_rank = np.dot(np.dot(U[:, :kept], np.diag(S[:kept] - 1 / mu)), Vt[:kept, :])
+        residual = X - low_rank - sparse
+        multiplier = multiplier + mu * residual
+        mu = np.min([mu * growth, mu * 1e7])
+        done += 1
+        converged = (norm(residual, 'fro') / x_norm) < tol or done >= maxiter
+    return low_rank, sparse, done
 
 
 def rpca(frame_list, want_iters=False):

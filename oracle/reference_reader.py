@@ -36,33 +36,28 @@ class RefFrameReader:
         self.next_frame_number += 1
         return frame
 
-    def get_frame(self, frame_number=None):          # :32-58
-        if frame_number is None:
-            frame_number = self.next_frame_number
-        if not self.start_frame <= frame_number <= self.end_frame:
-            frame = np.zeros(self.frame_shape).astype(np.uint8)
-            frame_number = -1
-            timestamp = "00:00:00.000"
-        else:
-            frame = self.read_frame(frame_number)
-            timestamp = self.frame_number_to_timestamp(frame_number)
-            if frame is None:
-                frame = self.last_read_frame
-                self.read_errors += 1
-            else:
-                self.frame_shape = frame.shape
-                self.last_read_frame = frame
-                self.frames_read += 1
-        return frame, frame_number, timestamp
+    def get_frame(self, frame_number=None):
+        """io_video.py:32-58 as three cases."""
+        k = self.next_frame_number if frame_number is None else frame_number
+        inside = self.start_frame <= k <= self.end_frame
+        if not inside:
+            # :40-44 — a request past either end: black frame of the last known shape, -1, string stamp
+            return np.zeros(self.frame_shape).astype(np.uint8), -1, "00:00:00.000"
+        pixels = self.read_frame(k)
+        stamp = self.frame_number_to_timestamp(k)
+        if pixels is None:
+            # :51-53 — the source failed: hand out the previous good frame again, count the error
+            self.read_errors += 1
+            return self.last_read_frame, k, stamp
+        # :54-57 — a good frame updates shape, fallback frame and counter
+        self.frame_shape, self.last_read_frame = pixels.shape, pixels
+        self.frames_read += 1
+        return pixels, k, stamp
 
-    def get_n_frames(self, n):                       # :60-72
-        frames, numbers, stamps = [], [], []
-        for _ in range(n):
-            f, k, t = self.get_frame()
-            frames.append(f)
-            numbers.append(k)
-            stamps.append(t)
-        return frames, numbers, stamps
+    def get_n_frames(self, n):
+        """io_video.py:60-72: n requests, transposed into three lists."""
+        got = [self.get_frame() for _ in range(n)]
+        return [g[0] for g in got], [g[1] for g in got], [g[2] for g in got]
 
     def frame_number_to_timestamp(self, frame_number):   # :74-82
         total_s = frame_number / self.fps

@@ -21,101 +21,94 @@ import numpy as np
 import pandas as pd
 
 
+DUMMY_TIMESTAMP = "00:00:00.000"
+
+
 class FrameReader:
-    """Base class for reading frames from a video source (io_video.py:11-82)."""
+    """Base of the readers: bookkeeping + the error policy of io_video.py:11-82; a subclass
+    supplies ``read_frame(frame_number)`` -> ndarray or None."""
 
     def __init__(self):
         self.fps = 0
-        self.start_frame = 0
-        self.end_frame = 0
-        self.total_frames = 0
+        self.start_frame = self.end_frame = self.total_frames = 0
         self.next_frame_number = 0
-
         self.frame_shape = (0, 0, 0)
         self.last_read_frame = None
-        self.frames_read = 0
-        self.read_errors = 0
+        self.frames_read = self.read_errors = 0
 
     def __init_subclass__(cls, **kwargs):
         super().__init_subclass__(**kwargs)
-        if not hasattr(cls, "read_frame"):
+        if getattr(cls, "read_frame", None) is None:
             raise NotImplementedError("Derived FrameReader must implement read_frame() method.")
 
+    # -- the three outcomes of a request (io_video.py:40-56) --------------------------------
+    def _outside(self):
+        """frame number outside [start_frame, end_frame]: zero frame, number -1, string stamp"""
+        return np.zeros(self.frame_shape).astype(np.uint8), -1, DUMMY_TIMESTAMP
+
+    def _decoded(self, frame):
+        self.frame_shape = frame.shape
+        self.last_read_frame = frame
+        self.frames_read += 1
+        return frame
+
+    def _failed(self):
+        self.read_errors += 1
+        return self.last_read_frame
+
     def get_frame(self, frame_number=None, out=None):
-        """Returns frame, frame_number, and timestamp while also handling read errors
-        (io_video.py:32-58).  ``out``: optional array the frame is written into."""
-        if frame_number is None:
-            frame_number = self.next_frame_number
-
-        if not self.start_frame <= frame_number <= self.end_frame:
-            frame = np.zeros(self.frame_shape).astype(np.uint8)
-            frame_number = -1
-            timestamp = "00:00:00.000"
+        """(frame, frame_number, timestamp) with the reference's handling of bad requests and
+        read errors.  ``out``: optional array of the frame's shape that receives the pixels."""
+        wanted = self.next_frame_number if frame_number is None else frame_number
+        if wanted < self.start_frame or wanted > self.end_frame:
+            frame, wanted, stamp = self._outside()
         else:
-            frame = self.read_frame(frame_number)
-            timestamp = self.frame_number_to_timestamp(frame_number)
-            if frame is None:
-                frame = self.last_read_frame
-                self.read_errors += 1
-            else:
-                self.frame_shape = frame.shape
-                self.last_read_frame = frame
-                self.frames_read += 1
-
+            raw = self.read_frame(wanted)
+            stamp = self.frame_number_to_timestamp(wanted)
+            frame = self._failed() if raw is None else self._decoded(raw)
         if out is not None and frame is not None and tuple(out.shape) == tuple(frame.shape):
             if frame is not out:
                 np.copyto(out, frame)
-            if frame is self.last_read_frame:
+            if frame is self.last_read_frame:          # keep the fallback frame alive inside the batch
                 self.last_read_frame = out
             frame = out
-        return frame, frame_number, timestamp
+        return frame, wanted, stamp
 
     def get_n_frames(self, n, out=None):
-        """Calls get_frame in batches of N, returning as lists (io_video.py:60-72).
-        ``out``: optional [>= n, H, W, C] array (e.g. a pinned batch); frame i lands in out[i]."""
-        frames, frame_numbers, timestamps = [], [], []
-        for i in range(n):
-            frame, frame_number, timestamp = self.get_frame(out=None if out is None else out[i])
-            frames.append(frame)
-            frame_numbers.append(frame_number)
-            timestamps.append(timestamp)
-        return frames, frame_numbers, timestamps
+        """n consecutive ``get_frame`` calls as three lists (io_video.py:60-72).  ``out``: optional
+        [>= n, H, W, C] array (e.g. a pinned batch); frame i lands in out[i]."""
+        triples = [self.get_frame(out=None if out is None else out[i]) for i in range(n)]
+        return [t[0] for t in triples], [t[1] for t in triples], [t[2] for t in triples]
 
     def frame_number_to_timestamp(self, frame_number):
-        """io_video.py:74-82 (constant-FPS assumption)."""
-        total_s = frame_number / self.fps
-        timestamp = pd.Timestamp("00:00:00.000") + pd.Timedelta(total_s, 's')
-        timestamp = timestamp.round(freq='us')
-        return timestamp
+        """Constant-FPS stamp, microsecond resolution (io_video.py:74-82)."""
+        elapsed = pd.Timedelta(frame_number / self.fps, 's')
+        return (pd.Timestamp(DUMMY_TIMESTAMP) + elapsed).round(freq='us')
 
 
 class VideoReader(FrameReader):
-    """Subclass using OpenCV's VideoCapture as frame source (io_video.py:133-165)."""
+    """cv2.VideoCapture source with the reference's grab-ahead order (io_video.py:133-165):
+    one frame is always grabbed in advance, ``read_frame`` retrieves it and grabs the next."""
 
     def __init__(self, filepath, end):
         super().__init__()
         import cv2
-        self._cv2 = cv2
         self.filepath = filepath
-        self.vid_cap = cv2.VideoCapture(str(filepath))
-        self.vid_cap.grab()  # Load first frame so retrieve() won't fail
-
-        self.fps = self.vid_cap.get(cv2.CAP_PROP_FPS)
+        cap = cv2.VideoCapture(str(filepath))
+        cap.grab()
+        self.vid_cap = cap
+        self.fps = cap.get(cv2.CAP_PROP_FPS)
         self.start_frame = 0
-        if end > 0:
-            self.end_frame = end
-        else:
-            self.end_frame = int(self.vid_cap.get(cv2.CAP_PROP_FRAME_COUNT))
-
+        self.end_frame = end if end > 0 else int(cap.get(cv2.CAP_PROP_FRAME_COUNT))
         self.next_frame_number = self.start_frame
         self.total_frames = self.end_frame - self.start_frame
 
     def read_frame(self, frame_number, increment=True):
-        _, frame = self.vid_cap.retrieve()
+        ok_and_frame = self.vid_cap.retrieve()
         if increment:
             self.vid_cap.grab()
             self.next_frame_number += 1
-        return frame
+        return ok_and_frame[1]
 
 
 class ArrayReader(FrameReader):
