@@ -405,7 +405,7 @@ cudaError_t rpca_run(cudaStream_t s, const uint8_t* X, int n, long long P, RpcaW
 
     double* Aold = w.A0;
     double* Anew = w.A1;
-    std::vector<double> g((size_t)n * n), d, v;
+    std::vector<double> g((size_t)n * n), d, v, vprev, tmp((size_t)n * n), vb;
     int itr = 0;
     while (true) {
         const double inv_mu = 1 / mu;
@@ -416,7 +416,33 @@ cudaError_t rpca_run(cudaStream_t s, const uint8_t* X, int n, long long P, RpcaW
         if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
         for (int i = 0, q = 0; i < n; ++i)
             for (int j = i; j < n; ++j, ++q) g[(size_t)i * n + j] = g[(size_t)j * n + i] = hG[q];
-        jacobi_eigh(n, g, d, v);
+        if (vprev.empty()) {
+            jacobi_eigh(n, g, d, v);
+        } else {
+            // warm start: in the eigenbasis of the previous iteration G is nearly diagonal, so the
+            // Jacobi sweeps that remain are two or three instead of seven (the eigenproblem is the
+            // bulk of an iteration for ROI-sized frames).  B = Vp^T G Vp;  G = (Vp Vb) diag(d) (Vp Vb)^T
+            for (int i = 0; i < n; ++i)
+                for (int j = 0; j < n; ++j) {
+                    double acc = 0.0;
+                    for (int k = 0; k < n; ++k) acc += g[(size_t)i * n + k] * vprev[(size_t)k * n + j];
+                    tmp[(size_t)i * n + j] = acc;
+                }
+            for (int i = 0; i < n; ++i)
+                for (int j = i; j < n; ++j) {
+                    double acc = 0.0;
+                    for (int k = 0; k < n; ++k) acc += vprev[(size_t)k * n + i] * tmp[(size_t)k * n + j];
+                    g[(size_t)i * n + j] = g[(size_t)j * n + i] = acc;
+                }
+            jacobi_eigh(n, g, d, vb);
+            v.assign((size_t)n * n, 0.0);
+            for (int i = 0; i < n; ++i)
+                for (int k = 0; k < n; ++k) {
+                    const double a = vprev[(size_t)i * n + k];
+                    for (int j = 0; j < n; ++j) v[(size_t)i * n + j] += a * vb[(size_t)k * n + j];
+                }
+        }
+        vprev = v;
         // W = V diag((S - 1/mu) / S) V^T  (svp == n: every singular value is shifted, none is dropped)
         for (int i = 0; i < n; ++i)
             for (int j = 0; j < n; ++j) {
