@@ -393,6 +393,36 @@ def test_sub_batches_equal_one_batch(monkeypatch, n, T, se, close, mode):
         assert np.array_equal(ctx.labels(), labels_d)
 
 
+def test_fuzz_small_shapes_and_parameters():
+    """Seeded sweep over odd frame / ROI shapes (down to one pixel), every window length,
+    both structuring elements, open / close combinations, thresholds, host and device frames."""
+    import torch
+    rng = np.random.default_rng(20241018)
+    for case in range(28):
+        H, W = int(rng.integers(1, 90)), int(rng.integers(1, 150))
+        T = int(rng.integers(1, 11))
+        n = int(rng.choice([1, 3, 5, 7, 9]))
+        se = int(rng.choice([3, 5]))
+        do_open, do_close = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+        if not (do_open or do_close):
+            do_open = True
+        x0, y0 = int(rng.integers(0, W)), int(rng.integers(0, H))
+        x1, y1 = int(rng.integers(x0 + 1, W + 1)), int(rng.integers(y0 + 1, H + 1))
+        region = [(x0, y0), (x1, y1)]
+        frames = synth.synth_video(100 + case, case % 3, int(rng.integers(0, 50)), T, H, W, int(rng.integers(0, 25)))
+        if case % 4 == 0:
+            frames = rng.integers(0, 256, size=frames.shape, dtype=np.uint8)          # pure noise: dense labelling
+        mode = "u8" if case % 2 else "i32"
+        thresh = int(rng.choice([0, 7, 15, 40]))
+        submit = torch.from_numpy(frames).cuda() if case % 3 == 0 else None
+        try:
+            check_against_oracle(frames, region, n=n, thresh=thresh, se=se, do_open=do_open, do_close=do_close,
+                                 mode=mode, submit_frames=submit, n_halo=0, max_segments=T * (H * W + 16))
+        except AssertionError as e:
+            raise AssertionError("case %d: H=%d W=%d T=%d n=%d se=%d open=%s close=%s roi=%r mode=%s thresh=%d: %s"
+                                 % (case, H, W, T, n, se, do_open, do_close, region, mode, thresh, e))
+
+
 def test_device_resident_input_zero_copy():
     import torch
     frames = synth.synth_video(28, 0, 0, 10, 72, 160, 30)
