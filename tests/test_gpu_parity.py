@@ -423,6 +423,40 @@ def test_fuzz_small_shapes_and_parameters():
                                  % (case, H, W, T, n, se, do_open, do_close, region, mode, thresh, e))
 
 
+def test_concurrent_contexts_on_their_own_streams():
+    """BASELINE configs[3]: several videos per GPU, one context + CUDA stream each, submits
+    interleaved without synchronising in between — every context must still produce exactly
+    what it produces alone."""
+    import torch
+    videos = []
+    for v, (H, W, region, n) in enumerate([(96, 160, [(10, 8), (150, 90)], 5), (120, 200, [(33, 20), (180, 100)], 9),
+                                            (80, 128, [(0, 0), (128, 80)], 5), (64, 256, [(40, 3), (250, 60)], 3)]):
+        frames = synth.synth_video(40 + v, v, 0, 24, H, W, 30)
+        par = rp.PathParams(region, n, 15, 3, True, False, "i32")
+        videos.append(dict(frames=torch.from_numpy(frames).cuda(), want=rp.run_path(frames, par), region=region, n=n,
+                           shape=frames.shape[1:], stream=torch.cuda.Stream()))
+    ctxs = [swb.FilterContext(d["shape"], d["region"], median_n=d["n"], label_mode="i32", max_frames=8) for d in videos]
+    try:
+        for c, d in zip(ctxs, videos):
+            c.set_stream(d["stream"].cuda_stream)
+        got = [[] for _ in videos]
+        for t0 in (0, 8, 16):                                   # three rounds of interleaved asynchronous submits
+            for c, d in zip(ctxs, videos):
+                c.submit(d["frames"][t0:t0 + 8])                # history carried; no sync between contexts
+            for k, c in enumerate(ctxs):
+                rows, counts = c.collect()
+                got[k].append((c.labels(), counts))
+        for k, d in enumerate(videos):
+            labels = np.concatenate([g[0] for g in got[k]])
+            counts = np.concatenate([g[1] for g in got[k]])
+            for t, rec in enumerate(d["want"]):
+                assert np.array_equal(labels[t], rec["labels"]), (k, t)
+                assert counts[t] == len(rec["props"]), (k, t)
+    finally:
+        for c in ctxs:
+            c.close()
+
+
 def test_device_resident_input_zero_copy():
     import torch
     frames = synth.synth_video(28, 0, 0, 10, 72, 160, 30)
