@@ -40,6 +40,7 @@ CONFIGS = {
     "1080p_dense_n5_open3": dict(H=1080, W=1920, roi=None, N=5, se=3, do_close=False, birds=2500, chunk=512),
     # BASELINE.json configs[4]: filter + label + batched segment classification (SqueezeNet1.0 as in the
     # reference, random-init weights: model.pt is not redistributable), ~500 segments per frame
+    "1080p_swarm500_n5_open3": dict(H=1080, W=1920, roi=None, N=5, se=3, do_close=False, birds=500, chunk=1024),
     "1080p_swarm500_classify": dict(H=1080, W=1920, roi=None, N=5, se=3, do_close=False, birds=500, chunk=16,
                                     classify=True),
 }
