@@ -1058,6 +1058,10 @@ static void launch_local(cudaStream_t s, const uint32_t* fbits, int T, const Geo
     }
 }
 
+// grid of the kernels that walk the partial list (its length is only known on the device): enough CTAs
+// that a thread sees one or two partials — they are chains of dependent loads, parallelism is what hides them
+constexpr int PART_GRID = 148 * 16;
+
 cudaError_t launch_ccl(cudaStream_t s, const uint32_t* fbits, int T, const Geom& g, const CclBuffers& b,
                        void* labels, int label_elem_size, int* n_launches, cudaEvent_t* ev, int n_ev,
                        const CclChain* chain) {
@@ -1088,7 +1092,7 @@ cudaError_t launch_ccl(cudaStream_t s, const uint32_t* fbits, int T, const Geom&
         }
         launches += 3;
         mark();
-        k_root_count<<<296, 256, 0, s>>>(b.parts, b.pcount, b.cap_parts, g, b.parent, b.rowcount);
+        k_root_count<<<PART_GRID, 256, 0, s>>>(b.parts, b.pcount, b.cap_parts, g, b.parent, b.rowcount);
     } else {
         k_ccl_init<<<ggrid, gblock, 0, s>>>(fbits, g, b.parent);
         k_ccl_merge<<<ggrid, gblock, 0, s>>>(fbits, g, b.parent);
@@ -1107,12 +1111,12 @@ cudaError_t launch_ccl(cudaStream_t s, const uint32_t* fbits, int T, const Geom&
     launches += 3;
     if (tiled) {
         uint32_t* rowfill = b.rowcount + (size_t)T * g.BH;
-        k_root_place<<<296, 256, 0, s>>>(b.parts, b.pcount, b.cap_parts, g, b.parent, b.rowcount, rowfill, b.segoff,
+        k_root_place<<<PART_GRID, 256, 0, s>>>(b.parts, b.pcount, b.cap_parts, g, b.parent, b.rowcount, rowfill, b.segoff,
                                          b.rootlist, b.cap_rows);
-        k_root_rank<<<296, 256, 0, s>>>(b.parts, b.pcount, b.cap_parts, g, b.parent, b.rowcount, rowfill, b.segoff,
+        k_root_rank<<<PART_GRID, 256, 0, s>>>(b.parts, b.pcount, b.cap_parts, g, b.parent, b.rowcount, rowfill, b.segoff,
                                         b.rootlist, b.cap_rows, chain ? chain->frame_base : 0, b.rows);
         mark();
-        k_props_final<<<296, 256, 0, s>>>(b.parts, b.pcount, b.cap_parts, g, b.parent, b.segoff, b.rows, b.cap_rows);
+        k_props_final<<<PART_GRID, 256, 0, s>>>(b.parts, b.pcount, b.cap_parts, g, b.parent, b.segoff, b.rows, b.cap_rows);
         launches += 3;
     } else {
         mark();
