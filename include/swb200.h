@@ -58,7 +58,11 @@ typedef struct swb_config {
     int32_t label_mode;      /* SWB_LABELS_I32 | SWB_LABELS_U8                               */
     int32_t out_flags;       /* SWB_OUT_MASK | SWB_OUT_LABELS                                */
     int32_t max_frames;      /* max output frames per submit                                 */
-    int32_t max_segments;    /* max segment rows per submit (0 = 1024 per frame)             */
+    int32_t max_segments;    /* max segment rows per submit (0 = 1024 per frame).  Exceeding it is
+                              * reported by swb_collect (SWB_ERR_CAPACITY), never silently.  A large
+                              * submit from host memory is filtered in up to four sub-batches of
+                              * frames, each with an equal share of the labelling scratch, so a
+                              * submit whose segments all sit in a few frames may need a larger value */
     int32_t bg_model;        /* SWB_BG_MEDIAN (rolling median, BASELINE.json) or SWB_BG_RPCA */
     int32_t reserved[2];
 } swb_config;
