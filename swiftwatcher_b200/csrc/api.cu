@@ -500,6 +500,7 @@ int swb_submit(swb_ctx* ctx, const uint8_t* frames, int32_t n_frames, int32_t n_
     int launches = 0;
     if (nsub == 1) {
         if (from_host) CU(ctx, stage_in(0, n_total, s));
+        ccl_prepare(s, n_frames, g, ctx->ccl, false);
         if (ctx->timing) CU(ctx, cudaEventRecord(ctx->ev[0], s));
         Geom gm = g;                                  // geometry of the morphology input bits
         if (c.bg_model == SWB_BG_RPCA) {
@@ -523,7 +524,7 @@ int swb_submit(swb_ctx* ctx, const uint8_t* frames, int32_t n_frames, int32_t n_
                                   ctx->fbits, ctx->mask, &launches));
         if (ctx->timing) CU(ctx, cudaEventRecord(ctx->ev[2], s));
         CU(ctx, launch_ccl(s, ctx->fbits, n_frames, g, ctx->ccl, ctx->labels, ctx->label_elem, &launches,
-                           ctx->timing ? &ctx->ev[3] : nullptr, 4));
+                           ctx->timing ? &ctx->ev[3] : nullptr, 4, nullptr, true));
         ctx->ev_valid = ctx->timing;
     } else {
         cudaStream_t sw = ctx->worker;
@@ -563,10 +564,11 @@ int swb_submit(swb_ctx* ctx, const uint8_t* frames, int32_t n_frames, int32_t n_
             CclChain chain;
             chain.frame_base = f0;
             chain.segoff_base = (b > 0) ? ctx->ccl.segoff + f0 : nullptr;   // left there by sub-batch b-1
+            ccl_prepare(sw, nb, g, cb, true);
             CU(ctx, launch_fg_bits(sw, sb, C, N, nb, g, c.threshold, raw_b, aligned, &launches));
             CU(ctx, launch_morph_mask(sw, reinterpret_cast<const uint32_t*>(raw_b), nb, g, ctx->morph, fbits_b, mask_b,
                                       &launches));
-            CU(ctx, launch_ccl(sw, fbits_b, nb, g, cb, labels_b, ctx->label_elem, &launches, nullptr, 0, &chain));
+            CU(ctx, launch_ccl(sw, fbits_b, nb, g, cb, labels_b, ctx->label_elem, &launches, nullptr, 0, &chain, true));
         }
         CU(ctx, cudaEventRecord(ctx->ev_join, sw));
         CU(ctx, cudaStreamWaitEvent(s, ctx->ev_join, 0));

@@ -40,6 +40,7 @@
 //   props_final   adds every partial sum to its component's table row
 //   write_labels  dense int32 / uint8 label image: bits + parent walk to the tagged root
 #include <algorithm>
+#include <cstdlib>
 
 #include "swb_internal.cuh"
 
@@ -296,6 +297,8 @@ k_ccl_merge(const uint32_t* __restrict__ fbits, Geom g, int* parent) {
 // row above it.  grid = (ceil(Q / 32), ceil(n_boundaries / 8), T), block = (32, 8).
 __global__ void __launch_bounds__(256)
 k_ccl_boundary(const uint32_t* __restrict__ fbits, Geom g, int tile_rows, int* parent) {
+    wait_for_previous_kernel();
+    let_next_kernel_launch();
     const int q = blockIdx.x * 32 + threadIdx.x;
     const int by = (blockIdx.y * 8 + threadIdx.y + 1) * tile_rows;
     const int f = blockIdx.z;
@@ -596,6 +599,7 @@ __global__ void __launch_bounds__(256)
 k_ccl_local(const uint32_t* __restrict__ fbits, Geom g, int* __restrict__ parent, Partial* __restrict__ parts,
             int* __restrict__ pcount, int cap_parts, int32_t* __restrict__ overflow, int* __restrict__ big_tiles,
             int* __restrict__ big_count) {
+    wait_for_previous_kernel();
     if (!ccl_local_tile<BX, LocalSmem::RUNS_FAST>(fbits, g, parent, parts, pcount, cap_parts, overflow,
                                                   (int)blockIdx.y, (int)blockIdx.x)) {
         if (threadIdx.x == 0) big_tiles[atomicAdd(big_count, 1)] = (int)(blockIdx.y * gridDim.x + blockIdx.x);
@@ -608,6 +612,8 @@ __global__ void __launch_bounds__(256)
 k_ccl_local_big(const uint32_t* __restrict__ fbits, Geom g, int* __restrict__ parent, Partial* __restrict__ parts,
                 int* __restrict__ pcount, int cap_parts, int32_t* __restrict__ overflow,
                 const int* __restrict__ big_tiles, const int* __restrict__ big_count, int tiles_per_frame) {
+    wait_for_previous_kernel();
+    let_next_kernel_launch();
     const int n = *big_count;
     for (int i = blockIdx.x; i < n; i += gridDim.x) {
         const int t = big_tiles[i];
@@ -684,6 +690,8 @@ k_ccl_roots(const uint32_t* __restrict__ fbits, int T, Geom g, int* __restrict__
 // warp per frame: rowcount -> exclusive row base; nseg[f] = total
 __global__ void __launch_bounds__(256)
 k_ccl_scan(int T, Geom g, uint32_t* __restrict__ rowcount, int32_t* __restrict__ nseg) {
+    wait_for_previous_kernel();
+    let_next_kernel_launch();
     const int lane = threadIdx.x & 31;
     const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (f >= T) return;
@@ -708,6 +716,8 @@ k_ccl_scan(int T, Geom g, uint32_t* __restrict__ rowcount, int32_t* __restrict__
 __global__ void __launch_bounds__(1024)
 k_ccl_offsets(int T, const int32_t* __restrict__ nseg, int32_t* segoff, const int32_t* base, int cap_rows,
               int32_t* __restrict__ overflow) {
+    wait_for_previous_kernel();
+    let_next_kernel_launch();
     __shared__ int32_t warp_tot[32];
     __shared__ int32_t carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -832,6 +842,8 @@ __device__ __forceinline__ bool is_root_partial(const Partial& p, const int* par
 __global__ void __launch_bounds__(256)
 k_root_count(const Partial* __restrict__ parts, const int* __restrict__ pcount, int cap_parts, Geom g,
              const int* __restrict__ parent, uint32_t* __restrict__ rowcount) {
+    wait_for_previous_kernel();
+    let_next_kernel_launch();
     const int n = min(*pcount, cap_parts);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const Partial p = parts[i];
@@ -846,6 +858,8 @@ k_root_place(const Partial* __restrict__ parts, const int* __restrict__ pcount, 
              const int* __restrict__ parent, const uint32_t* __restrict__ rowbase,
              uint32_t* __restrict__ rowfill, const int32_t* __restrict__ segoff, int* __restrict__ rootlist,
              int cap_rows) {
+    wait_for_previous_kernel();
+    let_next_kernel_launch();
     const int n = min(*pcount, cap_parts);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const Partial p = parts[i];
@@ -863,6 +877,8 @@ k_root_rank(const Partial* __restrict__ parts, const int* __restrict__ pcount, i
             int* __restrict__ parent, const uint32_t* __restrict__ rowbase, const uint32_t* __restrict__ rowfill,
             const int32_t* __restrict__ segoff, const int* __restrict__ rootlist, int cap_rows, int frame_base,
             swb_segment* __restrict__ rows) {
+    wait_for_previous_kernel();
+    let_next_kernel_launch();
     const int n = min(*pcount, cap_parts);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const Partial p = parts[i];
@@ -901,6 +917,8 @@ __global__ void __launch_bounds__(256)
 k_props_final(const Partial* __restrict__ parts, const int* __restrict__ pcount, int cap_parts, Geom g,
               const int* __restrict__ parent, const int32_t* __restrict__ segoff, swb_segment* rows,
               int cap_rows) {
+    wait_for_previous_kernel();
+    let_next_kernel_launch();
     const int n = min(*pcount, cap_parts);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const Partial p = parts[i];
@@ -919,6 +937,7 @@ template <typename LT, int PX>
 __global__ void __launch_bounds__(256)
 k_write_labels(const uint32_t* __restrict__ fbits, Geom g, const int* __restrict__ parent,
                const uint32_t* __restrict__ rowbase, LT* __restrict__ labels) {
+    wait_for_previous_kernel();
     constexpr int WPS = PX;                 // words per span row (32 * PX pixels / 32)
     constexpr int RPL = 32 / WPS;           // rows covered by one load round
     constexpr int ROWS = 8;
@@ -1045,16 +1064,16 @@ static void launch_local(cudaStream_t s, const uint32_t* fbits, int T, const Geo
                              (int)LocalSmem::bytes(LocalSmem::RUNS_MAX));
     }
     int* big_count = b.pcount + 1;
-    k_ccl_local<BX><<<grid, 256, LocalSmem::bytes(LocalSmem::RUNS_FAST), s>>>(
-        fbits, g, b.parent, b.parts, b.pcount, b.cap_parts, b.overflow, b.big_tiles, big_count);
+    launch_dependent(k_ccl_local<BX>, grid, dim3(256), LocalSmem::bytes(LocalSmem::RUNS_FAST), s, fbits, g, b.parent,
+                     b.parts, b.pcount, b.cap_parts, b.overflow, b.big_tiles, big_count);
     const int big_grid = (int)std::min<long long>((long long)tiles * T, 148 * 4);
-    k_ccl_local_big<BX><<<big_grid, 256, LocalSmem::bytes(LocalSmem::RUNS_MAX), s>>>(
-        fbits, g, b.parent, b.parts, b.pcount, b.cap_parts, b.overflow, b.big_tiles, big_count, tiles);
+    launch_dependent(k_ccl_local_big<BX>, dim3(big_grid), dim3(256), LocalSmem::bytes(LocalSmem::RUNS_MAX), s,
+                     fbits, g, b.parent, b.parts, b.pcount, b.cap_parts, b.overflow, b.big_tiles, big_count, tiles);
     const int n_boundaries = tiles - 1;
     if (n_boundaries > 0) {
         const int Q = g.wpr4 >> 2;
         dim3 bgrid((Q + 31) / 32, (n_boundaries + 7) / 8, T);
-        k_ccl_boundary<<<bgrid, dim3(32, 8), 0, s>>>(fbits, g, BY, b.parent);
+        launch_dependent(k_ccl_boundary, bgrid, dim3(32, 8), 0, s, fbits, g, BY, b.parent);
     }
 }
 
@@ -1062,9 +1081,23 @@ static void launch_local(cudaStream_t s, const uint32_t* fbits, int T, const Geo
 // that a thread sees one or two partials — they are chains of dependent loads, parallelism is what hides them
 constexpr int PART_GRID = 148 * 16;
 
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("SWB_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
+// The counters the labelling kernels start from.  Done before the filtering kernels of a submit so
+// that nothing but kernels sits between K2 and the labelling chain (programmatic dependent launch).
+void ccl_prepare(cudaStream_t s, int T, const Geom& g, const CclBuffers& b, bool chained) {
+    cudaMemsetAsync(b.pcount, 0, 2 * sizeof(int), s);                  // partial counter, listed-tile counter
+    if (!chained) cudaMemsetAsync(b.overflow, 0, sizeof(int32_t), s);  // a chained submit clears it once, before its first sub-batch
+    if ((g.wpr4 >> 2) <= 32)
+        cudaMemsetAsync(b.rowcount, 0, (size_t)2 * T * g.BH * sizeof(uint32_t), s);   // rowcount, rowfill (tiled path)
+}
+
 cudaError_t launch_ccl(cudaStream_t s, const uint32_t* fbits, int T, const Geom& g, const CclBuffers& b,
                        void* labels, int label_elem_size, int* n_launches, cudaEvent_t* ev, int n_ev,
-                       const CclChain* chain) {
+                       const CclChain* chain, bool prepared) {
     int evi = 0;
     auto mark = [&]() {
         if (ev && evi < n_ev) cudaEventRecord(ev[evi++], s);
@@ -1078,10 +1111,8 @@ cudaError_t launch_ccl(cudaStream_t s, const uint32_t* fbits, int T, const Geom&
     const bool tiled = Q <= 32;      // a tile spans the full width: frames up to 4096 pixels wide
     const uint32_t* rbase_for_labels = tiled ? nullptr : b.rowcount;
     int launches = 0;
-    cudaMemsetAsync(b.pcount, 0, 2 * sizeof(int), s);                  // partial counter, listed-tile counter
-    if (!chain) cudaMemsetAsync(b.overflow, 0, sizeof(int32_t), s);    // a chained submit clears it once, before its first sub-batch
+    if (!prepared) ccl_prepare(s, T, g, b, chain != nullptr);
     if (tiled) {
-        cudaMemsetAsync(b.rowcount, 0, (size_t)2 * T * g.BH * sizeof(uint32_t), s);   // rowcount, rowfill
         switch (bx) {
             case 1: launch_local<1>(s, fbits, T, g, b); break;
             case 2: launch_local<2>(s, fbits, T, g, b); break;
@@ -1092,7 +1123,8 @@ cudaError_t launch_ccl(cudaStream_t s, const uint32_t* fbits, int T, const Geom&
         }
         launches += 3;
         mark();
-        k_root_count<<<PART_GRID, 256, 0, s>>>(b.parts, b.pcount, b.cap_parts, g, b.parent, b.rowcount);
+        launch_dependent(k_root_count, dim3(PART_GRID), dim3(256), 0, s, b.parts, b.pcount, b.cap_parts, g, b.parent,
+                         b.rowcount);
     } else {
         k_ccl_init<<<ggrid, gblock, 0, s>>>(fbits, g, b.parent);
         k_ccl_merge<<<ggrid, gblock, 0, s>>>(fbits, g, b.parent);
@@ -1101,8 +1133,9 @@ cudaError_t launch_ccl(cudaStream_t s, const uint32_t* fbits, int T, const Geom&
         const long long n_rows_w = (long long)T * g.BH;
         k_ccl_roots<<<(int)((n_rows_w * 32 + 255) / 256), 256, 0, s>>>(fbits, T, g, b.parent, b.rowcount);
     }
-    k_ccl_scan<<<(T * 32 + 255) / 256, 256, 0, s>>>(T, g, b.rowcount, b.nseg);
-    k_ccl_offsets<<<1, 1024, 0, s>>>(T, b.nseg, b.segoff, chain ? chain->segoff_base : nullptr, b.cap_rows, b.overflow);
+    launch_dependent(k_ccl_scan, dim3((T * 32 + 255) / 256), dim3(256), 0, s, T, g, b.rowcount, b.nseg);
+    launch_dependent(k_ccl_offsets, dim3(1), dim3(1024), 0, s, T, b.nseg, b.segoff,
+                     chain ? chain->segoff_base : (const int32_t*)nullptr, b.cap_rows, b.overflow);
     if (!tiled) {
         dim3 grid(4, T);
         k_seg_init<<<grid, 256, 0, s>>>(T, chain ? chain->frame_base : 0, b.nseg, b.segoff, b.rows, b.cap_rows);
@@ -1111,12 +1144,13 @@ cudaError_t launch_ccl(cudaStream_t s, const uint32_t* fbits, int T, const Geom&
     launches += 3;
     if (tiled) {
         uint32_t* rowfill = b.rowcount + (size_t)T * g.BH;
-        k_root_place<<<PART_GRID, 256, 0, s>>>(b.parts, b.pcount, b.cap_parts, g, b.parent, b.rowcount, rowfill, b.segoff,
-                                         b.rootlist, b.cap_rows);
-        k_root_rank<<<PART_GRID, 256, 0, s>>>(b.parts, b.pcount, b.cap_parts, g, b.parent, b.rowcount, rowfill, b.segoff,
-                                        b.rootlist, b.cap_rows, chain ? chain->frame_base : 0, b.rows);
+        launch_dependent(k_root_place, dim3(PART_GRID), dim3(256), 0, s, b.parts, b.pcount, b.cap_parts, g, b.parent,
+                         b.rowcount, rowfill, b.segoff, b.rootlist, b.cap_rows);
+        launch_dependent(k_root_rank, dim3(PART_GRID), dim3(256), 0, s, b.parts, b.pcount, b.cap_parts, g, b.parent,
+                         b.rowcount, rowfill, b.segoff, b.rootlist, b.cap_rows, chain ? chain->frame_base : 0, b.rows);
         mark();
-        k_props_final<<<PART_GRID, 256, 0, s>>>(b.parts, b.pcount, b.cap_parts, g, b.parent, b.segoff, b.rows, b.cap_rows);
+        launch_dependent(k_props_final, dim3(PART_GRID), dim3(256), 0, s, b.parts, b.pcount, b.cap_parts, g, b.parent,
+                         b.segoff, b.rows, b.cap_rows);
         launches += 3;
     } else {
         mark();
@@ -1131,11 +1165,11 @@ cudaError_t launch_ccl(cudaStream_t s, const uint32_t* fbits, int T, const Geom&
         const int wpb = nspans < 8 ? nspans : 8;
         dim3 grid((nspans + wpb - 1) / wpb, (g.h + 7) / 8, T);
         if (label_elem_size == 4)
-            k_write_labels<int32_t, 4><<<grid, 32 * wpb, 0, s>>>(fbits, g, b.parent, rbase_for_labels,
-                                                                 (int32_t*)labels);
+            launch_dependent(k_write_labels<int32_t, 4>, grid, dim3(32 * wpb), 0, s, fbits, g, b.parent, rbase_for_labels,
+                             (int32_t*)labels);
         else
-            k_write_labels<uint8_t, 16><<<grid, 32 * wpb, 0, s>>>(fbits, g, b.parent, rbase_for_labels,
-                                                                  (uint8_t*)labels);
+            launch_dependent(k_write_labels<uint8_t, 16>, grid, dim3(32 * wpb), 0, s, fbits, g, b.parent, rbase_for_labels,
+                             (uint8_t*)labels);
         launches += 1;
     }
     mark();

@@ -196,6 +196,7 @@ k_morph_mask(const uint32_t* __restrict__ raw_bits, Geom g, uint32_t* __restrict
              uint8_t* __restrict__ mask) {
     constexpr int HR = n_ops(PAT) * R;
     constexpr int SR = strip_rows(R, PAT);
+    wait_for_previous_kernel();                              // launched as a dependent of K1 (raw bits)
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int slab = blockIdx.x;
@@ -220,7 +221,7 @@ cudaError_t launch_pat(cudaStream_t s, const uint32_t* raw_bits, int T, const Ge
     constexpr int SR = strip_rows(R, PAT);
     const int nstrips = (g.h + SR - 1) / SR;
     dim3 grid(nslabs, (nstrips + WPB - 1) / WPB, T);
-    k_morph_mask<R, PAT><<<grid, 32 * WPB, 0, s>>>(raw_bits, g, fbits, mask);
+    launch_dependent(k_morph_mask<R, PAT>, grid, dim3(32 * WPB), 0, s, raw_bits, g, fbits, mask);
     return cudaGetLastError();
 }
 

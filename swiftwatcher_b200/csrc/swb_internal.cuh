@@ -89,7 +89,8 @@ struct CclChain {
 cudaError_t launch_ccl(cudaStream_t s, const uint32_t* fbits, int T, const Geom& g,
                        const CclBuffers& b, void* labels, int label_elem_size,
                        int* n_launches, cudaEvent_t* stage_events, int n_stage_events,
-                       const CclChain* chain = nullptr);
+                       const CclChain* chain = nullptr, bool prepared = false);
+void ccl_prepare(cudaStream_t s, int T, const Geom& g, const CclBuffers& b, bool chained);
 
 cudaError_t launch_pack_bits(cudaStream_t s, const uint8_t* img, int h, int w, uint32_t* fbits,
                              int wpr4);
@@ -140,6 +141,31 @@ struct BilateralLut {
 void bilateral_lut(int d, double sigma_color, double sigma_space, BilateralLut& lut);
 cudaError_t launch_bilateral(cudaStream_t s, const uint8_t* in, int n, int h, int w, const BilateralLut* d_lut,
                              int reverse, uint8_t* out, int thresh, uint32_t* bits, int wpr_bits);
+
+// ---- programmatic dependent launch (sm_90+): a kernel launched with launch_dependent() may be
+// scheduled while its predecessor in the stream is still draining; it must call
+// wait_for_previous_kernel() before it touches anything the predecessor wrote.  The chain of small
+// labelling kernels is latency-bound, so hiding the launch gaps is a visible share of their time.
+#ifdef __CUDACC__
+__device__ __forceinline__ void wait_for_previous_kernel() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void let_next_kernel_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_dependent(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                    Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at{};
+    at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at.val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = &at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // single-stage kernels (stages.cu)
 cudaError_t launch_stage_gray(cudaStream_t s, const uint8_t* bgr, int h, int w, uint8_t* out);
