@@ -76,7 +76,18 @@ class RefSegmentClassifier:
         return keep
 
 
+_STATE_CACHE = {}
+
+
 def random_state_dict(seed):
+    if seed in _STATE_CACHE:
+        return {k: v.clone() for k, v in _STATE_CACHE[seed].items()}
+    sd = _random_state_dict(seed)
+    _STATE_CACHE[seed] = {k: v.clone() for k, v in sd.items()}
+    return sd
+
+
+def _random_state_dict(seed):
     """Seeded random-init weights of the reference architecture (there is no network for
     checkpoints on the GPU box; model.pt itself is not redistributed).  The bias of the
     class-0 output is centred on a fixed set of noise crops so that the two classes both
