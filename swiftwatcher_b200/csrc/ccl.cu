@@ -1003,6 +1003,77 @@ k_write_labels(const uint32_t* __restrict__ fbits, Geom g, const int* __restrict
     }
 }
 
+// Dense uint8 label image (SWB_LABELS_U8: labels.astype(np.uint8), image_filtering.py:329).  One byte
+// per pixel is a quarter of the int32 traffic, so the span-per-warp layout above would be bound by its
+// instruction stream (one lane with a bird in its 16 pixels stalls the warp in a long unrolled path).
+// Here a lane owns one 32-pixel bit word = 32 output bytes: background words are two 16-byte zero
+// stores, and a word with foreground runs one compact loop over its occupied 2x2 blocks (a parent load,
+// the walk to the tagged root only when the parent changes, two bytes ORed into a 64-bit quarter).
+__global__ void __launch_bounds__(256)
+k_write_labels_u8(const uint32_t* __restrict__ fbits, Geom g, int T, const int* __restrict__ parent,
+                  const uint32_t* __restrict__ rowbase, uint8_t* __restrict__ labels) {
+    wait_for_previous_kernel();
+    // block = (32 words, 8 block rows); grid = (ceil(words per row / 32), ceil(BH / 8), T): no index divisions.
+    // A lane owns one word of BOTH pixel rows of a block row: one label lookup per occupied 2x2 block.
+    const int j = blockIdx.x * 32 + threadIdx.x;
+    const int by = blockIdx.y * 8 + threadIdx.y;
+    const int f = blockIdx.z;
+    if (j >= (g.mpitch >> 5) || by >= g.BH) return;
+    const int y = 2 * by;
+    const bool two = y + 1 < g.h;
+    const long long row = (long long)f * g.h + y;
+    const uint32_t wa = __ldg(fbits + row * g.wpr4 + j);
+    const uint32_t wb = two ? __ldg(fbits + (row + 1) * g.wpr4 + j) : 0u;
+    unsigned long long qa[4] = {0ull, 0ull, 0ull, 0ull}, qb[4] = {0ull, 0ull, 0ull, 0ull};
+    if (wa | wb) {
+        const int* par = parent + (long long)f * g.BH * g.BW;
+        const uint32_t* rbase = rowbase ? rowbase + (long long)f * g.BH : nullptr;
+        const int b0 = by * g.BW + 16 * j;
+        const uint32_t P = wa | wb;
+        uint32_t occ = (P | (P >> 1)) & EVEN;
+        int last_p = 0x7FFFFFFF;
+        uint32_t lab = 0;
+        while (occ) {
+            const int b2 = __ffs((int)occ) - 1;              // bit 2k of block k
+            occ &= occ - 1;
+            const int k = b2 >> 1;
+            const int p0 = par[b0 + k];
+            if (p0 != last_p) {                              // walk to the tagged root (the tag is -label)
+                int x = b0 + k, v = p0;
+                while (v >= 0) {
+                    x = v;
+                    v = par[x];
+                }
+                lab = (uint32_t)(rbase ? (int)rbase[x / g.BW] - v : -v) & 0xFFu;
+                last_p = p0;
+            }
+            const uint32_t both = lab | (lab << 8);
+            const uint32_t pa = (wa >> b2) & 3u, pb = (wb >> b2) & 3u;
+            // two mask bits -> two bytes of 0xFF: bit 0 -> 0x00FF, bit 1 -> 0xFF00
+            const uint32_t ma = (pa & 1u) * 0xFFu | (pa >> 1) * 0xFF00u, mb = (pb & 1u) * 0xFFu | (pb >> 1) * 0xFF00u;
+            const int sh = 16 * (k & 3);
+            const unsigned long long ia = (unsigned long long)(both & ma) << sh, ib = (unsigned long long)(both & mb) << sh;
+            const int qi = k >> 2;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                qa[q] |= qi == q ? ia : 0ull;
+                qb[q] |= qi == q ? ib : 0ull;
+            }
+        }
+    }
+    // one 32-byte store per lane and row (STG.256): whole sectors, a warp writes 1 KB of a label row
+    uint8_t* o = labels + row * g.mpitch + 32 * j;
+    asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(o), "r"((uint32_t)qa[0]),
+                 "r"((uint32_t)(qa[0] >> 32)), "r"((uint32_t)qa[1]), "r"((uint32_t)(qa[1] >> 32)), "r"((uint32_t)qa[2]),
+                 "r"((uint32_t)(qa[2] >> 32)), "r"((uint32_t)qa[3]), "r"((uint32_t)(qa[3] >> 32))
+                 : "memory");
+    if (two)
+        asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(o + g.mpitch), "r"((uint32_t)qb[0]),
+                     "r"((uint32_t)(qb[0] >> 32)), "r"((uint32_t)qb[1]), "r"((uint32_t)(qb[1] >> 32)), "r"((uint32_t)qb[2]),
+                     "r"((uint32_t)(qb[2] >> 32)), "r"((uint32_t)qb[3]), "r"((uint32_t)(qb[3] >> 32))
+                     : "memory");
+}
+
 __global__ void __launch_bounds__(256)
 k_pack_bits(const uint8_t* __restrict__ img, int h, int w, uint32_t* __restrict__ fbits, int wpr4) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1168,8 +1239,11 @@ cudaError_t launch_ccl(cudaStream_t s, const uint32_t* fbits, int T, const Geom&
             launch_dependent(k_write_labels<int32_t, 4>, grid, dim3(32 * wpb), 0, s, fbits, g, b.parent, rbase_for_labels,
                              (int32_t*)labels);
         else
-            launch_dependent(k_write_labels<uint8_t, 16>, grid, dim3(32 * wpb), 0, s, fbits, g, b.parent, rbase_for_labels,
+        {
+            const dim3 ugrid(((g.mpitch >> 5) + 31) / 32, (g.BH + 7) / 8, T);
+            launch_dependent(k_write_labels_u8, ugrid, dim3(32, 8), 0, s, fbits, g, T, b.parent, rbase_for_labels,
                              (uint8_t*)labels);
+        }
         launches += 1;
     }
     mark();
