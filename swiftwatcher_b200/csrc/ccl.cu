@@ -929,15 +929,16 @@ k_props_final(const Partial* __restrict__ parts, const int* __restrict__ pcount,
     }
 }
 
-// Dense label image.  A warp owns a span of 32 * PX pixels (PX = 4 int32 or 16 uint8 labels
-// per lane = one 16-byte store) over 8 rows.  The bit words of the span are loaded once,
-// coalesced (one word per lane per round), and handed to the lanes that need them with
-// shuffles, so the row loop has no dependent global load on the (dominant) background path.
-template <typename LT, int PX>
+// Dense int32 label image.  A warp owns a span of 128 pixels (4 labels per lane = one 16-byte
+// store) over 8 rows.  The bit words of the span are loaded once, coalesced (one word per lane
+// per round), and handed to the lanes that need them with shuffles, so the row loop has no
+// dependent global load on the (dominant) background path; rows are taken in pairs because the
+// two pixel rows of a block row share their 2x2 blocks (one walk to the tagged root for both).
 __global__ void __launch_bounds__(256)
-k_write_labels(const uint32_t* __restrict__ fbits, Geom g, const int* __restrict__ parent,
-               const uint32_t* __restrict__ rowbase, LT* __restrict__ labels) {
+k_write_labels_i32(const uint32_t* __restrict__ fbits, Geom g, const int* __restrict__ parent,
+                   const uint32_t* __restrict__ rowbase, int32_t* __restrict__ labels) {
     wait_for_previous_kernel();
+    constexpr int PX = 4;                   // labels per lane and row = one 16-byte store
     constexpr int WPS = PX;                 // words per span row (32 * PX pixels / 32)
     constexpr int RPL = 32 / WPS;           // rows covered by one load round
     constexpr int ROWS = 8;
@@ -958,24 +959,25 @@ k_write_labels(const uint32_t* __restrict__ fbits, Geom g, const int* __restrict
     }
     const int* par = parent + (long long)f * g.BH * g.BW;
     const uint32_t* rbase = rowbase ? rowbase + (long long)f * g.BH : nullptr;
-    LT* out = labels + (long long)f * g.h * g.mpitch + x;
+    int32_t* out = labels + (long long)f * g.h * g.mpitch + x;
     const int wsel = (lane * PX) >> 5, sh = (lane * PX) & 31;
+    // the two pixel rows of a block row share their 2x2 blocks: one label lookup serves both
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
-        const uint32_t word = __shfl_sync(0xFFFFFFFFu, wreg[r / RPL], (r % RPL) * WPS + wsel);
+    for (int r = 0; r < ROWS; r += 2) {
+        const uint32_t wordA = __shfl_sync(0xFFFFFFFFu, wreg[r / RPL], (r % RPL) * WPS + wsel);
+        const uint32_t wordB = __shfl_sync(0xFFFFFFFFu, wreg[(r + 1) / RPL], ((r + 1) % RPL) * WPS + wsel);
         const int y = yb + r;
         if (y >= g.h || x >= g.mpitch) continue;
-        const uint32_t bits = (word >> sh) & ((1u << PX) - 1u);
-        uint4 o = make_uint4(0u, 0u, 0u, 0u);
-        if (bits) {
-            LT v[PX];
-#pragma unroll
-            for (int i = 0; i < PX; ++i) v[i] = 0;
+        const uint32_t bitsA = (wordA >> sh) & ((1u << PX) - 1u);
+        const uint32_t bitsB = (y + 1 < g.h) ? (wordB >> sh) & ((1u << PX) - 1u) : 0u;
+        int vA[PX] = {0, 0, 0, 0}, vB[PX] = {0, 0, 0, 0};
+        const uint32_t P = bitsA | bitsB;
+        if (P) {
             const int b0 = (y >> 1) * g.BW + (x >> 1);
             int last_p = 0x7FFFFFFF, last_lab = 0;
 #pragma unroll
             for (int i = 0; i < PX; i += 2) {
-                if ((bits >> i) & 3u) {
+                if ((P >> i) & 3u) {
                     const int p0 = par[b0 + (i >> 1)];
                     int lab;
                     if (p0 == last_p) {
@@ -984,22 +986,16 @@ k_write_labels(const uint32_t* __restrict__ fbits, Geom g, const int* __restrict
                         lab = label_of(par, b0 + (i >> 1), rbase, g.BW);
                         last_p = p0; last_lab = lab;
                     }
-                    if ((bits >> i) & 1u) v[i] = (LT)lab;
-                    if ((bits >> (i + 1)) & 1u) v[i + 1] = (LT)lab;
+                    if ((bitsA >> i) & 1u) vA[i] = lab;
+                    if ((bitsA >> (i + 1)) & 1u) vA[i + 1] = lab;
+                    if ((bitsB >> i) & 1u) vB[i] = lab;
+                    if ((bitsB >> (i + 1)) & 1u) vB[i + 1] = lab;
                 }
             }
-            if constexpr (sizeof(LT) == 4) {
-                o = make_uint4((uint32_t)v[0], (uint32_t)v[1], (uint32_t)v[2], (uint32_t)v[3]);
-            } else {
-                uint32_t w[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    w[q] = (uint32_t)v[4 * q] | ((uint32_t)v[4 * q + 1] << 8) | ((uint32_t)v[4 * q + 2] << 16) |
-                           ((uint32_t)v[4 * q + 3] << 24);
-                o = make_uint4(w[0], w[1], w[2], w[3]);
-            }
         }
-        __stcs(reinterpret_cast<uint4*>(out + (long long)y * g.mpitch), o);
+        __stcs(reinterpret_cast<int4*>(out + (long long)y * g.mpitch), make_int4(vA[0], vA[1], vA[2], vA[3]));
+        if (y + 1 < g.h)
+            __stcs(reinterpret_cast<int4*>(out + (long long)(y + 1) * g.mpitch), make_int4(vB[0], vB[1], vB[2], vB[3]));
     }
 }
 
@@ -1230,13 +1226,13 @@ cudaError_t launch_ccl(cudaStream_t s, const uint32_t* fbits, int T, const Geom&
     }
     mark();
     if (labels != nullptr) {
-        // one warp per span of 128 (int32) / 512 (uint8) pixels x 8 rows; up to 8 warps per CTA
-        const int px_per_span = (label_elem_size == 4) ? 128 : 512;
+        // int32: one warp per span of 128 pixels x 8 rows, up to 8 warps per CTA (uint8: see k_write_labels_u8)
+        const int px_per_span = 128;
         const int nspans = (g.mpitch + px_per_span - 1) / px_per_span;
         const int wpb = nspans < 8 ? nspans : 8;
         dim3 grid((nspans + wpb - 1) / wpb, (g.h + 7) / 8, T);
         if (label_elem_size == 4)
-            launch_dependent(k_write_labels<int32_t, 4>, grid, dim3(32 * wpb), 0, s, fbits, g, b.parent, rbase_for_labels,
+            launch_dependent(k_write_labels_i32, grid, dim3(32 * wpb), 0, s, fbits, g, b.parent, rbase_for_labels,
                              (int32_t*)labels);
         else
         {
