@@ -128,16 +128,17 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(self.reasons), "source": "nvml, 2 ms poll"}
 
 
-def algorithmic_bytes(cfg, h, w):
+def algorithmic_bytes(cfg, h, w, label_bytes=4):
     """Per OUTPUT frame.  Whole path: read BGR once,
-    write the uint8 mask once, write int32 labels once = 8*h*w."""
+    write the uint8 mask once, write int32 labels once = 8*h*w (A' = 5*h*w with the
+    reference's uint8 labels)."""
     hw = h * w
     return {
-        "path": 8 * hw,
+        "path": (4 + label_bytes) * hw,
         "fg_bits": 3 * hw + hw // 8,            # BGR read + 1 bit/px write
         "morph_mask": hw // 8 + hw // 8 + hw,   # bits read, bits write, uint8 mask write
         "ccl_merge": hw // 8, "ccl_rank": hw // 8, "ccl_label": hw // 8,
-        "write_labels": hw // 8 + 4 * hw,       # bits read + int32 label write
+        "write_labels": hw // 8 + label_bytes * hw,       # bits read + label write
     }
 
 
@@ -516,7 +517,7 @@ def main():
             per_kernel[k] = per_kernel.get(k, 0.0) + v / reps
     ctx.enable_timing(False)
     peak, peak_src = measured_peak()
-    alg = algorithmic_bytes(cfg, rh, rw)
+    alg = algorithmic_bytes(cfg, rh, rw, 1 if args.label_mode == "u8" else 4)
     dom = max(per_kernel, key=per_kernel.get)
     kernels = {k: {"ms": round(v, 4), "alg_gbs": round(alg[k] * T / (v * 1e-3) / 1e9, 1) if v > 0 else None}
                for k, v in per_kernel.items()}
