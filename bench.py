@@ -545,7 +545,7 @@ def main():
                                           "same scores as the padded 224x224 forward pass to 1e-4); the hot-path kernels "
                                           "in `kernels` are the filtering + labelling part of the step"}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(traffic_file):
+    if os.path.exists(traffic_file) and args.label_mode == "i32" and not args.chunk:   # captured at the config's own chunk size
         try:
             roofline["traffic"] = json.load(open(traffic_file)).get(args.config, {}).get(dom)
         except Exception:
