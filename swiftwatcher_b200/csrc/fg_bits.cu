@@ -16,7 +16,10 @@
 //
 // Work unit = (256-thread column group, temporal sub-chunk of Ts frames); each
 // sub-chunk re-reads its N-1 preceding frames as warm-up.
+#include <cuda.h>          // CUtensorMap (types only: the encoder is fetched through the runtime)
+
 #include <cstdlib>
+#include <cstring>
 
 #include "swb_internal.cuh"
 
@@ -363,6 +366,16 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  : "memory");
 }
 
+// One TMA tensor load: the box (row bytes, rows, 1 frame) at (x = 0, row y, frame z) of the ROI tensor
+// -> shared memory, completing on the mbarrier (SASS UTMALDG).  Out-of-range rows are zero-filled.
+__device__ __forceinline__ void tma_load_box(void* dst_smem, const CUtensorMap* tmap, int y, int z, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(0), "r"(y), "r"(z), "r"(smem_u32(bar))
+        : "memory");
+}
+
 // 2L BGR pixels (6L bytes, 3L/2 words) -> L u16x2 lanes of (gray[k], gray[k+L]) with IDP.2A
 template <int L>
 __device__ __forceinline__ void bgr_to_lanes_dp(const uint32_t (&w)[3 * L / 2], uint32_t (&out)[L]) {
@@ -476,6 +489,38 @@ int pick_ts(int T, int n_col_blocks, int median_n) {
     return ts;
 }
 
+// ---- tensor map of the ROI inside the frame stack: (row bytes / 8, ROI rows, frames) of 8-byte elements ----
+bool tma_enabled() {
+    static const bool on = [] { const char* e = getenv("SWB_K1_TMA"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+bool encode_roi_tensor(CUtensorMap* tmap, const uint8_t* base, long long row_bytes, int rows_total, int frames,
+                       long long pitch, long long frame_stride, int box_rows) {
+    static EncodeTiledFn encode = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            fn = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(fn);
+    }();
+    if (!encode) return false;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (pitch & 15) || (frame_stride & 15) || (row_bytes & 15)) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)(row_bytes / 8), (cuuint64_t)rows_total, (cuuint64_t)frames};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)frame_stride};
+    const cuuint32_t box[3] = {(cuuint32_t)(row_bytes / 8), (cuuint32_t)box_rows, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    if (box[0] > 256 || box[1] > 256) return false;
+    return encode(tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<uint8_t*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 constexpr int CONSUMERS = 256;               // 8 consumer warps: one pixel group per thread
 constexpr int V2_THREADS = CONSUMERS + 32;   // + 1 producer warp
 
@@ -484,7 +529,7 @@ constexpr int V2_THREADS = CONSUMERS + 32;   // + 1 producer warp
 template <int N, int C, int S, int L, int OCC>
 __global__ void __launch_bounds__(V2_THREADS, OCC)
 k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t one,
-             uint8_t* __restrict__ raw_bits) {
+             uint8_t* __restrict__ raw_bits, const __grid_constant__ CUtensorMap tmap, int tile_rows) {
     constexpr int PPT = 2 * L;               // pixels per thread
     constexpr int TB = PPT * C;              // bytes per thread per frame
     constexpr int STAGE_BYTES = CONSUMERS * TB;
@@ -497,7 +542,9 @@ k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t on
     const int tid = threadIdx.x;
     const int gpr = wa / PPT;                // pixel groups per row
     const int G = h * gpr;
-    const int g0 = blockIdx.x * CONSUMERS;
+    // tile_rows > 0: the CTA owns tile_rows whole ROI rows (a TMA box); else 256 consecutive groups
+    const int cta_groups = tile_rows > 0 ? tile_rows * gpr : CONSUMERS;
+    const int g0 = blockIdx.x * cta_groups;
     const int t_start = blockIdx.y * Ts;
     const int t_end = min(T, t_start + Ts);
     const int n_out = t_end - t_start;
@@ -519,10 +566,10 @@ k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t on
         // ===== producer warp: streams this CTA's slice of every frame =====
         // (groups per row and per CTA are multiples of 4, so every copy is 16-byte granular)
         const int lane = tid - CONSUMERS;
-        const int ngroups = min(CONSUMERS, G - g0);
+        const int ngroups = min(cta_groups, G - g0);
         const uint32_t bytes = (uint32_t)(ngroups * TB);
         const bool contiguous = (src.pitch == (long long)gpr * TB);
-        if (contiguous && lane != 0) return;          // one bulk copy per frame: one lane is enough
+        if ((contiguous || tile_rows > 0) && lane != 0) return;   // one copy per frame: one lane is enough
         // Rows of a cropped ROI are not adjacent in memory: the slice is one copy per row segment.
         // The lanes of the warp issue them side by side (lane i takes segments i, i + 32, ...):
         // a single lane issuing 12+ small copies per frame was slower than the eight consumer warps.
@@ -544,7 +591,12 @@ k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t on
             }
             if (j < -src.n_inline_halo) j = -src.n_inline_halo;   // replicate the earliest frame
             const uint8_t* fr = src.cur + (long long)j * src.frame_stride;
-            if (contiguous) {
+            if (tile_rows > 0) {
+                // the rows of a cropped ROI are apart in memory: one tensor-map box load brings the tile
+                // (tile_rows x row bytes; rows past the ROI are zero-filled and still counted by the barrier)
+                mbar_arrive_expect_tx(&full[st], (uint32_t)(tile_rows * gpr * TB));
+                tma_load_box(dst, &tmap, blockIdx.x * tile_rows, j + src.n_inline_halo, &full[st]);
+            } else if (contiguous) {
                 mbar_arrive_expect_tx(&full[st], bytes);
                 bulk_g2s(dst, fr + (long long)g0 * TB, bytes, &full[st]);
             } else {
@@ -563,7 +615,7 @@ k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t on
 
     // ===== consumer warps =====
     const int g = g0 + tid;
-    const bool active = g < G;
+    const bool active = g < G && tid < cta_groups;
     const int row = active ? g / gpr : 0;
     const int col = active ? g - row * gpr : 0;
     const uint32_t neg_th = ((uint32_t)(-thresh) & 0xFFFFu) * 0x00010001u;
@@ -836,12 +888,29 @@ cudaError_t launch_v2_occ(cudaStream_t s, const FrameSrc& src, int T, const Geom
         cudaError_t e = cudaFuncSetAttribute(k_fg_bits_v2<N, C, S, L, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) return e;
     }
-    const int G = g.h * (g.wa / (2 * L));
-    const int n_col_blocks = (G + CONSUMERS - 1) / CONSUMERS;
+    const int gpr = g.wa / (2 * L);
+    const int G = g.h * gpr;
+    int n_col_blocks = (G + CONSUMERS - 1) / CONSUMERS;
+    // Rows of a cropped ROI are not adjacent in memory.  When a row is at most 2 KB (TMA boxes are limited to
+    // 256 elements per dimension; the row is described in 8-byte elements) the CTA owns whole rows and
+    // the producer fetches its tile with one tensor-map load per frame instead of one bulk copy per row.
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    int tile_rows = 0;
+    const long long row_bytes = (long long)gpr * TB;
+    if (src.pitch != row_bytes && row_bytes <= 2048 && gpr <= CONSUMERS && tma_enabled()) {
+        const int rows = CONSUMERS / gpr;
+        const int frames = src.n_inline_halo + T;
+        const uint8_t* base = src.cur - (long long)src.n_inline_halo * src.frame_stride;
+        if (encode_roi_tensor(&tmap, base, row_bytes, g.h, frames, src.pitch, src.frame_stride, rows)) {
+            tile_rows = rows;
+            n_col_blocks = (g.h + rows - 1) / rows;
+        }
+    }
     const int Ts = pick_ts(T, n_col_blocks, N);
     dim3 grid(n_col_blocks, (T + Ts - 1) / Ts);
     k_fg_bits_v2<N, C, S, L, OCC><<<grid, V2_THREADS, SMEM, s>>>(src, T, Ts, g.h, g.wa, thresh, 1u,
-                                                                reinterpret_cast<uint8_t*>(raw_bits));
+                                                                reinterpret_cast<uint8_t*>(raw_bits), tmap, tile_rows);
     return cudaGetLastError();
 }
 

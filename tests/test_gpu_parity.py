@@ -423,6 +423,30 @@ def test_fuzz_small_shapes_and_parameters():
                                  % (case, H, W, T, n, se, do_open, do_close, region, mode, thresh, e))
 
 
+@pytest.mark.parametrize("n", [5, 9, 3])
+def test_device_roi_tiles_through_the_tensor_map(n):
+    """Device-resident frames + a cropped ROI: K1's producer fetches whole-row tiles with TMA tensor
+    loads (rows of the ROI are not adjacent in memory).  ROIs whose last tile is partial, one-row
+    tiles (wide ROI), ROIs at the frame borders; carried history across submits."""
+    import torch
+    frames = synth.synth_video(50 + n, 0, 0, 22, 150, 704, 60)
+    dev = torch.from_numpy(frames).cuda()
+    for region in ([(64, 10), (384, 131)], [(37, 0), (650, 150)], [(0, 3), (40, 147)], [(600, 50), (704, 149)],
+                   [(96, 20), (160, 21)]):
+        par = rp.PathParams(region, n, 15, 3, True, False, "i32")
+        want = rp.run_path(frames, par)
+        with swb.FilterContext(frames.shape[1:], region, median_n=n, label_mode="i32", max_frames=16) as ctx:
+            t = 0
+            for k in (16, 5, 1):
+                ctx.submit(dev[t:t + k])                        # carried history
+                rows, counts = ctx.collect()
+                labels = ctx.labels()
+                for i in range(k):
+                    assert np.array_equal(labels[i], want[t + i]["labels"]), (region, t + i)
+                    assert counts[i] == len(want[t + i]["props"])
+                t += k
+
+
 def test_concurrent_contexts_on_their_own_streams():
     """BASELINE configs[3]: several videos per GPU, one context + CUDA stream each, submits
     interleaved without synchronising in between — every context must still produce exactly
