@@ -363,7 +363,7 @@ __device__ __forceinline__ void emit_partial(Partial* parts, int idx, int f, int
 // warps are full instead of having a lane or two busy.  Run ids grow with the block index of
 // the run start, so "link the larger id under the smaller" keeps the minimum block as root.
 //
-// Two sizes of the run list: the common kernel holds up to RUNS_FAST runs (28 KB of shared
+// Two sizes of the run list: the common kernel holds up to RUNS_FAST runs (24-28 KB of shared
 // memory, eight CTAs per SM -- the tile is latency-bound on a few threads' union chains, so
 // resident tiles per SM are what buys throughput); a tile with more runs (dense noise) puts
 // itself on a list and is redone by the RUNS_MAX variant (8 runs per word, the worst case).
@@ -371,9 +371,11 @@ struct LocalSmem {
     static constexpr int RUNS_FAST = 1536;
     static constexpr int RUNS_MAX = 8192;
     static constexpr int MAXR = 256;            // components with a shared-memory accumulator
-    static constexpr int AB_WORDS = 256 * 6;    // worst case BY * (4 * BX + 2) at BX = 1
-    static constexpr size_t bytes(int maxruns) {
-        return (size_t)2 * AB_WORDS * 4 + 1024 * 2 + (size_t)2 * maxruns * 2 + MAXR * 30 + 64;
+    // words of one pixel-row plane of the tile: BY rows of 4 * BX words + a halo word each side
+    // (1536 at BX = 1 ... 1056 at BX = 16: 24 KB in all for the common kernel, eight CTAs per SM)
+    __host__ __device__ static constexpr int ab_words(int bx) { return (256 / bx) * (4 * bx + 2); }
+    static constexpr size_t bytes(int maxruns, int bx) {
+        return (size_t)2 * ab_words(bx) * 4 + 1024 * 2 + (size_t)2 * maxruns * 2 + MAXR * 30 + 64;
     }
 };
 
@@ -389,8 +391,8 @@ __device__ __forceinline__ bool ccl_local_tile(const uint32_t* __restrict__ fbit
     constexpr int MAXR = LocalSmem::MAXR;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t* sA = reinterpret_cast<uint32_t*>(smem_raw);                 // [BY][SW] pixel row 2by
-    uint32_t* sB = sA + LocalSmem::AB_WORDS;                              // [BY][SW] pixel row 2by + 1
-    unsigned short* swpre = reinterpret_cast<unsigned short*>(sB + LocalSmem::AB_WORDS);   // [1024] runs before word
+    uint32_t* sB = sA + LocalSmem::ab_words(BX);                             // [BY][SW] pixel row 2by + 1
+    unsigned short* swpre = reinterpret_cast<unsigned short*>(sB + LocalSmem::ab_words(BX));   // [1024] runs before word
     unsigned short* srun = swpre + 1024;                                  // [MAXRUNS] (word << 4) | first block
     unsigned short* spar = srun + MAXRUNS;                                // [MAXRUNS] parent run id / TAG | slot
     uint32_t* st_area = reinterpret_cast<uint32_t*>(spar + MAXRUNS);
@@ -1126,15 +1128,15 @@ static void launch_local(cudaStream_t s, const uint32_t* fbits, int T, const Geo
     static PerDeviceOnce once;
     if (once.need()) {
         cudaFuncSetAttribute(k_ccl_local<BX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)LocalSmem::bytes(LocalSmem::RUNS_FAST));
+                             (int)LocalSmem::bytes(LocalSmem::RUNS_FAST, BX));
         cudaFuncSetAttribute(k_ccl_local_big<BX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)LocalSmem::bytes(LocalSmem::RUNS_MAX));
+                             (int)LocalSmem::bytes(LocalSmem::RUNS_MAX, BX));
     }
     int* big_count = b.pcount + 1;
-    launch_dependent(k_ccl_local<BX>, grid, dim3(256), LocalSmem::bytes(LocalSmem::RUNS_FAST), s, fbits, g, b.parent,
+    launch_dependent(k_ccl_local<BX>, grid, dim3(256), LocalSmem::bytes(LocalSmem::RUNS_FAST, BX), s, fbits, g, b.parent,
                      b.parts, b.pcount, b.cap_parts, b.overflow, b.big_tiles, big_count);
     const int big_grid = (int)std::min<long long>((long long)tiles * T, 148 * 4);
-    launch_dependent(k_ccl_local_big<BX>, dim3(big_grid), dim3(256), LocalSmem::bytes(LocalSmem::RUNS_MAX), s,
+    launch_dependent(k_ccl_local_big<BX>, dim3(big_grid), dim3(256), LocalSmem::bytes(LocalSmem::RUNS_MAX, BX), s,
                      fbits, g, b.parent, b.parts, b.pcount, b.cap_parts, b.overflow, b.big_tiles, big_count, tiles);
     const int n_boundaries = tiles - 1;
     if (n_boundaries > 0) {
