@@ -1004,9 +1004,9 @@ k_write_labels_i32(const uint32_t* __restrict__ fbits, Geom g, const int* __rest
 // Dense uint8 label image (SWB_LABELS_U8: labels.astype(np.uint8), image_filtering.py:329).  One byte
 // per pixel is a quarter of the int32 traffic, so the span-per-warp layout above would be bound by its
 // instruction stream (one lane with a bird in its 16 pixels stalls the warp in a long unrolled path).
-// Here a lane owns one 32-pixel bit word = 32 output bytes: background words are two 16-byte zero
-// stores, and a word with foreground runs one compact loop over its occupied 2x2 blocks (a parent load,
-// the walk to the tagged root only when the parent changes, two bytes ORed into a 64-bit quarter).
+// Here a lane owns one 32-pixel bit word = 32 output bytes: background words are zero stores, and a
+// word with foreground runs one compact loop over its RUNS (the walk to the tagged root from the run's
+// first block, then the run's mask bits expanded to bytes and ANDed with the replicated label).
 __global__ void __launch_bounds__(256)
 k_write_labels_u8(const uint32_t* __restrict__ fbits, Geom g, int T, const int* __restrict__ parent,
                   const uint32_t* __restrict__ rowbase, uint8_t* __restrict__ labels) {
@@ -1022,53 +1022,47 @@ k_write_labels_u8(const uint32_t* __restrict__ fbits, Geom g, int T, const int* 
     const long long row = (long long)f * g.h + y;
     const uint32_t wa = __ldg(fbits + row * g.wpr4 + j);
     const uint32_t wb = two ? __ldg(fbits + (row + 1) * g.wpr4 + j) : 0u;
-    unsigned long long qa[4] = {0ull, 0ull, 0ull, 0ull}, qb[4] = {0ull, 0ull, 0ull, 0ull};
+    uint32_t oa[8], ob[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) oa[q] = ob[q] = 0u;
     if (wa | wb) {
         const int* par = parent + (long long)f * g.BH * g.BW;
         const uint32_t* rbase = rowbase ? rowbase + (long long)f * g.BH : nullptr;
         const int b0 = by * g.BW + 16 * j;
+        // one lookup per RUN (a maximal chain of touching 2x2 blocks inside the word: all of it is one
+        // component): the walk starts at the run's first block, whose parent chain ends at the tagged
+        // root (the tag is -label).  A word usually holds one run, so the lanes of a warp that see a
+        // bird do their two or three dependent loads side by side instead of once per block.
         const uint32_t P = wa | wb;
-        uint32_t occ = (P | (P >> 1)) & EVEN;
-        int last_p = 0x7FFFFFFF;
-        uint32_t lab = 0;
-        while (occ) {
-            const int b2 = __ffs((int)occ) - 1;              // bit 2k of block k
-            occ &= occ - 1;
-            const int k = b2 >> 1;
-            const int p0 = par[b0 + k];
-            if (p0 != last_p) {                              // walk to the tagged root (the tag is -label)
-                int x = b0 + k, v = p0;
-                while (v >= 0) {
-                    x = v;
-                    v = par[x];
-                }
-                lab = (uint32_t)(rbase ? (int)rbase[x / g.BW] - v : -v) & 0xFFu;
-                last_p = p0;
+        const uint32_t H = link_bits(P);
+        uint32_t rs = run_starts(P);
+        while (rs) {
+            const int k0 = (__ffs((int)rs) - 1) >> 1;
+            rs &= rs - 1;
+            const uint32_t m = run_mask(H, k0);
+            int x = b0 + k0, v = par[x];
+            while (v >= 0) {
+                x = v;
+                v = par[x];
             }
-            const uint32_t both = lab | (lab << 8);
-            const uint32_t pa = (wa >> b2) & 3u, pb = (wb >> b2) & 3u;
-            // two mask bits -> two bytes of 0xFF: bit 0 -> 0x00FF, bit 1 -> 0xFF00
-            const uint32_t ma = (pa & 1u) * 0xFFu | (pa >> 1) * 0xFF00u, mb = (pb & 1u) * 0xFFu | (pb >> 1) * 0xFF00u;
-            const int sh = 16 * (k & 3);
-            const unsigned long long ia = (unsigned long long)(both & ma) << sh, ib = (unsigned long long)(both & mb) << sh;
-            const int qi = k >> 2;
+            const uint32_t lab = (uint32_t)(rbase ? (int)rbase[x / g.BW] - v : -v) & 0xFFu;
+            const uint32_t rep = lab * 0x01010101u;
+            const uint32_t ma = wa & m, mb = wb & m;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                qa[q] |= qi == q ? ia : 0ull;
-                qb[q] |= qi == q ? ib : 0ull;
+            for (int q = 0; q < 8; ++q) {
+                oa[q] |= expand4((ma >> (4 * q)) & 0xFu) & rep;
+                ob[q] |= expand4((mb >> (4 * q)) & 0xFu) & rep;
             }
         }
     }
     // one 32-byte store per lane and row (STG.256): whole sectors, a warp writes 1 KB of a label row
     uint8_t* o = labels + row * g.mpitch + 32 * j;
-    asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(o), "r"((uint32_t)qa[0]),
-                 "r"((uint32_t)(qa[0] >> 32)), "r"((uint32_t)qa[1]), "r"((uint32_t)(qa[1] >> 32)), "r"((uint32_t)qa[2]),
-                 "r"((uint32_t)(qa[2] >> 32)), "r"((uint32_t)qa[3]), "r"((uint32_t)(qa[3] >> 32))
+    asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(o), "r"(oa[0]), "r"(oa[1]), "r"(oa[2]),
+                 "r"(oa[3]), "r"(oa[4]), "r"(oa[5]), "r"(oa[6]), "r"(oa[7])
                  : "memory");
     if (two)
-        asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(o + g.mpitch), "r"((uint32_t)qb[0]),
-                     "r"((uint32_t)(qb[0] >> 32)), "r"((uint32_t)qb[1]), "r"((uint32_t)(qb[1] >> 32)), "r"((uint32_t)qb[2]),
-                     "r"((uint32_t)(qb[2] >> 32)), "r"((uint32_t)qb[3]), "r"((uint32_t)(qb[3] >> 32))
+        asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(o + g.mpitch), "r"(ob[0]), "r"(ob[1]),
+                     "r"(ob[2]), "r"(ob[3]), "r"(ob[4]), "r"(ob[5]), "r"(ob[6]), "r"(ob[7])
                      : "memory");
 }
 

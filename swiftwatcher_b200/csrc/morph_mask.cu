@@ -54,15 +54,6 @@ __device__ __forceinline__ uint32_t hop(uint32_t l, uint32_t c, uint32_t r, bool
     return acc;
 }
 
-// 4 mask bits -> 4 bytes of 0x00 / 0xFF: put the bits on the byte sign positions
-// (disjoint shifted copies, no carries) and let PRMT replicate the sign bits.
-// (prmt.b32 directly: __byte_perm masks the replicate bit of the selector away.)
-__device__ __forceinline__ uint32_t expand4(uint32_t nibble) {
-    uint32_t d;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(nibble * 0x10204080u), "r"(0u), "r"(0x0000BA98u));
-    return d;
-}
-
 // One warp, one strip of rows.  INTERIOR: every row the strip touches (its own rows and the
 // vertical halo of every stage) lies inside the image, so no row needs the border fill and
 // the per-row validity tests disappear; DX0: the raw bit columns are already ROI-aligned

@@ -149,6 +149,14 @@ cudaError_t launch_bilateral(cudaStream_t s, const uint8_t* in, int n, int h, in
 #ifdef __CUDACC__
 __device__ __forceinline__ void wait_for_previous_kernel() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void let_next_kernel_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// 4 mask bits -> 4 bytes of 0x00 / 0xFF: put the bits on the byte sign positions
+// (disjoint shifted copies, no carries) and let PRMT replicate the sign bits.
+// (prmt.b32 directly: __byte_perm masks the replicate bit of the selector away.)
+__device__ __forceinline__ uint32_t expand4(uint32_t nibble) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(nibble * 0x10204080u), "r"(0u), "r"(0x0000BA98u));
+    return d;
+}
 #endif
 bool pdl_enabled();
 template <typename... KArgs, typename... Args>
