@@ -942,9 +942,8 @@ k_write_labels_i32(const uint32_t* __restrict__ fbits, Geom g, const int* __rest
     wait_for_previous_kernel();
     constexpr int PX = 4;                   // labels per lane and row = one 16-byte store
     constexpr int WPS = PX;                 // words per span row (32 * PX pixels / 32)
-    constexpr int RPL = 32 / WPS;           // rows covered by one load round
-    constexpr int ROWS = 8;
-    constexpr int ROUNDS = ROWS / RPL;
+    constexpr int ROWS = 8;                 // = 32 / WPS: one load round covers the span
+    constexpr int BR = ROWS / 2;            // block rows
     const int lane = threadIdx.x & 31;
     const int span = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int f = blockIdx.z;
@@ -952,52 +951,66 @@ k_write_labels_i32(const uint32_t* __restrict__ fbits, Geom g, const int* __rest
     const int x = span * (32 * PX) + lane * PX;          // first pixel of this lane
     if (span * (32 * PX) >= g.mpitch) return;            // warp-uniform
     const uint32_t* fb = fbits + (long long)f * g.h * g.wpr4;
-    uint32_t wreg[ROUNDS];
-#pragma unroll
-    for (int r = 0; r < ROUNDS; ++r) {
-        const int y = yb + r * RPL + lane / WPS;
+    uint32_t wreg;
+    {
+        const int y = yb + lane / WPS;
         const int j = span * WPS + lane % WPS;
-        wreg[r] = (y < g.h && j < g.wpr4) ? __ldg(fb + (long long)y * g.wpr4 + j) : 0u;
+        wreg = (y < g.h && j < g.wpr4) ? __ldg(fb + (long long)y * g.wpr4 + j) : 0u;
     }
     const int* par = parent + (long long)f * g.BH * g.BW;
+    const int wsel = (lane * PX) >> 5, sh = (lane * PX) & 31;
+    uint32_t bitsA[BR], bitsB[BR];
+#pragma unroll
+    for (int rr = 0; rr < BR; ++rr) {
+        const uint32_t wordA = __shfl_sync(0xFFFFFFFFu, wreg, (2 * rr) * WPS + wsel);
+        const uint32_t wordB = __shfl_sync(0xFFFFFFFFu, wreg, (2 * rr + 1) * WPS + wsel);
+        bitsA[rr] = (wordA >> sh) & ((1u << PX) - 1u);
+        bitsB[rr] = (wordB >> sh) & ((1u << PX) - 1u);   // rows past the image were loaded as 0
+    }
+    if (x >= g.mpitch) return;
+    // The lane's 2 blocks in each of the 4 block rows: all first-level parent loads are issued together
+    // and the (two or three deep) chains to the tagged roots advance in lock-step, so a warp that
+    // sees birds pays one chain of dependent loads, not one per block.
+    int v[BR][2], xr[BR][2];
+    const int b00 = (yb >> 1) * g.BW + (x >> 1);
+#pragma unroll
+    for (int rr = 0; rr < BR; ++rr) {
+        const uint32_t P = bitsA[rr] | bitsB[rr];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            xr[rr][i] = b00 + rr * g.BW + i;
+            v[rr][i] = ((P >> (2 * i)) & 3u) ? __ldg(par + xr[rr][i]) : -1;
+        }
+    }
+    bool more;
+    do {
+        more = false;
+#pragma unroll
+        for (int rr = 0; rr < BR; ++rr)
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+                if (v[rr][i] >= 0) {
+                    xr[rr][i] = v[rr][i];
+                    v[rr][i] = par[xr[rr][i]];
+                    more = true;
+                }
+    } while (more);
     const uint32_t* rbase = rowbase ? rowbase + (long long)f * g.BH : nullptr;
     int32_t* out = labels + (long long)f * g.h * g.mpitch + x;
-    const int wsel = (lane * PX) >> 5, sh = (lane * PX) & 31;
-    // the two pixel rows of a block row share their 2x2 blocks: one label lookup serves both
 #pragma unroll
-    for (int r = 0; r < ROWS; r += 2) {
-        const uint32_t wordA = __shfl_sync(0xFFFFFFFFu, wreg[r / RPL], (r % RPL) * WPS + wsel);
-        const uint32_t wordB = __shfl_sync(0xFFFFFFFFu, wreg[(r + 1) / RPL], ((r + 1) % RPL) * WPS + wsel);
-        const int y = yb + r;
-        if (y >= g.h || x >= g.mpitch) continue;
-        const uint32_t bitsA = (wordA >> sh) & ((1u << PX) - 1u);
-        const uint32_t bitsB = (y + 1 < g.h) ? (wordB >> sh) & ((1u << PX) - 1u) : 0u;
-        int vA[PX] = {0, 0, 0, 0}, vB[PX] = {0, 0, 0, 0};
-        const uint32_t P = bitsA | bitsB;
-        if (P) {
-            const int b0 = (y >> 1) * g.BW + (x >> 1);
-            int last_p = 0x7FFFFFFF, last_lab = 0;
+    for (int rr = 0; rr < BR; ++rr) {
+        const int y = yb + 2 * rr;
+        if (y >= g.h) break;
+        int lab[2];
 #pragma unroll
-            for (int i = 0; i < PX; i += 2) {
-                if ((P >> i) & 3u) {
-                    const int p0 = par[b0 + (i >> 1)];
-                    int lab;
-                    if (p0 == last_p) {
-                        lab = last_lab;
-                    } else {
-                        lab = label_of(par, b0 + (i >> 1), rbase, g.BW);
-                        last_p = p0; last_lab = lab;
-                    }
-                    if ((bitsA >> i) & 1u) vA[i] = lab;
-                    if ((bitsA >> (i + 1)) & 1u) vA[i + 1] = lab;
-                    if ((bitsB >> i) & 1u) vB[i] = lab;
-                    if ((bitsB >> (i + 1)) & 1u) vB[i + 1] = lab;
-                }
-            }
-        }
-        __stcs(reinterpret_cast<int4*>(out + (long long)y * g.mpitch), make_int4(vA[0], vA[1], vA[2], vA[3]));
-        if (y + 1 < g.h)
-            __stcs(reinterpret_cast<int4*>(out + (long long)(y + 1) * g.mpitch), make_int4(vB[0], vB[1], vB[2], vB[3]));
+        for (int i = 0; i < 2; ++i) lab[i] = rbase ? (int)rbase[xr[rr][i] / g.BW] - v[rr][i] : -v[rr][i];
+        int4 a, b;
+        a.x = (bitsA[rr] & 1u) ? lab[0] : 0; a.y = (bitsA[rr] & 2u) ? lab[0] : 0;
+        a.z = (bitsA[rr] & 4u) ? lab[1] : 0; a.w = (bitsA[rr] & 8u) ? lab[1] : 0;
+        b.x = (bitsB[rr] & 1u) ? lab[0] : 0; b.y = (bitsB[rr] & 2u) ? lab[0] : 0;
+        b.z = (bitsB[rr] & 4u) ? lab[1] : 0; b.w = (bitsB[rr] & 8u) ? lab[1] : 0;
+        __stcs(reinterpret_cast<int4*>(out + (long long)y * g.mpitch), a);
+        if (y + 1 < g.h) __stcs(reinterpret_cast<int4*>(out + (long long)(y + 1) * g.mpitch), b);
     }
 }
 
