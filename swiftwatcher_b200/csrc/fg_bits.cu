@@ -478,6 +478,8 @@ __device__ __forceinline__ uint32_t select4of7(uint32_t m2, uint32_t m3, uint32_
 // percent of the work, short enough that the grid has several waves of CTAs; a
 // multiple of 6 so that only the last sub-chunk of a submit has a partial group.
 int pick_ts(int T, int n_col_blocks, int median_n) {
+    static const int forced = [] { const char* e = getenv("SWB_K1_TS"); return e ? atoi(e) : 0; }();
+    if (forced > 0) return std::min(T, (forced + 5) / 6 * 6);
     const int target_ctas = 148 * 2 * 4;
     int ts = T;
     while (ts > 32 && (long long)n_col_blocks * ((T + ts - 1) / ts) < target_ctas) ts = (ts + 1) / 2;

@@ -61,15 +61,21 @@ __device__ __forceinline__ uint32_t hop(uint32_t l, uint32_t c, uint32_t r, bool
 // The row loop is unrolled by the window height 2R+1: a stage's window is "the last 2R+1
 // horizontally filtered rows", AND / OR do not care about their order, so row r simply
 // overwrites slot r mod (2R+1) — a static register after unrolling, no rotation moves.
-template <int R, int PAT, bool INTERIOR, bool DX0>
+// SEG: lanes per frame.  32: the warp works on one frame.  16 (rows of at most 14 words: narrow ROIs): the two
+// half-warps work on the same rows of two consecutive frames, each with its own halo lanes, so a narrow
+// ROI keeps 28 of 32 lanes busy instead of 12; `live` is false for the half-warp past the last frame.
+template <int R, int PAT, bool INTERIOR, bool DX0, int SEG>
 __device__ __forceinline__ void morph_strip(const uint32_t* __restrict__ raw_f, const Geom& g, uint32_t* __restrict__ fbits,
-                                            uint8_t* __restrict__ mask, int f, int slab, int lane, int y0) {
+                                            uint8_t* __restrict__ mask, int f, bool live, int slab, int lane, int y0) {
+    constexpr int SLABW = SEG - 2;                           // output words per segment
+    const int hl = lane & (SEG - 1);                         // lane within the segment
+    const int seg0 = lane & ~(SEG - 1);
     constexpr int NOPS = n_ops(PAT);
     constexpr int NW = NOPS > 0 ? NOPS : 1;
     constexpr int HR = NOPS * R;   // rows of vertical halo
     constexpr int SR = strip_rows(R, PAT);
     constexpr int W = 2 * R + 1;
-    const int j = slab * SLAB + lane - 1;                    // this lane's word
+    const int j = slab * SLABW + hl - 1;                     // this lane's word
     const uint32_t Vcol = colmask(j, g.w, g.wpr);
     const bool in_raw = (j >= 0 && j < g.wpr_raw);
     const bool in_raw_next = (j + 1 >= 0 && j + 1 < g.wpr_raw);
@@ -89,23 +95,23 @@ __device__ __forceinline__ void morph_strip(const uint32_t* __restrict__ raw_f, 
     const int y_end = min(y0 + SR, g.h);
     const int y_stop = y_end + HR;
     // mask output: lane -> two 16-byte chunks of the slab's row
-    const bool st_bits = lane >= 1 && lane <= SLAB && j < g.wpr4;
+    const bool st_bits = live && hl >= 1 && hl <= SLABW && j < g.wpr4;
     bool st_mask[2];
     int src_lane[2];
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
-        const int wi = (half * 32 + lane) >> 1;              // word within the slab
-        st_mask[half] = mask != nullptr && wi < SLAB && slab * SLAB + wi < g.wpr;
-        src_lane[half] = wi < SLAB ? wi + 1 : 31;
+        const int wi = (half * SEG + hl) >> 1;               // word within the slab
+        st_mask[half] = mask != nullptr && live && wi < SLABW && slab * SLABW + wi < g.wpr;
+        src_lane[half] = seg0 + (wi < SLABW ? wi + 1 : SEG - 1);
     }
     // raw words of row y (this lane's word; lane 31 also fetches the word after it), 0 outside the image
     auto fetch = [&](int y, uint32_t& lo, uint32_t& edge) {
         lo = 0u;
         edge = 0u;
-        if (INTERIOR || (unsigned)y < (unsigned)g.h) {
+        if ((INTERIOR || (unsigned)y < (unsigned)g.h) && live) {
             const uint32_t* rowp = raw_f + (long long)y * g.wpr_raw;
             if (in_raw) lo = __ldg(rowp + j);
-            if (!DX0 && lane == 31 && in_raw_next) edge = __ldg(rowp + j + 1);
+            if (!DX0 && hl == SEG - 1 && in_raw_next) edge = __ldg(rowp + j + 1);
         }
     };
     uint32_t lo_n, edge_n;
@@ -124,7 +130,7 @@ __device__ __forceinline__ void morph_strip(const uint32_t* __restrict__ raw_f, 
                 v = lo;
             } else {
                 uint32_t hi = __shfl_down_sync(0xFFFFFFFFu, lo, 1);
-                if (lane == 31) hi = edge;
+                if (hl == SEG - 1) hi = edge;
                 v = __funnelshift_r(lo, hi, g.dx);
             }
             uint32_t cur;
@@ -161,10 +167,10 @@ __device__ __forceinline__ void morph_strip(const uint32_t* __restrict__ raw_f, 
             const long long orow = orow0 + yout;
             if (st_bits) fbits[orow * g.wpr4 + j] = cur;
             if (mask != nullptr) {
-                uint8_t* mrow = mask + orow * g.mpitch + (long long)slab * (SLAB * 32);
+                uint8_t* mrow = mask + orow * g.mpitch + (long long)slab * (SLABW * 32);
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
-                    const int c = half * 32 + lane;              // 16-byte chunk of the slab's row
+                    const int c = half * SEG + hl;               // 16-byte chunk of the slab's row
                     const uint32_t word = __shfl_sync(0xFFFFFFFFu, cur, src_lane[half]);
                     if (st_mask[half]) {
                         const uint32_t b16 = (word >> ((c & 1) * 16)) & 0xFFFFu;
@@ -181,9 +187,9 @@ __device__ __forceinline__ void morph_strip(const uint32_t* __restrict__ raw_f, 
     }
 }
 
-template <int R, int PAT>
+template <int R, int PAT, int SEG>
 __global__ void __launch_bounds__(32 * WPB)
-k_morph_mask(const uint32_t* __restrict__ raw_bits, Geom g, uint32_t* __restrict__ fbits,
+k_morph_mask(const uint32_t* __restrict__ raw_bits, Geom g, int T, uint32_t* __restrict__ fbits,
              uint8_t* __restrict__ mask) {
     constexpr int HR = n_ops(PAT) * R;
     constexpr int SR = strip_rows(R, PAT);
@@ -191,28 +197,34 @@ k_morph_mask(const uint32_t* __restrict__ raw_bits, Geom g, uint32_t* __restrict
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int slab = blockIdx.x;
-    const int f = blockIdx.z;
+    const int f = blockIdx.z * (32 / SEG) + lane / SEG;      // SEG = 16: one frame per half-warp
+    const bool live = f < T;
     const int y0 = (blockIdx.y * WPB + warp) * SR;
     if (y0 >= g.h) return;                                   // warp-uniform
     const uint32_t* raw_f = raw_bits + (long long)f * g.h * g.wpr_raw;
     const bool interior = (y0 - HR >= 0) && (y0 + SR + HR <= g.h);   // warp-uniform
     if (g.dx == 0) {
-        if (interior) morph_strip<R, PAT, true, true>(raw_f, g, fbits, mask, f, slab, lane, y0);
-        else morph_strip<R, PAT, false, true>(raw_f, g, fbits, mask, f, slab, lane, y0);
+        if (interior) morph_strip<R, PAT, true, true, SEG>(raw_f, g, fbits, mask, f, live, slab, lane, y0);
+        else morph_strip<R, PAT, false, true, SEG>(raw_f, g, fbits, mask, f, live, slab, lane, y0);
     } else {
-        if (interior) morph_strip<R, PAT, true, false>(raw_f, g, fbits, mask, f, slab, lane, y0);
-        else morph_strip<R, PAT, false, false>(raw_f, g, fbits, mask, f, slab, lane, y0);
+        if (interior) morph_strip<R, PAT, true, false, SEG>(raw_f, g, fbits, mask, f, live, slab, lane, y0);
+        else morph_strip<R, PAT, false, false, SEG>(raw_f, g, fbits, mask, f, live, slab, lane, y0);
     }
 }
 
 template <int R, int PAT>
 cudaError_t launch_pat(cudaStream_t s, const uint32_t* raw_bits, int T, const Geom& g, uint32_t* fbits,
                        uint8_t* mask) {
-    const int nslabs = (g.wpr4 + SLAB - 1) / SLAB;
     constexpr int SR = strip_rows(R, PAT);
     const int nstrips = (g.h + SR - 1) / SR;
+    if (g.wpr4 <= 14 && g.wpr_raw <= 15) {                   // narrow ROI: two frames per warp
+        dim3 grid(1, (nstrips + WPB - 1) / WPB, (T + 1) / 2);
+        launch_dependent(k_morph_mask<R, PAT, 16>, grid, dim3(32 * WPB), 0, s, raw_bits, g, T, fbits, mask);
+        return cudaGetLastError();
+    }
+    const int nslabs = (g.wpr4 + SLAB - 1) / SLAB;
     dim3 grid(nslabs, (nstrips + WPB - 1) / WPB, T);
-    launch_dependent(k_morph_mask<R, PAT>, grid, dim3(32 * WPB), 0, s, raw_bits, g, fbits, mask);
+    launch_dependent(k_morph_mask<R, PAT, 32>, grid, dim3(32 * WPB), 0, s, raw_bits, g, T, fbits, mask);
     return cudaGetLastError();
 }
 
