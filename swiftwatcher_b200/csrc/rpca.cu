@@ -126,6 +126,79 @@ k_rpca_gram(const uint8_t* __restrict__ X, const double* __restrict__ A, const d
         if (pi[k] >= 0) gpart[(long long)blockIdx.x * npairs + t + k * RP_THREADS] = acc[k];
 }
 
+// pass 1 for n = 21 (the reference's batch size, data_structures.py:120): the same tiles and the same
+// shared-memory rows of M, but the products are register-tiled.  The 21 x 21 upper triangle is cut into
+// 28 blocks of 3 x 3 pairs; thread (block b, slice s) accumulates its nine pairs over rows s, s + 8, ...
+// of the tile: six shared-memory loads per nine multiply-adds instead of two per one (the plain kernel is
+// bound by its shared-memory reads).  The eight slices of a block sit in adjacent lanes and are added
+// with a fixed shuffle tree at the end, so the result is the same on every run.
+__global__ void __launch_bounds__(RP_THREADS)
+k_rpca_gram21(const uint8_t* __restrict__ X, const double* __restrict__ A, const double* __restrict__ Y,
+              long long P, double inv_mu, double thr, double* __restrict__ gpart) {
+    constexpr int n = 21, NB = 7, NBLK = NB * (NB + 1) / 2, NS = 8;
+    constexpr int npairs = n * (n + 1) / 2;
+    extern __shared__ double sm[];                 // [n][LD]
+    constexpr int LD = RP_THREADS + 8;             // 3 * LD = 8 mod 16: the two blocks of a half-warp read disjoint banks
+    const int t = threadIdx.x;
+    const int slice = t & (NS - 1), blk = t >> 3;
+    const bool worker = blk < NBLK;
+    int bi = 0, bj = 0;
+    if (worker) {                                  // row-major upper triangle of blocks: blk -> (bi, bj), bj >= bi
+        int q = blk;
+        while (q >= NB - bi) { q -= NB - bi; ++bi; }
+        bj = bi + q;
+    }
+    double acc[3][3];
+#pragma unroll
+    for (int x = 0; x < 3; ++x)
+#pragma unroll
+        for (int y = 0; y < 3; ++y) acc[x][y] = 0.0;
+    const double* a0 = sm + (3 * bi) * LD;
+    const double* b0 = sm + (3 * bj) * LD;
+    const long long ntiles = (P + RP_THREADS - 1) / RP_THREADS;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long p = tile * RP_THREADS + t;
+#pragma unroll 3
+        for (int i = 0; i < n; ++i) {
+            double m = 0.0;
+            if (p < P) {
+                const long long idx = (long long)i * P + p;
+                const double x = (double)X[idx];
+                const double t2 = __dmul_rn(inv_mu, Y[idx]);           // numpy rounds the product, then the sum
+                const double e = shrink(__dadd_rn(x - A[idx], t2), thr);
+                m = __dadd_rn(x - e, t2);
+            }
+            sm[i * LD + t] = m;
+        }
+        __syncthreads();
+        if (worker) {
+#pragma unroll 4
+            for (int r = slice; r < RP_THREADS; r += NS) {
+                const double a[3] = {a0[r], a0[LD + r], a0[2 * LD + r]};
+                const double b[3] = {b0[r], b0[LD + r], b0[2 * LD + r]};
+#pragma unroll
+                for (int x = 0; x < 3; ++x)
+#pragma unroll
+                    for (int y = 0; y < 3; ++y) acc[x][y] = fma(a[x], b[y], acc[x][y]);
+            }
+        }
+        __syncthreads();
+    }
+    // the eight slices of a block: adjacent lanes, fixed-order tree
+#pragma unroll
+    for (int x = 0; x < 3; ++x)
+#pragma unroll
+        for (int y = 0; y < 3; ++y) {
+            double v = acc[x][y];
+            v += __shfl_xor_sync(0xFFFFFFFFu, v, 4);
+            v += __shfl_xor_sync(0xFFFFFFFFu, v, 2);
+            v += __shfl_xor_sync(0xFFFFFFFFu, v, 1);
+            const int i = 3 * bi + x, j = 3 * bj + y;
+            if (worker && slice == 0 && j >= i)
+                gpart[(long long)blockIdx.x * npairs + i * n - (i * (i - 1)) / 2 + (j - i)] = v;
+        }
+}
+
 // fixed-order sum of the per-CTA partials -> packed upper triangle
 // (one warp per pair: lane l sums CTAs l, l + 32, ...; then a shuffle tree — the same order every run)
 __global__ void k_rpca_gram_reduce(const double* __restrict__ gpart, int nctas, int npairs, double* __restrict__ G) {
@@ -380,6 +453,7 @@ cudaError_t rpca_run(cudaStream_t s, const uint8_t* X, int n, long long P, RpcaW
     const int smem_apply = (RP_NMAX * RP_NMAX + 2 * RP_NMAX * RP_THREADS) * (int)sizeof(double);
     if (once.need()) {
         cudaFuncSetAttribute(k_rpca_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_gram);
+        cudaFuncSetAttribute(k_rpca_gram21, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_gram);
         cudaFuncSetAttribute(k_rpca_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_apply);
         cudaFuncSetAttribute(k_rpca_apply_n<21>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              21 * RP_THREADS * (int)sizeof(double));
@@ -410,7 +484,10 @@ cudaError_t rpca_run(cudaStream_t s, const uint8_t* X, int n, long long P, RpcaW
     while (true) {
         const double inv_mu = 1 / mu;
         const double thr = lmbda / mu;
-        k_rpca_gram<<<nctas, RP_THREADS, n * (RP_THREADS + 1) * sizeof(double), s>>>(X, Aold, w.Y, n, P, inv_mu, thr, w.gpart);
+        if (n == 21)
+            k_rpca_gram21<<<nctas, RP_THREADS, 21 * (RP_THREADS + 8) * sizeof(double), s>>>(X, Aold, w.Y, P, inv_mu, thr, w.gpart);
+        else
+            k_rpca_gram<<<nctas, RP_THREADS, n * (RP_THREADS + 1) * sizeof(double), s>>>(X, Aold, w.Y, n, P, inv_mu, thr, w.gpart);
         k_rpca_gram_reduce<<<(npairs * 32 + 127) / 128, 128, 0, s>>>(w.gpart, nctas, npairs, w.G);
         cudaMemcpyAsync(hG, w.G, (size_t)npairs * sizeof(double), cudaMemcpyDeviceToHost, s);
         if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
