@@ -325,7 +325,7 @@ def run_multi_video(args, cfg, name):
         synth_frames(SEED, v, 1000 - halo, halo + T, H, W, cfg["birds"], device=local_rank, out=x)
         ctx = swb.FilterContext((H, W, 3), roi, median_n=N, threshold=15, morph_size=cfg["se"], do_open=True,
                                 do_close=cfg["do_close"], label_mode=args.label_mode, max_frames=T,
-                                max_segments=T * 1024, device=local_rank)
+                                max_segments=T * 1024, device=local_rank, gpu_share=len(mine))
         st = torch.cuda.Stream()
         ctx.set_stream(st.cuda_stream)
         vids.append(dict(v=v, roi=roi, frames=x, ctx=ctx, stream=st, done=torch.cuda.Event()))

@@ -64,7 +64,11 @@ typedef struct swb_config {
                               * frames, each with an equal share of the labelling scratch, so a
                               * submit whose segments all sit in a few frames may need a larger value */
     int32_t bg_model;        /* SWB_BG_MEDIAN (rolling median, BASELINE.json) or SWB_BG_RPCA */
-    int32_t reserved[2];
+    int32_t gpu_share;       /* contexts expected to work side by side on this GPU (e.g. one per video,
+                              * each on its own stream); 0 or 1 = the context has the GPU to itself.
+                              * Only sizes grids (longer temporal sub-chunks, fewer CTAs per launch):
+                              * results do not depend on it                                         */
+    int32_t reserved;
 } swb_config;
 
 /* Background models.  SWB_BG_RPCA is the reference's own localisation (rpca + bilateral_blur,

@@ -29,7 +29,7 @@ class SwbConfig(C.Structure):
         ("median_n", C.c_int32), ("threshold", C.c_int32), ("morph_size", C.c_int32),
         ("do_open", C.c_int32), ("do_close", C.c_int32), ("label_mode", C.c_int32),
         ("out_flags", C.c_int32), ("max_frames", C.c_int32), ("max_segments", C.c_int32),
-        ("bg_model", C.c_int32), ("reserved", C.c_int32 * 2),
+        ("bg_model", C.c_int32), ("gpu_share", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

@@ -517,7 +517,7 @@ int swb_submit(swb_ctx* ctx, const uint8_t* frames, int32_t n_frames, int32_t n_
                                      reinterpret_cast<uint32_t*>(ctx->raw_bits), gm.wpr_raw));
             launches += 2;
         } else {
-            CU(ctx, launch_fg_bits(s, src, C, N, n_frames, g, c.threshold, ctx->raw_bits, aligned, &launches));
+            CU(ctx, launch_fg_bits(s, src, C, N, n_frames, g, c.threshold, ctx->raw_bits, aligned, &launches, c.gpu_share));
         }
         if (ctx->timing) CU(ctx, cudaEventRecord(ctx->ev[1], s));
         CU(ctx, launch_morph_mask(s, reinterpret_cast<const uint32_t*>(ctx->raw_bits), n_frames, gm, ctx->morph,
@@ -565,7 +565,7 @@ int swb_submit(swb_ctx* ctx, const uint8_t* frames, int32_t n_frames, int32_t n_
             chain.frame_base = f0;
             chain.segoff_base = (b > 0) ? ctx->ccl.segoff + f0 : nullptr;   // left there by sub-batch b-1
             ccl_prepare(sw, nb, g, cb, true);
-            CU(ctx, launch_fg_bits(sw, sb, C, N, nb, g, c.threshold, raw_b, aligned, &launches));
+            CU(ctx, launch_fg_bits(sw, sb, C, N, nb, g, c.threshold, raw_b, aligned, &launches, c.gpu_share));
             CU(ctx, launch_morph_mask(sw, reinterpret_cast<const uint32_t*>(raw_b), nb, g, ctx->morph, fbits_b, mask_b,
                                       &launches));
             CU(ctx, launch_ccl(sw, fbits_b, nb, g, cb, labels_b, ctx->label_elem, &launches, nullptr, 0, &chain, true));

@@ -477,10 +477,12 @@ __device__ __forceinline__ uint32_t select4of7(uint32_t m2, uint32_t m3, uint32_
 // Temporal sub-chunk length: long enough that the N-1 warm-up frames are a few
 // percent of the work, short enough that the grid has several waves of CTAs; a
 // multiple of 6 so that only the last sub-chunk of a submit has a partial group.
-int pick_ts(int T, int n_col_blocks, int median_n) {
+int pick_ts(int T, int n_col_blocks, int median_n, int gpu_share) {
     static const int forced = [] { const char* e = getenv("SWB_K1_TS"); return e ? atoi(e) : 0; }();
     if (forced > 0) return std::min(T, (forced + 5) / 6 * 6);
-    const int target_ctas = 148 * 2 * 4;
+    // several waves of CTAs when the context has the GPU to itself; its share of that when other contexts
+    // (videos) run beside it: their CTAs fill the machine together, and longer sub-chunks re-read less
+    const int target_ctas = gpu_share > 1 ? std::max(148 * 2 * 2 / gpu_share, 16) : 148 * 2 * 4;
     int ts = T;
     while (ts > 32 && (long long)n_col_blocks * ((T + ts - 1) / ts) < target_ctas) ts = (ts + 1) / 2;
     const int min_ts = 8 * (median_n - 1) > 0 ? 8 * (median_n - 1) : 1;   // <= 12.5% warm-up
@@ -880,7 +882,7 @@ k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t on
 
 template <int N, int C, int OCC>
 cudaError_t launch_v2_occ(cudaStream_t s, const FrameSrc& src, int T, const Geom& g, int thresh,
-                          uint16_t* raw_bits) {
+                          uint16_t* raw_bits, int gpu_share) {
     constexpr int L = (N <= 5) ? 8 : 4;
     constexpr int TB = 2 * L * C;
     constexpr int S = (N == 5) ? 4 : (N == 9 ? 6 : 8);   // grouped loops: stages = frames per unrolled body
@@ -909,7 +911,7 @@ cudaError_t launch_v2_occ(cudaStream_t s, const FrameSrc& src, int T, const Geom
             n_col_blocks = (g.h + rows - 1) / rows;
         }
     }
-    const int Ts = pick_ts(T, n_col_blocks, N);
+    const int Ts = pick_ts(T, n_col_blocks, N, gpu_share);
     dim3 grid(n_col_blocks, (T + Ts - 1) / Ts);
     k_fg_bits_v2<N, C, S, L, OCC><<<grid, V2_THREADS, SMEM, s>>>(src, T, Ts, g.h, g.wa, thresh, 1u,
                                                                 reinterpret_cast<uint8_t*>(raw_bits), tmap, tile_rows);
@@ -918,24 +920,24 @@ cudaError_t launch_v2_occ(cudaStream_t s, const FrameSrc& src, int T, const Geom
 
 template <int N, int C>
 cudaError_t launch_v2(cudaStream_t s, const FrameSrc& src, int T, const Geom& g, int thresh,
-                      uint16_t* raw_bits) {
+                      uint16_t* raw_bits, int gpu_share) {
     if constexpr (N == 9) {
         // the N = 9 loop fits 72 registers: three CTAs (24 consumer warps) per SM
         static const bool occ2 = [] { const char* e = getenv("SWB_K1_N9_OCC"); return e && e[0] == '2'; }();
-        if (!occ2) return launch_v2_occ<N, C, 3>(s, src, T, g, thresh, raw_bits);
+        if (!occ2) return launch_v2_occ<N, C, 3>(s, src, T, g, thresh, raw_bits, gpu_share);
     }
-    return launch_v2_occ<N, C, 2>(s, src, T, g, thresh, raw_bits);
+    return launch_v2_occ<N, C, 2>(s, src, T, g, thresh, raw_bits, gpu_share);
 }
 
 template <int N>
 cudaError_t launch_n(cudaStream_t s, const FrameSrc& src, int channels, int T, const Geom& g,
-                     int thresh, uint16_t* raw_bits, bool aligned) {
+                     int thresh, uint16_t* raw_bits, bool aligned, int gpu_share) {
     if (aligned) {   // 16-byte aligned rows: bulk-copy pipeline (v2)
-        if (channels == 3) return launch_v2<N, 3>(s, src, T, g, thresh, raw_bits);
-        return launch_v2<N, 1>(s, src, T, g, thresh, raw_bits);
+        if (channels == 3) return launch_v2<N, 3>(s, src, T, g, thresh, raw_bits, gpu_share);
+        return launch_v2<N, 1>(s, src, T, g, thresh, raw_bits, gpu_share);
     }
     const int G = g.h * (g.wa >> 4);
-    const int Ts = pick_ts(T, (G + 255) / 256, N);
+    const int Ts = pick_ts(T, (G + 255) / 256, N, gpu_share);
     dim3 grid((G + 255) / 256, (T + Ts - 1) / Ts);
     dim3 block(256);
     // odd pitches / frame widths: guarded byte loads (v1)
@@ -947,14 +949,15 @@ cudaError_t launch_n(cudaStream_t s, const FrameSrc& src, int channels, int T, c
 }  // namespace
 
 cudaError_t launch_fg_bits(cudaStream_t s, const FrameSrc& src, int channels, int median_n, int T,
-                           const Geom& g, int thresh, uint16_t* raw_bits, bool aligned, int* n_launches) {
+                           const Geom& g, int thresh, uint16_t* raw_bits, bool aligned, int* n_launches,
+                           int gpu_share) {
     if (n_launches) *n_launches += 1;
     switch (median_n) {
-        case 1: return launch_n<1>(s, src, channels, T, g, thresh, raw_bits, aligned);
-        case 3: return launch_n<3>(s, src, channels, T, g, thresh, raw_bits, aligned);
-        case 5: return launch_n<5>(s, src, channels, T, g, thresh, raw_bits, aligned);
-        case 7: return launch_n<7>(s, src, channels, T, g, thresh, raw_bits, aligned);
-        case 9: return launch_n<9>(s, src, channels, T, g, thresh, raw_bits, aligned);
+        case 1: return launch_n<1>(s, src, channels, T, g, thresh, raw_bits, aligned, gpu_share);
+        case 3: return launch_n<3>(s, src, channels, T, g, thresh, raw_bits, aligned, gpu_share);
+        case 5: return launch_n<5>(s, src, channels, T, g, thresh, raw_bits, aligned, gpu_share);
+        case 7: return launch_n<7>(s, src, channels, T, g, thresh, raw_bits, aligned, gpu_share);
+        case 9: return launch_n<9>(s, src, channels, T, g, thresh, raw_bits, aligned, gpu_share);
         default: return cudaErrorInvalidValue;
     }
 }

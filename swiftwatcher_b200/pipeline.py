@@ -57,12 +57,13 @@ class FilterContext:
     def __init__(self, frame_shape, crop_region=None, median_n=5, threshold=15,
                  morph_size=3, do_open=True, do_close=False, label_mode="u8",
                  max_frames=21, max_segments=0, device=0, want_mask=True,
-                 want_labels=True, frame_pitch=0, frame_stride=0, bg_model="median"):
+                 want_labels=True, frame_pitch=0, frame_stride=0, bg_model="median", gpu_share=0):
         """frame_shape: (H, W, 3) BGR or (H, W) gray.  crop_region: the
         reference's ``[(x0, y0), (x1, y1)]`` (image_filtering.py:199-203);
         None = whole frame.  bg_model: "median" (rolling temporal median, BASELINE.json) or
         "rpca" (the reference's own rpca + bilateral_blur, image_filtering.py:220-307: every
-        submit is one batch of <= 32 frames decomposed on its own)."""
+        submit is one batch of <= 32 frames decomposed on its own).  gpu_share: how many contexts
+        work side by side on this GPU (one per video): sizes grids only, results do not change."""
         self._lib = _lib.load()
         h, w = int(frame_shape[0]), int(frame_shape[1])
         ch = int(frame_shape[2]) if len(frame_shape) == 3 else 1
@@ -84,6 +85,7 @@ class FilterContext:
         if bg_model not in ("median", "rpca"):
             raise ValueError("bg_model must be 'median' or 'rpca'")
         cfg.bg_model = BG_RPCA if bg_model == "rpca" else BG_MEDIAN
+        cfg.gpu_share = int(gpu_share)
         self.bg_model = bg_model
         self.cfg = cfg
         self.frame_shape = (h, w, ch) if ch == 3 else (h, w)

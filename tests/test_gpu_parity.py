@@ -481,6 +481,18 @@ def test_concurrent_contexts_on_their_own_streams():
             c.close()
 
 
+def test_gpu_share_only_sizes_grids():
+    """swb_config.gpu_share (contexts working side by side on one GPU) changes the temporal
+    sub-chunking of the filtering kernel, never the results."""
+    frames = synth.synth_video(61, 0, 0, 8 + 300, 96, 224, 40)
+    for region, n in (([(0, 0), (224, 96)], 5), ([(37, 9), (200, 90)], 9)):
+        for share in (2, 16, 64):
+            ctx = swb.FilterContext(frames.shape[1:], region, median_n=n, label_mode="i32", max_frames=300,
+                                    gpu_share=share)
+            check_against_oracle(frames[n - 1:n - 1 + 300], region, n=n, history=list(frames[:n - 1]), ctx=ctx)
+            ctx.close()
+
+
 def test_device_resident_input_zero_copy():
     import torch
     frames = synth.synth_video(28, 0, 0, 10, 72, 160, 30)
