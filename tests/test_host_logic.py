@@ -147,3 +147,21 @@ def test_two_rank_gloo_gather_restores_global_order():
     for _, rb, cb in got:
         assert np.array_equal(np.frombuffer(rb, SEGMENT_DTYPE), rows_w)
         assert np.array_equal(np.frombuffer(cb, np.int32), counts_w)
+
+
+def test_bench_parallel_cpu_arm_two_processes():
+    """bench.py's CPU reference arm: one process per core, each on its own temporal chunk
+    (+ N-1 halo frames); here two processes on a tiny ROI workload."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    cfg = dict(H=96, W=160, roi=[(16, 8), (144, 88)], N=5, se=3, do_close=False, birds=20, chunk=8)
+    fps, dt, segs, procs = bench.cpu_baseline_parallel(cfg, 6, procs=2, steps=2)
+    assert procs == 2 and dt > 0 and fps == pytest.approx(2 * 2 * 6 / dt)
+    # the segments the two processes found are the oracle's for the same frames (two steps each)
+    par = rp.PathParams(cfg["roi"], 5, 15, 3, True, False, "u8")
+    want = 0
+    for i in range(2):
+        fr = synth.synth_video(bench.SEED, 0, 1000 + 6 * i - 4, 4 + 6, 96, 160, 20)
+        want += sum(len(o["props"]) for o in rp.run_path(fr[4:], par, history=list(fr[:4]), want_images=True))
+    assert segs == 2 * want
