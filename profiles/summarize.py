@@ -28,11 +28,13 @@ def launches(path):
     agg = collections.OrderedDict()
     for row in csv.DictReader(lines):
         agg.setdefault(row["Kernel Name"][:72], []).append(float(row["Metric Value"].replace(",", "")))
-    tot = sum(sum(v) for k, v in agg.items() if "k_background" not in k and "k_birds" not in k)
+    def aux(k):   # synthetic-frame generators and the bench's spin gate in front of the timed region
+        return "k_background" in k or "k_birds" in k or "spin_kernel" in k
+    tot = sum(sum(v) for k, v in agg.items() if not aux(k))
     print("# per-kernel device time from `ncu --metrics gpu__time_duration.sum --clock-control none`")
-    print("# (cold cache, serialised: compare shares, not absolutes; generator kernels excluded from shares)")
+    print("# (cold cache, serialised: compare shares, not absolutes; generator kernels and the bench's spin gate excluded from shares)")
     for k, v in agg.items():
-        gen = "k_background" in k or "k_birds" in k
+        gen = aux(k)
         share = "   gen" if gen else "%5.1f%%" % (100 * sum(v) / tot)
         print("%-72s n=%3d avg=%9.1f us  share=%s" % (k, len(v), sum(v) / len(v) / 1e3, share))
 
