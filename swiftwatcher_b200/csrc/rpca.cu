@@ -326,6 +326,113 @@ k_rpca_apply_n(const uint8_t* __restrict__ X, const double* __restrict__ A, doub
     }
 }
 
+// pass 2, two lanes per pixel row (N = 21).  The one-thread-per-row kernel above needs 128 registers
+// (22 accumulators + the row) = 16 warps per SM, and is bound by the latency of its loads.  Here lane
+// parity `par` of a lane pair loads the frames i = 2k + par of the row, computes their E / M values, and owns
+// the output columns j = 2k + par: the M values cross the pair with shuffles, so every accumulator still
+// sees m_0 .. m_20 in order (the same sums, bit for bit), with half the registers and twice the warps.
+template <int N>
+__global__ void __launch_bounds__(RP_THREADS, 3)
+k_rpca_apply_pair(const uint8_t* __restrict__ X, const double* __restrict__ A, double* __restrict__ Anew,
+                  double* __restrict__ Y, long long P, double inv_mu, double thr, double mu,
+                  const double* __restrict__ Wg, double* __restrict__ zpart, uint8_t* __restrict__ out) {
+    constexpr int KH = (N + 1) / 2;                // frames / columns per lane (11)
+    constexpr int KP = (KH + 1) & ~1;              // padded to an even count (12): double2 loads of W
+    constexpr int ROWS = RP_THREADS / 2;           // pixel rows per CTA step
+    constexpr int LD = ROWS + 8;                   // sE row pitch: the two parities of a half-warp use disjoint banks
+    __shared__ __align__(16) double sW[N * 2 * KP];   // [i][par][k] = W[i][2k + par] (0 past column N-1)
+    extern __shared__ double sE[];                 // [N][LD] the rows' E, then [N][LD] their Y, then [N][LD] bytes of X
+    double* sY = sE + N * LD;
+    uint8_t* sX = reinterpret_cast<uint8_t*>(sY + N * LD);
+    const int t = threadIdx.x, par = t & 1, rl = t >> 1;
+    for (int q = t; q < N * 2 * KP; q += RP_THREADS) {
+        const int i = q / (2 * KP), r = q - i * 2 * KP, pp = r / KP, k = r - pp * KP;
+        const int j = 2 * k + pp;
+        sW[q] = j < N ? Wg[i * N + j] : 0.0;
+    }
+    __syncthreads();
+    double zz = 0.0;
+    const long long ntiles = (P + ROWS - 1) / ROWS;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long p = tile * ROWS + rl;
+        const bool live = p < P;                   // both lanes of a pair agree; dead pairs still shuffle
+        // every load of the row first (they are all independent: the kernel lives on loads in flight) ...
+        double av[KH], yv[KH];
+        uint32_t xv[KH];
+#pragma unroll
+        for (int k = 0; k < KH; ++k) {
+            const int i = 2 * k + par;
+            av[k] = yv[k] = 0.0;
+            xv[k] = 0u;
+            if (live && i < N) {
+                const long long idx = (long long)i * P + p;
+                xv[k] = X[idx];
+                av[k] = A[idx];
+                yv[k] = Y[idx];
+            }
+        }
+        // ... then E and M; X, Y and E wait in shared memory for the update below (each lane reads back
+        // only what it wrote: it owns frame i = 2k + par and column j = 2k + par)
+        double mloc[KH];
+#pragma unroll
+        for (int k = 0; k < KH; ++k) {
+            const int i = 2 * k + par;
+            double m = 0.0;
+            if (live && i < N) {
+                const double x = (double)xv[k];
+                const double t2 = __dmul_rn(inv_mu, yv[k]);
+                const double e = shrink(__dadd_rn(x - av[k], t2), thr);
+                sE[i * LD + rl] = e;
+                sY[i * LD + rl] = yv[k];
+                sX[i * LD + rl] = (uint8_t)xv[k];
+                m = __dadd_rn(x - e, t2);
+                out[(long long)i * P + p] = (uint8_t)fmin(fmax(-e, 0.0), 255.0);
+            }
+            mloc[k] = m;
+        }
+        double acc[KP];
+#pragma unroll
+        for (int k = 0; k < KP; ++k) acc[k] = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double own = mloc[i >> 1];
+            const double other = __shfl_xor_sync(0xFFFFFFFFu, own, 1);
+            const double m = ((i & 1) == par) ? own : other;
+            const double2* wr = reinterpret_cast<const double2*>(sW + (i * 2 + par) * KP);
+#pragma unroll
+            for (int k = 0; k < KP / 2; ++k) {
+                const double2 w2 = wr[k];
+                acc[2 * k] = fma(m, w2.x, acc[2 * k]);
+                acc[2 * k + 1] = fma(m, w2.y, acc[2 * k + 1]);
+            }
+        }
+        __syncwarp();                              // the pair's E values are in shared memory
+        if (live) {
+#pragma unroll
+            for (int k = 0; k < KH; ++k) {
+                const int j = 2 * k + par;
+                if (j < N) {
+                    const long long idx = (long long)j * P + p;
+                    const double z = ((double)sX[j * LD + rl] - acc[k]) - sE[j * LD + rl];
+                    Anew[idx] = acc[k];
+                    Y[idx] = __dadd_rn(sY[j * LD + rl], __dmul_rn(mu, z));
+                    zz = fma(z, z, zz);
+                }
+            }
+        }
+        __syncwarp();                              // sE is rewritten by the next tile
+    }
+    __shared__ double red[RP_THREADS / 32];
+    for (int d = 16; d > 0; d >>= 1) zz += __shfl_down_sync(0xFFFFFFFFu, zz, d);
+    if ((t & 31) == 0) red[t >> 5] = zz;
+    __syncthreads();
+    if (t == 0) {
+        double s = 0.0;
+        for (int w = 0; w < RP_THREADS / 32; ++w) s += red[w];
+        zpart[blockIdx.x] = s;
+    }
+}
+
 // crop + gray into the compact [n][h*w] stack (convert_grayscale, image_filtering.py:188-196;
 // crop_frame :199-203); column order = `order[k]` picks the source frame of column k
 __global__ void __launch_bounds__(RP_THREADS)
@@ -457,6 +564,8 @@ cudaError_t rpca_run(cudaStream_t s, const uint8_t* X, int n, long long P, RpcaW
         cudaFuncSetAttribute(k_rpca_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_apply);
         cudaFuncSetAttribute(k_rpca_apply_n<21>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              21 * RP_THREADS * (int)sizeof(double));
+        cudaFuncSetAttribute(k_rpca_apply_pair<21>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             21 * (RP_THREADS / 2 + 8) * 17);
     }
 
     cudaMemsetAsync(w.sumsq, 0, 16, s);
@@ -532,17 +641,24 @@ cudaError_t rpca_run(cudaStream_t s, const uint8_t* X, int n, long long P, RpcaW
                 hW[(size_t)i * n + j] = acc;
             }
         cudaMemcpyAsync(w.W, hW, (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice, s);
-        if (n == 21)
+        static const bool apply_one = [] { const char* e = getenv("SWB_RPCA_APPLY1"); return e && e[0] == '1'; }();
+        int napply = nctas;                        // CTAs of the apply pass = |Z|^2 partials to add up
+        if (n == 21 && !apply_one) {
+            napply = std::min(nctas, 148 * 3);     // three CTAs per SM are resident: one round of equal shares
+            k_rpca_apply_pair<21><<<napply, RP_THREADS, 21 * (RP_THREADS / 2 + 8) * 17, s>>>(   // E, Y (doubles), X (bytes)
+                X, Aold, Anew, w.Y, P, inv_mu, thr, mu, w.W, w.zpart, out);
+        }
+        else if (n == 21)
             k_rpca_apply_n<21><<<nctas, RP_THREADS, 21 * RP_THREADS * sizeof(double), s>>>(X, Aold, Anew, w.Y, P, inv_mu, thr, mu,
                                                                                            w.W, w.zpart, out);
         else
             k_rpca_apply<<<nctas, RP_THREADS, (size_t)(n * n + 2 * n * RP_THREADS) * sizeof(double), s>>>(
                 X, Aold, Anew, w.Y, n, P, inv_mu, thr, mu, w.W, w.zpart, out);
-        cudaMemcpyAsync(hZ, w.zpart, (size_t)nctas * sizeof(double), cudaMemcpyDeviceToHost, s);
+        cudaMemcpyAsync(hZ, w.zpart, (size_t)napply * sizeof(double), cudaMemcpyDeviceToHost, s);
         launches += 3;
         if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
         double zz = 0.0;
-        for (int c = 0; c < nctas; ++c) zz += hZ[c];
+        for (int c = 0; c < napply; ++c) zz += hZ[c];
         std::swap(Aold, Anew);
         mu = std::min(mu * rho, mu * 1e7);
         ++itr;
