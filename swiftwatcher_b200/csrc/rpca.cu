@@ -331,16 +331,26 @@ k_rpca_apply_n(const uint8_t* __restrict__ X, const double* __restrict__ A, doub
 // parity `par` of a lane pair loads the frames i = 2k + par of the row, computes their E / M values, and owns
 // the output columns j = 2k + par: the M values cross the pair with shuffles, so every accumulator still
 // sees m_0 .. m_20 in order (the same sums, bit for bit), with half the registers and twice the warps.
-template <int N>
+//
+// FUSE: the pass also leaves the Gram partials of the NEXT iteration.  At the end of the update the lane holds
+// x, A' and the new Y of its elements, which is all M of the next iteration needs (its mu is known in advance):
+// the values replace E in shared memory and the CTA adds the tile's 21 x 21 products to its partial Gram
+// matrix with the register-tiled scheme of k_rpca_gram21 (28 blocks of 3 x 3 pairs x 8 row slices).  The
+// separate Gram pass (a second sweep over X, A, Y) and one of the two stream synchronisations per iteration
+// disappear; only the first iteration still runs k_rpca_gram21.
+template <int N, bool FUSE>
 __global__ void __launch_bounds__(RP_THREADS, 3)
 k_rpca_apply_pair(const uint8_t* __restrict__ X, const double* __restrict__ A, double* __restrict__ Anew,
                   double* __restrict__ Y, long long P, double inv_mu, double thr, double mu,
-                  const double* __restrict__ Wg, double* __restrict__ zpart, uint8_t* __restrict__ out) {
+                  const double* __restrict__ Wg, double* __restrict__ zpart, uint8_t* __restrict__ out,
+                  double inv_mu_next, double thr_next, double* __restrict__ gpart_next) {
     constexpr int KH = (N + 1) / 2;                // frames / columns per lane (11)
     constexpr int KP = (KH + 1) & ~1;              // padded to an even count (12): double2 loads of W
     constexpr int ROWS = RP_THREADS / 2;           // pixel rows per CTA step
     constexpr int LD = ROWS + 8;                   // sE row pitch: the two parities of a half-warp use disjoint banks
     __shared__ __align__(16) double sW[N * 2 * KP];   // [i][par][k] = W[i][2k + par] (0 past column N-1)
+    constexpr int NPAIRS = N * (N + 1) / 2;
+    __shared__ double sG[FUSE ? NPAIRS : 1];       // the CTA's partial Gram matrix of the next iteration
     extern __shared__ double sE[];                 // [N][LD] the rows' E, then [N][LD] their Y, then [N][LD] bytes of X
     double* sY = sE + N * LD;
     uint8_t* sX = reinterpret_cast<uint8_t*>(sY + N * LD);
@@ -350,6 +360,19 @@ k_rpca_apply_pair(const uint8_t* __restrict__ X, const double* __restrict__ A, d
         const int j = 2 * k + pp;
         sW[q] = j < N ? Wg[i * N + j] : 0.0;
     }
+    // Gram work split (FUSE): thread = (block of 3 x 3 pairs, slice of every 8th row)
+    constexpr int NB = N / 3, NBLK = NB * (NB + 1) / 2, NS = 8;
+    static_assert(!FUSE || (N % 3 == 0 && NBLK * NS <= RP_THREADS), "28 blocks x 8 slices");
+    const int gslice = t & (NS - 1), gblk = t >> 3;
+    const bool gworker = FUSE && gblk < NBLK;
+    int bi = 0, bj = 0;
+    if (gworker) {
+        int q = gblk;
+        while (q >= NB - bi) { q -= NB - bi; ++bi; }
+        bj = bi + q;
+    }
+    if (FUSE)
+        for (int q = t; q < NPAIRS; q += RP_THREADS) sG[q] = 0.0;
     __syncthreads();
     double zz = 0.0;
     const long long ntiles = (P + ROWS - 1) / ROWS;
@@ -413,14 +436,63 @@ k_rpca_apply_pair(const uint8_t* __restrict__ X, const double* __restrict__ A, d
                 const int j = 2 * k + par;
                 if (j < N) {
                     const long long idx = (long long)j * P + p;
-                    const double z = ((double)sX[j * LD + rl] - acc[k]) - sE[j * LD + rl];
+                    const double x = (double)sX[j * LD + rl];
+                    const double z = (x - acc[k]) - sE[j * LD + rl];
                     Anew[idx] = acc[k];
-                    Y[idx] = __dadd_rn(sY[j * LD + rl], __dmul_rn(mu, z));
+                    const double ynew = __dadd_rn(sY[j * LD + rl], __dmul_rn(mu, z));
+                    Y[idx] = ynew;
                     zz = fma(z, z, zz);
+                    if (FUSE) {                    // M of the next iteration, exactly as k_rpca_gram21 would compute it
+                        const double t2 = __dmul_rn(inv_mu_next, ynew);
+                        const double e = shrink(__dadd_rn(x - acc[k], t2), thr_next);
+                        sE[j * LD + rl] = __dadd_rn(x - e, t2);
+                    }
                 }
             }
+        } else if (FUSE) {
+#pragma unroll
+            for (int k = 0; k < KH; ++k)
+                if (2 * k + par < N) sE[(2 * k + par) * LD + rl] = 0.0;
         }
-        __syncwarp();                              // sE is rewritten by the next tile
+        if (FUSE) {
+            __syncthreads();                       // the tile's M values are complete
+            if (gworker) {
+                const double* a0 = sE + (3 * bi) * LD;
+                const double* b0 = sE + (3 * bj) * LD;
+                double g9[3][3];
+#pragma unroll
+                for (int x = 0; x < 3; ++x)
+#pragma unroll
+                    for (int y = 0; y < 3; ++y) g9[x][y] = 0.0;
+#pragma unroll 4
+                for (int r = gslice; r < ROWS; r += NS) {
+                    const double a[3] = {a0[r], a0[LD + r], a0[2 * LD + r]};
+                    const double b[3] = {b0[r], b0[LD + r], b0[2 * LD + r]};
+#pragma unroll
+                    for (int x = 0; x < 3; ++x)
+#pragma unroll
+                        for (int y = 0; y < 3; ++y) g9[x][y] = fma(a[x], b[y], g9[x][y]);
+                }
+#pragma unroll
+                for (int x = 0; x < 3; ++x)
+#pragma unroll
+                    for (int y = 0; y < 3; ++y) {
+                        double v = g9[x][y];       // the eight slices of a block: adjacent lanes, fixed-order tree
+                        v += __shfl_xor_sync(0xFFFFFFFFu, v, 4);
+                        v += __shfl_xor_sync(0xFFFFFFFFu, v, 2);
+                        v += __shfl_xor_sync(0xFFFFFFFFu, v, 1);
+                        const int i = 3 * bi + x, j = 3 * bj + y;
+                        if (gslice == 0 && j >= i) sG[i * N - (i * (i - 1)) / 2 + (j - i)] += v;
+                    }
+            }
+            __syncthreads();                       // sE is rewritten by the next tile
+        } else {
+            __syncwarp();                          // sE is rewritten by the next tile
+        }
+    }
+    if (FUSE) {
+        __syncthreads();
+        for (int q = t; q < NPAIRS; q += RP_THREADS) gpart_next[(long long)blockIdx.x * NPAIRS + q] = sG[q];
     }
     __shared__ double red[RP_THREADS / 32];
     for (int d = 16; d > 0; d >>= 1) zz += __shfl_down_sync(0xFFFFFFFFu, zz, d);
@@ -564,7 +636,9 @@ cudaError_t rpca_run(cudaStream_t s, const uint8_t* X, int n, long long P, RpcaW
         cudaFuncSetAttribute(k_rpca_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_apply);
         cudaFuncSetAttribute(k_rpca_apply_n<21>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              21 * RP_THREADS * (int)sizeof(double));
-        cudaFuncSetAttribute(k_rpca_apply_pair<21>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(k_rpca_apply_pair<21, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             21 * (RP_THREADS / 2 + 8) * 17);
+        cudaFuncSetAttribute(k_rpca_apply_pair<21, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              21 * (RP_THREADS / 2 + 8) * 17);
     }
 
@@ -590,16 +664,20 @@ cudaError_t rpca_run(cudaStream_t s, const uint8_t* X, int n, long long P, RpcaW
     double* Anew = w.A1;
     std::vector<double> g((size_t)n * n), d, v, vprev, tmp((size_t)n * n), vb;
     int itr = 0;
+    bool have_G = false;                           // hG already holds this iteration's Gram matrix (fused pass)
     while (true) {
         const double inv_mu = 1 / mu;
         const double thr = lmbda / mu;
-        if (n == 21)
-            k_rpca_gram21<<<nctas, RP_THREADS, 21 * (RP_THREADS + 8) * sizeof(double), s>>>(X, Aold, w.Y, P, inv_mu, thr, w.gpart);
-        else
-            k_rpca_gram<<<nctas, RP_THREADS, n * (RP_THREADS + 1) * sizeof(double), s>>>(X, Aold, w.Y, n, P, inv_mu, thr, w.gpart);
-        k_rpca_gram_reduce<<<(npairs * 32 + 127) / 128, 128, 0, s>>>(w.gpart, nctas, npairs, w.G);
-        cudaMemcpyAsync(hG, w.G, (size_t)npairs * sizeof(double), cudaMemcpyDeviceToHost, s);
-        if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+        if (!have_G) {                             // first iteration (or no fused pass): the Gram pass on its own
+            if (n == 21)
+                k_rpca_gram21<<<nctas, RP_THREADS, 21 * (RP_THREADS + 8) * sizeof(double), s>>>(X, Aold, w.Y, P, inv_mu, thr, w.gpart);
+            else
+                k_rpca_gram<<<nctas, RP_THREADS, n * (RP_THREADS + 1) * sizeof(double), s>>>(X, Aold, w.Y, n, P, inv_mu, thr, w.gpart);
+            k_rpca_gram_reduce<<<(npairs * 32 + 127) / 128, 128, 0, s>>>(w.gpart, nctas, npairs, w.G);
+            cudaMemcpyAsync(hG, w.G, (size_t)npairs * sizeof(double), cudaMemcpyDeviceToHost, s);
+            launches += 2;
+            if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+        }
         for (int i = 0, q = 0; i < n; ++i)
             for (int j = i; j < n; ++j, ++q) g[(size_t)i * n + j] = g[(size_t)j * n + i] = hG[q];
         if (vprev.empty()) {
@@ -643,10 +721,23 @@ cudaError_t rpca_run(cudaStream_t s, const uint8_t* X, int n, long long P, RpcaW
         cudaMemcpyAsync(w.W, hW, (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice, s);
         static const bool apply_one = [] { const char* e = getenv("SWB_RPCA_APPLY1"); return e && e[0] == '1'; }();
         int napply = nctas;                        // CTAs of the apply pass = |Z|^2 partials to add up
+        static const bool no_fuse = [] { const char* e = getenv("SWB_RPCA_FUSE"); return e && e[0] == '0'; }();
         if (n == 21 && !apply_one) {
             napply = std::min(nctas, 148 * 3);     // three CTAs per SM are resident: one round of equal shares
-            k_rpca_apply_pair<21><<<napply, RP_THREADS, 21 * (RP_THREADS / 2 + 8) * 17, s>>>(   // E, Y (doubles), X (bytes)
-                X, Aold, Anew, w.Y, P, inv_mu, thr, mu, w.W, w.zpart, out);
+            const size_t smem = 21 * (RP_THREADS / 2 + 8) * 17;        // E, Y (doubles), X (bytes)
+            if (no_fuse) {
+                k_rpca_apply_pair<21, false><<<napply, RP_THREADS, smem, s>>>(X, Aold, Anew, w.Y, P, inv_mu, thr, mu, w.W,
+                                                                             w.zpart, out, 0.0, 0.0, nullptr);
+            } else {
+                // the pass also leaves the Gram partials of the next iteration (its mu is known now)
+                const double mu_next = std::min(mu * rho, mu * 1e7);
+                k_rpca_apply_pair<21, true><<<napply, RP_THREADS, smem, s>>>(X, Aold, Anew, w.Y, P, inv_mu, thr, mu, w.W,
+                                                                            w.zpart, out, 1 / mu_next, lmbda / mu_next, w.gpart);
+                k_rpca_gram_reduce<<<(npairs * 32 + 127) / 128, 128, 0, s>>>(w.gpart, napply, npairs, w.G);
+                cudaMemcpyAsync(hG, w.G, (size_t)npairs * sizeof(double), cudaMemcpyDeviceToHost, s);
+                have_G = true;
+                launches += 1;
+            }
         }
         else if (n == 21)
             k_rpca_apply_n<21><<<nctas, RP_THREADS, 21 * RP_THREADS * sizeof(double), s>>>(X, Aold, Anew, w.Y, P, inv_mu, thr, mu,
@@ -655,7 +746,7 @@ cudaError_t rpca_run(cudaStream_t s, const uint8_t* X, int n, long long P, RpcaW
             k_rpca_apply<<<nctas, RP_THREADS, (size_t)(n * n + 2 * n * RP_THREADS) * sizeof(double), s>>>(
                 X, Aold, Anew, w.Y, n, P, inv_mu, thr, mu, w.W, w.zpart, out);
         cudaMemcpyAsync(hZ, w.zpart, (size_t)napply * sizeof(double), cudaMemcpyDeviceToHost, s);
-        launches += 3;
+        launches += 1;
         if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
         double zz = 0.0;
         for (int c = 0; c < napply; ++c) zz += hZ[c];
