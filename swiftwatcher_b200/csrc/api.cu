@@ -514,7 +514,7 @@ int swb_submit(swb_ctx* ctx, const uint8_t* frames, int32_t n_frames, int32_t n_
             gm.wpr_raw = g.wpr;
             gm.wa = g.wpr * 32;
             CU(ctx, launch_bilateral(s, ctx->rp_sparse, n_frames, g.h, g.w, ctx->d_lut, 1, nullptr, c.threshold,
-                                     reinterpret_cast<uint32_t*>(ctx->raw_bits), gm.wpr_raw));
+                                     reinterpret_cast<uint32_t*>(ctx->raw_bits), gm.wpr_raw, 3));
             launches += 2;
         } else {
             CU(ctx, launch_fg_bits(s, src, C, N, n_frames, g, c.threshold, ctx->raw_bits, aligned, &launches, c.gpu_share));
@@ -956,7 +956,7 @@ int swb_stage_bilateral(int32_t device, const uint8_t* in, int32_t h, int32_t w,
     bilateral_lut(d, sigma_color, sigma_space, lut);
     CU(nullptr, cudaMemcpy(d_lut, &lut, sizeof(lut), cudaMemcpyHostToDevice));
     CU(nullptr, cudaMemcpy(d_in, in, n, cudaMemcpyHostToDevice));
-    CU(nullptr, launch_bilateral(0, d_in, 1, h, w, d_lut, 0, d_out, 0, nullptr, 0));
+    CU(nullptr, launch_bilateral(0, d_in, 1, h, w, d_lut, 0, d_out, 0, nullptr, 0, lut.radius));
     CU(nullptr, cudaMemcpy(out, d_out, n, cudaMemcpyDeviceToHost));
     return SWB_OK;
 }

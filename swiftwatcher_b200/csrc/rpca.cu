@@ -842,13 +842,79 @@ k_bilateral(const uint8_t* __restrict__ in, int n, int h, int w, const Bilateral
     }
 }
 
+// The same filter for radius 3 (d = 7, what the reference calls): the 29 taps are unrolled at compile time in
+// OpenCV's order (offsets become immediates, the tap index a constant) and pixels at least 3 away from every
+// border skip the reflection.  Same operations in the same order as k_bilateral: bit-identical results.
+__global__ void __launch_bounds__(256)
+k_bilateral_r3(const uint8_t* __restrict__ in, int n, int h, int w, const BilateralLut* __restrict__ lutp, int reverse,
+               uint8_t* __restrict__ out, int thresh, uint32_t* __restrict__ bits, int wpr_bits) {
+    __shared__ float s_color[256];
+    __shared__ float s_space[32];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_color[i] = lutp->color[i];
+    if (threadIdx.x < 32) s_space[threadIdx.x] = lutp->space[threadIdx.x];
+    __syncthreads();
+    const int wpr = (w + 31) / 32;
+    const int lane = threadIdx.x & 31;
+    const long long nwords = (long long)n * h * wpr;
+    for (long long word = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; word < nwords;
+         word += ((long long)gridDim.x * blockDim.x) >> 5) {
+        const int f = (int)(word / ((long long)h * wpr));
+        const long long rem = word - (long long)f * h * wpr;
+        const int y = (int)(rem / wpr), x = (int)(rem - (long long)y * wpr) * 32 + lane;
+        const uint8_t* img = in + (long long)(reverse ? n - 1 - f : f) * h * w;
+        int res = 0;
+        if (x < w) {
+            const uint8_t* ctr = img + (long long)y * w + x;
+            const int c = *ctr;
+            float sum = 0.f, wsum = 0.f;
+            if (y >= 3 && y < h - 3 && x >= 3 && x < w - 3) {
+                int k = 0;
+#pragma unroll
+                for (int i = -3; i <= 3; ++i)
+#pragma unroll
+                    for (int j = -3; j <= 3; ++j) {
+                        if (i * i + j * j > 9) continue;
+                        const int v = ctr[i * w + j];
+                        const float wk = __fmul_rn(s_space[k], s_color[abs(v - c)]);
+                        wsum = __fadd_rn(wsum, wk);
+                        sum = __fadd_rn(sum, __fmul_rn((float)v, wk));
+                        ++k;
+                    }
+            } else {
+                int k = 0;
+#pragma unroll
+                for (int i = -3; i <= 3; ++i)
+#pragma unroll
+                    for (int j = -3; j <= 3; ++j) {
+                        if (i * i + j * j > 9) continue;
+                        const int v = img[(long long)reflect101(y + i, h) * w + reflect101(x + j, w)];
+                        const float wk = __fmul_rn(s_space[k], s_color[abs(v - c)]);
+                        wsum = __fadd_rn(wsum, wk);
+                        sum = __fadd_rn(sum, __fmul_rn((float)v, wk));
+                        ++k;
+                    }
+            }
+            res = __float2int_rn(__fdiv_rn(sum, wsum));
+            res = min(max(res, 0), 255);
+            if (out) out[((long long)f * h + y) * w + x] = (uint8_t)res;
+        }
+        if (bits) {
+            const uint32_t b = __ballot_sync(0xFFFFFFFFu, res > thresh);
+            if (lane == 0 && x / 32 < wpr_bits) bits[((long long)f * h + y) * wpr_bits + x / 32] = b;
+        }
+    }
+}
+
 }  // namespace
 
 cudaError_t launch_bilateral(cudaStream_t s, const uint8_t* in, int n, int h, int w, const BilateralLut* d_lut,
-                             int reverse, uint8_t* out, int thresh, uint32_t* bits, int wpr_bits) {
+                             int reverse, uint8_t* out, int thresh, uint32_t* bits, int wpr_bits, int radius) {
     const long long nwords = (long long)n * h * ((w + 31) / 32);
     const int grid = (int)std::min<long long>((nwords * 32 + 255) / 256, 148 * 32);
-    k_bilateral<<<grid, 256, 0, s>>>(in, n, h, w, d_lut, reverse, out, thresh, bits, wpr_bits);
+    if (radius == 3 && h >= 7 && w >= 7)
+        k_bilateral_r3<<<grid, 256, 0, s>>>(in, n, h, w, d_lut, reverse, out, thresh, bits, wpr_bits);
+    else
+        k_bilateral<<<grid, 256, 0, s>>>(in, n, h, w, d_lut, reverse, out, thresh, bits, wpr_bits);
     return cudaGetLastError();
 }
 

@@ -131,7 +131,8 @@ cudaError_t launch_crop_gray(cudaStream_t s, const uint8_t* frames, long long fr
 // bilateral_blur (image_filtering.py:304-307 = cv2.bilateralFilter, 8-bit, one channel) for a stack of
 // frames; `out` (uint8 images) and / or `bits` (the thresholded result as 1 bit per pixel, rows of
 // wpr_bits words: the input of the morphology kernel) may be null.  frame_map: frame f reads image
-// (reverse ? n - 1 - f : f) of the stack.
+// (reverse ? n - 1 - f : f) of the stack.  radius: the LUT's radius when the caller knows it (3 selects the
+// unrolled kernel), 0 = use the generic kernel.
 struct BilateralLut {
     float color[256];
     float space[64];
@@ -140,7 +141,7 @@ struct BilateralLut {
 };
 void bilateral_lut(int d, double sigma_color, double sigma_space, BilateralLut& lut);
 cudaError_t launch_bilateral(cudaStream_t s, const uint8_t* in, int n, int h, int w, const BilateralLut* d_lut,
-                             int reverse, uint8_t* out, int thresh, uint32_t* bits, int wpr_bits);
+                             int reverse, uint8_t* out, int thresh, uint32_t* bits, int wpr_bits, int radius = 0);
 
 // ---- programmatic dependent launch (sm_90+): a kernel launched with launch_dependent() may be
 // scheduled while its predecessor in the stream is still draining; it must call
