@@ -561,8 +561,11 @@ def main():
     if clf is None:
         # ~10 ms of spinning on the launch stream in front of the first event: the host enqueues the K steps
         # behind it, so the device-timed region holds back-to-back launches whatever the host thread is doing
-        with torch.cuda.stream(stream):
-            torch.cuda._sleep(20_000_000)
+        try:
+            with torch.cuda.stream(stream):
+                torch.cuda._sleep(20_000_000)
+        except Exception:                                  # private torch helper: the gate is optional
+            pass
     ev0.record(stream)
     for i in range(args.steps):
         run_step(ctx, bufs[i % n_buf])
