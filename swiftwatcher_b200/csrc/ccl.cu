@@ -1020,7 +1020,7 @@ k_write_labels_i32(const uint32_t* __restrict__ fbits, Geom g, const int* __rest
 // Here a lane owns one 32-pixel bit word = 32 output bytes: background words are zero stores, and a
 // word with foreground runs one compact loop over its RUNS (the walk to the tagged root from the run's
 // first block, then the run's mask bits expanded to bytes and ANDed with the replicated label).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)
 k_write_labels_u8(const uint32_t* __restrict__ fbits, Geom g, int T, const int* __restrict__ parent,
                   const uint32_t* __restrict__ rowbase, uint8_t* __restrict__ labels) {
     wait_for_previous_kernel();
