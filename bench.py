@@ -35,7 +35,7 @@ CONFIGS = {
     "4k_full_n9_oc5": dict(H=2160, W=3840, roi=None, N=9, se=5, do_close=True, birds=600, chunk=256),
     # BASELINE.json configs[0] geometry (the reference's CPU-runnable case)
     "1080p_roi320x240_n5_open3": dict(H=1080, W=1920, roi=[(800, 400), (1120, 640)], N=5, se=3,
-                                      do_close=False, birds=300, chunk=2048),
+                                      do_close=False, birds=300, chunk=2048, dropin=True, cpu_in_also=True),
     # BASELINE.json configs[4] filtering part (dense swarm, ~500 segments/frame)
     "1080p_dense_n5_open3": dict(H=1080, W=1920, roi=None, N=5, se=3, do_close=False, birds=2500, chunk=512),
     # BASELINE.json configs[4]: filter + label + batched segment classification (SqueezeNet1.0 as in the
@@ -54,6 +54,107 @@ CONFIGS["16x1080p_rois_n5_open3"] = dict(H=1080, W=1920, roi=None, N=5, se=3, do
                                          videos=16)
 DEFAULT_CONFIG = "1080p_full_n5_open3"
 SEED = 2
+# Sub-lines of the default run ("also": [...]): every other BASELINE.json config, measured in the same process
+# right after the headline config (fewer steps; the CPU arm only where it is cheap).
+ALSO = [("4k_full_n9_oc5", "i32"), ("1080p_roi320x240_n5_open3", "i32"), ("1080p_full_n5_open3", "u8"),
+        ("16x1080p_rois_n5_open3", "i32"), ("1080p_swarm500_classify", "i32")]
+
+
+class Env:
+    """Process-group state shared by every config of one bench.py run."""
+
+    def __init__(self):
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.dist = None
+
+    def init(self):
+        import torch
+        torch.cuda.set_device(self.local_rank)
+        if self.world > 1:
+            import torch.distributed as dist
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            self.dist = dist
+
+    def barrier(self):
+        import torch
+        if self.dist is not None:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        import torch
+        if self.dist is None:
+            return float(x)
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_ok(self, ok):
+        return self.max_over_ranks(0.0 if ok else 1.0) == 0.0
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def parity_frames(T, ts, n):
+    """Frames to compare with the oracle after the timed region: first, last, both sides of the first
+    temporal sub-chunk boundary of the filtering kernel, then a spread."""
+    picks = [0, T - 1]
+    if 0 < ts < T:
+        picks += [ts - 1, ts]
+    k = 1
+    while len(set(picks)) < min(n, T):
+        picks.append((k * 2654435761) % T)
+        k += 1
+    return sorted(set(picks))[:max(n, 1)] if len(set(picks)) > n else sorted(set(picks))
+
+
+def parity_check(ctx, dev, halo, par, n_frames, roi_w):
+    """Untimed result guard: the submit the bench just timed, compared with the oracle (masks, labels,
+    table rows: bit-exact) on a few frames.  Returns {"frames": n, "ok": bool, ...}."""
+    from oracle import reference_path as rp
+    from swiftwatcher_b200.pipeline import centroids
+    ctx.submit(dev, n_halo=halo)
+    rows, counts = ctx.collect()
+    T = len(counts)
+    offs = np.concatenate([[0], np.cumsum(counts)])
+    picks = parity_frames(T, ctx.last_subchunk(), n_frames)
+    bad = []
+    for t in picks:
+        host = dev[t:t + halo + 1].cpu().numpy()
+        rec = rp.run_path(host[halo:], par, history=list(host[:halo]))[0]
+        r = rows[offs[t]:offs[t + 1]]
+        exp = rp.props_table(rec["props"])
+        ok = np.array_equal(ctx.masks(t, 1)[0], rec["mask"]) and np.array_equal(ctx.labels(t, 1)[0], rec["labels"]) \
+            and len(r) == len(exp)
+        if ok and len(r):
+            got = np.zeros((len(r), 8))
+            got[:, 0], got[:, 1], got[:, 2:6] = r["label"], r["area"], r["bbox"]
+            got[:, 6:8] = centroids(r)
+            ok = np.array_equal(got, exp)
+        if not ok:
+            bad.append(int(t))
+    return {"frames": len(picks), "ok": not bad, "frame_list": [int(t) for t in picks], "mismatches": bad,
+            "what": "masks, labels and table rows of these frames of the timed submit == oracle/reference_path.run_path"}
+
+
+def h2d_attainable(env, host, dev, reps):
+    """What the host -> device fabric gives this run: every rank copies its pinned chunk with one plain
+    cudaMemcpyAsync per step, all ranks at once (GB/s summed over ranks, max-over-ranks time)."""
+    import torch
+    dev.copy_(host, non_blocking=True)
+    env.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        dev.copy_(host, non_blocking=True)
+    torch.cuda.synchronize()
+    dt = env.max_over_ranks(time.perf_counter() - t0)
+    return env.world * reps * host.numel() / dt / 1e9
 
 
 def measured_peak():
@@ -298,22 +399,17 @@ def video_roi(v, H, W):
     return [(int(x0), int(y0)), (int(x0 + w), int(y0 + h))]
 
 
-def run_multi_video(args, cfg, name):
+def run_multi_video(args, cfg, name, env, label_mode="i32", secondary=False):
     """configs[3]: whole videos are dealt round-robin to the GPUs (no temporal split, no
     collective); on each GPU every video has its own context and CUDA stream, so the small ROI
     kernels of different videos overlap.  A step = one chunk of every video of this rank."""
     import torch
-    import torch.distributed as dist
     import swiftwatcher_b200 as swb
     from swiftwatcher_b200.pipeline import synth_frames
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    world, rank, local_rank = env.world, env.rank, env.local_rank
+    steps = max(3, args.steps // 2) if secondary else args.steps
+    e2e_steps = 2 if secondary else args.e2e_steps
     H, W, N, T = cfg["H"], cfg["W"], cfg["N"], cfg["chunk"]
     halo = N - 1
     mine = [v for v in range(cfg["videos"]) if v % world == rank]
@@ -324,17 +420,12 @@ def run_multi_video(args, cfg, name):
         x = torch.empty((halo + T, H, W, 3), dtype=torch.uint8, device="cuda")
         synth_frames(SEED, v, 1000 - halo, halo + T, H, W, cfg["birds"], device=local_rank, out=x)
         ctx = swb.FilterContext((H, W, 3), roi, median_n=N, threshold=15, morph_size=cfg["se"], do_open=True,
-                                do_close=cfg["do_close"], label_mode=args.label_mode, max_frames=T,
+                                do_close=cfg["do_close"], label_mode=label_mode, max_frames=T,
                                 max_segments=T * 1024, device=local_rank, gpu_share=len(mine))
         st = torch.cuda.Stream()
         ctx.set_stream(st.cuda_stream)
         vids.append(dict(v=v, roi=roi, frames=x, ctx=ctx, stream=st, done=torch.cuda.Event()))
     torch.cuda.synchronize()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     def step(fork):
         for d in vids:
@@ -350,42 +441,47 @@ def run_multi_video(args, cfg, name):
 
     sampler = ClockSampler(local_rank)
     launches0 = sum(d["ctx"].launch_count() for d in vids)
-    barrier()
+    env.barrier()
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(main_stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         step(ev0)
     for d in vids:
         d["done"].record(d["stream"])
         main_stream.wait_event(d["done"])
     ev1.record(main_stream)
-    barrier()
+    env.barrier()
     clocks = sampler.stop()
-    ms = ev0.elapsed_time(ev1)
+    ms = env.max_over_ranks(ev0.elapsed_time(ev1))
     launches = sum(d["ctx"].launch_count() for d in vids) - launches0
-    if world > 1:
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    frames_total = cfg["videos"] * T * args.steps
+    frames_total = cfg["videos"] * T * steps
     fps = frames_total / (ms * 1e-3)
     peak, peak_src = measured_peak()
     px = [(video_roi(v, H, W)[1][0] - video_roi(v, H, W)[0][0]) * (video_roi(v, H, W)[1][1] - video_roi(v, H, W)[0][1])
           for v in range(cfg["videos"])]
     alg_per_step = 8 * sum(px) * T                      # all videos, one chunk each
-    path_gbs = alg_per_step * args.steps / (ms * 1e-3) / 1e9 / world
+    path_gbs = alg_per_step * steps / (ms * 1e-3) / 1e9 / world
     # one video alone on one stream, for comparison (what concurrency buys)
     solo = None
     if vids:
         d = vids[0]
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(d["stream"])
-        for _ in range(args.steps):
+        for _ in range(steps):
             d["ctx"].submit(d["frames"], n_halo=halo)
         b.record(d["stream"])
         torch.cuda.synchronize()
-        solo = T * args.steps / (a.elapsed_time(b) * 1e-3)
+        solo = T * steps / (a.elapsed_time(b) * 1e-3)
+
+    # result guard: this rank's first video against the oracle
+    check = {"frames": 0, "ok": True}
+    if vids and not args.no_parity:
+        from oracle import reference_path as rp
+        d = vids[0]
+        par = rp.PathParams(d["roi"], N, 15, cfg["se"], True, cfg["do_close"], label_mode)
+        check = parity_check(d["ctx"], d["frames"], halo, par, 3, W)
+    check["ok"] = env.all_ok(check["ok"])
 
     # end to end: pinned host frames of every video, ROI staged by swb_submit, tables read back
     e2e = None
@@ -398,9 +494,9 @@ def run_multi_video(args, cfg, name):
             hosts.append(hbuf)
         torch.cuda.synchronize()
         h2d = d2h = 0
-        for rep_i in range(args.e2e_steps + 1):
+        for rep_i in range(e2e_steps + 1):
             if rep_i == 1:
-                barrier()
+                env.barrier()
                 t0 = time.perf_counter()
                 h2d = d2h = 0
             for d, hbuf in zip(vids, hosts):
@@ -413,19 +509,15 @@ def run_multi_video(args, cfg, name):
                 wa = ((x1 + 31) & ~31) - x0a
                 h2d += (halo + Te) * (y1 - y0) * min(wa, W - x0a) * 3
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt = float(tt.item())
-        e2e = {"value": cfg["videos"] * Te * args.e2e_steps / dt, "unit": "frames/s",
-               "h2d_bytes_per_step": h2d // max(args.e2e_steps, 1), "d2h_bytes_per_step": d2h // max(args.e2e_steps, 1),
-               "steps": args.e2e_steps, "frames_per_video_per_step": Te,
+        dt = env.max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": cfg["videos"] * Te * e2e_steps / dt, "unit": "frames/s",
+               "h2d_bytes_per_step": h2d // max(e2e_steps, 1), "d2h_bytes_per_step": d2h // max(e2e_steps, 1),
+               "steps": e2e_steps, "frames_per_video_per_step": Te,
                "note": "pinned host frames of every video -> swb_submit (ROI staged over PCIe) -> swb_collect"}
         del hosts
 
     cpu = None
-    if not args.no_cpu and world == 1:
+    if not args.no_cpu and world == 1 and not secondary:
         c1 = dict(cfg)
         c1["roi"] = video_roi(0, H, W)
         n_cpu = args.cpu_frames or 200
@@ -433,80 +525,120 @@ def run_multi_video(args, cfg, name):
         cpu = {"value": cpu_fps, "unit": "frames/s", "cores": threads, "kind": "port",
                "sample": "%d frames of video 0 (ROI %r, %.1f s) through oracle/reference_path.py; the reference "
                          "processes its videos one after another" % (n_cpu, c1["roi"], cpu_dt)}
-    if rank == 0:
-        line = {
-            "metric": "frames/sec (filter + label hot path)", "value": fps, "unit": "frames/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": name, "frame": [H, W, 3], "videos": cfg["videos"],
-                       "videos_per_gpu": len(mine), "rois": [video_roi(v, H, W) for v in range(cfg["videos"])],
-                       "median_n": N, "threshold": 15, "morph": cfg["se"], "labels": args.label_mode,
-                       "frames_per_video_per_step": T, "segments_per_frame": round(segs, 1),
-                       "l2": "full 1080p frames of all videos resident (%.1f GB on this GPU) >> 126 MB L2; no flush"
-                             % (len(mine) * (halo + T) * H * W * 3 / 1e9),
-                       "partition": "whole videos round-robin over GPUs, one context + stream per video, no collective"},
-            "roofline": {"bound": "hbm", "kernel": "whole path (launch/latency bound at ROI size)",
-                         "achieved": round(path_gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(path_gbs / peak, 4),
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_per_step,
-                         "single_video_fps_alone": solo},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        }
-        print(json.dumps(line))
+    line = {
+        "metric": "frames/sec (filter + label hot path)", "value": fps, "unit": "frames/s", "n_gpus": world,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": ms / steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": name, "frame": [H, W, 3], "videos": cfg["videos"],
+                   "videos_per_gpu": len(mine), "rois": [video_roi(v, H, W) for v in range(cfg["videos"])],
+                   "median_n": N, "threshold": 15, "morph": cfg["se"], "labels": label_mode,
+                   "frames_per_video_per_step": T, "segments_per_frame": round(segs, 1),
+                   "l2": "full 1080p frames of all videos resident (%.1f GB on this GPU) >> 126 MB L2; no flush"
+                         % (len(mine) * (halo + T) * H * W * 3 / 1e9),
+                   "partition": "whole videos round-robin over GPUs, one context + stream per video, no collective"},
+        "roofline": {"bound": "hbm", "kernel": "whole path (launch/latency bound at ROI size)",
+                     "achieved": round(path_gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(path_gbs / peak, 4),
+                     "path_frac": round(path_gbs / peak, 4),
+                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_per_step,
+                     "single_video_fps_alone": solo},
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "parity_check": check,
+    }
     for d in vids:
         d["ctx"].close()
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    del vids
+    torch.cuda.empty_cache()
+    return line
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default=DEFAULT_CONFIG, choices=sorted(CONFIGS))
-    ap.add_argument("--chunk", type=int, default=0, help="frames per step (0 = config default)")
-    ap.add_argument("--label-mode", default="i32", choices=["i32", "u8"])
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-frames", type=int, default=0)
-    args = ap.parse_args()
-    cfg = dict(CONFIGS[args.config])
-    if args.chunk:
-        cfg["chunk"] = args.chunk
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+def dropin_latency(cfg, env, batches=40):
+    """The reference's own unit of work through the reference's own API: 21-frame batches pushed into
+    ``FrameQueue`` -> preprocess_queue -> segment_queue (masks, labels, Segment objects with their colour
+    crops attached to every Frame: data_structures.py:171-217), frames popped oldest first."""
+    import swiftwatcher_b200.data_structures as ds
+    from swiftwatcher_b200.pipeline import synth_frames
+    H, W = cfg["H"], cfg["W"]
+    roi = cfg["roi"] or [(0, 0), (W, H)]
+    queue = ds.FrameQueue(queue_size=21, median_n=cfg["N"], morph_size=cfg["se"], do_close=cfg["do_close"],
+                          device=env.local_rank)
+    video = synth_frames(SEED, 0, 1000, 63, H, W, cfg["birds"], device=env.local_rank)
+    stamps = ["00:00:00.000"] * 21
+    segs = 0
 
-    if args.impl == "reference":
-        if cfg.get("videos"):
-            cfg["roi"] = video_roi(0, cfg["H"], cfg["W"])
-        run_reference(args, cfg, args.config)
-        return
-    if cfg.get("videos"):
-        run_multi_video(args, cfg, args.config)
-        return
+    def one(b):
+        nonlocal segs
+        batch = queue.pinned_batch((H, W, 3), 21)
+        np.copyto(batch, video[21 * (b % 3):21 * (b % 3) + 21])       # stands in for the decoder writing the frames
+        t0 = time.perf_counter()
+        queue.push_list_of_frames(list(batch), list(range(21 * b, 21 * b + 21)), stamps)
+        queue.preprocess_queue(roi, (300, 150))
+        queue.segment_queue((24, 24), roi)
+        dt = time.perf_counter() - t0
+        while not queue.is_empty():
+            segs += queue.pop_frame().get_num_segments()
+        return dt
+    for b in range(5):
+        one(b)
+    segs = 0
+    dts = [one(b) for b in range(batches)]
+    dt = float(np.median(dts))
+    return {"value": 21 / dt, "unit": "frames/s", "us_per_21_frame_batch": round(dt * 1e6, 1),
+            "batches": batches, "segments_per_frame": round(segs / (21.0 * batches), 2),
+            "h2d_bytes_per_step": 21 * (roi[1][1] - roi[0][1]) * ((((roi[1][0] + 31) & ~31) - (roi[0][0] & ~31)) * 3),
+            "d2h_bytes_per_step": 21 * (roi[1][1] - roi[0][1]) * (roi[1][0] - roi[0][0]) * 2,
+            "note": "FrameQueue.push_list_of_frames + preprocess_queue + segment_queue per 21-frame batch (median of "
+                    "%d batches): masks, uint8 labels, Segment objects and crops attached to the Frames" % batches}
 
+
+def partition_check(env, cfg, frames_per_rank=48):
+    """N > 1 only, untimed: ONE video split by temporal chunk over the N ranks (chunking.run_rank: every
+    rank its range + the N-1 halo frames), tables gathered over NCCL (chunking.gather_tables), and the
+    result compared with rank 0 processing the whole range alone."""
+    import hashlib
     import torch
-    import torch.distributed as dist
+    import swiftwatcher_b200 as swb
+    from swiftwatcher_b200 import chunking
+    from swiftwatcher_b200.pipeline import synth_frames
+    H, W, N = cfg["H"], cfg["W"], cfg["N"]
+    total = frames_per_rank * env.world + 5            # uneven split: the first ranks get one frame more
+    chunk = 32
+
+    def read(a, b):
+        x = torch.empty((b - a, H, W, 3), dtype=torch.uint8, device="cuda")
+        synth_frames(SEED, 7, a, b - a, H, W, cfg["birds"], device=env.local_rank, out=x)
+        return x
+    with swb.FilterContext((H, W, 3), cfg["roi"], median_n=N, threshold=15, morph_size=cfg["se"], do_open=True,
+                           do_close=cfg["do_close"], label_mode="i32", max_frames=chunk, max_segments=chunk * 4096,
+                           device=env.local_rank) as ctx:
+        rows, counts, t0, t1 = chunking.run_rank(ctx, read, total, env.rank, env.world, chunk_frames=chunk)
+        all_rows, all_counts = chunking.gather_tables(rows, counts)
+        ok, sha = True, None
+        if env.rank == 0:
+            ctx.reset()
+            solo_rows, solo_counts, _, _ = chunking.run_rank(ctx, read, total, 0, 1, chunk_frames=chunk)
+            ok = np.array_equal(solo_rows, all_rows) and np.array_equal(solo_counts, all_counts)
+            sha = hashlib.sha256(all_rows.tobytes() + all_counts.tobytes()).hexdigest()[:16]
+    ok = env.all_ok(ok)
+    return {"ok": ok, "frames": total, "ranks": env.world, "rows": int(len(all_rows)), "table_sha16": sha,
+            "what": "one %dx%d video of %d frames split by chunking.run_rank over %d ranks (+%d halo frames each), "
+                    "chunking.gather_tables over NCCL == rank 0 alone" % (W, H, total, env.world, N - 1)}
+
+
+def run_single(args, cfg, name, env, label_mode="i32", secondary=False):
+    """One config on this rank's GPU: device-timed steps, per-kernel roofline, result guard, end-to-end
+    from pinned host memory, the CPU arm.  Returns the JSON line (identical on every rank)."""
+    import torch
     import swiftwatcher_b200 as swb
     from swiftwatcher_b200.pipeline import synth_frames
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if swb.device_count() < 1:
-        raise RuntimeError("bench.py needs a CUDA device: libswb200 has no CPU path")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
+    world, rank, local_rank = env.world, env.rank, env.local_rank
+    steps = max(3, args.steps // 2) if secondary else args.steps
+    e2e_steps = 2 if secondary else args.e2e_steps
     H, W, N, T = cfg["H"], cfg["W"], cfg["N"], cfg["chunk"]
     roi = cfg["roi"]
     halo = N - 1
     rh, rw = (H, W) if roi is None else (roi[1][1] - roi[0][1], roi[1][0] - roi[0][0])
     frame_bytes = H * W * 3
+    rpca_mode = cfg.get("bg_model") == "rpca"
 
     # ---- inputs resident in HBM: n_buf distinct chunks of this rank's part of the video
     n_buf = max(1, min(4, int(24e9 // ((halo + T) * frame_bytes))))
@@ -519,15 +651,10 @@ def main():
     torch.cuda.synchronize()
 
     ctx = swb.FilterContext((H, W, 3), roi, median_n=N, threshold=15, morph_size=cfg["se"], do_open=True,
-                            do_close=cfg["do_close"], label_mode=args.label_mode, max_frames=T,
+                            do_close=cfg["do_close"], label_mode=label_mode, max_frames=T,
                             max_segments=T * 4096, device=local_rank, bg_model=cfg.get("bg_model", "median"))
     stream = torch.cuda.Stream()          # a real (non-default) stream: the library launches on it and the
     ctx.set_stream(stream.cuda_stream)    # CUDA events below are recorded on it
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     clf = None
     if cfg.get("classify"):
@@ -542,7 +669,7 @@ def main():
         if clf is not None:
             rows_s, _ = context.collect()
             with torch.cuda.stream(stream):
-                keep = clf.classify_submit(context, len(rows_s))
+                keep = clf.classify_submit(context, len(rows_s), empty="drop")
                 stats["kept"] += int(keep.sum().item())      # device -> host read of the result
             stats["segments"] += len(rows_s)
 
@@ -555,10 +682,10 @@ def main():
     # ---- timed region: K steps, device-timed on the launch stream
     sampler = ClockSampler(local_rank)
     launches0 = ctx.launch_count()
-    barrier()
+    env.barrier()
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if clf is None:
+    if clf is None and not rpca_mode:
         # ~10 ms of spinning on the launch stream in front of the first event: the host enqueues the K steps
         # behind it, so the device-timed region holds back-to-back launches whatever the host thread is doing
         try:
@@ -567,23 +694,19 @@ def main():
         except Exception:                                  # private torch helper: the gate is optional
             pass
     ev0.record(stream)
-    for i in range(args.steps):
+    for i in range(steps):
         run_step(ctx, bufs[i % n_buf])
     ev1.record(stream)
-    barrier()
+    env.barrier()
     clocks = sampler.stop()
-    ms = ev0.elapsed_time(ev1)
+    ms = env.max_over_ranks(ev0.elapsed_time(ev1))
     launches = ctx.launch_count() - launches0
-    if world > 1:
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    fps = world * args.steps * T / (ms * 1e-3)
+    fps = world * steps * T / (ms * 1e-3)
 
     # ---- per-kernel durations (CUDA events between launches, same stream)
     ctx.enable_timing(True)
     per_kernel = {}
-    reps = min(args.steps, 8)
+    reps = min(steps, 8)
     for i in range(reps):
         ctx.submit(bufs[i % n_buf], n_halo=halo)
         ctx.sync()
@@ -591,16 +714,23 @@ def main():
             per_kernel[k] = per_kernel.get(k, 0.0) + v / reps
     ctx.enable_timing(False)
     peak, peak_src = measured_peak()
-    alg = algorithmic_bytes(cfg, rh, rw, 1 if args.label_mode == "u8" else 4)
+    alg = algorithmic_bytes(cfg, rh, rw, 1 if label_mode == "u8" else 4)
     dom = max(per_kernel, key=per_kernel.get)
     kernels = {k: {"ms": round(v, 4), "alg_gbs": round(alg[k] * T / (v * 1e-3) / 1e9, 1) if v > 0 else None}
                for k, v in per_kernel.items()}
     dom_ach = alg[dom] * T / (per_kernel[dom] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": round(dom_ach, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(dom_ach / peak, 4), "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg[dom] * T,
-                "path_achieved": round(alg["path"] * fps / world / 1e9, 1),
-                "path_frac": round(alg["path"] * fps / world / 1e9 / peak, 4), "kernels": kernels}
+    path_ach = alg["path"] * fps / world / 1e9
+    # `frac` answers BASELINE.json's target (whole path: 8 h w bytes per frame over the step time);
+    # the dominant kernel's own figure sits beside it
+    roofline = {"bound": "hbm", "kernel": "whole path", "achieved": round(path_ach, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(path_ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg["path"] * T,
+                "path_achieved": round(path_ach, 1), "path_frac": round(path_ach / peak, 4),
+                "dominant_kernel": {"kernel": dom, "achieved": round(dom_ach, 1), "frac": round(dom_ach / peak, 4),
+                                    "algorithmic_bytes_per_launch": alg[dom] * T, "traffic": None},
+                "kernels": kernels}
+    if rpca_mode:
+        roofline = rpca_roofline(ctx, roofline, per_kernel, rh, rw, T, peak)
     if clf is not None:
         # the classifier (cuDNN convolutions, library code) dominates this config: time it alone
         crops = torch.randint(0, 256, (4096, 24, 24, 3), dtype=torch.uint8, device="cuda")
@@ -613,23 +743,36 @@ def main():
         torch.cuda.synchronize()
         roofline["classifier"] = {"crops_per_s": round(4096 / (c0.elapsed_time(c1) * 1e-3), 1),
                                   "segments_per_frame": round(segs_per_frame, 1),
+                                  "tf32": bool(torch.backends.cudnn.allow_tf32),
                                   "note": "torchvision SqueezeNet1.0 weights and layers as in the reference (float32, "
                                           "cuDNN, library code), evaluated on the window of positions the device-gathered "
                                           "24x24 crop can influence + cached blank-canvas activations (WindowedSqueezeNet: "
                                           "same scores as the padded 224x224 forward pass to 1e-4); the hot-path kernels "
                                           "in `kernels` are the filtering + labelling part of the step"}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(traffic_file) and args.label_mode == "i32" and not args.chunk:   # captured at the config's own chunk size
+    if os.path.exists(traffic_file) and label_mode == "i32" and not args.chunk:   # captured at the config's own chunk size
         try:
-            roofline["traffic"] = json.load(open(traffic_file)).get(args.config, {}).get(dom)
+            tr = json.load(open(traffic_file)).get(name, {})
+            roofline["dominant_kernel"]["traffic"] = tr.get(dom)
+            if all(k in tr for k in per_kernel):
+                roofline["traffic"] = sum(tr[k] for k in per_kernel)
         except Exception:
             pass
+
+    # ---- result guard (untimed): the timed submit against the oracle on a few frames
+    check = {"frames": 0, "ok": True, "what": "skipped"}
+    if not args.no_parity and not rpca_mode:
+        from oracle import reference_path as rp
+        par = rp.PathParams(roi or [(0, 0), (W, H)], N, 15, cfg["se"], True, cfg["do_close"], label_mode)
+        n_chk = (3 if H > 1080 else 6) if not secondary else (2 if H > 1080 else 3)
+        check = parity_check(ctx, bufs[0], halo, par, n_chk if rank == 0 else min(n_chk, 2), rw)
+    check["ok"] = env.all_ok(check["ok"])
 
     # ---- end to end through the C ABI with HOST buffers
     e2e = None
     if not args.no_e2e:
         ctx_h = swb.FilterContext((H, W, 3), roi, median_n=N, threshold=15, morph_size=cfg["se"], do_open=True,
-                                  do_close=cfg["do_close"], label_mode=args.label_mode, max_frames=T,
+                                  do_close=cfg["do_close"], label_mode=label_mode, max_frames=T,
                                   max_segments=T * 4096, device=local_rank, bg_model=cfg.get("bg_model", "median"))
         host = torch.empty((halo + T, H, W, 3), dtype=torch.uint8, pin_memory=True)
         host.copy_(bufs[0])
@@ -638,40 +781,49 @@ def main():
         run_step(ctx_h, host)
         rows_h, counts_h = ctx_h.collect()
         d2h = 0
-        barrier()
+        env.barrier()
         t0 = time.perf_counter()
-        for i in range(args.e2e_steps):
+        for i in range(e2e_steps):
             run_step(ctx_h, host)
             rows_h, counts_h = ctx_h.collect()
             d2h = rows_h.nbytes + counts_h.nbytes + 4 * (T + 1) + (8 if clf is not None else 0)
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt = float(tt.item())
+        dt = env.max_over_ranks(time.perf_counter() - t0)
         if roi is None:
             h2d = (halo + T) * frame_bytes
         else:
             x0a = roi[0][0] & ~31
             wa = ((roi[1][0] + 31) & ~31) - x0a
             h2d = (halo + T) * rh * min(wa, W - x0a) * 3
-        e2e = {"value": world * args.e2e_steps * T / dt, "unit": "frames/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps,
+        e2e = {"value": world * e2e_steps * T / dt, "unit": "frames/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                "note": "pinned host frames -> swb_submit (H2D) -> swb_collect (D2H segment table)"
                        + (" -> device crops -> classifier -> kept count (D2H)" if clf is not None else "; PCIe-bound")}
         ctx_h.close()
+        if roi is None and clf is None:
+            # the roof of this number: the same bytes with one plain cudaMemcpyAsync per step on every rank at once
+            gbs = h2d_attainable(env, host, bufs[0], max(e2e_steps, 2))
+            e2e["h2d_gbs"] = round(e2e["value"] * h2d / T / 1e9, 1)
+            e2e["attainable_h2d_gbs"] = round(gbs, 1)
+            e2e["attainable"] = round(gbs * 1e9 / (h2d / T), 1)
+            e2e["frac"] = round(e2e["value"] / e2e["attainable"], 4)
+            e2e["attainable_note"] = ("%d rank(s) copying their pinned chunk with one plain cudaMemcpyAsync per step at the "
+                                      "same time (sum over ranks / max-over-ranks time): the host-memory / PCIe fabric's "
+                                      "limit for this run" % world)
         del host
+    e2e_dropin = None
+    if cfg.get("dropin") and not args.no_e2e and rank == 0:
+        e2e_dropin = dropin_latency(cfg, env)
 
     # ---- the reference's CPU path on this box's host cores (rank 0, N=1 only)
     cpu = None
-    if not args.no_cpu and world == 1:
+    if not args.no_cpu and world == 1 and (not secondary or cfg.get("cpu_in_also")):
         n_cpu = args.cpu_frames or (64 if roi is None and H >= 1080 else 300)
         if H > 1080:
             n_cpu = args.cpu_frames or 12
         if cfg.get("classify"):
             n_cpu = args.cpu_frames or 2
-        if cfg.get("bg_model") == "rpca":
+        if rpca_mode:
             n_cpu = T                              # one batch: the decomposition cannot be sampled
             if roi is None and not args.cpu_frames:
                 n_cpu = 0                          # ~86 s per 21-frame 1080p batch: only with --cpu-frames
@@ -688,7 +840,7 @@ def main():
             cpu = {"value": cpu_fps, "unit": "frames/s", "cores": procs, "kind": "port",
                    "sample": "%d processes x %d frames of %s (%.1f s) through oracle/reference_path.py: the reference's "
                              "cv2/scipy calls + np.median/absdiff, each process on its own temporal chunk (+ %d halo frames), "
-                             "one cv2 thread each; host has %d CPUs" % (procs, per_proc, args.config, cpu_dt, halo,
+                             "one cv2 thread each; host has %d CPUs" % (procs, per_proc, name, cpu_dt, halo,
                                                                         os.cpu_count()),
                    "single_process": {"value": one_fps, "cv2_threads": one_threads,
                                       "sample": "%d frames (%.1f s)" % (max(2, n_cpu // 8), one_dt)}}
@@ -697,36 +849,122 @@ def main():
             cpu = {"value": cpu_fps, "unit": "frames/s", "cores": threads, "kind": "port",
                    "sample": "%d frames of %s (%.1f s) through oracle/reference_path.py: the reference's cv2/scipy calls "
                              "+ %s; cv2 pool of %d threads, numpy/scipy stages single-threaded; host has %d CPUs"
-                             % (n_cpu, args.config, cpu_dt,
-                                "its IALM rpca (numpy/LAPACK svd)" if cfg.get("bg_model") == "rpca" else "np.median/absdiff",
+                             % (n_cpu, name, cpu_dt,
+                                "its IALM rpca (numpy/LAPACK svd)" if rpca_mode else "np.median/absdiff",
                                 threads, os.cpu_count())}
         else:
             cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "port",
                    "sample": "skipped by default (SURVEY.md measured 86 s per 21-frame 1080p batch = 0.24 frames/s for "
                              "the reference as written); pass --cpu-frames 21 to time it here"}
 
-    if rank == 0:
-        line = {
-            "metric": "frames/sec (filter + label hot path%s)" % (" + segment classification" if clf is not None else ""),
-            "value": fps, "unit": "frames/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": args.config, "frame": [H, W, 3], "roi": roi, "median_n": N,
-                       "threshold": 15, "morph": cfg["se"], "open": True, "close": cfg["do_close"],
-                       "labels": args.label_mode, "frames_per_step": T, "halo_frames": halo,
-                       "resident_chunks": n_buf, "segments_per_frame": round(segs_per_frame, 1),
-                       "l2": "inputs (%.1f GB/step) >> 126 MB L2; no flush" % ((halo + T) * frame_bytes / 1e9),
-                       "partition": "temporal chunks, %d-frame halo, no collective" % halo,
-                       **({"classifier": "squeezenet1_0 (2 classes), random-init weights, float32, eval mode"}
-                          if clf is not None else {})},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks,
-        }
-        print(json.dumps(line))
+    line = {
+        "metric": "frames/sec (filter + label hot path%s)" % (" + segment classification" if clf is not None else ""),
+        "value": fps, "unit": "frames/s",
+        "n_gpus": world, "steps": steps, "warmup": args.warmup, "ms_per_step": ms / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": name, "frame": [H, W, 3], "roi": roi, "median_n": N,
+                   "threshold": 15, "morph": cfg["se"], "open": True, "close": cfg["do_close"],
+                   "labels": label_mode, "frames_per_step": T, "halo_frames": halo,
+                   "resident_chunks": n_buf, "segments_per_frame": round(segs_per_frame, 1),
+                   "l2": "inputs (%.1f GB/step) >> 126 MB L2; no flush" % ((halo + T) * frame_bytes / 1e9),
+                   "partition": "temporal chunks, %d-frame halo, no collective" % halo,
+                   **({"classifier": "squeezenet1_0 (2 classes), random-init weights, float32, eval mode, TF32 %s"
+                                     % ("on" if torch.backends.cudnn.allow_tf32 else "off"),
+                       "kept_fraction": round(stats["kept"] / max(stats["segments"], 1), 4)}
+                      if clf is not None else {})},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+        "clocks": clocks, "parity_check": check,
+    }
+    if e2e_dropin is not None:
+        line["e2e_dropin"] = e2e_dropin
     ctx.close()
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    del bufs, ctx
+    torch.cuda.empty_cache()
+    return line
+
+
+def rpca_roofline(ctx, roofline, per_kernel, h, w, T, peak):
+    """bg_model = rpca: the step is the IALM iteration loop, not the median kernel.  Algorithmic bytes of
+    one iteration's fused pass (read X 1 + read A 8 + write A' 8 + read Y 8 + write Y 8 + write E image 1
+    = 34 bytes per matrix element, n x P elements); `fg_bits` in the per-kernel table is the whole loop."""
+    iters = ctx.rpca_iterations()
+    P = h * w
+    loop_ms = per_kernel.get("fg_bits", 0.0)
+    it_bytes = 34 * T * P
+    detail = ctx.rpca_timing()
+    fused_ms = detail.get("fused_pass_ms")
+    ach = it_bytes / (fused_ms * 1e-3) / 1e9 if fused_ms else None
+    roofline = dict(roofline)
+    roofline["kernels"] = {k: {"ms": v["ms"]} if k == "fg_bits" else v for k, v in roofline["kernels"].items()}
+    roofline["kernels"]["fg_bits"]["note"] = "crop+gray, the whole IALM loop and bilateral+threshold"
+    roofline["dominant_kernel"] = {"kernel": "k_rpca_apply_pair (fused apply + next Gram pass of one IALM iteration)",
+                                   "achieved": round(ach, 1) if ach else None,
+                                   "frac": round(ach / peak, 4) if ach else None,
+                                   "algorithmic_bytes_per_launch": it_bytes, "traffic": None,
+                                   "ms_per_iteration": fused_ms}
+    roofline["rpca"] = {"iterations": iters, "loop_ms": round(loop_ms, 4), **detail}
+    # whole path in this mode: every iteration streams the batch once
+    roofline["kernel"] = "IALM iterations (34 B per element and iteration) + filtering/labelling (8 B per pixel)"
+    return roofline
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default=DEFAULT_CONFIG, choices=sorted(CONFIGS))
+    ap.add_argument("--chunk", type=int, default=0, help="frames per step (0 = config default)")
+    ap.add_argument("--label-mode", default="i32", choices=["i32", "u8"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="only the headline config (no `also` sub-lines)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the untimed oracle comparison")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-frames", type=int, default=0)
+    args = ap.parse_args()
+    cfg = dict(CONFIGS[args.config])
+    if args.chunk:
+        cfg["chunk"] = args.chunk
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        if cfg.get("videos"):
+            cfg["roi"] = video_roi(0, cfg["H"], cfg["W"])
+        run_reference(args, cfg, args.config)
+        return
+
+    import swiftwatcher_b200 as swb
+    if swb.device_count() < 1:
+        raise RuntimeError("bench.py needs a CUDA device: libswb200 has no CPU path")
+    env = Env()
+    env.init()
+    t_start = time.perf_counter()
+
+    def run(name, c, mode, secondary):
+        fn = run_multi_video if c.get("videos") else run_single
+        return fn(args, c, name, env, label_mode=mode, secondary=secondary)
+
+    line = run(args.config, cfg, args.label_mode, False)
+    default_run = (args.config == DEFAULT_CONFIG and args.label_mode == "i32" and not args.chunk)
+    if default_run and not args.no_also:
+        line["also"] = []
+        for name, mode in ALSO:
+            sub = run(name, dict(CONFIGS[name]), mode, True)
+            sub.pop("cpu_baseline", None) if sub.get("cpu_baseline") is None else None
+            line["also"].append(sub)
+    if env.world > 1 and not args.no_parity:
+        line["partition_check"] = partition_check(env, cfg if not cfg.get("videos") else CONFIGS[DEFAULT_CONFIG])
+    line["bench_wall_s"] = round(time.perf_counter() - t_start, 1)
+    ok = line["parity_check"]["ok"] and all(s["parity_check"]["ok"] for s in line.get("also", [])) and \
+        line.get("partition_check", {"ok": True})["ok"]
+    if env.rank == 0:
+        print(json.dumps(line))
+    env.close()
+    if not ok:
+        sys.stderr.write("bench.py: PARITY CHECK FAILED (see parity_check / partition_check in the line)\n")
+        sys.exit(3)
 
 
 if __name__ == "__main__":

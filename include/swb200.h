@@ -62,7 +62,9 @@ typedef struct swb_config {
                               * reported by swb_collect (SWB_ERR_CAPACITY), never silently.  A large
                               * submit from host memory is filtered in up to four sub-batches of
                               * frames, each with an equal share of the labelling scratch, so a
-                              * submit whose segments all sit in a few frames may need a larger value */
+                              * submit whose segments all sit in a few frames may need a larger value.
+                              * SWB_LABELS_U8: the limit applies to the components before they are
+                              * merged mod 256 */
     int32_t bg_model;        /* SWB_BG_MEDIAN (rolling median, BASELINE.json) or SWB_BG_RPCA */
     int32_t gpu_share;       /* contexts expected to work side by side on this GPU (e.g. one per video,
                               * each on its own stream); 0 or 1 = the context has the GPU to itself.
@@ -139,6 +141,26 @@ int swb_submit(swb_ctx* ctx, const uint8_t* frames, int32_t n_frames,
 int swb_collect(swb_ctx* ctx, swb_segment* rows, int64_t cap, int64_t* n_rows,
                 int32_t* per_frame_counts);
 int swb_sync(swb_ctx* ctx);
+/* swb_collect plus the dense outputs of the whole submit in one call and (normally) one stream
+ * synchronisation: masks [n_frames][roi_h][roi_w] uint8 and labels [n_frames][roi_h][roi_w] (int32 or
+ * uint8 as configured), tightly packed, either may be NULL.  With page-locked destinations
+ * (swb_host_alloc) all copies are DMA transfers queued behind the kernels.  This is what one
+ * FrameQueue.segment_queue batch needs back (data_structures.py:202-217). */
+int swb_collect_all(swb_ctx* ctx, swb_segment* rows, int64_t cap, int64_t* n_rows,
+                    int32_t* per_frame_counts, uint8_t* masks, void* labels);
+/* The same in two halves: swb_collect_begin queues every device -> host copy behind the kernels of the
+ * last submit and returns at once; swb_collect_end waits for them and reports the counts.  Between the two
+ * the caller is free to work (e.g. the tracker on the previous batch); the destination buffers must stay
+ * valid and page-locked destinations are what makes the copies asynchronous.  No swb_submit in between. */
+int swb_collect_begin(swb_ctx* ctx, swb_segment* rows, int64_t cap, uint8_t* masks, void* labels);
+int swb_collect_end(swb_ctx* ctx, int64_t* n_rows, int32_t* per_frame_counts);
+/* Tuning knobs that never change a result: "host_pipeline" (0/1: cut large host submits into
+ * sub-batches that are filtered while later frames are still being copied; default 1),
+ * "sub_batch_min_px" (least work per sub-batch in pixels; default 64 Mi). */
+int swb_set_option(swb_ctx* ctx, const char* name, int64_t value);
+/* Frames per temporal sub-chunk the filtering kernel used for the last submit (each sub-chunk
+ * re-reads its median_n - 1 predecessors); lets tests aim at the sub-chunk boundaries. */
+int swb_last_subchunk(swb_ctx* ctx, int32_t* frames);
 
 /* Dense per-frame outputs of the last submit, frames [t0, t0 + n):
  * mask: uint8 {0,255}, == (opened > 0) of data_structures.py:202-204;

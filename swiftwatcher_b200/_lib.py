@@ -53,6 +53,11 @@ SYMBOLS = {
     "swb_submit": (C.c_int, [_P, _P, _I32, _I32, _I32]),
     "swb_collect": (C.c_int, [_P, _P, _I64, C.POINTER(_I64), _P]),
     "swb_sync": (C.c_int, [_P]),
+    "swb_collect_all": (C.c_int, [_P, _P, _I64, C.POINTER(_I64), _P, _P, _P]),
+    "swb_collect_begin": (C.c_int, [_P, _P, _I64, _P, _P]),
+    "swb_collect_end": (C.c_int, [_P, C.POINTER(_I64), _P]),
+    "swb_set_option": (C.c_int, [_P, C.c_char_p, _I64]),
+    "swb_last_subchunk": (C.c_int, [_P, C.POINTER(_I32)]),
     "swb_get_masks": (C.c_int, [_P, _I32, _I32, _P, _I32]),
     "swb_get_labels": (C.c_int, [_P, _I32, _I32, _P, _I32]),
     "swb_get_mask_bits": (C.c_int, [_P, _I32, _I32, _P, _I32]),
@@ -130,6 +135,14 @@ def ptr(a):
     raise TypeError("cannot take the address of %r" % type(a))
 
 
+_PINNED = []          # (first address, end address) of the live swb_host_alloc allocations
+
+
+def is_pinned(address, nbytes):
+    """True when [address, address + nbytes) lies inside one live swb_host_alloc allocation."""
+    return any(a <= address and address + nbytes <= b for a, b in _PINNED)
+
+
 class _PinnedOwner:
     """Owns one swb_host_alloc allocation; freed when the last numpy view goes away."""
 
@@ -137,10 +150,14 @@ class _PinnedOwner:
         self.ptr = _P()
         check(load().swb_host_alloc(C.byref(self.ptr), nbytes))
         self.nbytes = nbytes
+        self.range = (self.ptr.value, self.ptr.value + nbytes)
+        _PINNED.append(self.range)
 
     def __del__(self):
         try:
             if self.ptr:
+                if self.range in _PINNED:
+                    _PINNED.remove(self.range)
                 load().swb_host_free(self.ptr)
                 self.ptr = _P()
         except Exception:

@@ -23,21 +23,46 @@ def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
     deps.append(os.path.join(HERE, "..", "include", "swb200.h"))
     return any(os.path.getmtime(d) > t for d in deps)
 
 
 def build_library(force=False, verbose=False):
-    """Compile every CUDA source into swiftwatcher_b200/libswb200.so."""
+    """Compile every CUDA source into swiftwatcher_b200/libswb200.so: one object per source
+    (compiled side by side, only the stale ones unless ``force``), then one link."""
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    from concurrent.futures import ThreadPoolExecutor
+    nvcc = _nvcc()
+    objdir = os.path.join(CSRC, "_obj")
+    os.makedirs(objdir, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers.append(os.path.join(HERE, "..", "include", "swb200.h"))
+    newest_header = max(os.path.getmtime(h) for h in headers)
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src[:-3] + ".o")
+        path = os.path.join(CSRC, src)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(path), newest_header):
+            return obj, None
+        cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "-shared"] + ["-c", "-o", obj, path]
+        if verbose:
+            print(" ".join(cmd))
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        return obj, (res.stdout + res.stderr) if res.returncode != 0 else None
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    errors = [e for _, e in results if e]
+    if errors:
+        raise RuntimeError("nvcc failed:\n" + "\n".join(errors))
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + [o for o, _ in results]
     if verbose:
         print(" ".join(cmd))
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
     return LIB
 
 

@@ -54,6 +54,8 @@ struct swb_ctx {
     uint8_t* mask = nullptr;
     void* labels = nullptr;
     CclBuffers ccl{};
+    // uint8 compatibility table (label_mode U8): merged on the device, see launch_u8_merge
+    U8Table u8{};
     // RPCA background model (SWB_BG_RPCA)
     RpcaWork rpca{};
     uint8_t* rp_gray = nullptr;     // [n][h*w] cropped gray stack, newest frame first (the reference's column order)
@@ -65,6 +67,11 @@ struct swb_ctx {
     int32_t* h_overflow = nullptr;
     // state of the last submit
     int last_T = 0;
+    int last_ts = 0;                // temporal sub-chunk length the filtering kernel used (swb_last_subchunk)
+    int64_t rows_guess = 256;       // rows copied speculatively by swb_collect* before the count is known
+    swb_segment* fetch_rows = nullptr;   // swb_collect_begin .. swb_collect_end
+    int64_t fetch_cap = 0, fetch_guess = 0;
+    bool fetching = false;
     bool pending = false;
     const uint8_t* last_frames_dev = nullptr;   // frame 0 (first OUTPUT frame) of full frames on device, or null
     long long last_stride = 0, last_pitch = 0;
@@ -160,6 +167,10 @@ void free_ctx_buffers(swb_ctx* c) {
     cudaFree(c->ccl.pcount);
     cudaFree(c->ccl.big_tiles);
     cudaFree(c->ccl.rootlist);
+    cudaFree(c->u8.stage);
+    cudaFree(c->u8.rows);
+    cudaFree(c->u8.nseg);
+    cudaFree(c->u8.segoff);
     rpca_free(c->rpca);
     cudaFree(c->rp_gray);
     cudaFree(c->rp_sparse);
@@ -191,49 +202,6 @@ int alloc_ccl(swb_ctx* ctx, CclBuffers& b, const Geom& g, int T, int cap_rows) {
     CU(ctx, dalloc(&b.big_tiles, (size_t)T * ((g.BH + 7) / 8)));   // tiles are at least 8 block rows tall
     CU(ctx, dalloc(&b.rootlist, (size_t)cap_rows));
     return SWB_OK;
-}
-
-// reference behaviour for label_mode U8: regionprops of labels.astype(uint8)
-// (image_filtering.py:329,335): components whose int32 labels agree mod 256 form
-// one region; labels that are 0 mod 256 disappear into the background.
-int64_t merge_u8(const swb_segment* in, const int32_t* off, int T, swb_segment* out, int64_t cap,
-                 int32_t* counts, bool& overflow) {
-    int64_t n_out = 0;
-    overflow = false;
-    std::vector<swb_segment> acc(256);
-    std::vector<char> used(256);
-    for (int f = 0; f < T; ++f) {
-        std::fill(used.begin(), used.end(), 0);
-        for (int32_t i = off[f]; i < off[f + 1]; ++i) {
-            const swb_segment& s = in[i];
-            const int v = s.label & 0xFF;
-            if (v == 0) continue;
-            if (!used[v]) {
-                used[v] = 1;
-                acc[v] = s;
-                acc[v].label = v;
-            } else {
-                swb_segment& a = acc[v];
-                a.area += s.area;
-                a.bbox[0] = std::min(a.bbox[0], s.bbox[0]);
-                a.bbox[1] = std::min(a.bbox[1], s.bbox[1]);
-                a.bbox[2] = std::max(a.bbox[2], s.bbox[2]);
-                a.bbox[3] = std::max(a.bbox[3], s.bbox[3]);
-                a.sum_row += s.sum_row;
-                a.sum_col += s.sum_col;
-            }
-        }
-        int32_t cnt = 0;
-        for (int v = 1; v < 256; ++v) {
-            if (!used[v]) continue;
-            if (n_out < cap) out[n_out] = acc[v];
-            else overflow = true;
-            ++n_out;
-            ++cnt;
-        }
-        if (counts) counts[f] = cnt;
-    }
-    return n_out;
 }
 
 }  // namespace
@@ -332,12 +300,6 @@ int swb_create(const swb_config* cfg, swb_ctx** out) {
     CUB(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CUB(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     for (auto& e : ctx->ev_h2d) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    {
-        const char* e = getenv("SWB_PIPELINE");
-        ctx->pipeline = !(e && e[0] == '0');
-        const char* m = getenv("SWB_SUB_MIN_PX");    // test hook: small frames never reach the default
-        if (m && atoll(m) > 0) ctx->sub_min_px = atoll(m);
-    }
     if (nh > 0) {
         CUB(dalloc(&ctx->hist[0], (size_t)nh * g.h * g.wa));
         CUB(dalloc(&ctx->hist[1], (size_t)nh * g.h * g.wa));
@@ -349,6 +311,13 @@ int swb_create(const swb_config* cfg, swb_ctx** out) {
         CUB(cudaMalloc(&ctx->labels, (size_t)T * g.h * g.mpitch * ctx->label_elem));
     rc = alloc_ccl(ctx, ctx->ccl, g, T, ctx->cap_rows);
     if (rc != SWB_OK) return bail(rc);
+    if (c.label_mode == SWB_LABELS_U8) {
+        ctx->u8.cap = (int)std::min<long long>(ctx->cap_rows, 255ll * T);
+        CUB(dalloc(&ctx->u8.stage, (size_t)255 * T));
+        CUB(dalloc(&ctx->u8.rows, (size_t)ctx->u8.cap));
+        CUB(dalloc(&ctx->u8.nseg, (size_t)T));
+        CUB(dalloc(&ctx->u8.segoff, (size_t)T + 1));
+    }
     if (c.bg_model == SWB_BG_RPCA) {
         const long long P = (long long)g.h * g.w;
         CUB(rpca_alloc(ctx->rpca, P, T));
@@ -401,6 +370,7 @@ int swb_submit(swb_ctx* ctx, const uint8_t* frames, int32_t n_frames, int32_t n_
     if (n_halo != SWB_HALO_CARRY && (n_halo < 0 || n_halo > N - 1))
         return fail(ctx, SWB_ERR_INVALID, "n_halo %d outside 0..%d", n_halo, N - 1);
     if (mem_kind != SWB_MEM_HOST && mem_kind != SWB_MEM_DEVICE) return fail(ctx, SWB_ERR_INVALID, "bad mem_kind");
+    if (ctx->fetching) return fail(ctx, SWB_ERR_STATE, "swb_submit between swb_collect_begin and swb_collect_end");
     CU(ctx, cudaSetDevice(c.device));
     cudaStream_t s = ctx->stream;
     const int inline_halo = n_halo == SWB_HALO_CARRY ? 0 : n_halo;
@@ -525,6 +495,8 @@ int swb_submit(swb_ctx* ctx, const uint8_t* frames, int32_t n_frames, int32_t n_
         if (ctx->timing) CU(ctx, cudaEventRecord(ctx->ev[2], s));
         CU(ctx, launch_ccl(s, ctx->fbits, n_frames, g, ctx->ccl, ctx->labels, ctx->label_elem, &launches,
                            ctx->timing ? &ctx->ev[3] : nullptr, 4, nullptr, true));
+        if (c.label_mode == SWB_LABELS_U8) CU(ctx, launch_u8_merge(s, n_frames, ctx->ccl, ctx->u8, nullptr, &launches));
+        ctx->last_ts = (c.bg_model == SWB_BG_MEDIAN) ? last_temporal_subchunk() : n_frames;
         ctx->ev_valid = ctx->timing;
     } else {
         cudaStream_t sw = ctx->worker;
@@ -569,6 +541,14 @@ int swb_submit(swb_ctx* ctx, const uint8_t* frames, int32_t n_frames, int32_t n_
             CU(ctx, launch_morph_mask(sw, reinterpret_cast<const uint32_t*>(raw_b), nb, g, ctx->morph, fbits_b, mask_b,
                                       &launches));
             CU(ctx, launch_ccl(sw, fbits_b, nb, g, cb, labels_b, ctx->label_elem, &launches, nullptr, 0, &chain, true));
+            if (c.label_mode == SWB_LABELS_U8) {
+                U8Table ub = ctx->u8;
+                ub.stage += (size_t)255 * f0;
+                ub.nseg += f0;
+                ub.segoff += f0;
+                CU(ctx, launch_u8_merge(sw, nb, cb, ub, b > 0 ? ctx->u8.segoff + f0 : nullptr, &launches));
+            }
+            ctx->last_ts = last_temporal_subchunk();
         }
         CU(ctx, cudaEventRecord(ctx->ev_join, sw));
         CU(ctx, cudaStreamWaitEvent(s, ctx->ev_join, 0));
@@ -591,41 +571,105 @@ int swb_sync(swb_ctx* ctx) {
     return SWB_OK;
 }
 
-int swb_collect(swb_ctx* ctx, swb_segment* rows, int64_t cap, int64_t* n_rows, int32_t* per_frame_counts) {
+// swb_collect / swb_collect_all / swb_collect_begin + swb_collect_end: the table (and optionally the dense
+// outputs) of the last submit with ONE stream synchronisation in the common case.  The number of rows is
+// only known on the device, so a guessed number of rows (twice the last submit's) is copied along with
+// the offsets; a second copy follows only when the guess was too small.
+static int collect_begin_impl(swb_ctx* ctx, swb_segment* rows, int64_t cap, uint8_t* masks, void* labels) {
     if (!ctx) return fail(nullptr, SWB_ERR_INVALID, "null context");
     if (!ctx->pending) return fail(ctx, SWB_ERR_STATE, "swb_collect without a preceding swb_submit");
+    if (masks && !ctx->mask) return fail(ctx, SWB_ERR_STATE, "masks were not enabled in swb_config.out_flags");
+    if (labels && !ctx->labels) return fail(ctx, SWB_ERR_STATE, "labels were not enabled in swb_config.out_flags");
+    CU(ctx, cudaSetDevice(ctx->cfg.device));
+    cudaStream_t s = ctx->stream;
+    const Geom& g = ctx->g;
+    const int T = ctx->last_T;
+    const bool u8 = ctx->cfg.label_mode == SWB_LABELS_U8;
+    const int32_t* d_segoff = u8 ? ctx->u8.segoff : ctx->ccl.segoff;
+    const swb_segment* d_rows = u8 ? ctx->u8.rows : ctx->ccl.rows;
+    const int64_t dev_cap = u8 ? ctx->u8.cap : ctx->cap_rows;
+    CU(ctx, cudaMemcpyAsync(ctx->h_segoff, d_segoff, ((size_t)T + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CU(ctx, cudaMemcpyAsync(ctx->h_overflow, ctx->ccl.overflow, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    const int64_t guess = rows ? std::min<int64_t>({cap, dev_cap, ctx->rows_guess}) : 0;
+    if (guess > 0)
+        CU(ctx, cudaMemcpyAsync(rows, d_rows, (size_t)guess * sizeof(swb_segment), cudaMemcpyDeviceToHost, s));
+    if (masks)
+        CU(ctx, cudaMemcpy2DAsync(masks, (size_t)g.w, ctx->mask, (size_t)g.mpitch, (size_t)g.w, (size_t)T * g.h,
+                                  cudaMemcpyDeviceToHost, s));
+    if (labels)
+        CU(ctx, cudaMemcpy2DAsync(labels, (size_t)g.w * ctx->label_elem, ctx->labels, (size_t)g.mpitch * ctx->label_elem,
+                                  (size_t)g.w * ctx->label_elem, (size_t)T * g.h, cudaMemcpyDeviceToHost, s));
+    ctx->fetch_rows = rows;
+    ctx->fetch_cap = cap;
+    ctx->fetch_guess = guess;
+    ctx->fetching = true;
+    return SWB_OK;
+}
+
+static int collect_end_impl(swb_ctx* ctx, int64_t* n_rows, int32_t* per_frame_counts) {
+    if (!ctx) return fail(nullptr, SWB_ERR_INVALID, "null context");
+    if (!ctx->fetching) return fail(ctx, SWB_ERR_STATE, "swb_collect_end without swb_collect_begin");
+    ctx->fetching = false;
     CU(ctx, cudaSetDevice(ctx->cfg.device));
     cudaStream_t s = ctx->stream;
     const int T = ctx->last_T;
-    CU(ctx, cudaMemcpyAsync(ctx->h_segoff, ctx->ccl.segoff, ((size_t)T + 1) * sizeof(int32_t),
-                            cudaMemcpyDeviceToHost, s));
-    CU(ctx, cudaMemcpyAsync(ctx->h_overflow, ctx->ccl.overflow, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    const bool u8 = ctx->cfg.label_mode == SWB_LABELS_U8;
+    const swb_segment* d_rows = u8 ? ctx->u8.rows : ctx->ccl.rows;
+    const int64_t dev_cap = u8 ? ctx->u8.cap : ctx->cap_rows;
+    swb_segment* rows = ctx->fetch_rows;
+    const int64_t cap = ctx->fetch_cap, guess = ctx->fetch_guess;
     CU(ctx, cudaStreamSynchronize(s));
     const int64_t total = ctx->h_segoff[T];
-    if (*ctx->h_overflow || total > ctx->cap_rows)
+    if (*ctx->h_overflow || total > dev_cap)
         return fail(ctx, SWB_ERR_CAPACITY, "%lld segments in this submit exceed max_segments (%d)", (long long)total,
                     ctx->cap_rows);
-    if (ctx->cfg.label_mode == SWB_LABELS_I32) {
-        if (n_rows) *n_rows = total;
-        if (per_frame_counts)
-            for (int f = 0; f < T; ++f) per_frame_counts[f] = ctx->h_segoff[f + 1] - ctx->h_segoff[f];
-        if (total > cap) return fail(ctx, SWB_ERR_CAPACITY, "%lld rows do not fit the caller's %lld", (long long)total, (long long)cap);
-        if (total > 0 && rows) {
-            CU(ctx, cudaMemcpyAsync(rows, ctx->ccl.rows, (size_t)total * sizeof(swb_segment), cudaMemcpyDeviceToHost, s));
-            CU(ctx, cudaStreamSynchronize(s));
-        }
-    } else {
-        std::vector<swb_segment> tmp((size_t)std::max<int64_t>(total, 1));
-        if (total > 0) {
-            CU(ctx, cudaMemcpyAsync(tmp.data(), ctx->ccl.rows, (size_t)total * sizeof(swb_segment),
-                                    cudaMemcpyDeviceToHost, s));
-            CU(ctx, cudaStreamSynchronize(s));
-        }
-        bool ovf = false;
-        const int64_t n = merge_u8(tmp.data(), ctx->h_segoff, T, rows, rows ? cap : 0, per_frame_counts, ovf);
-        if (n_rows) *n_rows = n;
-        if (ovf && rows) return fail(ctx, SWB_ERR_CAPACITY, "%lld rows do not fit the caller's %lld", (long long)n, (long long)cap);
+    ctx->rows_guess = std::max<int64_t>(256, 2 * total);
+    if (n_rows) *n_rows = total;
+    if (per_frame_counts)
+        for (int f = 0; f < T; ++f) per_frame_counts[f] = ctx->h_segoff[f + 1] - ctx->h_segoff[f];
+    if (rows && total > cap)
+        return fail(ctx, SWB_ERR_CAPACITY, "%lld rows do not fit the caller's %lld", (long long)total, (long long)cap);
+    if (rows && total > guess) {
+        CU(ctx, cudaMemcpyAsync(rows + guess, d_rows + guess, (size_t)(total - guess) * sizeof(swb_segment),
+                                cudaMemcpyDeviceToHost, s));
+        CU(ctx, cudaStreamSynchronize(s));
     }
+    return SWB_OK;
+}
+
+int swb_collect(swb_ctx* ctx, swb_segment* rows, int64_t cap, int64_t* n_rows, int32_t* per_frame_counts) {
+    const int rc = collect_begin_impl(ctx, rows, cap, nullptr, nullptr);
+    return rc != SWB_OK ? rc : collect_end_impl(ctx, n_rows, per_frame_counts);
+}
+
+int swb_collect_all(swb_ctx* ctx, swb_segment* rows, int64_t cap, int64_t* n_rows, int32_t* per_frame_counts,
+                    uint8_t* masks, void* labels) {
+    const int rc = collect_begin_impl(ctx, rows, cap, masks, labels);
+    return rc != SWB_OK ? rc : collect_end_impl(ctx, n_rows, per_frame_counts);
+}
+
+int swb_collect_begin(swb_ctx* ctx, swb_segment* rows, int64_t cap, uint8_t* masks, void* labels) {
+    return collect_begin_impl(ctx, rows, cap, masks, labels);
+}
+
+int swb_collect_end(swb_ctx* ctx, int64_t* n_rows, int32_t* per_frame_counts) {
+    return collect_end_impl(ctx, n_rows, per_frame_counts);
+}
+
+int swb_last_subchunk(swb_ctx* ctx, int32_t* frames) {
+    if (!ctx || !frames) return fail(ctx, SWB_ERR_INVALID, "null argument");
+    if (!ctx->pending) return fail(ctx, SWB_ERR_STATE, "no submit yet");
+    *frames = ctx->last_ts;
+    return SWB_OK;
+}
+
+int swb_set_option(swb_ctx* ctx, const char* name, int64_t value) {
+    if (!ctx || !name) return fail(ctx, SWB_ERR_INVALID, "null argument");
+    if (!strcmp(name, "host_pipeline")) ctx->pipeline = value != 0;
+    else if (!strcmp(name, "sub_batch_min_px")) {
+        if (value <= 0) return fail(ctx, SWB_ERR_INVALID, "sub_batch_min_px must be positive");
+        ctx->sub_min_px = value;
+    } else return fail(ctx, SWB_ERR_INVALID, "unknown option '%s'", name);
     return SWB_OK;
 }
 
@@ -709,8 +753,6 @@ int swb_gather_crops(swb_ctx* ctx, int32_t crop, uint8_t* dst, int32_t mem_kind)
         return fail(ctx, SWB_ERR_STATE, "full frames are not resident on the device (host submit with a partial ROI); "
                                         "crop on the host instead");
     if (crop <= 0 || crop > 256) return fail(ctx, SWB_ERR_INVALID, "crop must be in 1..256");
-    if (ctx->cfg.label_mode != SWB_LABELS_I32)
-        return fail(ctx, SWB_ERR_STATE, "swb_gather_crops needs label_mode SWB_LABELS_I32");
     const swb_config& c = ctx->cfg;
     CU(ctx, cudaSetDevice(c.device));
     cudaStream_t s = ctx->stream;

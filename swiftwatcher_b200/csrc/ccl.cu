@@ -1079,6 +1079,72 @@ k_write_labels_u8(const uint32_t* __restrict__ fbits, Geom g, int T, const int* 
                      : "memory");
 }
 
+// ------------------------------------------------------------------------------------
+// uint8 compatibility (SWB_LABELS_U8): regionprops of labels.astype(np.uint8)
+// (image_filtering.py:329,335).  Components whose int32 labels agree mod 256 are ONE region of
+// the truncated image (area / sums add, bbox is the union) and labels that are 0 mod 256
+// vanish into the background.  One CTA per frame folds the frame's rows into 255 shared-memory
+// accumulators and leaves them compacted (ascending label) in the frame's slice of `stage`;
+// k_ccl_offsets then scans the per-frame counts and k_u8_compact packs the table.
+__global__ void __launch_bounds__(256)
+k_u8_merge(const swb_segment* __restrict__ rows, const int32_t* __restrict__ segoff, int cap_rows,
+           swb_segment* __restrict__ stage, int32_t* __restrict__ nseg_u8) {
+    wait_for_previous_kernel();
+    let_next_kernel_launch();
+    __shared__ int s_area[256], s_b0[256], s_b1[256], s_b2[256], s_b3[256], s_frame;
+    __shared__ unsigned long long s_sr[256], s_sc[256];
+    __shared__ int s_wtot[8];
+    const int f = blockIdx.x, v = threadIdx.x;
+    s_area[v] = 0; s_b0[v] = 0x7FFFFFFF; s_b1[v] = 0x7FFFFFFF; s_b2[v] = 0; s_b3[v] = 0;
+    s_sr[v] = 0ull; s_sc[v] = 0ull;
+    __syncthreads();
+    const int lo = min(segoff[f], cap_rows), hi = min(segoff[f + 1], cap_rows);
+    for (int i = lo + v; i < hi; i += 256) {
+        const swb_segment r = rows[i];
+        if (i == lo) s_frame = r.frame;
+        const int k = r.label & 0xFF;
+        if (k == 0) continue;
+        atomicAdd(&s_area[k], r.area);
+        atomicMin(&s_b0[k], r.bbox[0]);
+        atomicMin(&s_b1[k], r.bbox[1]);
+        atomicMax(&s_b2[k], r.bbox[2]);
+        atomicMax(&s_b3[k], r.bbox[3]);
+        atomicAdd(&s_sr[k], (unsigned long long)r.sum_row);
+        atomicAdd(&s_sc[k], (unsigned long long)r.sum_col);
+    }
+    __syncthreads();
+    const bool used = s_area[v] > 0;
+    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, used);
+    const int lane = v & 31, warp = v >> 5;
+    if (lane == 0) s_wtot[warp] = __popc(bal);
+    __syncthreads();
+    int pos = __popc(bal & ((1u << lane) - 1u)), total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        if (w < warp) pos += s_wtot[w];
+        total += s_wtot[w];
+    }
+    if (used) {
+        swb_segment o;
+        o.frame = s_frame; o.label = v; o.area = s_area[v];
+        o.bbox[0] = s_b0[v]; o.bbox[1] = s_b1[v]; o.bbox[2] = s_b2[v]; o.bbox[3] = s_b3[v];
+        o.reserved = 0;
+        o.sum_row = (long long)s_sr[v]; o.sum_col = (long long)s_sc[v];
+        stage[(long long)f * 255 + pos] = o;
+    }
+    if (v == 0) nseg_u8[f] = total;
+}
+
+__global__ void __launch_bounds__(256)
+k_u8_compact(const swb_segment* __restrict__ stage, const int32_t* __restrict__ segoff_u8,
+             swb_segment* __restrict__ out, int cap) {
+    wait_for_previous_kernel();
+    let_next_kernel_launch();
+    const int f = blockIdx.x, i = threadIdx.x;
+    const int lo = segoff_u8[f], n = segoff_u8[f + 1] - lo;
+    if (i < n && lo + i < cap) out[lo + i] = stage[(long long)f * 255 + i];
+}
+
 __global__ void __launch_bounds__(256)
 k_pack_bits(const uint8_t* __restrict__ img, int h, int w, uint32_t* __restrict__ fbits, int wpr4) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1253,6 +1319,18 @@ cudaError_t launch_ccl(cudaStream_t s, const uint32_t* fbits, int T, const Geom&
     }
     mark();
     if (n_launches) *n_launches += launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_u8_merge(cudaStream_t s, int T, const CclBuffers& b, const U8Table& u, const int32_t* base,
+                            int* n_launches) {
+    launch_dependent(k_u8_merge, dim3(T), dim3(256), 0, s, (const swb_segment*)b.rows, (const int32_t*)b.segoff,
+                     b.cap_rows, u.stage, u.nseg);
+    launch_dependent(k_ccl_offsets, dim3(1), dim3(1024), 0, s, T, (const int32_t*)u.nseg, u.segoff, base, u.cap,
+                     b.overflow);
+    launch_dependent(k_u8_compact, dim3(T), dim3(256), 0, s, (const swb_segment*)u.stage, (const int32_t*)u.segoff,
+                     u.rows, u.cap);
+    if (n_launches) *n_launches += 3;
     return cudaGetLastError();
 }
 

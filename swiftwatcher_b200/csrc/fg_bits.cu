@@ -477,7 +477,9 @@ __device__ __forceinline__ uint32_t select4of7(uint32_t m2, uint32_t m3, uint32_
 // Temporal sub-chunk length: long enough that the N-1 warm-up frames are a few
 // percent of the work, short enough that the grid has several waves of CTAs; a
 // multiple of 6 so that only the last sub-chunk of a submit has a partial group.
-int pick_ts(int T, int n_col_blocks, int median_n, int gpu_share) {
+thread_local int g_last_ts = 0;   // what the last launch on this thread used (swb_last_subchunk)
+
+int pick_ts_impl(int T, int n_col_blocks, int median_n, int gpu_share) {
     static const int forced = [] { const char* e = getenv("SWB_K1_TS"); return e ? atoi(e) : 0; }();
     if (forced > 0) return std::min(T, (forced + 5) / 6 * 6);
     // several waves of CTAs when the context has the GPU to itself; its share of that when other contexts
@@ -491,6 +493,9 @@ int pick_ts(int T, int n_col_blocks, int median_n, int gpu_share) {
     if (ts > T) ts = T;
     if (ts < 1) ts = 1;
     return ts;
+}
+int pick_ts(int T, int n_col_blocks, int median_n, int gpu_share) {
+    return g_last_ts = pick_ts_impl(T, n_col_blocks, median_n, gpu_share);
 }
 
 // ---- tensor map of the ROI inside the frame stack: (row bytes / 8, ROI rows, frames) of 8-byte elements ----
@@ -947,6 +952,8 @@ cudaError_t launch_n(cudaStream_t s, const FrameSrc& src, int channels, int T, c
 }
 
 }  // namespace
+
+int last_temporal_subchunk() { return g_last_ts; }
 
 cudaError_t launch_fg_bits(cudaStream_t s, const FrameSrc& src, int channels, int median_n, int T,
                            const Geom& g, int thresh, uint16_t* raw_bits, bool aligned, int* n_launches,

@@ -51,6 +51,7 @@ struct MorphCfg {
 cudaError_t launch_fg_bits(cudaStream_t s, const FrameSrc& src, int channels, int median_n,
                            int T, const Geom& g, int thresh, uint16_t* raw_bits, bool aligned,
                            int* n_launches, int gpu_share = 1);
+int last_temporal_subchunk();   // frames per temporal sub-chunk of this thread's last launch_fg_bits
 cudaError_t launch_morph_mask(cudaStream_t s, const uint32_t* raw_bits, int T, const Geom& g,
                               const MorphCfg& m, uint32_t* fbits, uint8_t* mask, int* n_launches);
 
@@ -90,6 +91,17 @@ cudaError_t launch_ccl(cudaStream_t s, const uint32_t* fbits, int T, const Geom&
                        const CclBuffers& b, void* labels, int label_elem_size,
                        int* n_launches, cudaEvent_t* stage_events, int n_stage_events,
                        const CclChain* chain = nullptr, bool prepared = false);
+// uint8 compatibility table (SWB_LABELS_U8): the rows of components whose labels agree mod 256
+// merged on the device (image_filtering.py:329,335).  The pointers are those of the (sub-)batch.
+struct U8Table {
+    swb_segment* stage;   // [T][255] per-frame merged rows before compaction
+    swb_segment* rows;    // [cap] compacted table (whole submit)
+    int32_t* nseg;        // [T]
+    int32_t* segoff;      // [T+1]
+    int cap;
+};
+cudaError_t launch_u8_merge(cudaStream_t s, int T, const CclBuffers& b, const U8Table& u, const int32_t* base,
+                            int* n_launches);
 void ccl_prepare(cudaStream_t s, int T, const Geom& g, const CclBuffers& b, bool chained);
 
 cudaError_t launch_pack_bits(cudaStream_t s, const uint8_t* img, int h, int w, uint32_t* fbits,

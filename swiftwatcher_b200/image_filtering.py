@@ -7,10 +7,12 @@ against the reference keeps working unchanged; the fast path is the fused,
 batched ``FilterContext`` (pipeline.py) that ``data_structures.FrameQueue``
 uses.  No function here has a CPU fallback.
 
-Reference functions that are NOT on the per-frame path (generate_regions,
-generate_roi_mask and helpers: once per video, image_filtering.py:20-180) and
-the RPCA/bilateral background model (image_filtering.py:220-307) are out of
-scope and not provided.
+The reference's own background model is provided too: ``rpca`` and
+``bilateral_blur`` (image_filtering.py:220-307; at most 32 frames per batch,
+``d <= 7``); structuring elements must be odd-sized.  Reference functions
+that are NOT on the per-frame path (generate_regions, generate_roi_mask and
+helpers: once per video, image_filtering.py:20-180) are out of scope
+ and not provided.
 """
 
 import ctypes as C

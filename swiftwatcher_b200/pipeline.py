@@ -11,6 +11,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
+from ._lib import pinned_empty
 from ._lib import (BG_MEDIAN, BG_RPCA, HALO_CARRY, LABELS_I32, LABELS_U8, MEM_DEVICE, MEM_HOST, OUT_LABELS,
                    OUT_MASK, SEGMENT_DTYPE, SwbConfig, check, ptr)
 
@@ -51,6 +52,19 @@ def props_from_rows(rows):
             for i, r in enumerate(rows)]
 
 
+def clamp_crop_region(crop_region, frame_shape):
+    """``crop_frame`` is a numpy slice (image_filtering.py:199-203): a region that runs past the right or
+    bottom edge of the frame is silently truncated — ``generate_crop_region`` produces such regions for a
+    chimney near the border (image_filtering.py:48-51).  Same here; negative or empty regions raise
+    (the reference would wrap around / return an empty image and fail later in cv2)."""
+    h, w = int(frame_shape[0]), int(frame_shape[1])
+    (x0, y0), (x1, y1) = crop_region
+    x0, y0, x1, y1 = int(x0), int(y0), min(int(x1), w), min(int(y1), h)
+    if x0 < 0 or y0 < 0 or x1 <= x0 or y1 <= y0:
+        raise ValueError("crop_region %r is negative or empty inside a %dx%d frame" % (crop_region, w, h))
+    return [(x0, y0), (x1, y1)]
+
+
 class FilterContext:
     """One context per (GPU, video).  Not thread-safe (include/swb200.h)."""
 
@@ -69,7 +83,7 @@ class FilterContext:
         ch = int(frame_shape[2]) if len(frame_shape) == 3 else 1
         if crop_region is None:
             crop_region = [(0, 0), (w, h)]
-        (x0, y0), (x1, y1) = crop_region
+        (x0, y0), (x1, y1) = clamp_crop_region(crop_region, (h, w))
         cfg = SwbConfig()
         cfg.device = device
         cfg.frame_h, cfg.frame_w, cfg.channels = h, w, ch
@@ -99,6 +113,8 @@ class FilterContext:
         check(self._lib.swb_create(C.byref(cfg), C.byref(self._ctx)))
         self._n_last = 0
         self._keepalive = None
+        self._rows_buf = None
+        self._fetch = None
 
     # -- lifetime ---------------------------------------------------------
     def close(self):
@@ -167,6 +183,71 @@ class FilterContext:
         n_rows = C.c_int64(0)
         check(self._lib.swb_collect(self._ctx, ptr(rows), cap, C.byref(n_rows), ptr(counts)), self._ctx)
         return rows[:n_rows.value], counts
+
+    def collect_begin(self, masks=None, labels=None, cap=None):
+        """Queue every device -> host copy of the last submit (table, masks, labels) behind its kernels and
+        return at once (swb_collect_begin); ``collect_end`` waits.  ``masks`` / ``labels``: (n, roi_h, roi_w)
+        arrays, page-locked ones (``_lib.pinned_empty``) make the copies asynchronous DMA transfers."""
+        n = self._n_last
+        cap = int(cap if cap is not None else max(self.cfg.max_segments, 1024 * self.max_frames))
+        if self._rows_buf is None or len(self._rows_buf) < cap:
+            self._rows_buf = pinned_empty(cap, SEGMENT_DTYPE) if cap * SEGMENT_DTYPE.itemsize <= (8 << 20) \
+                else np.empty(cap, dtype=SEGMENT_DTYPE)
+        if masks is None:
+            masks = np.empty((n, self.roi_h, self.roi_w), dtype=np.uint8)
+        if labels is None:
+            labels = np.empty((n, self.roi_h, self.roi_w), dtype=self.label_dtype)
+        if masks.shape != (n, self.roi_h, self.roi_w) or labels.shape != masks.shape or \
+                labels.dtype != self.label_dtype or masks.dtype != np.uint8:
+            raise ValueError("masks / labels must be (n, roi_h, roi_w) uint8 / %s" % np.dtype(self.label_dtype))
+        check(self._lib.swb_collect_begin(self._ctx, ptr(self._rows_buf), cap, ptr(masks), ptr(labels)), self._ctx)
+        self._fetch = (n, masks, labels)
+
+    def collect_end(self):
+        """-> (rows, counts, masks, labels) of the ``collect_begin`` in flight."""
+        n, masks, labels = self._fetch
+        self._fetch = None
+        counts = np.zeros(n, dtype=np.int32)
+        n_rows = C.c_int64(0)
+        check(self._lib.swb_collect_end(self._ctx, C.byref(n_rows), ptr(counts)), self._ctx)
+        return self._rows_buf[:n_rows.value].copy(), counts, masks, labels
+
+    def collect_all(self, masks=None, labels=None, cap=None):
+        """-> (rows, counts, masks, labels) of the last submit with one stream synchronisation."""
+        self.collect_begin(masks, labels, cap)
+        return self.collect_end()
+
+    def device_views(self):
+        """Zero-copy CUDA torch tensors over the context-owned outputs of the last submit:
+        (masks [n, roi_h, pitch] uint8, labels [n, roi_h, pitch] int32/uint8); columns >= roi_w are padding."""
+        import torch
+        mask, labels = C.c_void_p(), C.c_void_p()
+        mp, lp = C.c_int64(0), C.c_int64(0)
+        check(self._lib.swb_device_views(self._ctx, C.byref(mask), C.byref(mp), C.byref(labels), C.byref(lp),
+                                         None, None), self._ctx)
+        dev = "cuda:%d" % self.cfg.device
+
+        def wrap(address, pitch, typestr, dtype):
+            if not address:
+                return None
+            class _Dev:
+                pass
+            d = _Dev()
+            d.__cuda_array_interface__ = {"shape": (self._n_last, self.roi_h, int(pitch)), "typestr": typestr,
+                                          "data": (int(address), False), "version": 2, "strides": None}
+            return torch.as_tensor(d, device=dev)
+        lt = "|u1" if self.label_dtype == np.uint8 else "<i4"
+        return wrap(mask.value, mp.value, "|u1", torch.uint8), wrap(labels.value, lp.value, lt, None)
+
+    def set_option(self, name, value):
+        """Tuning knobs that never change a result (swb_set_option): "host_pipeline", "sub_batch_min_px"."""
+        check(self._lib.swb_set_option(self._ctx, name.encode(), int(value)), self._ctx)
+
+    def last_subchunk(self):
+        """Frames per temporal sub-chunk the filtering kernel used for the last submit."""
+        n = C.c_int32(0)
+        check(self._lib.swb_last_subchunk(self._ctx, C.byref(n)), self._ctx)
+        return n.value
 
     def collect_props(self):
         """-> list (per frame) of list[RegionProperties]."""

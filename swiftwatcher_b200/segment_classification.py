@@ -269,7 +269,7 @@ class SegmentClassifier:
 
     # -- device-resident path -------------------------------------------------------
     @torch.no_grad()
-    def classify_submit(self, ctx, n_rows):
+    def classify_submit(self, ctx, n_rows, empty="raise"):
         """Keep mask [n_rows] (bool, device) for the segment table of ``ctx``'s last
         submit: crops are gathered on the device from the BGR frames
         (``swb_gather_crops``) and never visit the host.  Needs device-resident

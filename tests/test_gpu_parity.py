@@ -361,19 +361,19 @@ def test_many_temporal_subchunks(n, T):
 
 @pytest.mark.parametrize("n,T,se,close,mode", [(9, 71, 5, True, "i32"), (5, 50, 3, False, "u8"), (5, 26, 3, False, "i32"),
                                                (3, 31, 3, True, "i32")])
-def test_sub_batches_equal_one_batch(monkeypatch, n, T, se, close, mode):
+def test_sub_batches_equal_one_batch(n, T, se, close, mode):
     """A host submit cut into sub-batches that are filtered while later frames are still being
-    copied (forced here with the SWB_SUB_MIN_PX test hook; real frames reach it at >= 64 Mpx per
+    copied (forced here with the "sub_batch_min_px" option; real frames reach it at >= 64 Mpx per
     sub-batch) gives exactly the oracle's masks, labels and table, the same as the one-batch
     device-resident submit, and leaves the right history behind."""
     import torch
-    monkeypatch.setenv("SWB_SUB_MIN_PX", "1")
     frames = synth.synth_video(33, 0, 0, T + 6, 44, 100, 25)
     region = [(3, 2), (99, 43)]
     par = rp.PathParams(region, n, 15, se, True, close, mode)
     want = rp.run_path(frames, par)
     with swb.FilterContext(frames.shape[1:], region, median_n=n, morph_size=se, do_close=close, label_mode=mode,
                            max_frames=T) as ctx:
+        ctx.set_option("sub_batch_min_px", 1)
         check_against_oracle(frames[:T], region, n=n, se=se, do_close=close, mode=mode, ctx=ctx, n_halo=0)
         ctx.submit(np.ascontiguousarray(frames[T:]))            # CARRY: history written by the last sub-batch
         labels = ctx.labels()
@@ -384,9 +384,9 @@ def test_sub_batches_equal_one_batch(monkeypatch, n, T, se, close, mode):
         ctx.submit(dev[:T], n_halo=0)
         rows_d, counts_d = ctx.collect()
         labels_d = ctx.labels()
-    monkeypatch.setenv("SWB_PIPELINE", "0")                     # one batch on one stream
     with swb.FilterContext(frames.shape[1:], region, median_n=n, morph_size=se, do_close=close, label_mode=mode,
                            max_frames=T) as ctx:
+        ctx.set_option("host_pipeline", 0)                      # one batch on one stream
         ctx.submit(frames[:T], n_halo=0)
         rows_1, counts_1 = ctx.collect()
         assert np.array_equal(rows_1, rows_d) and np.array_equal(counts_1, counts_d)
