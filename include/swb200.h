@@ -183,11 +183,19 @@ int swb_get_timing(swb_ctx* ctx, const char** names, float* ms, int32_t cap, int
 /* Number of kernels launched by this context since creation. */
 int64_t swb_launch_count(const swb_ctx* ctx);
 
-/* Batched segment crops for the classifier: extract_segment_images
- * (image_filtering.py:338-369) for every row of the last submit's table, as
- * fixed crop x crop x channels tiles gathered from the full frames that were
- * submitted; out-of-frame pixels are zero.  dst: [n_rows][crop][crop][channels]. */
-int swb_gather_crops(swb_ctx* ctx, int32_t crop, uint8_t* dst, int32_t mem_kind);
+/* Batched segment crops for the classifier, on the device: extract_segment_images
+ * (image_filtering.py:338-369) for every row of the last submit's table, followed by what the
+ * classifier's transforms.Resize((24, 24)) (segment_classification.py:20) does to it.
+ * rects [n_rows][4] (may be NULL) receives the rectangle (y0, x0, y1, x1) the reference slices from
+ * the FULL frame: the bbox grown symmetrically to crop x crop where it is smaller, shifted by the ROI
+ * origin, numpy slice semantics — a start left / above the frame wraps around (an empty image unless
+ * the frame is tiny), an end past the frame is truncated, a bbox larger than crop is kept whole.
+ * dst [n_rows][crop][crop][channels]: the rectangle itself when it is exactly crop x crop; otherwise
+ * the rectangle resampled to crop x crop exactly as Pillow's Image.resize(BILINEAR) does it (two
+ * passes, 22-bit fixed-point coefficients); all zeros when the rectangle is empty (the reference's
+ * ToPILImage raises there — the caller sees it in rects).  crop <= 64.  SWB_LABELS_U8: the rows are
+ * those of the merged table.  Needs the full frames of the last submit on the device. */
+int swb_gather_crops(swb_ctx* ctx, int32_t crop, uint8_t* dst, int32_t* rects, int32_t mem_kind);
 
 /* Single-stage entry points: one reference function each, host buffers in/out,
  * tightly packed.  They exist so that each reference function has a drop-in
@@ -225,6 +233,24 @@ int swb_stage_bilateral(int32_t device, const uint8_t* in, int32_t h, int32_t w,
 /* SWB_BG_RPCA only: the "RPCA" images (clip(-E, 0, 255), uint8, ROI-sized) of frames
  * [t0, t0 + n) of the last submit. */
 int swb_get_rpca(swb_ctx* ctx, int32_t t0, int32_t n, uint8_t* dst, int32_t mem_kind);
+
+/* Tracker cost matrix: formulate_cost_matrix, segment_tracking.py:46-102, for two
+ * consecutive frames' segments on the GPU.  A workspace owns its device / page-locked buffers (sized for
+ * max_segments = the most segments two consecutive frames may hold together); no allocation per call.
+ * prev_yx / curr_yx: centroids (row, col) as float64 pairs; first_yx[i]: the centroid of
+ * segment_history[0] of previous segment i, read only where has_history[i] != 0 (:217-222).
+ * *matrix: the (n_prev + n_curr)^2 row-major float64 cost matrix in page-locked memory owned by the
+ * workspace (valid until the next call): match block 0.5 * 2^(dist - 25) + 0.5 * angle cost (:190-243),
+ * diagonal 1 (:246-250), everything else 1 + DBL_EPSILON (:179-187).  The Hungarian step
+ * (scipy.optimize.linear_sum_assignment, :253-260) stays with the caller. */
+typedef struct swb_tracker swb_tracker;
+int swb_tracker_create(int32_t device, int32_t max_segments, swb_tracker** out);
+int swb_tracker_destroy(swb_tracker* t);
+int swb_tracker_costs(swb_tracker* t, const double* prev_yx, const double* first_yx,
+                      const uint8_t* has_history, int32_t n_prev, const double* curr_yx, int32_t n_curr,
+                      double** matrix);
+const char* swb_tracker_last_error(const swb_tracker* t);
+int64_t swb_tracker_launch_count(const swb_tracker* t);
 
 /* Page-locked host memory for frame ingest (io_video.py:11-165 decodes frames into host
  * arrays; frames decoded into these buffers reach the device by DMA at full PCIe speed

@@ -160,3 +160,64 @@ def build_reference_classifier(mod, model_path):
         return mod.SegmentClassifier(model_path)
     finally:
         torch.load = real_load
+
+
+# ----------------------------------------------------------------------------------------------------
+# transforms.Resize((24, 24)) on a PIL image (segment_classification.py:20): Pillow's Image.resize with the
+# BILINEAR filter.  Pillow is a third-party dependency that is not under /root/reference (reference pins
+# Pillow==6.1.0, requirements.txt; installed here: 12.2.0); its published algorithm (src/libImaging/
+# Resample.c: precompute_coeffs, normalize_coeffs_8bpc, ImagingResampleHorizontal/Vertical_8bpc) restated in
+# numpy.  tests/test_classifier.py pins it bit for bit against the installed Pillow.
+# ----------------------------------------------------------------------------------------------------
+PIL_PRECISION_BITS = 32 - 8 - 2
+
+
+def pil_bilinear_coeffs(in_size, out_size):
+    """precompute_coeffs + normalize_coeffs_8bpc for the whole-image box: per output index the first input
+    index, the tap count and the 22-bit fixed-point weights."""
+    import numpy as np
+    scale = float(np.float32(in_size) - np.float32(0)) / out_size
+    filterscale = max(scale, 1.0)
+    support = 1.0 * filterscale                       # bilinear: support 1
+    ss = 1.0 / filterscale
+    out = []
+    for xx in range(out_size):
+        center = 0.0 + (xx + 0.5) * scale
+        xmin = max(int(center - support + 0.5), 0)    # C cast: truncation
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        w = []
+        for x in range(xmax):
+            a = abs((x + xmin - center + 0.5) * ss)
+            w.append(1.0 - a if a < 1.0 else 0.0)
+        ww = 0.0
+        for v in w:
+            ww += v
+        k = [(v / ww if ww != 0.0 else v) for v in w]
+        out.append((xmin, [int(0.5 + v * (1 << PIL_PRECISION_BITS)) for v in k]))
+    return out
+
+
+def pil_bilinear_resize(image, size):
+    """``np.asarray(Image.fromarray(image).resize((size[1], size[0]), BILINEAR))`` for a uint8 image
+    [h, w] or [h, w, c]: horizontal pass, rounding to uint8, then the vertical pass; a pass whose size
+    already matches is skipped (ImagingResample's need_horizontal / need_vertical)."""
+    import numpy as np
+
+    def one_pass(a, out_size):                        # resample axis 0
+        if a.shape[0] == out_size:
+            return a
+        res = np.empty((out_size,) + a.shape[1:], np.uint8)
+        for i, (lo, k) in enumerate(pil_bilinear_coeffs(a.shape[0], out_size)):
+            acc = np.full(a.shape[1:], 1 << (PIL_PRECISION_BITS - 1), np.int64)
+            for j, kv in enumerate(k):
+                acc += a[lo + j].astype(np.int64) * kv
+            res[i] = np.clip(acc >> PIL_PRECISION_BITS, 0, 255).astype(np.uint8)
+        return res
+    a = np.asarray(image)
+    if a.shape[0] > a.shape[1] * 100 and size[0] < a.shape[0]:
+        # Image.resize (Pillow >= 9.1): an image more than 100 times taller than wide that shrinks vertically is
+        # resampled vertically FIRST (two im.resize calls); every other shape goes horizontal first
+        a = one_pass(a, size[0])
+        return np.ascontiguousarray(np.swapaxes(one_pass(np.swapaxes(a, 0, 1), size[1]), 0, 1))
+    a = np.swapaxes(one_pass(np.swapaxes(a, 0, 1), size[1]), 0, 1)       # horizontal first
+    return np.ascontiguousarray(one_pass(a, size[0]))

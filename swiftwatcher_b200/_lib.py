@@ -67,7 +67,7 @@ SYMBOLS = {
     "swb_get_timing": (C.c_int, [_P, C.POINTER(C.c_char_p), C.POINTER(C.c_float), _I32,
                                  C.POINTER(_I32)]),
     "swb_launch_count": (_I64, [_P]),
-    "swb_gather_crops": (C.c_int, [_P, _I32, _P, _I32]),
+    "swb_gather_crops": (C.c_int, [_P, _I32, _P, _P, _I32]),
     "swb_stage_gray": (C.c_int, [_I32, _P, _I32, _I32, _P]),
     "swb_stage_median": (C.c_int, [_I32, _P, _I32, _I32, _I32, _P]),
     "swb_stage_absdiff": (C.c_int, [_I32, _P, _P, _I32, _I32, _P]),
@@ -78,6 +78,11 @@ SYMBOLS = {
     "swb_stage_rpca": (C.c_int, [_I32, _P, _I32, _I32, _I32, _P, C.POINTER(_I32)]),
     "swb_stage_bilateral": (C.c_int, [_I32, _P, _I32, _I32, _I32, C.c_double, C.c_double, _P]),
     "swb_get_rpca": (C.c_int, [_P, _I32, _I32, _P, _I32]),
+    "swb_tracker_create": (C.c_int, [_I32, _I32, C.POINTER(_P)]),
+    "swb_tracker_destroy": (C.c_int, [_P]),
+    "swb_tracker_costs": (C.c_int, [_P, _P, _P, _P, _I32, _P, _I32, C.POINTER(_P)]),
+    "swb_tracker_last_error": (C.c_char_p, [_P]),
+    "swb_tracker_launch_count": (_I64, [_P]),
     "swb_host_alloc": (C.c_int, [C.POINTER(_P), C.c_uint64]),
     "swb_host_free": (C.c_int, [_P]),
     "swb_synth_frames": (C.c_int, [_I32, _P, _I32, _U32, _U32, _I32, _I32, _I32, _I32, _I32]),

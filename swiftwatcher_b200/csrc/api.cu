@@ -746,34 +746,42 @@ int swb_get_timing(swb_ctx* ctx, const char** names, float* ms, int32_t cap, int
 
 int64_t swb_launch_count(const swb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
-int swb_gather_crops(swb_ctx* ctx, int32_t crop, uint8_t* dst, int32_t mem_kind) {
+int swb_gather_crops(swb_ctx* ctx, int32_t crop, uint8_t* dst, int32_t* rects, int32_t mem_kind) {
     if (!ctx || !dst) return fail(ctx, SWB_ERR_INVALID, "null argument");
     if (!ctx->pending) return fail(ctx, SWB_ERR_STATE, "no submit to read from");
+    if (ctx->fetching) return fail(ctx, SWB_ERR_STATE, "swb_gather_crops between swb_collect_begin and swb_collect_end");
     if (!ctx->last_frames_dev)
         return fail(ctx, SWB_ERR_STATE, "full frames are not resident on the device (host submit with a partial ROI); "
                                         "crop on the host instead");
-    if (crop <= 0 || crop > 256) return fail(ctx, SWB_ERR_INVALID, "crop must be in 1..256");
+    if (crop <= 0 || crop > 64) return fail(ctx, SWB_ERR_INVALID, "crop must be in 1..64");
     const swb_config& c = ctx->cfg;
     CU(ctx, cudaSetDevice(c.device));
     cudaStream_t s = ctx->stream;
     const int T = ctx->last_T;
-    CU(ctx, cudaMemcpyAsync(ctx->h_segoff, ctx->ccl.segoff, ((size_t)T + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    const bool u8 = c.label_mode == SWB_LABELS_U8;       // the merged table: regionprops of the uint8 image
+    const int32_t* d_segoff = u8 ? ctx->u8.segoff : ctx->ccl.segoff;
+    const swb_segment* d_rows = u8 ? ctx->u8.rows : ctx->ccl.rows;
+    CU(ctx, cudaMemcpyAsync(ctx->h_segoff, d_segoff, ((size_t)T + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     CU(ctx, cudaStreamSynchronize(s));
-    const int total = std::min<int>(ctx->h_segoff[T], ctx->cap_rows);
+    const int total = std::min<int>(ctx->h_segoff[T], u8 ? ctx->u8.cap : ctx->cap_rows);
     if (total == 0) return SWB_OK;
     const size_t bytes = (size_t)total * crop * crop * c.channels;
+    const size_t rbytes = (size_t)total * 4 * sizeof(int32_t);
     uint8_t* d = dst;
-    uint8_t* tmp = nullptr;
+    int32_t* dr = rects;
+    DevTmp tmp;
     if (mem_kind == SWB_MEM_HOST) {
-        CU(ctx, cudaMalloc(reinterpret_cast<void**>(&tmp), bytes));
-        d = tmp;
+        CU(ctx, tmp.alloc(&d, bytes));
+        if (rects) CU(ctx, tmp.alloc(&dr, (size_t)total * 4));
     }
     cudaError_t e = launch_gather_crops_n(s, ctx->last_frames_dev, ctx->last_stride, ctx->last_pitch, c.channels,
-                                          c.frame_h, c.frame_w, c.roi_x0, c.roi_y0, ctx->ccl.rows, total, crop, d);
+                                          c.frame_h, c.frame_w, c.roi_x0, c.roi_y0, d_rows, total, crop, d, dr);
     ctx->launches += 1;
-    if (e == cudaSuccess && tmp) e = cudaMemcpyAsync(dst, tmp, bytes, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && mem_kind == SWB_MEM_HOST) {
+        e = cudaMemcpyAsync(dst, d, bytes, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && rects) e = cudaMemcpyAsync(rects, dr, rbytes, cudaMemcpyDeviceToHost, s);
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    if (tmp) cudaFree(tmp);
     if (e != cudaSuccess) return fail(ctx, SWB_ERR_CUDA, "gather_crops: %s", cudaGetErrorString(e));
     return SWB_OK;
 }

@@ -1159,35 +1159,144 @@ k_pack_bits(const uint8_t* __restrict__ img, int h, int w, uint32_t* __restrict_
     fbits[idx] = bits;
 }
 
-// extract_segment_images (image_filtering.py:338-369) as fixed crop x crop tiles:
-// bbox grown symmetrically to crop x crop (floor/ceil split), shifted by the ROI
-// origin, read from the full frame; pixels outside the frame are 0.  Segments
-// whose bbox exceeds the crop are centre-cropped (the reference would hand the
-// larger crop to the classifier's Resize).
+// extract_segment_images (image_filtering.py:338-369) + the classifier's Resize((24, 24))
+// (segment_classification.py:20) for every row of the segment table, one CTA per row.
+//
+// The rectangle is the reference's: bbox grown symmetrically to crop x crop where it is smaller
+// (floor / ceil split), shifted by the ROI origin and cut from the FULL frame with numpy's slice
+// semantics — a negative start wraps around (in practice: an empty image), an end past the frame
+// is truncated, a bbox larger than the crop is kept whole.  A crop x crop rectangle is copied.
+// Anything else goes through what transforms.Resize does to the PIL image: Pillow's two-pass
+// BILINEAR resampling (src/libImaging/Resample.c: precompute_coeffs in double, coefficients in
+// 22-bit fixed point, the first pass rounded to uint8, horizontal first — vertical first when the
+// image is more than 100 times taller than wide and shrinks vertically, Image.resize).  An empty
+// rectangle gives a zero tile; rects[] tells the caller which case a row was.
+struct ResampleAxis {           // one output axis of `crop` samples over n_in input samples
+    double scale, support, ss;
+    int n_in;
+};
+__device__ __forceinline__ ResampleAxis make_axis(int n_in, int n_out) {
+    ResampleAxis a;
+    a.n_in = n_in;
+    a.scale = __ddiv_rn((double)(float)n_in, (double)n_out);
+    const double fs = a.scale < 1.0 ? 1.0 : a.scale;
+    a.support = fs;               // bilinear: support 1.0 * filterscale
+    a.ss = __ddiv_rn(1.0, fs);
+    return a;
+}
+struct Taps { int lo, n; double center, ww; };
+__device__ __forceinline__ double tap_weight(const ResampleAxis& a, const Taps& t, int j) {
+    double x = __dmul_rn(__dadd_rn(__dsub_rn((double)(j + t.lo), t.center), 0.5), a.ss);
+    if (x < 0.0) x = -x;
+    return x < 1.0 ? __dsub_rn(1.0, x) : 0.0;
+}
+__device__ __forceinline__ Taps make_taps(const ResampleAxis& a, int out_index) {
+    Taps t;
+    t.center = __dadd_rn(0.0, __dmul_rn(__dadd_rn((double)out_index, 0.5), a.scale));
+    int lo = (int)__dadd_rn(__dsub_rn(t.center, a.support), 0.5);
+    if (lo < 0) lo = 0;
+    int hi = (int)__dadd_rn(__dadd_rn(t.center, a.support), 0.5);
+    if (hi > a.n_in) hi = a.n_in;
+    t.lo = lo;
+    t.n = hi - lo;
+    t.ww = 0.0;
+    for (int j = 0; j < t.n; ++j) t.ww = __dadd_rn(t.ww, tap_weight(a, t, j));
+    return t;
+}
+__device__ __forceinline__ int tap_fixed(const ResampleAxis& a, const Taps& t, int j) {
+    double k = tap_weight(a, t, j);
+    if (t.ww != 0.0) k = __ddiv_rn(k, t.ww);
+    return (int)__dadd_rn(0.5, __dmul_rn(k, 4194304.0));        // 1 << PRECISION_BITS (22)
+}
+__device__ __forceinline__ int clip8(int acc) {
+    const int v = acc >> 22;
+    return v < 0 ? 0 : (v > 255 ? 255 : v);
+}
+
+constexpr int MAX_CROP = 64;
+
 __global__ void __launch_bounds__(256)
 k_gather_crops(const uint8_t* __restrict__ frames, long long frame_stride, long long pitch, int channels,
                int frame_h, int frame_w, int roi_x0, int roi_y0, const swb_segment* __restrict__ rows,
-               int n_rows, int crop, uint8_t* __restrict__ dst) {
+               int n_rows, int crop, uint8_t* __restrict__ dst, int32_t* __restrict__ rects) {
+    __shared__ Taps s_taps[2][MAX_CROP];          // [0]: along x (horizontal pass), [1]: along y
     const int r = blockIdx.x;
     if (r >= n_rows) return;
     const swb_segment s = rows[r];
-    const int bh = s.bbox[2] - s.bbox[0], bw = s.bbox[3] - s.bbox[1];
-    // floor((crop - dim) / 2) also for negative differences (centre crop)
-    const int dy = crop - bh, dxx = crop - bw;
-    const int oy = s.bbox[0] - ((dy >= 0) ? dy / 2 : -((-dy + 1) / 2)) + roi_y0;
-    const int ox = s.bbox[1] - ((dxx >= 0) ? dxx / 2 : -((-dxx + 1) / 2)) + roi_x0;
-    const uint8_t* fr = frames + (long long)s.frame * frame_stride;
+    int lo[2], hi[2];                              // [0] = rows (y), [1] = columns (x)
+    const int lim[2] = {frame_h, frame_w};
+    const int org[2] = {roi_y0, roi_x0};
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        int b0 = s.bbox[a], b1 = s.bbox[a + 2];
+        const int d = crop - (b1 - b0);
+        if (d > 0) { b0 -= d / 2; b1 += (d + 1) / 2; }
+        b0 += org[a];
+        b1 += org[a];
+        // frame[b0:b1]: numpy slice semantics
+        lo[a] = b0 < 0 ? max(b0 + lim[a], 0) : min(b0, lim[a]);
+        hi[a] = b1 < 0 ? max(b1 + lim[a], 0) : min(b1, lim[a]);
+        if (hi[a] < lo[a]) hi[a] = lo[a];
+    }
+    const int ny = hi[0] - lo[0], nx = hi[1] - lo[1];
+    if (rects && threadIdx.x < 4)
+        rects[4 * r + threadIdx.x] = threadIdx.x == 0 ? lo[0] : (threadIdx.x == 1 ? lo[1] : (threadIdx.x == 2 ? hi[0] : hi[1]));
+    const uint8_t* src = frames + (long long)s.frame * frame_stride + (long long)lo[0] * pitch + (long long)lo[1] * channels;
     uint8_t* out = dst + (long long)r * crop * crop * channels;
     const int n = crop * crop * channels;
+    if (ny == 0 || nx == 0) {                      // block-uniform
+        for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = 0;
+        return;
+    }
+    const bool need_h = nx != crop, need_v = ny != crop;
+    if (!need_h && !need_v) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int c = i % channels, px = (i / channels) % crop, py = i / (channels * crop);
+            out[i] = src[(long long)py * pitch + px * channels + c];
+        }
+        return;
+    }
+    const ResampleAxis ax = make_axis(nx, crop), ay = make_axis(ny, crop);
+    if (threadIdx.x < crop) {
+        if (need_h) s_taps[0][threadIdx.x] = make_taps(ax, threadIdx.x);
+    } else if (threadIdx.x >= 64 && threadIdx.x < 64 + crop) {
+        if (need_v) s_taps[1][threadIdx.x - 64] = make_taps(ay, threadIdx.x - 64);
+    }
+    __syncthreads();
+    const bool v_first = need_h && need_v && (long long)ny > 100ll * nx;   // ny > crop is implied (nx >= 1, crop <= 64)
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int c = i % channels;
-        const int px = (i / channels) % crop;
-        const int py = i / (channels * crop);
-        const int y = oy + py, x = ox + px;
-        uint8_t v = 0;
-        if ((unsigned)y < (unsigned)frame_h && (unsigned)x < (unsigned)frame_w)
-            v = fr[(long long)y * pitch + (long long)x * channels + c];
-        out[i] = v;
+        const int c = i % channels, px = (i / channels) % crop, py = i / (channels * crop);
+        int val;
+        if (need_h && need_v) {
+            // outer pass over the second axis, inner (first) pass evaluated on the fly and rounded to uint8
+            const int oa = v_first ? 0 : 1;                      // outer axis: 0 = x taps, 1 = y taps
+            const ResampleAxis& A_out = oa == 0 ? ax : ay;
+            const ResampleAxis& A_in = oa == 0 ? ay : ax;
+            const Taps& T_out = s_taps[oa][oa == 0 ? px : py];
+            const Taps& T_in = s_taps[oa ^ 1][oa == 0 ? py : px];
+            int acc = 1 << 21;
+            for (int jo = 0; jo < T_out.n; ++jo) {
+                int inner = 1 << 21;
+                for (int ji = 0; ji < T_in.n; ++ji) {
+                    const int y = oa == 0 ? T_in.lo + ji : T_out.lo + jo;
+                    const int x = oa == 0 ? T_out.lo + jo : T_in.lo + ji;
+                    inner += (int)src[(long long)y * pitch + x * channels + c] * tap_fixed(A_in, T_in, ji);
+                }
+                acc += clip8(inner) * tap_fixed(A_out, T_out, jo);
+            }
+            val = clip8(acc);
+        } else if (need_h) {
+            const Taps& T = s_taps[0][px];
+            int acc = 1 << 21;
+            for (int j = 0; j < T.n; ++j) acc += (int)src[(long long)py * pitch + (T.lo + j) * channels + c] * tap_fixed(ax, T, j);
+            val = clip8(acc);
+        } else {
+            const Taps& T = s_taps[1][py];
+            int acc = 1 << 21;
+            for (int j = 0; j < T.n; ++j) acc += (int)src[(long long)(T.lo + j) * pitch + px * channels + c] * tap_fixed(ay, T, j);
+            val = clip8(acc);
+        }
+        out[i] = (uint8_t)val;
     }
 }
 
@@ -1341,10 +1450,11 @@ cudaError_t launch_pack_bits(cudaStream_t s, const uint8_t* img, int h, int w, u
 
 cudaError_t launch_gather_crops_n(cudaStream_t s, const uint8_t* frames, long long frame_stride, long long pitch,
                                   int channels, int frame_h, int frame_w, int roi_x0, int roi_y0,
-                                  const swb_segment* rows, int n_rows, int crop, uint8_t* dst) {
+                                  const swb_segment* rows, int n_rows, int crop, uint8_t* dst, int32_t* rects) {
     if (n_rows <= 0) return cudaSuccess;
+    if (crop > MAX_CROP) return cudaErrorInvalidValue;
     k_gather_crops<<<n_rows, 256, 0, s>>>(frames, frame_stride, pitch, channels, frame_h, frame_w, roi_x0, roi_y0,
-                                          rows, n_rows, crop, dst);
+                                          rows, n_rows, crop, dst, rects);
     return cudaGetLastError();
 }
 

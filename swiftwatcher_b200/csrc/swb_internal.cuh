@@ -109,7 +109,7 @@ cudaError_t launch_pack_bits(cudaStream_t s, const uint8_t* img, int h, int w, u
 cudaError_t launch_gather_crops_n(cudaStream_t s, const uint8_t* frames, long long frame_stride,
                                   long long pitch, int channels, int frame_h, int frame_w,
                                   int roi_x0, int roi_y0, const swb_segment* rows, int n_rows,
-                                  int crop, uint8_t* dst);
+                                  int crop, uint8_t* dst, int32_t* rects);
 
 // cudaFuncSetAttribute is per device: remember which devices a kernel's dynamic shared-memory
 // limit has been raised on (one process may drive several GPUs, one context each).

@@ -31,7 +31,7 @@ import numpy as np
 
 from . import image_filtering as img
 from ._lib import HALO_CARRY, MEM_HOST, is_pinned, pinned_empty
-from .pipeline import FilterContext, clamp_crop_region, props_from_rows
+from .pipeline import FilterContext, centroids, clamp_crop_region, props_from_rows  # noqa: F401
 
 
 class Segment:
@@ -345,13 +345,24 @@ class FrameQueue(deque):
         self.store_processed_queue([labels[n - 1 - pos] for pos in range(n)], "cc_labeling")
         self._attach_lazy_stages(ctx, [f.processed_frames["crop"] if "crop" in f.processed_frames
                                        else img.crop_frame(f.frame, crop_region) for f in reversed(self)])
-        offs = np.concatenate([[0], np.cumsum(counts)])
-        props_lists, image_lists = [], []
+        # Segments straight from the table (no per-row numpy scalar conversions): what Frame.set_segments /
+        # Segment.__init__ build (data_structures.py:16-30,61-63), with the crops of extract_segment_images
+        # (image_filtering.py:338-369; copied: a segment outlives the pinned batch its frame was decoded into)
+        offs = np.concatenate([[0], np.cumsum(counts)]).tolist()
+        label, area, bbox = rows["label"].tolist(), rows["area"].tolist(), rows["bbox"].tolist()
+        cen = centroids(rows).tolist() if len(rows) else []
+        box = img.expand_bboxes(rows["bbox"], min_seg_size, crop_region).tolist() if len(rows) else []
         for pos in range(n):
             t = n - 1 - pos
-            props = props_from_rows(rows[offs[t]:offs[t + 1]])
-            props_lists.append(props)
-            # copies (24x24x3): a segment outlives the pinned batch its frame was decoded into
-            image_lists.append([np.array(c) for c in
-                                img.extract_segment_images(props, frames[pos], min_seg_size, crop_region)])
-        self.store_segmented_queue(props_lists, image_lists)
+            fr = self[pos]
+            full, number, stamp = fr.frame, fr.frame_number, fr.timestamp
+            segs = []
+            for i in range(offs[t], offs[t + 1]):
+                b = box[i]
+                seg = Segment.__new__(Segment)
+                seg.__dict__ = {"parent_frame_number": number, "parent_timestamp": stamp,
+                                "segment_image": full[b[0]:b[2], b[1]:b[3]].copy(), "segment_history": [],
+                                "status": None, "label": label[i], "area": area[i], "bbox": tuple(bbox[i]),
+                                "centroid": tuple(cen[i])}
+                segs.append(seg)
+            fr.segments = segs

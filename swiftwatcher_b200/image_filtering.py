@@ -182,6 +182,18 @@ def expand_bbox(bbox, min_seg_size, crop_region):
     return [bbox[0] + oy, bbox[1] + ox, bbox[2] + oy, bbox[3] + ox]
 
 
+def expand_bboxes(bboxes, min_seg_size, crop_region):
+    """``expand_bbox`` for a whole table at once: [k, 4] int array -> [k, 4] int64 (full-frame coordinates)."""
+    b = np.asarray(bboxes, dtype=np.int64).reshape(-1, 4).copy()
+    for lo, hi, want in ((0, 2, int(min_seg_size[0])), (1, 3, int(min_seg_size[1]))):
+        diff = np.maximum(want - (b[:, hi] - b[:, lo]), 0)
+        b[:, lo] -= diff // 2
+        b[:, hi] += (diff + 1) // 2
+    b[:, 0::2] += int(crop_region[0][1])
+    b[:, 1::2] += int(crop_region[0][0])
+    return b
+
+
 def extract_segment_images(segments, frame, min_seg_size, crop_region):
     """image_filtering.py:338-369 — colour crops from the un-cropped host
     frame: numpy views with the reference's slice semantics.  (Pure indexing

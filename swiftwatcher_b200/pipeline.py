@@ -284,15 +284,27 @@ class FilterContext:
         check(self._lib.swb_get_mask_bits(self._ctx, t0, n, ptr(out), MEM_HOST), self._ctx)
         return out
 
-    def gather_crops(self, n_rows, crop=24, out=None):
-        """(n_rows, crop, crop, C) uint8 crops for the last submit's table
-        (device-resident full frames only)."""
+    def gather_crops(self, n_rows, crop=24, out=None, rects=None):
+        """-> (tiles, rects) for the last submit's table (device-resident full frames only):
+        tiles (n_rows, crop, crop, C) uint8 = ``Resize((crop, crop))(ToPILImage()(segment_image))`` of the
+        reference's ``extract_segment_images`` (the crop itself where it already is crop x crop, zeros
+        where it is empty); rects (n_rows, 4) int32 = the rectangle (y0, x0, y1, x1) the reference slices
+        from the full frame.  ``out`` / ``rects`` may be CUDA torch tensors (then nothing visits the host)."""
         ch = self.cfg.channels
+        on_device = hasattr(out, "is_cuda") and out.is_cuda
         if out is None:
             out = np.empty((n_rows, crop, crop, ch), dtype=np.uint8)
-        kind = MEM_DEVICE if (hasattr(out, "is_cuda") and out.is_cuda) else MEM_HOST
-        check(self._lib.swb_gather_crops(self._ctx, crop, ptr(out), kind), self._ctx)
-        return out
+        if rects is None:
+            if on_device:
+                import torch
+                rects = torch.empty((n_rows, 4), dtype=torch.int32, device=out.device)
+            else:
+                rects = np.empty((n_rows, 4), dtype=np.int32)
+        if (hasattr(rects, "is_cuda") and rects.is_cuda) != on_device:
+            raise ValueError("out and rects must both be host arrays or both CUDA tensors")
+        check(self._lib.swb_gather_crops(self._ctx, crop, ptr(out), ptr(rects), MEM_DEVICE if on_device else MEM_HOST),
+              self._ctx)
+        return out, rects
 
     # -- instrumentation --------------------------------------------------------
     def enable_timing(self, on=True):

@@ -270,12 +270,22 @@ class SegmentClassifier:
     # -- device-resident path -------------------------------------------------------
     @torch.no_grad()
     def classify_submit(self, ctx, n_rows, empty="raise"):
-        """Keep mask [n_rows] (bool, device) for the segment table of ``ctx``'s last
-        submit: crops are gathered on the device from the BGR frames
-        (``swb_gather_crops``) and never visit the host.  Needs device-resident
-        full frames (device submit, or host submit of a full-frame ROI)."""
+        """Keep mask [n_rows] (bool, device) for the segment table of ``ctx``'s last submit: the
+        reference's segment images are cut AND (where they are not 24 x 24: a bird larger than 24 px, a
+        bbox truncated by the frame edge) resized on the device exactly as ``transforms.Resize`` would
+        (``swb_gather_crops``), and never visit the host.  A segment whose image is EMPTY (bbox within
+        12 px of the frame's top / left edge: the reference's unclamped slice wraps around,
+        image_filtering.py:363-365) makes the reference's ``ToPILImage`` raise: ``empty="raise"`` does the
+        same (ValueError), ``empty="drop"`` classifies such segments as not kept.
+        Needs device-resident full frames (device submit, or host submit of a full-frame ROI)."""
+        if empty not in ("raise", "drop"):
+            raise ValueError("empty must be 'raise' or 'drop'")
         if n_rows == 0:
             return torch.zeros((0,), dtype=torch.bool, device=self.device)
         crops = torch.empty((n_rows, CROP, CROP, 3), dtype=torch.uint8, device=self.device)
-        ctx.gather_crops(n_rows, CROP, out=crops)
-        return self.predict(crops)
+        _, rects = ctx.gather_crops(n_rows, CROP, out=crops)
+        nonempty = (rects[:, 2] > rects[:, 0]) & (rects[:, 3] > rects[:, 1])
+        if empty == "raise" and not bool(nonempty.all().item()):
+            bad = int((~nonempty).nonzero()[0].item())
+            raise ValueError("segment %d has an empty segment_image (bbox outside the frame)" % bad)
+        return self.predict(crops) & nonempty

@@ -148,7 +148,9 @@ def test_gpu_batched_scores_and_device_crops():
         assert n > 20
         crops = torch.empty((n, 24, 24, 3), dtype=torch.uint8, device="cuda")
         ctx.gather_crops(n, 24, out=crops)
-        keep_dev = clf.classify_submit(ctx, n).cpu().numpy()
+        with pytest.raises(ValueError):                          # birds at the top / left edge: empty segment images,
+            clf.classify_submit(ctx, n)                          # the reference's ToPILImage raises there too
+        keep_dev = clf.classify_submit(ctx, n, empty="drop").cpu().numpy()
     # host crops with the reference's slicing; interior segments up to 24 px give the same 24x24 tile
     props = swb.props_from_rows(rows)
     same = []
@@ -175,3 +177,61 @@ def test_gpu_batched_scores_and_device_crops():
     kept_idx = np.zeros(len(segs), dtype=bool)
     kept_idx[[segs.index(s) for s in kept]] = True
     assert np.array_equal(kept_idx[decided], keep_dev[same][decided])
+
+
+@pytest.mark.gpu
+def test_gpu_classify_submit_keeps_what_the_per_segment_reference_keeps():
+    """Large birds (> 24 px: resized by transforms.Resize in the reference) and birds cut by the frame edge go
+    through the device path with the same tiles, hence the same decisions, as the per-segment oracle."""
+    import swiftwatcher_b200 as swb
+    from swiftwatcher_b200.segment_classification import SegmentClassifier
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sd = rc.random_state_dict(5)
+    clf = SegmentClassifier(sd, device="cuda:0", batch_size=64)
+    ref = rc.RefSegmentClassifier({k: v.cuda() for k, v in sd.items()}, "cuda:0")
+    rng = np.random.default_rng(7)
+    H, W = 240, 400
+    base = rng.integers(100, 256, (H, W, 3), dtype=np.uint8)
+    frames = np.repeat(base[None], 7, axis=0)
+    boxes = []
+    for _ in range(60):
+        h, w = int(rng.integers(4, 70)), int(rng.integers(4, 70))
+        y, x = int(rng.integers(0, H - h + 1)), int(rng.integers(0, W - w + 1))
+        if any(y < b[0] + b[2] + 2 and b[0] < y + h + 2 and x < b[1] + b[3] + 2 and b[1] < x + w + 2 for b in boxes):
+            continue
+        boxes.append((y, x, h, w))
+        frames[5:, y:y + h, x:x + w] = rng.integers(0, 60, (h, w, 3), dtype=np.uint8)
+    region = [(0, 0), (W, H)]
+    dev = torch.from_numpy(frames).cuda()
+    with swb.FilterContext(frames.shape[1:], region, label_mode="i32", max_frames=7) as ctx:
+        ctx.submit(dev, n_halo=0)
+        rows, counts = ctx.collect()
+        keep_dev = clf.classify_submit(ctx, len(rows), empty="drop").cpu().numpy()
+    props = swb.props_from_rows(rows)
+    big = decided = 0
+    for i, (p, r) in enumerate(zip(props, rows)):
+        im = rp.extract_segment_images([p], frames[r["frame"]], (24, 24), region)[0]
+        if im.size == 0:
+            assert not keep_dev[i]
+            continue
+        score = ref.score(np.ascontiguousarray(im))[0]
+        if abs(float(score[1] - score[0])) > 10 * TOL:
+            assert bool(keep_dev[i]) == bool(score[1] > score[0]), (i, im.shape)
+            decided += 1
+            big += im.shape[:2] != (24, 24)
+    assert decided > 20 and big > 10
+
+
+def test_pil_bilinear_restatement_equals_pillow():
+    """oracle.reference_classifier.pil_bilinear_resize (Pillow's Resample.c restated; the arithmetic the device
+    crop kernel implements) against transforms.Resize((24, 24)) of the installed Pillow, bit for bit."""
+    from torchvision import transforms
+    rng = np.random.default_rng(3)
+    shapes = [(24, 24), (24, 30), (15, 16), (40, 30), (1, 1), (1, 50), (50, 1), (24, 1), (100, 237), (333, 24),
+              (25, 25), (23, 24), (47, 49), (7, 640), (500, 3), (301, 3), (300, 3), (1000, 9), (1000, 10), (101, 1)]
+    for h, w in shapes:
+        for ch in (3, 1):
+            a = rng.integers(0, 256, (h, w, ch) if ch == 3 else (h, w), dtype=np.uint8)
+            want = np.asarray(transforms.Resize((24, 24))(transforms.ToPILImage()(a)))
+            assert np.array_equal(rc.pil_bilinear_resize(a, (24, 24)), want), (h, w, ch)

@@ -140,7 +140,7 @@ def test_ring_feeds_the_queue_in_place_and_batches_are_submitted_ahead(tmp_path)
     queue = ds.FrameQueue(queue_size=B)
     queue.attach_ring(ring)
     ds.Frame.src_video = "ring"
-    seen, ahead_hits, exported = 0, 0, 0
+    seen, ahead_hits, exported, empty_raised = 0, 0, 0, False
     try:
         while queue.frames_processed < total:
             fr, numbers, stamps = ring.get_n_frames(B)
@@ -166,10 +166,18 @@ def test_ring_feeds_the_queue_in_place_and_batches_are_submitted_ahead(tmp_path)
                     for s, p, c in zip(f.segments, rec["props"], rec["crops"]):
                         assert (s.label, s.area, s.bbox, s.centroid) == (p.label, p.area, p.bbox, tuple(p.centroid))
                         assert np.array_equal(s.segment_image, c)
-                    if f.frame_number == 30:
+                    sizes = [s.segment_image.size for s in f.segments]
+                    if not exported and sizes and min(sizes) > 0:
                         f.export_segments((24, 24), region, tmp_path / "segments")
                         exported = len(list((tmp_path / "segments").glob("*.png")))
                         assert exported == f.get_num_segments() > 0
+                    elif sizes and min(sizes) == 0 and not empty_raised:
+                        # a bbox within 12 px of the frame's top / left edge slices to an empty image
+                        # (image_filtering.py:363-365) and cv2.imwrite refuses it: the reference's behaviour
+                        import cv2
+                        with pytest.raises(cv2.error):
+                            f.export_segments((24, 24), region, tmp_path / "empty")
+                        empty_raised = True
     finally:
         queue.close()
         ring.close()

@@ -521,28 +521,83 @@ def test_capacity_errors_are_loud():
         assert e.value.code == -3
 
 
-def test_gather_crops_matches_reference_slicing():
-    import torch
-    frames = synth.synth_video(30, 0, 0, 8, 120, 200, 25)
-    dev = torch.from_numpy(frames).cuda()
-    region = [(20, 10), (180, 110)]
-    with swb.FilterContext(frames.shape[1:], region, label_mode="i32", max_frames=8) as ctx:
-        ctx.submit(dev, n_halo=0)
-        rows, counts = ctx.collect()
-        crops = ctx.gather_crops(len(rows), 24)
-    checked = 0
-    for r, crop in zip(rows, crops):
-        bh, bw = r["bbox"][2] - r["bbox"][0], r["bbox"][3] - r["bbox"][1]
-        if bh > 24 or bw > 24:
-            continue
-        seg = rp.RegionProperties(int(r["label"]), int(r["area"]), tuple(r["bbox"]), (0, 0))
+def _blob_video(H, W, blobs, seed, T=7):
+    """Static random texture; from frame 5 on, dark textured rectangles (y, x, h, w) appear."""
+    rng = np.random.default_rng(seed)
+    base = rng.integers(100, 256, (H, W, 3), dtype=np.uint8)
+    frames = np.repeat(base[None], T, axis=0)
+    for (y, x, h, w) in blobs:
+        frames[5:, y:y + h, x:x + w] = rng.integers(0, 60, (h, w, 3), dtype=np.uint8)
+    return frames
+
+
+def _reference_tile(image):
+    """What the classifier's first two transforms make of a segment image (segment_classification.py:19-20)."""
+    from torchvision import transforms
+    return np.asarray(transforms.Resize((24, 24))(transforms.ToPILImage()(np.ascontiguousarray(image))))
+
+
+def _check_device_crops(frames, region, rows, tiles, rects):
+    H, W = frames.shape[1:3]
+    kinds = {"exact": 0, "resized": 0, "empty": 0}
+    for r, tile, rect in zip(rows, tiles, rects):
+        seg = rp.RegionProperties(int(r["label"]), int(r["area"]), tuple(int(v) for v in r["bbox"]), (0, 0))
+        want = rp.extract_segment_images([seg], frames[r["frame"]], (24, 24), region)[0]     # the reference's slice
         b = rp.expand_bbox(seg.bbox, (24, 24), region)
-        if b[0] < 0 or b[1] < 0 or b[2] > 120 or b[3] > 200:
-            continue        # the reference wraps/truncates here; the tile is zero-padded instead
-        want = rp.extract_segment_images([seg], frames[r["frame"]], (24, 24), region)[0]
-        assert np.array_equal(crop, want)
-        checked += 1
-    assert checked > 10
+        ys, xs = slice(b[0], b[2]).indices(H), slice(b[1], b[3]).indices(W)
+        y1, x1 = max(ys[1], ys[0]), max(xs[1], xs[0])
+        assert tuple(rect) == (ys[0], xs[0], y1, x1), (tuple(rect), b)
+        assert want.shape[:2] == (y1 - ys[0], x1 - xs[0])
+        if want.size == 0:
+            assert not tile.any()
+            kinds["empty"] += 1
+        else:
+            assert np.array_equal(tile.squeeze(), _reference_tile(want)), (r["bbox"], want.shape)
+            kinds["exact" if want.shape[:2] == (24, 24) else "resized"] += 1
+    return kinds
+
+
+def test_device_crops_are_the_reference_segment_images_resized():
+    """a9, on the device and exact: every row of the table, whatever its size and position — interior birds
+    (24x24 copy), birds larger than 24 px (kept whole by image_filtering.py:349-358, resized by
+    segment_classification.py:20), bboxes truncated by the right / bottom frame edge, bboxes within 12 px of
+    the top / left edge (empty image: numpy's negative start wraps around)."""
+    import torch
+    H, W = 200, 320
+    blobs = [(60, 50, 9, 14), (100, 100, 40, 30), (20, 180, 30, 100), (150, 20, 45, 25), (3, 3, 8, 8),
+             (2, 120, 10, 10), (90, 1, 10, 10), (190, 300, 10, 20), (100, 311, 30, 9), (185, 150, 15, 26),
+             (130, 200, 25, 24), (60, 250, 24, 24), (30, 30, 23, 30)]
+    frames = _blob_video(H, W, blobs, 40)
+    dev = torch.from_numpy(frames).cuda()
+    for region in ([(0, 0), (W, H)], [(16, 1), (320, 199)]):
+        for mode in ("i32", "u8"):
+            with swb.FilterContext(frames.shape[1:], region, label_mode=mode, max_frames=7) as ctx:
+                ctx.submit(dev, n_halo=0)
+                rows, counts = ctx.collect()
+                tiles, rects = ctx.gather_crops(len(rows), 24)
+                t_dev = torch.empty((len(rows), 24, 24, 3), dtype=torch.uint8, device="cuda")
+                _, r_dev = ctx.gather_crops(len(rows), 24, out=t_dev)
+            assert np.array_equal(t_dev.cpu().numpy(), tiles) and np.array_equal(r_dev.cpu().numpy(), rects)
+            kinds = _check_device_crops(frames, region, rows, tiles, rects)
+            assert kinds["exact"] >= 2 and kinds["resized"] >= 8 and (kinds["empty"] >= 2 or region[0] != (0, 0))
+
+
+def test_device_crops_tall_thin_and_tiny_frames():
+    """Pillow resamples an image more than 100 times taller than wide vertically first; numpy's wrap-around
+    of a negative slice start yields a NON-empty image when the frame is narrower than the crop."""
+    import torch
+    for (H, W) in ((300, 2), (260, 1), (30, 20), (5, 300)):
+        frames = np.full((7, H, W), 200, np.uint8)
+        frames[5:] = np.random.default_rng(H).integers(0, 100, (2, H, W), dtype=np.uint8)
+        region = [(0, 0), (W, H)]
+        dev = torch.from_numpy(frames).cuda()
+        with swb.FilterContext(frames.shape[1:], region, label_mode="i32", max_frames=7) as ctx:
+            ctx.submit(dev, n_halo=0)
+            rows, _ = ctx.collect()
+            tiles, rects = ctx.gather_crops(len(rows), 24)
+        assert len(rows) >= 2
+        kinds = _check_device_crops(frames, region, rows, tiles, rects)
+        assert kinds["resized"] + kinds["empty"] == len(rows)
 
 
 # ---------------------------------------------------------------------------------
