@@ -156,7 +156,8 @@ int swb_collect_begin(swb_ctx* ctx, swb_segment* rows, int64_t cap, uint8_t* mas
 int swb_collect_end(swb_ctx* ctx, int64_t* n_rows, int32_t* per_frame_counts);
 /* Tuning knobs that never change a result: "host_pipeline" (0/1: cut large host submits into
  * sub-batches that are filtered while later frames are still being copied; default 1),
- * "sub_batch_min_px" (least work per sub-batch in pixels; default 64 Mi). */
+ * "sub_batch_min_px" (least work per sub-batch in pixels; default 64 Mi), "temporal_subchunk" (frames per
+ * temporal sub-chunk of the filtering kernel, rounded up to a multiple of 6; 0 = chosen from the grid size). */
 int swb_set_option(swb_ctx* ctx, const char* name, int64_t value);
 /* Frames per temporal sub-chunk the filtering kernel used for the last submit (each sub-chunk
  * re-reads its median_n - 1 predecessors); lets tests aim at the sub-chunk boundaries. */

@@ -42,6 +42,7 @@ struct swb_ctx {
     cudaEvent_t ev_h2d[MAX_SUB] = {};
     bool pipeline = true;
     long long sub_min_px = 64ll << 20;   // least work (pixels) per sub-batch
+    int forced_ts = 0;                   // option "temporal_subchunk": frames per temporal sub-chunk of K1 (0 = automatic)
     // device buffers
     uint8_t* in_buf = nullptr;      // host-mode staging: [N-1 + max_frames][h][in_pitch]
     size_t in_buf_bytes = 0;
@@ -487,7 +488,7 @@ int swb_submit(swb_ctx* ctx, const uint8_t* frames, int32_t n_frames, int32_t n_
                                      reinterpret_cast<uint32_t*>(ctx->raw_bits), gm.wpr_raw, 3));
             launches += 2;
         } else {
-            CU(ctx, launch_fg_bits(s, src, C, N, n_frames, g, c.threshold, ctx->raw_bits, aligned, &launches, c.gpu_share));
+            CU(ctx, launch_fg_bits(s, src, C, N, n_frames, g, c.threshold, ctx->raw_bits, aligned, &launches, c.gpu_share, ctx->forced_ts));
         }
         if (ctx->timing) CU(ctx, cudaEventRecord(ctx->ev[1], s));
         CU(ctx, launch_morph_mask(s, reinterpret_cast<const uint32_t*>(ctx->raw_bits), n_frames, gm, ctx->morph,
@@ -537,7 +538,7 @@ int swb_submit(swb_ctx* ctx, const uint8_t* frames, int32_t n_frames, int32_t n_
             chain.frame_base = f0;
             chain.segoff_base = (b > 0) ? ctx->ccl.segoff + f0 : nullptr;   // left there by sub-batch b-1
             ccl_prepare(sw, nb, g, cb, true);
-            CU(ctx, launch_fg_bits(sw, sb, C, N, nb, g, c.threshold, raw_b, aligned, &launches, c.gpu_share));
+            CU(ctx, launch_fg_bits(sw, sb, C, N, nb, g, c.threshold, raw_b, aligned, &launches, c.gpu_share, ctx->forced_ts));
             CU(ctx, launch_morph_mask(sw, reinterpret_cast<const uint32_t*>(raw_b), nb, g, ctx->morph, fbits_b, mask_b,
                                       &launches));
             CU(ctx, launch_ccl(sw, fbits_b, nb, g, cb, labels_b, ctx->label_elem, &launches, nullptr, 0, &chain, true));
@@ -669,6 +670,9 @@ int swb_set_option(swb_ctx* ctx, const char* name, int64_t value) {
     else if (!strcmp(name, "sub_batch_min_px")) {
         if (value <= 0) return fail(ctx, SWB_ERR_INVALID, "sub_batch_min_px must be positive");
         ctx->sub_min_px = value;
+    } else if (!strcmp(name, "temporal_subchunk")) {
+        if (value < 0 || value > 32768) return fail(ctx, SWB_ERR_INVALID, "temporal_subchunk must be in 0..32768");
+        ctx->forced_ts = (int)value;
     } else return fail(ctx, SWB_ERR_INVALID, "unknown option '%s'", name);
     return SWB_OK;
 }

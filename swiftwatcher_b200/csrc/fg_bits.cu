@@ -494,7 +494,9 @@ int pick_ts_impl(int T, int n_col_blocks, int median_n, int gpu_share) {
     if (ts < 1) ts = 1;
     return ts;
 }
+thread_local int g_forced_ts = 0;  // swb_set_option("temporal_subchunk"): set around a launch by launch_fg_bits
 int pick_ts(int T, int n_col_blocks, int median_n, int gpu_share) {
+    if (g_forced_ts > 0) return g_last_ts = std::min(T, (g_forced_ts + 5) / 6 * 6);
     return g_last_ts = pick_ts_impl(T, n_col_blocks, median_n, gpu_share);
 }
 
@@ -957,8 +959,9 @@ int last_temporal_subchunk() { return g_last_ts; }
 
 cudaError_t launch_fg_bits(cudaStream_t s, const FrameSrc& src, int channels, int median_n, int T,
                            const Geom& g, int thresh, uint16_t* raw_bits, bool aligned, int* n_launches,
-                           int gpu_share) {
+                           int gpu_share, int forced_ts) {
     if (n_launches) *n_launches += 1;
+    g_forced_ts = forced_ts;
     switch (median_n) {
         case 1: return launch_n<1>(s, src, channels, T, g, thresh, raw_bits, aligned, gpu_share);
         case 3: return launch_n<3>(s, src, channels, T, g, thresh, raw_bits, aligned, gpu_share);

@@ -50,7 +50,7 @@ struct MorphCfg {
 // ---- launchers (each returns the cudaError_t of the launch) ---------------
 cudaError_t launch_fg_bits(cudaStream_t s, const FrameSrc& src, int channels, int median_n,
                            int T, const Geom& g, int thresh, uint16_t* raw_bits, bool aligned,
-                           int* n_launches, int gpu_share = 1);
+                           int* n_launches, int gpu_share = 1, int forced_ts = 0);
 int last_temporal_subchunk();   // frames per temporal sub-chunk of this thread's last launch_fg_bits
 cudaError_t launch_morph_mask(cudaStream_t s, const uint32_t* raw_bits, int T, const Geom& g,
                               const MorphCfg& m, uint32_t* fbits, uint8_t* mask, int* n_launches);

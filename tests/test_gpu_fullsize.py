@@ -71,7 +71,7 @@ def compare_frame(rec, mask, labels, rows_t, t):
     assert np.array_equal(got[:, 6:], exp[:, 6:])                            # integer sums: in fact bit-exact
 
 
-def bench_geometry(H, W, n, se, do_close, T, birds, repeats=20, pieces=8):
+def bench_geometry(H, W, n, se, do_close, T, birds, repeats=20, pieces=8, subchunk=0):
     import torch
     halo = n - 1
     dev = torch.empty((halo + T, H, W, 3), dtype=torch.uint8, device="cuda")
@@ -79,6 +79,8 @@ def bench_geometry(H, W, n, se, do_close, T, birds, repeats=20, pieces=8):
     par = rp.PathParams([(0, 0), (W, H)], n, 15, se, True, do_close, "i32")
     with swb.FilterContext((H, W, 3), None, median_n=n, morph_size=se, do_close=do_close, label_mode="i32",
                            max_frames=T, max_segments=T * 4096) as ctx:
+        if subchunk:
+            ctx.set_option("temporal_subchunk", subchunk)
         ctx.submit(dev, n_halo=halo)
         rows, counts = ctx.collect()
         ts = ctx.last_subchunk()
@@ -140,7 +142,14 @@ def test_bench_geometry_1080p_n5_open3_t1024():
 
 def test_bench_geometry_4k_n9_openclose5_t256():
     n, ts = bench_geometry(2160, 3840, 9, 5, True, 256, 600)
-    assert n >= 12 and ts < 256
+    assert n >= 12 and ts == 256          # 4050 column blocks fill the GPU: no temporal split at this size
+
+
+def test_bench_geometry_4k_n9_with_temporal_subchunks():
+    """The same 4K submit with the filtering kernel forced to cut it into sub-chunks of 66 frames (what a
+    smaller grid would get): boundaries at 66, 132, 198 against the oracle, and nothing else may change."""
+    n, ts = bench_geometry(2160, 3840, 9, 5, True, 256, 600, repeats=3, pieces=2, subchunk=66)
+    assert n >= 12 and ts == 66
 
 
 def test_bench_geometry_dense_swarm_t512():
