@@ -887,6 +887,378 @@ k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t on
     }
 }
 
+// ------------------------------------------------------------------------------------
+// v3, N = 9 only: the same three-outputs-per-iteration median (see "shared-core sliding medians"),
+// with the loop's non-arithmetic instructions cut down.  ncu on v2 at 4K: 19.6 instructions per pixel
+// and frame, of which ~13 are arithmetic; the kernel is bound by instruction issue and the ALU pipe,
+// not by HBM.  What changed:
+//  * a pipeline stage holds the THREE frames of one loop iteration (one mbarrier wait, one release and
+//    one producer round per iteration instead of three), three stages deep; the stage index is a
+//    run-time offset, so the loop is unrolled by two (triple roles swap) instead of by the stage count;
+//  * the three frames are converted back to back: the gray weights are materialised once per iteration;
+//  * the steady-state loop carries no carried-history code: the iterations that see one of the
+//    submit's last eight frames run a second copy of the body;
+//  * output bytes come from one multiply and one shift (the byte is stored with STG.U8);
+//  * column blocks are balanced over the last wave: the blocks that would run alone at the end of the
+//    grid are cut into short temporal sub-chunks (see launch_n9).
+// ------------------------------------------------------------------------------------
+template <int V>
+struct IntC { static constexpr int value = V; };
+
+template <int C, int OCC>
+__global__ void __launch_bounds__(V2_THREADS, OCC)
+k_fg_n9(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t one, uint8_t* __restrict__ raw_bits,
+        const __grid_constant__ CUtensorMap tmap, int tile_rows, int n_long_blocks, int ts_tail) {
+    constexpr int N = 9, L = 4, PPT = 8;
+    constexpr int TB = PPT * C;                   // bytes per thread per frame
+    constexpr int FRAME_BYTES = CONSUMERS * TB;
+    constexpr int STAGE_BYTES = 3 * FRAME_BYTES;  // one loop iteration
+    constexpr int S = 3;
+    constexpr int NWORDS = TB / 4;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + S * STAGE_BYTES);
+    uint64_t* empty = full + S;
+    uint4* rw_ring = reinterpret_cast<uint4*>(smem + S * STAGE_BYTES + 2 * S * 8 + 16) + threadIdx.x;   // [3][CONSUMERS]
+
+    const int tid = threadIdx.x;
+    const int gpr = wa / PPT;
+    const int G = h * gpr;
+    const int cta_groups = tile_rows > 0 ? tile_rows * gpr : CONSUMERS;
+    // block -> (column block, temporal sub-chunk).  The first n_long_blocks column blocks walk sub-chunks of
+    // Ts frames; the remaining ones (the partial last wave of the grid) are cut into sub-chunks of ts_tail.
+    int cb, t_start, t_len;
+    {
+        const int per_long = (T + Ts - 1) / Ts;
+        const int long_ctas = n_long_blocks * per_long;
+        if ((int)blockIdx.x < long_ctas) {
+            cb = blockIdx.x / per_long;
+            t_start = (blockIdx.x - cb * per_long) * Ts;
+            t_len = Ts;
+        } else {
+            const int per_tail = (T + ts_tail - 1) / ts_tail;
+            const int i = blockIdx.x - long_ctas;
+            cb = n_long_blocks + i / per_tail;
+            t_start = (i - (i / per_tail) * per_tail) * ts_tail;
+            t_len = ts_tail;
+        }
+    }
+    const int g0 = cb * cta_groups;
+    const int t_end = min(T, t_start + t_len);
+    const int n_out = t_end - t_start;
+    if (n_out <= 0) return;                       // block-uniform
+    const int n_iter = (n_out + 2) / 3;
+    const int n_groups = n_iter + 3;              // group j = pipeline frames 3j-1, 3j, 3j+1 (group 0: frames 0, 1)
+    const int j_first = t_start - (N - 1);
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], CONSUMERS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (tid >= CONSUMERS) {
+        // ===== producer warp: one round per loop iteration =====
+        const int lane = tid - CONSUMERS;
+        const int ngroups = min(cta_groups, G - g0);
+        const uint32_t bytes = (uint32_t)(ngroups * TB);
+        const bool contiguous = (src.pitch == (long long)gpr * TB);
+        if ((contiguous || tile_rows > 0) && lane != 0) return;
+        const int r0 = g0 / gpr, c0 = g0 - r0 * gpr;
+        const int len0 = min(gpr - c0, ngroups);
+        const int nseg = contiguous ? 1 : 1 + (ngroups - len0 + gpr - 1) / gpr;
+        for (int jg = 0; jg < n_groups; ++jg) {
+            const int st = jg % S;
+            if (jg >= S) mbar_wait(&empty[st], (uint32_t)((jg / S - 1) & 1));
+            // bytes this round will deliver
+            uint32_t expect = 0;
+            for (int f = (jg == 0 ? 1 : 0); f < 3; ++f) {
+                const int p = 3 * jg - 1 + f;
+                const int j = min(j_first + p, T - 1);
+                if (j < 0 && src.hist_valid) expect += (uint32_t)(ngroups * PPT);
+                else expect += tile_rows > 0 ? (uint32_t)(tile_rows * gpr * TB) : bytes;
+            }
+            if (lane == 0) mbar_arrive_expect_tx(&full[st], expect);
+            __syncwarp();                          // the expectation is posted before any copy can complete
+            for (int f = (jg == 0 ? 1 : 0); f < 3; ++f) {
+                const int p = 3 * jg - 1 + f;
+                int j = min(j_first + p, T - 1);
+                uint8_t* dst = smem + st * STAGE_BYTES + f * FRAME_BYTES;
+                if (j < 0 && src.hist_valid) {    // carried history: compact gray frames
+                    if (lane == 0) {
+                        const uint8_t* hf = src.hist + (long long)(j + (N - 1)) * h * wa;
+                        bulk_g2s(dst, hf + (long long)g0 * PPT, (uint32_t)(ngroups * PPT), &full[st]);
+                    }
+                    continue;
+                }
+                if (j < -src.n_inline_halo) j = -src.n_inline_halo;   // replicate the earliest frame
+                const uint8_t* fr = src.cur + (long long)j * src.frame_stride;
+                if (tile_rows > 0) {
+                    tma_load_box(dst, &tmap, cb * tile_rows, j + src.n_inline_halo, &full[st]);
+                } else if (contiguous) {
+                    bulk_g2s(dst, fr + (long long)g0 * TB, bytes, &full[st]);
+                } else {
+                    for (int i = lane; i < nseg; i += 32) {
+                        const int off = (i == 0) ? 0 : len0 + (i - 1) * gpr;
+                        const int n = (i == 0) ? len0 : min(gpr, ngroups - off);
+                        bulk_g2s(dst + off * TB, fr + (long long)(r0 + i) * src.pitch + (long long)(i == 0 ? c0 : 0) * TB,
+                                 (uint32_t)(n * TB), &full[st]);
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== consumer warps =====
+    const int g = g0 + tid;
+    const bool active = g < G && tid < cta_groups;
+    const int row = active ? g / gpr : 0;
+    const int col = active ? g - row * gpr : 0;
+    const uint32_t neg_th = ((uint32_t)(-thresh) & 0xFFFFu) * 0x00010001u;
+    FmaAdd fa;
+    fa.one = one;
+    fa.mone = 0u - one;
+    const uint32_t k1001 = one * 0x1001u;
+    uint8_t* out = raw_bits + ((long long)t_start * h + row) * gpr + col;    // one byte per thread and frame
+    const uint32_t out_step = (uint32_t)h * (uint32_t)gpr;
+    const bool lane0 = (tid & 31) == 0;
+    const int hist_to = (T - 1) - j_first;
+    const int hist_from = (src.hist_out != nullptr && t_end == T) ? hist_to - (N - 2) : 0x7FFFFFFF;
+    const bool hist_src = (C == 3) && src.hist_valid && j_first < 0;         // some warm-up frames are carried gray frames
+
+    // pipeline frame p (slot f of the stage at `sp`) as packed gray lanes
+    auto take = [&](const uint8_t* sp, int f, int p, uint32_t (&dst)[L], bool maybe_hist) {
+        if (maybe_hist && hist_src && j_first + p < 0) {                    // block-uniform
+            uint32_t gw[L / 2];
+            const uint32_t* sg = reinterpret_cast<const uint32_t*>(sp + f * FRAME_BYTES + tid * PPT);
+#pragma unroll
+            for (int i = 0; i < L / 2; ++i) gw[i] = sg[i];
+            gray_to_lanes<L>(gw, dst);
+        } else {
+            uint32_t w[NWORDS];
+            const uint2* sp2 = reinterpret_cast<const uint2*>(sp + f * FRAME_BYTES + tid * TB);
+#pragma unroll
+            for (int i = 0; i < TB / 8; ++i) {
+                const uint2 v = sp2[i];
+                w[2 * i] = v.x; w[2 * i + 1] = v.y;
+            }
+            if constexpr (C == 3) bgr_to_lanes_dp<L>(w, dst);
+            else gray_to_lanes<L>(w, dst);
+        }
+    };
+    auto keep_for_next = [&](int p, const uint32_t (&v)[L]) {
+        if (p >= hist_from && p <= hist_to && active) {
+            uint32_t hw[L / 2];
+            lanes_to_gray<L>(v, hw);
+            uint32_t* hp = reinterpret_cast<uint32_t*>(
+                src.hist_out + (((long long)(p - hist_from) * h + row) * gpr + col) * PPT);
+#pragma unroll
+            for (int i = 0; i < L / 2; ++i) hp[i] = hw[i];
+        }
+    };
+    auto fg_flag = [&](uint32_t x, uint32_t med) -> uint32_t {
+        return __viaddmin_s16x2_relu(__vabsdiffu4(x, med), neg_th, 0x00010001u);
+    };
+    // acc = sum over lanes q of flag << q: bits 0..3 = pixels 0..3, bits 16..19 = pixels 4..7
+    // `ok`: this thread owns pixels (and, in the last iteration of a sub-chunk, the output frame exists);
+    // a predicated store, no branch
+    auto emit_acc = [&](uint8_t* o, uint32_t acc, bool ok) {
+        uint32_t y;
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(y) : "r"(acc), "r"(k1001), "r"(0u));   // acc | acc << 12 (disjoint bits)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.global.u8 [%0], %1;\n\t}" ::"l"(o),
+                     "r"(y >> 12), "r"((uint32_t)ok)
+                     : "memory");
+    };
+    // mbarriers by shared-window address (computed once: the generic -> shared conversion reads a special register)
+    const uint32_t full_a = smem_u32(full), empty_a = smem_u32(empty);
+    auto wait_full = [&](int st, uint32_t parity) {
+        const uint32_t addr = full_a + 8u * st;
+        uint32_t done = 0;
+        int spins = 0;
+        while (true) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(addr), "r"(parity)
+                : "memory");
+            if (done) break;
+            if (++spins > (1 << 26)) __trap();   // never hang the GPU on a pipeline bug
+        }
+    };
+    auto release = [&](int st, const uint32_t (&a)[L], const uint32_t (&b)[L], const uint32_t (&c)[L]) {
+        // only after the loaded words have been consumed (the lanes depend on every LDS)
+        asm volatile("" ::"r"(a[0]), "r"(a[L - 1]), "r"(b[0]), "r"(b[L - 1]), "r"(c[0]), "r"(c[L - 1]) : "memory");
+        __syncwarp();
+        if (lane0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_a + 8u * st) : "memory");
+    };
+
+    const uint8_t* stage0 = smem;
+    uint32_t st[2][3][L];         // sorted triples: st[m & 1] = A, st[(m + 1) & 1] = B
+    {
+        // ---- prologue: groups 0 (frames 0, 1), 1 (frames 2..4), 2 (frames 5..7)
+        const bool short_tail = hist_from < N - 1;
+        uint32_t a[L], b[L], c[L];
+        wait_full(0, 0u);
+        take(stage0, 1, 0, a, true);
+        take(stage0, 2, 1, b, true);
+        release(0, a, b, b);
+        if (short_tail) { keep_for_next(0, a); keep_for_next(1, b); }
+        rw_ring[0] = make_uint4(a[0] | (b[0] << 8), a[1] | (b[1] << 8), a[2] | (b[2] << 8), a[3] | (b[3] << 8));
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const uint8_t* sp = stage0 + (1 + i) * STAGE_BYTES;
+            wait_full(1 + i, 0u);
+            take(sp, 0, 2 + 3 * i, a, true);
+            take(sp, 1, 3 + 3 * i, b, true);
+            take(sp, 2, 4 + 3 * i, c, true);
+            release(1 + i, a, b, c);
+            if (short_tail) { keep_for_next(2 + 3 * i, a); keep_for_next(3 + 3 * i, b); keep_for_next(4 + 3 * i, c); }
+#pragma unroll
+            for (int q = 0; q < L; ++q) {
+                const Sorted3 s3 = sort3_lanes(a[q], b[q], c[q], fa);
+                st[i][0][q] = s3.lo; st[i][1][q] = s3.mid; st[i][2][q] = s3.hi;
+            }
+            rw_ring[(1 + i) * CONSUMERS] =
+                make_uint4(b[0] | (c[0] << 8), b[1] | (c[1] << 8), b[2] | (c[2] << 8), b[3] | (c[3] << 8));
+        }
+    }
+
+    // iteration m: outputs t_start + 3m .. + 2 from group m + 3 (stage (m + 3) % 3 = m % 3), ring slot m % 3
+    uint8_t* optr = out;          // output byte of frame t_start + 3m
+    int sidx = 0;                 // m % 3: stage and ring slot
+    uint32_t par = 1u;            // parity of round (m + 3) / 3
+    auto iterate = [&](auto UC, auto HC, int m) {
+        constexpr int ia = decltype(UC)::value, ib = ia ^ 1;
+        constexpr bool HIST = decltype(HC)::value != 0;
+        const uint8_t* sp = stage0 + sidx * STAGE_BYTES;
+        uint32_t x0[L], x1[L], x2[L];
+        wait_full(sidx, par);
+        take(sp, 0, 3 * m + 8, x0, false);
+        take(sp, 1, 3 * m + 9, x1, false);
+        take(sp, 2, 3 * m + 10, x2, false);
+        release(sidx, x0, x1, x2);
+        if constexpr (HIST) {
+            keep_for_next(3 * m + 8, x0);
+            keep_for_next(3 * m + 9, x1);
+            keep_for_next(3 * m + 10, x2);
+        }
+        uint4* rwp = rw_ring + sidx * CONSUMERS;
+        const uint4 e4 = *rwp;
+        const uint32_t ep[L] = {e4.x, e4.y, e4.z, e4.w};
+        uint32_t np[L];
+        uint32_t acc0 = 0u, acc1 = 0u, acc2 = 0u;
+#pragma unroll
+        for (int q = 0; q < L; ++q) {
+            // middle four of A U B
+            const uint32_t pp = vmax2(st[ia][0][q], st[ib][0][q]);
+            const uint32_t qq = vmin2(st[ia][2][q], st[ib][2][q]);
+            const uint32_t uu = vmin2(st[ia][1][q], st[ib][1][q]);
+            const uint32_t vv = fa.sub(fa.add(st[ia][1][q], st[ib][1][q]), uu);
+            const uint32_t m2 = vmin2(pp, uu), m5 = vmax2(qq, vv);
+            const uint32_t gg = vmax2(pp, uu), hh = vmin2(qq, vv);
+            const uint32_t m3 = vmin2(gg, hh);
+            const uint32_t m4 = fa.sub(fa.add(gg, hh), m3);
+            const uint32_t e0 = ep[q] & 0x00FF00FFu, e1 = (ep[q] >> 8) & 0x00FF00FFu;
+            Sorted3 y = sort3_lanes(e0, e1, x0[q], fa);             // extras of window t
+            acc0 += fg_flag(x0[q], select4of7(m2, m3, m4, m5, y)) << q;
+            y = sort3_lanes(e1, x0[q], x1[q], fa);                  // extras of window t+1
+            acc1 += fg_flag(x1[q], select4of7(m2, m3, m4, m5, y)) << q;
+            y = sort3_lanes(x0[q], x1[q], x2[q], fa);               // extras of window t+2 = the new triple
+            acc2 += fg_flag(x2[q], select4of7(m2, m3, m4, m5, y)) << q;
+            st[ia][0][q] = y.lo; st[ia][1][q] = y.mid; st[ia][2][q] = y.hi;   // A is dead: the next B
+            np[q] = fa.add(x1[q], x2[q] << 8);
+        }
+        *rwp = make_uint4(np[0], np[1], np[2], np[3]);
+        if constexpr (HIST) {                                    // the last iteration of a sub-chunk may be partial
+            emit_acc(optr, acc0, active && 3 * m < n_out);
+            emit_acc(optr + out_step, acc1, active && 3 * m + 1 < n_out);
+            emit_acc(optr + 2 * out_step, acc2, active && 3 * m + 2 < n_out);
+        } else {
+            emit_acc(optr, acc0, active);
+            emit_acc(optr + out_step, acc1, active);
+            emit_acc(optr + 2 * out_step, acc2, active);
+        }
+        optr += 3 * out_step;
+        if (sidx == 2) { sidx = 0; par ^= 1u; } else { ++sidx; }
+    };
+    // iterations that cannot see one of the submit's last eight frames: 3m + 10 < hist_from
+    // ... and whose three output frames all exist
+    int m_plain = hist_from == 0x7FFFFFFF ? n_iter : min(n_iter, max(0, (hist_from - 10 + 2) / 3));
+    m_plain = min(m_plain, n_out / 3) & ~1;                                              // pairs: the triple roles swap every iteration
+    int m = 0;
+    for (; m < m_plain; m += 2) {
+        iterate(IntC<0>{}, IntC<0>{}, m);
+        iterate(IntC<1>{}, IntC<0>{}, m + 1);
+    }
+    for (; m < n_iter; m += 2) {
+        iterate(IntC<0>{}, IntC<1>{}, m);
+        if (m + 1 < n_iter) iterate(IntC<1>{}, IntC<1>{}, m + 1);
+    }
+}
+
+// Column blocks of the N = 9 kernel over the machine: with `slots` CTAs resident at a time, the blocks of
+// the last, partial wave would run on a mostly idle GPU for as long as a full wave takes.  Those blocks are
+// cut into temporal sub-chunks short enough to spread them over all slots.
+template <int C, int OCC>
+cudaError_t launch_n9(cudaStream_t s, const FrameSrc& src, int T, const Geom& g, int thresh, uint16_t* raw_bits,
+                      int gpu_share) {
+    constexpr int N = 9, L = 4, TB = 2 * L * C;
+    constexpr int SMEM = 3 * 3 * CONSUMERS * TB + 2 * 3 * 8 + 16 + 3 * CONSUMERS * 16;
+    static PerDeviceOnce once;
+    if (once.need()) {
+        cudaError_t e = cudaFuncSetAttribute(k_fg_n9<C, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) return e;
+    }
+    const int gpr = g.wa / (2 * L);
+    const int G = g.h * gpr;
+    int n_col_blocks = (G + CONSUMERS - 1) / CONSUMERS;
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    int tile_rows = 0;
+    const long long row_bytes = (long long)gpr * TB;
+    if (src.pitch != row_bytes && row_bytes <= 2048 && gpr <= CONSUMERS && tma_enabled()) {
+        const int rows = CONSUMERS / gpr;
+        const int frames = src.n_inline_halo + T;
+        const uint8_t* base = src.cur - (long long)src.n_inline_halo * src.frame_stride;
+        if (encode_roi_tensor(&tmap, base, row_bytes, g.h, frames, src.pitch, src.frame_stride, rows)) {
+            tile_rows = rows;
+            n_col_blocks = (g.h + rows - 1) / rows;
+        }
+    }
+    const int Ts = pick_ts(T, n_col_blocks, N, gpu_share);
+    const int per_long = (T + Ts - 1) / Ts;
+    // tail balancing (only when the context has the GPU to itself and nobody forced a sub-chunk length)
+    int n_long = n_col_blocks, ts_tail = Ts;
+    static const bool balance = [] { const char* e = getenv("SWB_K1_BALANCE"); return !(e && e[0] == '0'); }();
+    if (balance && gpu_share <= 1 && g_forced_ts == 0) {
+        const long long slots = 148ll * OCC;
+        const long long ctas = (long long)n_col_blocks * per_long;
+        const long long rem = ctas % slots;
+        if (ctas > slots && rem != 0 && rem * 4 < slots * 3 && Ts >= 48) {
+            const int tail_blocks = (int)(rem / per_long);       // whole column blocks of the partial wave
+            if (tail_blocks > 0) {
+                // enough pieces to occupy every slot about once, each at least 24 frames (warm-up: 8)
+                int pieces = (int)std::min<long long>((slots + tail_blocks - 1) / tail_blocks, (long long)(Ts / 24));
+                if (pieces > 1) {
+                    ts_tail = ((Ts + pieces - 1) / pieces + 5) / 6 * 6;
+                    n_long = n_col_blocks - tail_blocks;
+                }
+            }
+        }
+    }
+    const int per_tail = (T + ts_tail - 1) / ts_tail;
+    const long long grid = (long long)n_long * per_long + (long long)(n_col_blocks - n_long) * per_tail;
+    k_fg_n9<C, OCC><<<(unsigned)grid, V2_THREADS, SMEM, s>>>(src, T, Ts, g.h, g.wa, thresh, 1u,
+                                                            reinterpret_cast<uint8_t*>(raw_bits), tmap, tile_rows,
+                                                            n_long, ts_tail);
+    return cudaGetLastError();
+}
+
 template <int N, int C, int OCC>
 cudaError_t launch_v2_occ(cudaStream_t s, const FrameSrc& src, int T, const Geom& g, int thresh,
                           uint16_t* raw_bits, int gpu_share) {
@@ -931,6 +1303,9 @@ cudaError_t launch_v2(cudaStream_t s, const FrameSrc& src, int T, const Geom& g,
     if constexpr (N == 9) {
         // the N = 9 loop fits 72 registers: three CTAs (24 consumer warps) per SM
         static const bool occ2 = [] { const char* e = getenv("SWB_K1_N9_OCC"); return e && e[0] == '2'; }();
+        static const bool v2 = [] { const char* e = getenv("SWB_K1_N9_V2"); return e && e[0] == '1'; }();
+        if (!v2) return occ2 ? launch_n9<C, 2>(s, src, T, g, thresh, raw_bits, gpu_share)
+                             : launch_n9<C, 3>(s, src, T, g, thresh, raw_bits, gpu_share);
         if (!occ2) return launch_v2_occ<N, C, 3>(s, src, T, g, thresh, raw_bits, gpu_share);
     }
     return launch_v2_occ<N, C, 2>(s, src, T, g, thresh, raw_bits, gpu_share);
