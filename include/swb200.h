@@ -77,8 +77,11 @@ typedef struct swb_config {
  * image_filtering.py:220-307, data_structures.py:191-196): every submit is one batch of
  * n_frames <= 32 frames (the reference's queue holds 21) that is decomposed on its own — no
  * temporal history, n_halo is ignored, median_n is unused — then bilateralFilter(7, 15, 1),
- * threshold, opening and labelling as usual.  swb_submit synchronises in this mode (the
- * stopping test of the IALM iteration runs on the host). */
+ * threshold, opening and labelling as usual.  For the reference's batch of 21 frames the whole iteration
+ * loop runs on the device (a CUDA-graph WHILE node: eigenproblem, stopping test and all) and swb_submit is
+ * asynchronous as in the median mode; for other batch sizes the stopping test and the n x n eigenproblem
+ * run on the host and swb_submit BLOCKS until the decomposition has converged (it cannot be used on a
+ * stream that is being captured). */
 #define SWB_BG_MEDIAN 0
 #define SWB_BG_RPCA   1
 
@@ -156,7 +159,10 @@ int swb_collect_begin(swb_ctx* ctx, swb_segment* rows, int64_t cap, uint8_t* mas
 int swb_collect_end(swb_ctx* ctx, int64_t* n_rows, int32_t* per_frame_counts);
 /* Tuning knobs that never change a result: "host_pipeline" (0/1: cut large host submits into
  * sub-batches that are filtered while later frames are still being copied; default 1),
- * "sub_batch_min_px" (least work per sub-batch in pixels; default 64 Mi), "temporal_subchunk" (frames per
+ * "sub_batch_min_px" (least work per sub-batch in pixels; default 64 Mi), "label_overlap" (0/1: label a large
+ * device-resident submit in four pieces of frames on a second stream while the label writer of the previous piece
+ * runs; default 1), "label_overlap_min_px" (least label pixels per submit for that; default 128 Mi),
+ * "temporal_subchunk" (frames per
  * temporal sub-chunk of the filtering kernel, rounded up to a multiple of 6; 0 = chosen from the grid size). */
 int swb_set_option(swb_ctx* ctx, const char* name, int64_t value);
 /* Frames per temporal sub-chunk the filtering kernel used for the last submit (each sub-chunk
@@ -231,6 +237,10 @@ int swb_stage_rpca(int32_t device, const uint8_t* frames, int32_t n, int32_t h, 
  * sigma_space) for an 8-bit single-channel image, d <= 7. */
 int swb_stage_bilateral(int32_t device, const uint8_t* in, int32_t h, int32_t w, int32_t d,
                         double sigma_color, double sigma_space, uint8_t* out);
+/* SWB_BG_RPCA only: IALM iterations the last submit took (image_filtering.py:281-298), the Jacobi sweeps its
+ * eigenproblems needed in all, and whether the iteration loop ran on the device (1: a CUDA-graph WHILE node,
+ * the 21-frame batch of the reference; 0: the host loop, other batch sizes).  Waits for the submit. */
+int swb_rpca_stats(swb_ctx* ctx, int32_t* iterations, int32_t* jacobi_sweeps, int32_t* device_loop);
 /* SWB_BG_RPCA only: the "RPCA" images (clip(-E, 0, 255), uint8, ROI-sized) of frames
  * [t0, t0 + n) of the last submit. */
 int swb_get_rpca(swb_ctx* ctx, int32_t t0, int32_t n, uint8_t* dst, int32_t mem_kind);

@@ -77,6 +77,7 @@ SYMBOLS = {
     "swb_stage_regionprops": (C.c_int, [_I32, _P, _I32, _I32, _I32, _P, _I32, C.POINTER(_I32)]),
     "swb_stage_rpca": (C.c_int, [_I32, _P, _I32, _I32, _I32, _P, C.POINTER(_I32)]),
     "swb_stage_bilateral": (C.c_int, [_I32, _P, _I32, _I32, _I32, C.c_double, C.c_double, _P]),
+    "swb_rpca_stats": (C.c_int, [_P, C.POINTER(_I32), C.POINTER(_I32), C.POINTER(_I32)]),
     "swb_get_rpca": (C.c_int, [_P, _I32, _I32, _P, _I32]),
     "swb_tracker_create": (C.c_int, [_I32, _I32, C.POINTER(_P)]),
     "swb_tracker_destroy": (C.c_int, [_P]),

@@ -381,7 +381,11 @@ struct LocalSmem {
 
 // One tile (frame f, block rows tile * BY ...).  Returns false (block-uniform, nothing written)
 // when the tile has more than MAXRUNS runs.
-template <int BX, int MAXRUNS>
+// CAN_EXIT: the caller does nothing after the tile, so the warps that have no run to work on leave after the
+// run list is built (the later phases are one thread per run: with the usual few dozen runs per tile seven of
+// the eight warps would only walk from barrier to barrier) and the remaining phases synchronise on a named
+// barrier sized for the warps that stay.
+template <int BX, int MAXRUNS, bool CAN_EXIT>
 __device__ __forceinline__ bool ccl_local_tile(const uint32_t* __restrict__ fbits, const Geom& g, int* __restrict__ parent,
                                                Partial* __restrict__ parts, int* __restrict__ pcount, int cap_parts,
                                                int32_t* __restrict__ overflow, int f, int tile) {
@@ -465,6 +469,13 @@ __device__ __forceinline__ bool ccl_local_tile(const uint32_t* __restrict__ fbit
     }
     __syncthreads();
 
+    const int nact = CAN_EXIT ? min(256, (nruns + 31) & ~31) : 256;   // threads of the per-run phases (block-uniform)
+    if (CAN_EXIT && tid >= nact) return true;
+    auto phase_barrier = [&]() {
+        if (CAN_EXIT) asm volatile("bar.sync 1, %0;" ::"r"(nact) : "memory");
+        else __syncthreads();
+    };
+
     // id of the run that contains (occupied) block k of the word at smem position sw / raster index wi
     auto run_id = [&](int sw, int wi, int k) -> int {
         const uint32_t rsu = run_starts(sA[sw] | sB[sw]);
@@ -512,7 +523,7 @@ __device__ __forceinline__ bool ccl_local_tile(const uint32_t* __restrict__ fbit
             last_b = b;
         }
     }
-    __syncthreads();
+    phase_barrier();
 
     // ---- phase C: roots claim an accumulator slot (entry becomes TAG | slot)
     for (int r = tid; r < nruns; r += 256) {
@@ -528,7 +539,7 @@ __device__ __forceinline__ bool ccl_local_tile(const uint32_t* __restrict__ fbit
             spar[r] = (unsigned short)(TAG | NOSLOT);
         }
     }
-    __syncthreads();
+    phase_barrier();
 
     // tile-local run id -> global block id of its first block
     auto run_gid = [&](int r) -> int {
@@ -577,12 +588,12 @@ __device__ __forceinline__ bool ccl_local_tile(const uint32_t* __restrict__ fbit
             else *overflow = 1;
         }
     }
-    __syncthreads();
+    phase_barrier();
 
     // ---- phase E: one partial per tile-local component -> global list
     const int n = min(s_misc[8], MAXR);
     if (tid == 0) s_misc[9] = atomicAdd(pcount, n);
-    __syncthreads();
+    phase_barrier();
     for (int s = tid; s < n; s += 256) {
         const int idx = s_misc[9] + s;
         if (idx < cap_parts) {
@@ -602,7 +613,7 @@ k_ccl_local(const uint32_t* __restrict__ fbits, Geom g, int* __restrict__ parent
             int* __restrict__ pcount, int cap_parts, int32_t* __restrict__ overflow, int* __restrict__ big_tiles,
             int* __restrict__ big_count) {
     wait_for_previous_kernel();
-    if (!ccl_local_tile<BX, LocalSmem::RUNS_FAST>(fbits, g, parent, parts, pcount, cap_parts, overflow,
+    if (!ccl_local_tile<BX, LocalSmem::RUNS_FAST, true>(fbits, g, parent, parts, pcount, cap_parts, overflow,
                                                   (int)blockIdx.y, (int)blockIdx.x)) {
         if (threadIdx.x == 0) big_tiles[atomicAdd(big_count, 1)] = (int)(blockIdx.y * gridDim.x + blockIdx.x);
     }
@@ -619,7 +630,7 @@ k_ccl_local_big(const uint32_t* __restrict__ fbits, Geom g, int* __restrict__ pa
     const int n = *big_count;
     for (int i = blockIdx.x; i < n; i += gridDim.x) {
         const int t = big_tiles[i];
-        ccl_local_tile<BX, LocalSmem::RUNS_MAX>(fbits, g, parent, parts, pcount, cap_parts, overflow,
+        ccl_local_tile<BX, LocalSmem::RUNS_MAX, false>(fbits, g, parent, parts, pcount, cap_parts, overflow,
                                                 t / tiles_per_frame, t % tiles_per_frame);
         __syncthreads();                     // shared memory is reused by the next tile
     }
@@ -1346,6 +1357,28 @@ void ccl_prepare(cudaStream_t s, int T, const Geom& g, const CclBuffers& b, bool
         cudaMemsetAsync(b.rowcount, 0, (size_t)2 * T * g.BH * sizeof(uint32_t), s);   // rowcount, rowfill (tiled path)
 }
 
+// The dense label image of T frames (after the ranking kernels have tagged the roots).
+cudaError_t launch_write_labels(cudaStream_t s, const uint32_t* fbits, int T, const Geom& g, const CclBuffers& b,
+                                void* labels, int label_elem_size, int* n_launches) {
+    const bool tiled = (g.wpr4 >> 2) <= 32;
+    const uint32_t* rbase_for_labels = tiled ? nullptr : b.rowcount;
+    // int32: one warp per span of 128 pixels x 8 rows, up to 8 warps per CTA (uint8: see k_write_labels_u8)
+    const int px_per_span = 128;
+    const int nspans = (g.mpitch + px_per_span - 1) / px_per_span;
+    const int wpb = nspans < 8 ? nspans : 8;
+    dim3 grid((nspans + wpb - 1) / wpb, (g.h + 7) / 8, T);
+    if (label_elem_size == 4) {
+        launch_dependent(k_write_labels_i32, grid, dim3(32 * wpb), 0, s, fbits, g, b.parent, rbase_for_labels,
+                         (int32_t*)labels);
+    } else {
+        const dim3 ugrid(((g.mpitch >> 5) + 31) / 32, (g.BH + 7) / 8, T);
+        launch_dependent(k_write_labels_u8, ugrid, dim3(32, 8), 0, s, fbits, g, T, b.parent, rbase_for_labels,
+                         (uint8_t*)labels);
+    }
+    if (n_launches) *n_launches += 1;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_ccl(cudaStream_t s, const uint32_t* fbits, int T, const Geom& g, const CclBuffers& b,
                        void* labels, int label_elem_size, int* n_launches, cudaEvent_t* ev, int n_ev,
                        const CclChain* chain, bool prepared) {
@@ -1360,7 +1393,6 @@ cudaError_t launch_ccl(cudaStream_t s, const uint32_t* fbits, int T, const Geom&
     dim3 gblock(bx, 256 / bx);
     dim3 ggrid((Q + bx - 1) / bx, (g.BH + gblock.y - 1) / gblock.y, T);
     const bool tiled = Q <= 32;      // a tile spans the full width: frames up to 4096 pixels wide
-    const uint32_t* rbase_for_labels = tiled ? nullptr : b.rowcount;
     int launches = 0;
     if (!prepared) ccl_prepare(s, T, g, b, chain != nullptr);
     if (tiled) {
@@ -1410,20 +1442,7 @@ cudaError_t launch_ccl(cudaStream_t s, const uint32_t* fbits, int T, const Geom&
     }
     mark();
     if (labels != nullptr) {
-        // int32: one warp per span of 128 pixels x 8 rows, up to 8 warps per CTA (uint8: see k_write_labels_u8)
-        const int px_per_span = 128;
-        const int nspans = (g.mpitch + px_per_span - 1) / px_per_span;
-        const int wpb = nspans < 8 ? nspans : 8;
-        dim3 grid((nspans + wpb - 1) / wpb, (g.h + 7) / 8, T);
-        if (label_elem_size == 4)
-            launch_dependent(k_write_labels_i32, grid, dim3(32 * wpb), 0, s, fbits, g, b.parent, rbase_for_labels,
-                             (int32_t*)labels);
-        else
-        {
-            const dim3 ugrid(((g.mpitch >> 5) + 31) / 32, (g.BH + 7) / 8, T);
-            launch_dependent(k_write_labels_u8, ugrid, dim3(32, 8), 0, s, fbits, g, T, b.parent, rbase_for_labels,
-                             (uint8_t*)labels);
-        }
+        launch_write_labels(s, fbits, T, g, b, labels, label_elem_size, nullptr);
         launches += 1;
     }
     mark();

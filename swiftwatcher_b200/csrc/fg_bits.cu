@@ -1163,7 +1163,8 @@ k_fg_n9(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t one, ui
             const uint32_t gg = vmax2(pp, uu), hh = vmin2(qq, vv);
             const uint32_t m3 = vmin2(gg, hh);
             const uint32_t m4 = fa.sub(fa.add(gg, hh), m3);
-            const uint32_t e0 = ep[q] & 0x00FF00FFu, e1 = (ep[q] >> 8) & 0x00FF00FFu;
+            // (first | second << 8) per u16 half -> two lanes: one PRMT each (bytes 0, 2 / bytes 1, 3 into the low bytes)
+            const uint32_t e0 = __byte_perm(ep[q], 0u, 0x4240), e1 = __byte_perm(ep[q], 0u, 0x4341);
             Sorted3 y = sort3_lanes(e0, e1, x0[q], fa);             // extras of window t
             acc0 += fg_flag(x0[q], select4of7(m2, m3, m4, m5, y)) << q;
             y = sort3_lanes(e1, x0[q], x1[q], fa);                  // extras of window t+1

@@ -64,10 +64,12 @@ k_rpca_norms(const uint8_t* __restrict__ x, long long total, unsigned long long*
 
 __global__ void __launch_bounds__(RP_THREADS)
 k_rpca_init(const uint8_t* __restrict__ x, long long total, double dual_norm, double* __restrict__ A,
-            double* __restrict__ Y) {
+            double* __restrict__ Y, const RpcaState* __restrict__ st, uint8_t* __restrict__ out) {
+    if (st) dual_norm = st->dual_norm;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         A[i] = 0.0;
         Y[i] = (double)x[i] / dual_norm;
+        if (out) out[i] = 0;                       // what an all-black batch (no iteration at all) leaves behind
     }
 }
 
@@ -134,7 +136,8 @@ k_rpca_gram(const uint8_t* __restrict__ X, const double* __restrict__ A, const d
 // with a fixed shuffle tree at the end, so the result is the same on every run.
 __global__ void __launch_bounds__(RP_THREADS)
 k_rpca_gram21(const uint8_t* __restrict__ X, const double* __restrict__ A, const double* __restrict__ Y,
-              long long P, double inv_mu, double thr, double* __restrict__ gpart) {
+              long long P, double inv_mu, double thr, double* __restrict__ gpart, const RpcaState* __restrict__ st) {
+    if (st) { inv_mu = st->inv_mu; thr = st->thr; }
     constexpr int n = 21, NB = 7, NBLK = NB * (NB + 1) / 2, NS = 8;
     constexpr int npairs = n * (n + 1) / 2;
     extern __shared__ double sm[];                 // [n][LD]
@@ -202,6 +205,20 @@ k_rpca_gram21(const uint8_t* __restrict__ X, const double* __restrict__ A, const
 // fixed-order sum of the per-CTA partials -> packed upper triangle
 // (one warp per pair: lane l sums CTAs l, l + 32, ...; then a shuffle tree — the same order every run)
 __global__ void k_rpca_gram_reduce(const double* __restrict__ gpart, int nctas, int npairs, double* __restrict__ G) {
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (q >= npairs) return;
+    double s = 0.0;
+    for (int c = lane; c < nctas; c += 32) s += gpart[(long long)c * npairs + q];
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_down_sync(0xFFFFFFFFu, s, d);
+    if (lane == 0) G[q] = s;
+}
+
+// the same inside the graph loop: the first iteration reduces k_rpca_gram21's partials (n_first CTAs), the later
+// ones the fused pass's (n_later CTAs)
+__global__ void k_rpca_gram_reduce_st(const double* __restrict__ gpart, int n_first, int n_later, int npairs,
+                                      double* __restrict__ G, const RpcaState* __restrict__ st) {
+    const int nctas = st->itr == 0 ? n_first : n_later;
     const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (q >= npairs) return;
@@ -340,10 +357,16 @@ k_rpca_apply_n(const uint8_t* __restrict__ X, const double* __restrict__ A, doub
 // disappear; only the first iteration still runs k_rpca_gram21.
 template <int N, bool FUSE>
 __global__ void __launch_bounds__(RP_THREADS, 3)
-k_rpca_apply_pair(const uint8_t* __restrict__ X, const double* __restrict__ A, double* __restrict__ Anew,
+k_rpca_apply_pair(const uint8_t* __restrict__ X, const double* A, double* Anew,
                   double* __restrict__ Y, long long P, double inv_mu, double thr, double mu,
                   const double* __restrict__ Wg, double* __restrict__ zpart, uint8_t* __restrict__ out,
-                  double inv_mu_next, double thr_next, double* __restrict__ gpart_next) {
+                  double inv_mu_next, double thr_next, double* __restrict__ gpart_next,
+                  const RpcaState* __restrict__ st) {
+    if (st) {                                      // graph loop: parameters and the ping-pong role of the A buffers from the state
+        inv_mu = st->inv_mu; thr = st->thr; mu = st->mu;
+        inv_mu_next = st->inv_mu_next; thr_next = st->thr_next;
+        if (st->itr & 1) { const double* t = A; A = Anew; Anew = const_cast<double*>(t); }
+    }
     constexpr int KH = (N + 1) / 2;                // frames / columns per lane (11)
     constexpr int KP = (KH + 1) & ~1;              // padded to an even count (12): double2 loads of W
     constexpr int ROWS = RP_THREADS / 2;           // pixel rows per CTA step
@@ -584,6 +607,9 @@ cudaError_t rpca_alloc(RpcaWork& w, long long P, int nmax) {
     if ((e = cudaMalloc(&w.W, (size_t)nmax * nmax * sizeof(double))) != cudaSuccess) return e;
     if ((e = cudaMalloc(&w.zpart, (size_t)w.nctas * sizeof(double))) != cudaSuccess) return e;
     if ((e = cudaMalloc(&w.sumsq, 16)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&w.state, 256)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&w.Vprev, (size_t)nmax * nmax * sizeof(double))) != cudaSuccess) return e;
+    if ((e = cudaMemset(w.gpart, 0, (size_t)w.nctas * npairs * sizeof(double))) != cudaSuccess) return e;
     if ((e = cudaMallocHost(&w.h_buf, (size_t)(npairs + nmax * nmax + w.nctas + 4) * sizeof(double))) != cudaSuccess) return e;
     return cudaSuccess;
 }
@@ -597,6 +623,10 @@ void rpca_free(RpcaWork& w) {
     cudaFree(w.W);
     cudaFree(w.zpart);
     cudaFree(w.sumsq);
+    cudaFree(w.state);
+    cudaFree(w.Vprev);
+    if (w.graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)w.graph_exec);
+    if (w.graph) cudaGraphDestroy((cudaGraph_t)w.graph);
     if (w.h_buf) cudaFreeHost(w.h_buf);
     memset(&w, 0, sizeof(w));
 }
@@ -609,12 +639,305 @@ cudaError_t launch_crop_gray(cudaStream_t s, const uint8_t* frames, long long fr
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------
+// The IALM loop without the host (n = 21, the reference's batch).  One CUDA graph per work area:
+//   norms -> setup -> init -> gram21 -> WHILE (not converged) { gram_reduce -> eigen -> fused apply pass -> check }
+// The WHILE node is a conditional graph node; k_rpca_check ends the loop with cudaGraphSetConditional.
+// Nothing is copied to the host and nothing synchronises: swb_submit stays asynchronous in RPCA mode and
+// the per-iteration cost is the kernels plus a few microseconds of graph scheduling instead of two
+// stream synchronisations, three small copies and the host eigenproblem.
+// ------------------------------------------------------------------------------------------
+__global__ void k_rpca_setup(const unsigned long long* __restrict__ sumsq, RpcaState* __restrict__ st, double lmbda,
+                             cudaGraphConditionalHandle loop) {
+    if (threadIdx.x != 0) return;
+    const double norm_two = sqrt((double)sumsq[0]);                       // norm(Y.ravel(), 2) == norm(X, 'fro')
+    const double norm_inf = (double)(unsigned int)sumsq[1] / lmbda;
+    RpcaState r;
+    r.zero = norm_two == 0.0;
+    r.dual_norm = r.zero ? 1.0 : fmax(norm_two, norm_inf);
+    r.dnorm = norm_two;
+    r.mu = r.zero ? 1.0 : 1.25 / norm_two;
+    r.inv_mu = 1 / r.mu;
+    r.thr = lmbda / r.mu;
+    const double mu_next = fmin(r.mu * 1.5, r.mu * 1e7);
+    r.inv_mu_next = 1 / mu_next;
+    r.thr_next = lmbda / mu_next;
+    r.itr = 0;
+    r.done = r.zero;
+    r.sweeps = 0;
+    *st = r;
+    cudaGraphSetConditional(loop, r.zero ? 0u : 1u);                      // an all-black batch: E == 0, no iteration
+}
+
+// G (packed upper triangle) -> W = V diag((S - 1/mu) / S) V^T with G = V diag(S^2) V^T, for n = 21.
+// One CTA.  The eigenproblem is a parallel-order Jacobi iteration run by ONE warp on shared memory
+// (round-robin schedule: 21 rounds of 10 disjoint rotations per sweep, lane k owns row / column k, __syncwarp
+// between the three steps of a round), warm-started in the eigenbasis of the previous IALM iteration, where G
+// is nearly diagonal (two or three sweeps instead of seven).  The dense 21 x 21 products around it use all
+// 256 threads.  Rotation formulas and stopping rule are those of the host solver (jacobi_eigh).
+__global__ void __launch_bounds__(256)
+k_rpca_eigen21(const double* __restrict__ G, double* __restrict__ Wg, double* __restrict__ Vprev,
+               RpcaState* __restrict__ st) {
+    constexpr int n = 21, LD = 23;
+    __shared__ double a[n * LD], v[n * LD], vp[n * LD], tmp[n * LD], dsc[n];
+    __shared__ double cs[10][2];
+    __shared__ int pq[10][2];
+    __shared__ int s_go;
+    const int t = threadIdx.x, lane = t & 31;
+    const bool warm = st->itr > 0;
+    const double inv_mu = st->inv_mu;
+    for (int q = t; q < n * n; q += 256) {
+        const int i = q / n, j = q - i * n;
+        const int lo = min(i, j), hi = max(i, j);
+        a[i * LD + j] = G[lo * n - (lo * (lo - 1)) / 2 + (hi - lo)];
+        vp[i * LD + j] = warm ? Vprev[q] : (i == j ? 1.0 : 0.0);
+        v[i * LD + j] = (i == j) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    if (warm) {
+        // B = Vp^T G Vp (symmetric by construction of the second product: upper triangle mirrored)
+        for (int q = t; q < n * n; q += 256) {
+            const int i = q / n, j = q - i * n;
+            double acc = 0.0;
+            for (int k = 0; k < n; ++k) acc = __dadd_rn(acc, __dmul_rn(a[i * LD + k], vp[k * LD + j]));
+            tmp[i * LD + j] = acc;
+        }
+        __syncthreads();
+        double mine[2] = {0.0, 0.0};
+        for (int r = 0, q = t; q < n * n; q += 256, ++r) {
+            const int i = q / n, j = q - i * n;
+            const int lo = min(i, j), hi = max(i, j);
+            double acc = 0.0;
+            for (int k = 0; k < n; ++k) acc = __dadd_rn(acc, __dmul_rn(vp[k * LD + lo], tmp[k * LD + hi]));
+            mine[r] = acc;
+        }
+        __syncthreads();
+        for (int r = 0, q = t; q < n * n; q += 256, ++r) a[(q / n) * LD + (q % n)] = mine[r];
+        __syncthreads();
+    }
+    if (t < 32) {
+        // ---- Jacobi sweeps, one warp
+        int sweeps = 0;
+        for (int sweep = 0; sweep < 100; ++sweep) {
+            double off = 0.0, diag = 0.0;
+            if (lane < n) {
+                diag = a[lane * LD + lane] * a[lane * LD + lane];
+                for (int j = lane + 1; j < n; ++j) off = fma(a[lane * LD + j], a[lane * LD + j], off);
+            }
+            for (int d = 16; d > 0; d >>= 1) {
+                off += __shfl_xor_sync(0xFFFFFFFFu, off, d);
+                diag += __shfl_xor_sync(0xFFFFFFFFu, diag, d);
+            }
+            if (off <= 1e-34 * diag || off == 0.0) break;      // off-diagonal mass below eps^2 of the diagonal
+            ++sweeps;
+            for (int r = 0; r < n; ++r) {
+                // round r of the circle schedule on 22 players (player 21 = the bye, paired with r)
+                if (lane < 10) {
+                    int p = (r + lane + 1) % n, q = (r + n - lane - 1) % n;
+                    if (p > q) { const int x = p; p = q; q = x; }
+                    const double apq = a[p * LD + q];
+                    double c = 1.0, sn = 0.0;
+                    if (apq != 0.0) {
+                        const double app = a[p * LD + p], aqq = a[q * LD + q];
+                        const double theta = __ddiv_rn(aqq - app, __dmul_rn(2.0, apq));
+                        const double tt = __ddiv_rn(theta >= 0 ? 1.0 : -1.0,
+                                                    __dadd_rn(fabs(theta), sqrt(__dadd_rn(__dmul_rn(theta, theta), 1.0))));
+                        c = __ddiv_rn(1.0, sqrt(__dadd_rn(__dmul_rn(tt, tt), 1.0)));
+                        sn = __dmul_rn(tt, c);
+                    }
+                    cs[lane][0] = c; cs[lane][1] = sn;
+                    pq[lane][0] = p; pq[lane][1] = q;
+                }
+                __syncwarp();
+                if (lane < n) {                                // columns p, q of a and of v, row `lane`
+#pragma unroll
+                    for (int i = 0; i < 10; ++i) {
+                        const int p = pq[i][0], q = pq[i][1];
+                        const double c = cs[i][0], sn = cs[i][1];
+                        const double akp = a[lane * LD + p], akq = a[lane * LD + q];
+                        a[lane * LD + p] = __dsub_rn(__dmul_rn(c, akp), __dmul_rn(sn, akq));
+                        a[lane * LD + q] = __dadd_rn(__dmul_rn(sn, akp), __dmul_rn(c, akq));
+                        const double vkp = v[lane * LD + p], vkq = v[lane * LD + q];
+                        v[lane * LD + p] = __dsub_rn(__dmul_rn(c, vkp), __dmul_rn(sn, vkq));
+                        v[lane * LD + q] = __dadd_rn(__dmul_rn(sn, vkp), __dmul_rn(c, vkq));
+                    }
+                }
+                __syncwarp();
+                if (lane < n) {                                // rows p, q of a, column `lane`
+#pragma unroll
+                    for (int i = 0; i < 10; ++i) {
+                        const int p = pq[i][0], q = pq[i][1];
+                        const double c = cs[i][0], sn = cs[i][1];
+                        const double apk = a[p * LD + lane], aqk = a[q * LD + lane];
+                        a[p * LD + lane] = __dsub_rn(__dmul_rn(c, apk), __dmul_rn(sn, aqk));
+                        a[q * LD + lane] = __dadd_rn(__dmul_rn(sn, apk), __dmul_rn(c, aqk));
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        if (lane < n) {
+            const double d = a[lane * LD + lane];
+            const double sv = d > 0.0 ? sqrt(d) : 0.0;
+            dsc[lane] = sv > 0.0 ? __ddiv_rn(sv - inv_mu, sv) : 0.0;   // exactly dependent columns are skipped (see header)
+        }
+        if (lane == 0) st->sweeps += sweeps;
+    }
+    __syncthreads();
+    // V = Vp Vb (kept for the next warm start), then W = V diag(f) V^T
+    for (int q = t; q < n * n; q += 256) {
+        const int i = q / n, j = q - i * n;
+        double acc = 0.0;
+        for (int k = 0; k < n; ++k) acc = __dadd_rn(acc, __dmul_rn(vp[i * LD + k], v[k * LD + j]));
+        tmp[i * LD + j] = acc;
+        Vprev[q] = acc;
+    }
+    __syncthreads();
+    for (int q = t; q < n * n; q += 256) {
+        const int i = q / n, j = q - i * n;
+        double acc = 0.0;
+        for (int k = 0; k < n; ++k) acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(tmp[i * LD + k], dsc[k]), tmp[j * LD + k]));
+        Wg[q] = acc;
+    }
+    (void)s_go;
+}
+
+// |Z|_F^2 from the per-CTA partials (fixed order), the stopping test (image_filtering.py:296-298), mu *= rho
+__global__ void k_rpca_check(const double* __restrict__ zpart, int napply, RpcaState* __restrict__ st, double lmbda,
+                             double tol, double rho, int maxiter, cudaGraphConditionalHandle loop) {
+    if (threadIdx.x != 0) return;
+    double zz = 0.0;
+    for (int c = 0; c < napply; ++c) zz += zpart[c];
+    RpcaState r = *st;
+    r.mu = fmin(r.mu * rho, r.mu * 1e7);
+    r.inv_mu = 1 / r.mu;
+    r.thr = lmbda / r.mu;
+    const double mu_next = fmin(r.mu * rho, r.mu * 1e7);
+    r.inv_mu_next = 1 / mu_next;
+    r.thr_next = lmbda / mu_next;
+    r.itr += 1;
+    r.done = (sqrt(zz) / r.dnorm < tol) || r.itr >= maxiter;
+    *st = r;
+    cudaGraphSetConditional(loop, r.done ? 0u : 1u);
+}
+
+// Builds (once per work area and buffer set) and launches the graph.  Returns cudaErrorNotSupported when the
+// graph cannot be built (the caller then runs the host loop).
+static cudaError_t rpca_run_graph(cudaStream_t s, const uint8_t* X, long long P, RpcaWork& w, uint8_t* out,
+                                  int* n_launches) {
+    constexpr int n = 21;
+    const double lmbda = 0.01, tol = 0.001, rho = 1.5;
+    const int maxiter = 100;
+    const long long total = (long long)n * P;
+    const int npairs = n * (n + 1) / 2;
+    const int nctas = (int)std::min<long long>(w.nctas, (P + RP_THREADS - 1) / RP_THREADS);
+    const int napply = std::min(nctas, 148 * 3);
+    if (w.graph_failed) return cudaErrorNotSupported;
+    if (!w.graph_exec || w.g_X != X || w.g_out != out || w.g_P != P) {
+        if (w.graph_exec) { cudaGraphExecDestroy((cudaGraphExec_t)w.graph_exec); w.graph_exec = nullptr; }
+        if (w.graph) { cudaGraphDestroy((cudaGraph_t)w.graph); w.graph = nullptr; }
+        cudaStream_t c1 = nullptr, c2 = nullptr;
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        bool capturing1 = false, capturing2 = false;
+        auto fail = [&](cudaError_t e) {
+            cudaGraph_t junk = nullptr;
+            if (capturing2) cudaStreamEndCapture(c2, &junk);
+            if (capturing1) { junk = nullptr; cudaStreamEndCapture(c1, &junk); if (junk) cudaGraphDestroy(junk); }
+            if (c1) cudaStreamDestroy(c1);
+            if (c2) cudaStreamDestroy(c2);
+            cudaGetLastError();
+            w.graph_failed = 1;
+            (void)e;
+            return cudaErrorNotSupported;
+        };
+        cudaError_t e;
+        if ((e = cudaStreamCreateWithFlags(&c1, cudaStreamNonBlocking)) != cudaSuccess) return fail(e);
+        if ((e = cudaStreamCreateWithFlags(&c2, cudaStreamNonBlocking)) != cudaSuccess) return fail(e);
+        if ((e = cudaStreamBeginCapture(c1, cudaStreamCaptureModeRelaxed)) != cudaSuccess) return fail(e);
+        capturing1 = true;
+        RpcaState* st = reinterpret_cast<RpcaState*>(w.state);
+        // the loop handle is needed by k_rpca_setup, which comes before the loop node: create it first
+        cudaStreamCaptureStatus status;
+        const cudaGraphNode_t* deps = nullptr;
+        size_t ndeps = 0;
+        if ((e = cudaStreamGetCaptureInfo(c1, &status, nullptr, &graph, &deps, &ndeps)) != cudaSuccess) return fail(e);
+        cudaGraphConditionalHandle loop;
+        if ((e = cudaGraphConditionalHandleCreate(&loop, graph, 1, cudaGraphCondAssignDefault)) != cudaSuccess) return fail(e);
+        cudaMemsetAsync(w.sumsq, 0, 16, c1);
+        k_rpca_norms<<<nctas, RP_THREADS, 0, c1>>>(X, total, w.sumsq, reinterpret_cast<unsigned int*>(w.sumsq + 1));
+        k_rpca_setup<<<1, 32, 0, c1>>>(w.sumsq, st, lmbda, loop);
+        k_rpca_init<<<nctas, RP_THREADS, 0, c1>>>(X, total, 1.0, w.A0, w.Y, st, out);
+        k_rpca_gram21<<<nctas, RP_THREADS, 21 * (RP_THREADS + 8) * sizeof(double), c1>>>(X, w.A0, w.Y, P, 0.0, 0.0, w.gpart, st);
+        if ((e = cudaGetLastError()) != cudaSuccess) return fail(e);
+        if ((e = cudaStreamGetCaptureInfo(c1, &status, nullptr, &graph, &deps, &ndeps)) != cudaSuccess) return fail(e);
+        cudaGraphNodeParams cp = {};
+        cp.type = cudaGraphNodeTypeConditional;
+        cp.conditional.handle = loop;
+        cp.conditional.type = cudaGraphCondTypeWhile;
+        cp.conditional.size = 1;
+        cudaGraphNode_t loop_node;
+        if ((e = cudaGraphAddNode(&loop_node, graph, deps, ndeps, &cp)) != cudaSuccess) return fail(e);
+        cudaGraph_t body = cp.conditional.phGraph_out[0];
+        if ((e = cudaStreamUpdateCaptureDependencies(c1, &loop_node, 1, cudaStreamSetCaptureDependencies)) != cudaSuccess)
+            return fail(e);
+        // ---- loop body: the first iteration's Gram partials come from k_rpca_gram21 (nctas CTAs), the later ones
+        // from the fused pass (napply CTAs): both are padded to nctas rows of partials (zeros) so one reduce fits
+        if ((e = cudaStreamBeginCaptureToGraph(c2, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed)) != cudaSuccess)
+            return fail(e);
+        capturing2 = true;
+        k_rpca_gram_reduce_st<<<(npairs * 32 + 127) / 128, 128, 0, c2>>>(w.gpart, nctas, napply, npairs, w.G, st);
+        k_rpca_eigen21<<<1, 256, 0, c2>>>(w.G, w.W, w.Vprev, st);
+        k_rpca_apply_pair<21, true><<<napply, RP_THREADS, 21 * (RP_THREADS / 2 + 8) * 17, c2>>>(
+            X, w.A0, w.A1, w.Y, P, 0.0, 0.0, 0.0, w.W, w.zpart, out, 0.0, 0.0, w.gpart, st);
+        k_rpca_check<<<1, 32, 0, c2>>>(w.zpart, napply, st, lmbda, tol, rho, maxiter, loop);
+        if ((e = cudaGetLastError()) != cudaSuccess) return fail(e);
+        cudaGraph_t body_out = nullptr;
+        e = cudaStreamEndCapture(c2, &body_out);
+        capturing2 = false;
+        if (e != cudaSuccess) return fail(e);
+        e = cudaStreamEndCapture(c1, &graph);
+        capturing1 = false;
+        if (e != cudaSuccess) return fail(e);
+        if ((e = cudaGraphInstantiate(&exec, graph, 0)) != cudaSuccess) { cudaGraphDestroy(graph); return fail(e); }
+        cudaStreamDestroy(c1);
+        cudaStreamDestroy(c2);
+        w.graph = graph;
+        w.graph_exec = exec;
+        w.g_X = X;
+        w.g_out = out;
+        w.g_P = P;
+    }
+    cudaError_t e = cudaGraphLaunch((cudaGraphExec_t)w.graph_exec, s);
+    if (e != cudaSuccess) return e;
+    if (n_launches) *n_launches += 5;          // the loop's launches are counted when the state is read back
+    return cudaSuccess;
+}
+
 // inexact_augmented_lagrange_multiplier (image_filtering.py:256-301) on the device.
 // X: [n][P] uint8 (column k of the reference's matrix = X[k]); out: [n][P] uint8 = clip(-E, 0, 255).
 // Synchronises the stream every iteration (the stopping test and the 21 x 21 eigenproblem run on the host).
 cudaError_t rpca_run(cudaStream_t s, const uint8_t* X, int n, long long P, RpcaWork& w, uint8_t* out, int* iters,
                      int* n_launches) {
     if (n < 1 || n > w.nmax || P > w.P) return cudaErrorInvalidValue;
+    w.last_mode = 0;
+    static const bool host_loop = [] { const char* e = getenv("SWB_RPCA_HOST_LOOP"); return e && e[0] == '1'; }();
+    if (n == 21 && !host_loop) {
+        static PerDeviceOnce once_g;
+        if (once_g.need()) {
+            cudaFuncSetAttribute(k_rpca_gram21, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 RP_NMAX * (RP_THREADS + 1) * (int)sizeof(double));
+            cudaFuncSetAttribute(k_rpca_apply_pair<21, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 21 * (RP_THREADS / 2 + 8) * 17);
+        }
+        const cudaError_t eg = rpca_run_graph(s, X, P, w, out, n_launches);
+        if (eg == cudaSuccess) {
+            w.last_mode = 1;
+            if (iters) *iters = -1;                 // not known yet: rpca_read_state() after the stream has drained
+            return cudaSuccess;
+        }
+        if (eg != cudaErrorNotSupported) return eg;
+    }
     const double lmbda = 0.01, tol = 0.001, rho = 1.5;
     const int maxiter = 100;
     const long long total = (long long)n * P;
@@ -657,7 +980,7 @@ cudaError_t rpca_run(cudaStream_t s, const uint8_t* X, int n, long long P, RpcaW
     const double dual_norm = std::max(norm_two, norm_inf);
     const double dnorm = norm_two;
     double mu = 1.25 / norm_two;
-    k_rpca_init<<<nctas, RP_THREADS, 0, s>>>(X, total, dual_norm, w.A0, w.Y);
+    k_rpca_init<<<nctas, RP_THREADS, 0, s>>>(X, total, dual_norm, w.A0, w.Y, nullptr, nullptr);
     launches += 2;
 
     double* Aold = w.A0;
@@ -670,7 +993,7 @@ cudaError_t rpca_run(cudaStream_t s, const uint8_t* X, int n, long long P, RpcaW
         const double thr = lmbda / mu;
         if (!have_G) {                             // first iteration (or no fused pass): the Gram pass on its own
             if (n == 21)
-                k_rpca_gram21<<<nctas, RP_THREADS, 21 * (RP_THREADS + 8) * sizeof(double), s>>>(X, Aold, w.Y, P, inv_mu, thr, w.gpart);
+                k_rpca_gram21<<<nctas, RP_THREADS, 21 * (RP_THREADS + 8) * sizeof(double), s>>>(X, Aold, w.Y, P, inv_mu, thr, w.gpart, nullptr);
             else
                 k_rpca_gram<<<nctas, RP_THREADS, n * (RP_THREADS + 1) * sizeof(double), s>>>(X, Aold, w.Y, n, P, inv_mu, thr, w.gpart);
             k_rpca_gram_reduce<<<(npairs * 32 + 127) / 128, 128, 0, s>>>(w.gpart, nctas, npairs, w.G);
@@ -727,12 +1050,12 @@ cudaError_t rpca_run(cudaStream_t s, const uint8_t* X, int n, long long P, RpcaW
             const size_t smem = 21 * (RP_THREADS / 2 + 8) * 17;        // E, Y (doubles), X (bytes)
             if (no_fuse) {
                 k_rpca_apply_pair<21, false><<<napply, RP_THREADS, smem, s>>>(X, Aold, Anew, w.Y, P, inv_mu, thr, mu, w.W,
-                                                                             w.zpart, out, 0.0, 0.0, nullptr);
+                                                                             w.zpart, out, 0.0, 0.0, nullptr, nullptr);
             } else {
                 // the pass also leaves the Gram partials of the next iteration (its mu is known now)
                 const double mu_next = std::min(mu * rho, mu * 1e7);
                 k_rpca_apply_pair<21, true><<<napply, RP_THREADS, smem, s>>>(X, Aold, Anew, w.Y, P, inv_mu, thr, mu, w.W,
-                                                                            w.zpart, out, 1 / mu_next, lmbda / mu_next, w.gpart);
+                                                                            w.zpart, out, 1 / mu_next, lmbda / mu_next, w.gpart, nullptr);
                 k_rpca_gram_reduce<<<(npairs * 32 + 127) / 128, 128, 0, s>>>(w.gpart, napply, npairs, w.G);
                 cudaMemcpyAsync(hG, w.G, (size_t)npairs * sizeof(double), cudaMemcpyDeviceToHost, s);
                 have_G = true;
@@ -756,8 +1079,27 @@ cudaError_t rpca_run(cudaStream_t s, const uint8_t* X, int n, long long P, RpcaW
         if (std::sqrt(zz) / dnorm < tol || itr >= maxiter) break;
     }
     if (iters) *iters = itr;
+    w.host_iters = itr;
     if (n_launches) *n_launches += launches;
     return cudaGetLastError();
+}
+
+// Iterations / Jacobi sweeps of the last run (synchronises the stream when the graph loop ran).
+cudaError_t rpca_read_state(cudaStream_t s, RpcaWork& w, int* iters, int* sweeps, int* mode) {
+    if (mode) *mode = w.last_mode;
+    if (w.last_mode == 1) {
+        RpcaState r;
+        cudaError_t e = cudaMemcpyAsync(w.h_buf, w.state, sizeof(RpcaState), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) return e;
+        memcpy(&r, w.h_buf, sizeof(r));
+        if (iters) *iters = r.itr;
+        if (sweeps) *sweeps = r.sweeps;
+    } else {
+        if (iters) *iters = w.host_iters;
+        if (sweeps) *sweeps = 0;
+    }
+    return cudaSuccess;
 }
 
 

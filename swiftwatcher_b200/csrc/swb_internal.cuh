@@ -102,6 +102,8 @@ struct U8Table {
 };
 cudaError_t launch_u8_merge(cudaStream_t s, int T, const CclBuffers& b, const U8Table& u, const int32_t* base,
                             int* n_launches);
+cudaError_t launch_write_labels(cudaStream_t s, const uint32_t* fbits, int T, const Geom& g, const CclBuffers& b,
+                                void* labels, int label_elem_size, int* n_launches);
 void ccl_prepare(cudaStream_t s, int T, const Geom& g, const CclBuffers& b, bool chained);
 
 cudaError_t launch_pack_bits(cudaStream_t s, const uint8_t* img, int h, int w, uint32_t* fbits,
@@ -126,6 +128,15 @@ struct PerDeviceOnce {
 };
 
 // ---- RPCA background model (rpca.cu): the reference's own localisation, SURVEY.md §8f #4 ----
+// Device-resident state of one IALM run (rpca_run_graph): the iteration loop is a conditional WHILE node of a
+// CUDA graph, so everything the host loop kept in local variables lives here and the kernels read it.
+struct RpcaState {
+    double mu, inv_mu, thr;          // this iteration: mu, 1 / mu, lambda / mu
+    double inv_mu_next, thr_next;    // the next iteration's (the fused pass prepares its Gram matrix)
+    double dnorm, dual_norm;         // |X|_F;  max(|X|_2-ish, |X|_inf / lambda)  (image_filtering.py:269-275)
+    int itr, done, zero, sweeps;     // iterations taken; stop flag; all-black batch; Jacobi sweeps so far
+};
+
 struct RpcaWork {
     double *A0, *A1, *Y;            // [n][P] low-rank iterate (ping-pong) and the Lagrange multiplier
     double *gpart, *G, *W, *zpart;  // per-CTA Gram partials, packed Gram matrix, W = V f(S) V^T, |Z|^2 partials
@@ -133,11 +144,20 @@ struct RpcaWork {
     double* h_buf;                  // pinned host staging (G, W, |Z|^2 partials, norms)
     long long P;
     int nmax, nctas;
+    // device-side iteration loop (n = 21): state, eigenbasis of the previous iteration, the graph and what it was built for
+    void* state;
+    double* Vprev;
+    void *graph, *graph_exec;
+    const uint8_t* g_X;
+    uint8_t* g_out;
+    long long g_P;
+    int graph_failed, last_mode, host_iters;   // last_mode: 1 = graph loop, 0 = host loop
 };
 cudaError_t rpca_alloc(RpcaWork& w, long long P, int nmax);
 void rpca_free(RpcaWork& w);
 cudaError_t rpca_run(cudaStream_t s, const uint8_t* X, int n, long long P, RpcaWork& w, uint8_t* out, int* iters,
                      int* n_launches);
+cudaError_t rpca_read_state(cudaStream_t s, RpcaWork& w, int* iters, int* sweeps, int* mode);
 cudaError_t launch_crop_gray(cudaStream_t s, const uint8_t* frames, long long frame_stride, long long pitch,
                              int channels, int x0, int y0, int h, int w, int n, int newest_first, uint8_t* out);
 // bilateral_blur (image_filtering.py:304-307 = cv2.bilateralFilter, 8-bit, one channel) for a stack of

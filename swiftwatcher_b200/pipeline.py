@@ -277,6 +277,12 @@ class FilterContext:
         check(self._lib.swb_get_rpca(self._ctx, t0, n, ptr(out), MEM_HOST), self._ctx)
         return out
 
+    def rpca_stats(self):
+        """bg_model="rpca": {"iterations", "jacobi_sweeps", "device_loop"} of the last submit (waits for it)."""
+        it, sw, mode = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        check(self._lib.swb_rpca_stats(self._ctx, C.byref(it), C.byref(sw), C.byref(mode)), self._ctx)
+        return {"iterations": it.value, "jacobi_sweeps": sw.value, "device_loop": bool(mode.value)}
+
     def mask_bits(self, t0=0, n=None):
         n = self._n_last - t0 if n is None else n
         wpr = (self.roi_w + 31) // 32

@@ -102,6 +102,19 @@ def test_fused_rpca_path_against_golden(golden_dir, name, mode):
             ctx.submit(frames if src == "host" else torch.from_numpy(frames).cuda(), n_halo=0)
             rows, counts = ctx.collect()
             masks, labels, sparse = ctx.masks(), ctx.labels(), ctx.rpca_images()
+            stats = ctx.rpca_stats()
+            # the reference's own batch size runs its whole iteration loop on the device (CUDA-graph WHILE node)
+            assert stats["iterations"] == iters and stats["device_loop"] == (T == 21)
+            if T == 21:                                            # the graph is reused by the next submits
+                assert 2 * iters <= stats["jacobi_sweeps"] <= 12 * iters
+                for _ in range(2):
+                    ctx.submit(frames, n_halo=0)
+                    assert np.array_equal(ctx.rpca_images(), z["rpca"])
+                    assert ctx.rpca_stats()["iterations"] == iters
+                ctx.submit(np.zeros_like(frames), n_halo=0)       # all black: no iteration at all
+                assert ctx.rpca_images().max() == 0 and ctx.rpca_stats()["iterations"] == 0 and len(ctx.collect()[0]) == 0
+                ctx.submit(frames, n_halo=0)
+                assert np.array_equal(ctx.rpca_images(), z["rpca"])
         assert np.array_equal(sparse, z["rpca"])
         # expectations come from the golden vectors only (no LAPACK on this machine): the golden
         # mask, labelled and measured by the oracle's integer stages
