@@ -78,10 +78,11 @@ typedef struct swb_config {
  * n_frames <= 32 frames (the reference's queue holds 21) that is decomposed on its own — no
  * temporal history, n_halo is ignored, median_n is unused — then bilateralFilter(7, 15, 1),
  * threshold, opening and labelling as usual.  For the reference's batch of 21 frames the whole iteration
- * loop runs on the device (a CUDA-graph WHILE node: eigenproblem, stopping test and all) and swb_submit is
- * asynchronous as in the median mode; for other batch sizes the stopping test and the n x n eigenproblem
- * run on the host and swb_submit BLOCKS until the decomposition has converged (it cannot be used on a
- * stream that is being captured). */
+ * loop can run on the device (a CUDA-graph WHILE node: eigenproblem, stopping test and all; swb_submit is
+ * then asynchronous as in the median mode): the default from 256 Ki pixels per frame, see the option
+ * "rpca_device_loop".  Otherwise (smaller frames, other batch sizes) the stopping test and the n x n
+ * eigenproblem run on the host and swb_submit BLOCKS until the decomposition has converged (it cannot be
+ * used on a stream that is being captured). */
 #define SWB_BG_MEDIAN 0
 #define SWB_BG_RPCA   1
 
@@ -159,10 +160,9 @@ int swb_collect_begin(swb_ctx* ctx, swb_segment* rows, int64_t cap, uint8_t* mas
 int swb_collect_end(swb_ctx* ctx, int64_t* n_rows, int32_t* per_frame_counts);
 /* Tuning knobs that never change a result: "host_pipeline" (0/1: cut large host submits into
  * sub-batches that are filtered while later frames are still being copied; default 1),
- * "sub_batch_min_px" (least work per sub-batch in pixels; default 64 Mi), "label_overlap" (0/1: label a large
- * device-resident submit in four pieces of frames on a second stream while the label writer of the previous piece
- * runs; default 1), "label_overlap_min_px" (least label pixels per submit for that; default 128 Mi),
- * "temporal_subchunk" (frames per
+ * "sub_batch_min_px" (least work per sub-batch in pixels; default 64 Mi), "rpca_device_loop" (SWB_BG_RPCA, 21-frame batches: 1 = the
+ * iteration loop as a CUDA-graph WHILE node on the device, swb_submit asynchronous; 0 = the host loop, swb_submit
+ * blocks; -1 = automatic, the default: device from 256 Ki pixels per frame), "temporal_subchunk" (frames per
  * temporal sub-chunk of the filtering kernel, rounded up to a multiple of 6; 0 = chosen from the grid size). */
 int swb_set_option(swb_ctx* ctx, const char* name, int64_t value);
 /* Frames per temporal sub-chunk the filtering kernel used for the last submit (each sub-chunk

@@ -42,8 +42,6 @@ struct swb_ctx {
     cudaEvent_t ev_h2d[MAX_SUB] = {};
     bool pipeline = true;
     long long sub_min_px = 64ll << 20;   // least work (pixels) per sub-batch
-    bool label_overlap = true;           // option "label_overlap": label a large submit in pieces beside the label writer
-    long long overlap_min_px = 128ll << 20;   // least label-image pixels per submit for that
     int forced_ts = 0;                   // option "temporal_subchunk": frames per temporal sub-chunk of K1 (0 = automatic)
     // device buffers
     uint8_t* in_buf = nullptr;      // host-mode staging: [N-1 + max_frames][h][in_pitch]
@@ -496,58 +494,9 @@ int swb_submit(swb_ctx* ctx, const uint8_t* frames, int32_t n_frames, int32_t n_
         CU(ctx, launch_morph_mask(s, reinterpret_cast<const uint32_t*>(ctx->raw_bits), n_frames, gm, ctx->morph,
                                   ctx->fbits, ctx->mask, &launches));
         if (ctx->timing) CU(ctx, cudaEventRecord(ctx->ev[2], s));
-        // Labelling in pieces: the chain of labelling kernels is latency-bound (tiles waiting on a few threads'
-        // union chains, a dozen small launches) and uses a fraction of the memory bandwidth, the label writer is
-        // purely bandwidth-bound.  A large submit is therefore labelled in up to MAX_SUB pieces of frames on the
-        // worker stream while the writer of the previous piece runs on the main stream: only the first piece's
-        // labelling is exposed.  (Unlike running the bandwidth-bound kernels of two sub-batches side by side —
-        // measured slower, DESIGN.md — the two sides here do not compete for the same resource.)
-        int npieces = 1;
-        if (!ctx->timing && ctx->label_overlap && ctx->labels && n_frames >= 16 * MAX_SUB &&
-            (long long)g.h * g.mpitch * n_frames >= ctx->overlap_min_px)
-            npieces = MAX_SUB;
-        if (npieces == 1) {
-            CU(ctx, launch_ccl(s, ctx->fbits, n_frames, g, ctx->ccl, ctx->labels, ctx->label_elem, &launches,
-                               ctx->timing ? &ctx->ev[3] : nullptr, 4, nullptr, true));
-            if (c.label_mode == SWB_LABELS_U8) CU(ctx, launch_u8_merge(s, n_frames, ctx->ccl, ctx->u8, nullptr, &launches));
-        } else {
-            cudaStream_t sw = ctx->worker;
-            CU(ctx, cudaEventRecord(ctx->ev_fork, s));
-            CU(ctx, cudaStreamWaitEvent(sw, ctx->ev_fork, 0));
-            const int tp = (n_frames + npieces - 1) / npieces;
-            const int cap_parts_sub = ctx->ccl.cap_parts / npieces;
-            for (int b = 0; b < npieces; ++b) {
-                const int f0 = b * tp;
-                const int nb = std::min(tp, n_frames - f0);
-                if (nb <= 0) break;
-                const uint32_t* fbits_b = ctx->fbits + (size_t)f0 * g.h * g.wpr4;
-                void* labels_b = static_cast<uint8_t*>(ctx->labels) + (size_t)f0 * g.h * g.mpitch * ctx->label_elem;
-                CclBuffers cb = ctx->ccl;
-                cb.parent += (size_t)f0 * g.BH * g.BW;
-                cb.rowcount += (size_t)2 * f0 * g.BH;
-                cb.nseg += f0;
-                cb.segoff += f0;
-                cb.parts += (size_t)b * cap_parts_sub;
-                cb.cap_parts = cap_parts_sub;
-                cb.pcount += 2 * b;
-                cb.big_tiles += (size_t)f0 * ((g.BH + 7) / 8);
-                CclChain chain;
-                chain.frame_base = f0;
-                chain.segoff_base = (b > 0) ? ctx->ccl.segoff + f0 : nullptr;   // left there by piece b-1
-                ccl_prepare(sw, nb, g, cb, true);
-                CU(ctx, launch_ccl(sw, fbits_b, nb, g, cb, nullptr, ctx->label_elem, &launches, nullptr, 0, &chain, true));
-                if (c.label_mode == SWB_LABELS_U8) {
-                    U8Table ub = ctx->u8;
-                    ub.stage += (size_t)255 * f0;
-                    ub.nseg += f0;
-                    ub.segoff += f0;
-                    CU(ctx, launch_u8_merge(sw, nb, cb, ub, b > 0 ? ctx->u8.segoff + f0 : nullptr, &launches));
-                }
-                CU(ctx, cudaEventRecord(ctx->ev_h2d[b], sw));
-                CU(ctx, cudaStreamWaitEvent(s, ctx->ev_h2d[b], 0));
-                CU(ctx, launch_write_labels(s, fbits_b, nb, g, cb, labels_b, ctx->label_elem, &launches));
-            }
-        }
+        CU(ctx, launch_ccl(s, ctx->fbits, n_frames, g, ctx->ccl, ctx->labels, ctx->label_elem, &launches,
+                           ctx->timing ? &ctx->ev[3] : nullptr, 4, nullptr, true));
+        if (c.label_mode == SWB_LABELS_U8) CU(ctx, launch_u8_merge(s, n_frames, ctx->ccl, ctx->u8, nullptr, &launches));
         ctx->last_ts = (c.bg_model == SWB_BG_MEDIAN) ? last_temporal_subchunk() : n_frames;
         ctx->ev_valid = ctx->timing;
     } else {
@@ -721,11 +670,9 @@ int swb_set_option(swb_ctx* ctx, const char* name, int64_t value) {
     else if (!strcmp(name, "sub_batch_min_px")) {
         if (value <= 0) return fail(ctx, SWB_ERR_INVALID, "sub_batch_min_px must be positive");
         ctx->sub_min_px = value;
-    } else if (!strcmp(name, "label_overlap")) {
-        ctx->label_overlap = value != 0;
-    } else if (!strcmp(name, "label_overlap_min_px")) {
-        if (value <= 0) return fail(ctx, SWB_ERR_INVALID, "label_overlap_min_px must be positive");
-        ctx->overlap_min_px = value;
+    } else if (!strcmp(name, "rpca_device_loop")) {
+        if (value < -1 || value > 1) return fail(ctx, SWB_ERR_INVALID, "rpca_device_loop must be -1 (automatic), 0 or 1");
+        ctx->rpca.device_loop = (int)value;
     } else if (!strcmp(name, "temporal_subchunk")) {
         if (value < 0 || value > 32768) return fail(ctx, SWB_ERR_INVALID, "temporal_subchunk must be in 0..32768");
         ctx->forced_ts = (int)value;

@@ -369,14 +369,17 @@ __device__ __forceinline__ void emit_partial(Partial* parts, int idx, int f, int
 // itself on a list and is redone by the RUNS_MAX variant (8 runs per word, the worst case).
 struct LocalSmem {
     static constexpr int RUNS_FAST = 1536;
-    static constexpr int RUNS_MAX = 8192;
     static constexpr int MAXR = 256;            // components with a shared-memory accumulator
     // words of one pixel-row plane of the tile: BY rows of 4 * BX words + a halo word each side
     // (1536 at BX = 1 ... 1056 at BX = 16: 24 KB in all for the common kernel, eight CTAs per SM)
-    __host__ __device__ static constexpr int ab_words(int bx) { return (256 / bx) * (4 * bx + 2); }
-    static constexpr size_t bytes(int maxruns, int bx) {
-        return (size_t)2 * ab_words(bx) * 4 + 1024 * 2 + (size_t)2 * maxruns * 2 + MAXR * 30 + 64;
+    __host__ __device__ static constexpr int ab_words(int bx, int gpt = 1) { return gpt * (256 / bx) * (4 * bx + 2); }
+    // gpt = groups (of four words) per thread: the tile holds 1024 * gpt words.  Frames small enough to fit ONE
+    // tile of up to 4096 words (gpt <= 4) are labelled AND ranked by a single CTA (see SINGLE below).
+    static constexpr size_t bytes(int maxruns, int bx, int gpt = 1) {
+        return (size_t)2 * ab_words(bx, gpt) * 4 + (size_t)1024 * gpt * 2 + (size_t)2 * maxruns * 2 + MAXR * 30 + 64 +
+               (size_t)((maxruns + 31) / 32) * 8;
     }
+    __host__ __device__ static constexpr int runs_max(int gpt) { return 8192 * gpt; }    // 8 runs per word: the worst case
 };
 
 // One tile (frame f, block rows tile * BY ...).  Returns false (block-uniform, nothing written)
@@ -385,19 +388,25 @@ struct LocalSmem {
 // run list is built (the later phases are one thread per run: with the usual few dozen runs per tile seven of
 // the eight warps would only walk from barrier to barrier) and the remaining phases synchronise on a named
 // barrier sized for the warps that stay.
-template <int BX, int MAXRUNS, bool CAN_EXIT>
+// SINGLE: the tile is the whole frame (tiles per frame == 1).  Then a tile-local root is a component and its
+// rank among the tile's roots — run ids grow with the first block's raster index, i.e. in OpenCV's label order —
+// is its label: the kernel tags the roots itself (parent[root] = -label), writes the frame's segment count, and
+// the boundary / root_count / scan / root_place / root_rank launches disappear from the chain.
+template <int BX, int GPT, int MAXRUNS, bool CAN_EXIT, bool SINGLE>
 __device__ __forceinline__ bool ccl_local_tile(const uint32_t* __restrict__ fbits, const Geom& g, int* __restrict__ parent,
                                                Partial* __restrict__ parts, int* __restrict__ pcount, int cap_parts,
-                                               int32_t* __restrict__ overflow, int f, int tile) {
-    constexpr int BY = 256 / BX;
+                                               int32_t* __restrict__ overflow, int32_t* __restrict__ nseg, int f, int tile) {
+    constexpr int BY = GPT * 256 / BX;
     constexpr int WR = BX * 4;               // words per tile row (power of two)
     constexpr int SW = WR + 2;               // + one halo word each side
     constexpr int MAXR = LocalSmem::MAXR;
+    constexpr int NW = 1024 * GPT;           // words per tile
+    constexpr int RBW = (MAXRUNS + 31) / 32; // words of the root bitmap (SINGLE)
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t* sA = reinterpret_cast<uint32_t*>(smem_raw);                 // [BY][SW] pixel row 2by
-    uint32_t* sB = sA + LocalSmem::ab_words(BX);                             // [BY][SW] pixel row 2by + 1
-    unsigned short* swpre = reinterpret_cast<unsigned short*>(sB + LocalSmem::ab_words(BX));   // [1024] runs before word
-    unsigned short* srun = swpre + 1024;                                  // [MAXRUNS] (word << 4) | first block
+    uint32_t* sB = sA + LocalSmem::ab_words(BX, GPT);                        // [BY][SW] pixel row 2by + 1
+    unsigned short* swpre = reinterpret_cast<unsigned short*>(sB + LocalSmem::ab_words(BX, GPT));   // [NW] runs before word
+    unsigned short* srun = swpre + NW;                                    // [MAXRUNS] (word << 4) | first block
     unsigned short* spar = srun + MAXRUNS;                                // [MAXRUNS] parent run id / TAG | slot
     uint32_t* st_area = reinterpret_cast<uint32_t*>(spar + MAXRUNS);
     uint32_t* st_sr = st_area + MAXR;
@@ -408,31 +417,38 @@ __device__ __forceinline__ bool ccl_local_tile(const uint32_t* __restrict__ fbit
     int* st_maxc = st_maxr + MAXR;
     unsigned short* sroot = reinterpret_cast<unsigned short*>(st_maxc + MAXR);
     int* s_misc = reinterpret_cast<int*>(sroot + MAXR);                   // [0..7] warp totals, [8] slots, [9] base
+    uint32_t* rootbits = reinterpret_cast<uint32_t*>(s_misc + 16);        // [RBW] roots by run id (SINGLE)
+    uint32_t* rootpre = rootbits + RBW;                                   // [RBW] roots in earlier words
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tx = tid % BX, ty = tid / BX;
     const int by0 = tile * BY;
-    const int by = by0 + ty;
     const int Q = g.wpr4 >> 2;
     const uint32_t* fb = fbits + (long long)f * g.h * g.wpr4;
 
-    // ---- phase A: load, publish the rows, number the runs in raster order
-    Group gr;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) gr.A[i] = gr.B[i] = 0u;
-    if (tx < Q && by < g.BH) load_group(gr, fb, g, by, tx);
-    const int w0 = ty * SW + 1 + 4 * tx;     // smem index of this thread's word 0
-    uint32_t RS[4];
+    // ---- phase A: load, publish the rows, number the runs in raster order (a thread's GPT groups are
+    // consecutive in tile-raster order, so thread order == raster order)
+    uint32_t RS[GPT][4];
     int cnt = 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        sA[w0 + i] = gr.A[i];
-        sB[w0 + i] = gr.B[i];
-        RS[i] = run_starts(gr.A[i] | gr.B[i]);
-        cnt += __popc(RS[i]);
+    for (int gi = 0; gi < GPT; ++gi) {
+        const int idx = tid * GPT + gi;
+        const int tx = idx % BX, ty = idx / BX;
+        const int by = by0 + ty;
+        Group gr;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) gr.A[i] = gr.B[i] = 0u;
+        if (tx < Q && by < g.BH) load_group(gr, fb, g, by, tx);
+        const int w0 = ty * SW + 1 + 4 * tx;     // smem index of this group's word 0
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            sA[w0 + i] = gr.A[i];
+            sB[w0 + i] = gr.B[i];
+            RS[gi][i] = run_starts(gr.A[i] | gr.B[i]);
+            cnt += __popc(RS[gi][i]);
+        }
+        if (tx == 0) { sA[ty * SW] = 0u; sB[ty * SW] = 0u; }
+        if (tx == BX - 1) { sA[ty * SW + SW - 1] = 0u; sB[ty * SW + SW - 1] = 0u; }
     }
-    if (tx == 0) { sA[ty * SW] = 0u; sB[ty * SW] = 0u; }
-    if (tx == BX - 1) { sA[ty * SW + SW - 1] = 0u; sB[ty * SW + SW - 1] = 0u; }
     int incl = cnt;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -449,24 +465,33 @@ __device__ __forceinline__ bool ccl_local_tile(const uint32_t* __restrict__ fbit
         if (w < warp) base += t;
         nruns += t;
     }
-    if (nruns == 0) return true;             // empty tile (block-uniform): nothing to write anywhere
+    if (nruns == 0) {                        // empty tile (block-uniform): nothing to write anywhere ...
+        if (SINGLE && tid == 0) nseg[f] = 0; // ... but the frame's (zero) segment count
+        return true;
+    }
     if (nruns > MAXRUNS) return false;       // block-uniform: left to the RUNS_MAX variant
     {
-        const int wi0 = ty * WR + 4 * tx;    // tile-raster word index
         int r = base;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            swpre[wi0 + i] = (unsigned short)r;
-            uint32_t rs = RS[i];
-            while (rs) {
-                const int k0 = (__ffs((int)rs) - 1) >> 1;
-                rs &= rs - 1;
-                srun[r] = (unsigned short)(((wi0 + i) << 4) | k0);
-                spar[r] = (unsigned short)r;
-                ++r;
+        for (int gi = 0; gi < GPT; ++gi) {
+            const int idx = tid * GPT + gi;
+            const int wi0 = (idx / BX) * WR + 4 * (idx % BX);    // tile-raster word index
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                swpre[wi0 + i] = (unsigned short)r;
+                uint32_t rs = RS[gi][i];
+                while (rs) {
+                    const int k0 = (__ffs((int)rs) - 1) >> 1;
+                    rs &= rs - 1;
+                    srun[r] = (unsigned short)(((wi0 + i) << 4) | k0);
+                    spar[r] = (unsigned short)r;
+                    ++r;
+                }
             }
         }
     }
+    if (SINGLE)
+        for (int w = tid; w < RBW; w += 256) rootbits[w] = 0u;
     __syncthreads();
 
     const int nact = CAN_EXIT ? min(256, (nruns + 31) & ~31) : 256;   // threads of the per-run phases (block-uniform)
@@ -528,6 +553,7 @@ __device__ __forceinline__ bool ccl_local_tile(const uint32_t* __restrict__ fbit
     // ---- phase C: roots claim an accumulator slot (entry becomes TAG | slot)
     for (int r = tid; r < nruns; r += 256) {
         if ((int)spar[r] != r) continue;
+        if (SINGLE) atomicOr(&rootbits[r >> 5], 1u << (r & 31));
         const int slot = atomicAdd(&s_misc[8], 1);
         if (slot < MAXR) {
             sroot[slot] = (unsigned short)r;
@@ -540,6 +566,30 @@ __device__ __forceinline__ bool ccl_local_tile(const uint32_t* __restrict__ fbit
         }
     }
     phase_barrier();
+    if (SINGLE) {
+        // roots in earlier bitmap words (one warp, fixed order); label of root r = 1 + roots with a smaller run id
+        if (tid < 32) {
+            uint32_t running = 0;
+            const int nwords = (nruns + 31) >> 5;
+            for (int w0 = 0; w0 < nwords; w0 += 32) {
+                const int w = w0 + lane;
+                const uint32_t c = w < nwords ? __popc(rootbits[w]) : 0u;
+                uint32_t inc = c;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                    if (lane >= d) inc += v;
+                }
+                if (w < nwords) rootpre[w] = running + inc - c;
+                running += __shfl_sync(0xFFFFFFFFu, inc, 31);
+            }
+            if (lane == 0) nseg[f] = (int32_t)running;
+        }
+        phase_barrier();
+    }
+    auto root_label = [&](int r) -> int {
+        return 1 + (int)rootpre[r >> 5] + __popc(rootbits[r >> 5] & ((1u << (r & 31)) - 1u));
+    };
 
     // tile-local run id -> global block id of its first block
     auto run_gid = [&](int r) -> int {
@@ -572,6 +622,7 @@ __device__ __forceinline__ bool ccl_local_tile(const uint32_t* __restrict__ fbit
             par[(__ffs((int)O) - 1) >> 1] = rgid;
             O &= O - 1;
         }
+        if (SINGLE && x == r) par[k0] = -root_label(r);          // the root's own block carries the tag: -label
         const RunStats s = run_stats(A & m, B & m, 2 * (by0 + rty), 32 * wx);
         if (slot < (uint32_t)MAXR) {
             atomicAdd(&st_area[slot], s.area);
@@ -607,31 +658,32 @@ __device__ __forceinline__ bool ccl_local_tile(const uint32_t* __restrict__ fbit
 }
 
 // grid = (tiles per frame, T): every tile; tiles with too many runs go on the list
-template <int BX>
+template <int BX, int GPT, bool SINGLE>
 __global__ void __launch_bounds__(256)
 k_ccl_local(const uint32_t* __restrict__ fbits, Geom g, int* __restrict__ parent, Partial* __restrict__ parts,
             int* __restrict__ pcount, int cap_parts, int32_t* __restrict__ overflow, int* __restrict__ big_tiles,
-            int* __restrict__ big_count) {
+            int* __restrict__ big_count, int32_t* __restrict__ nseg) {
     wait_for_previous_kernel();
-    if (!ccl_local_tile<BX, LocalSmem::RUNS_FAST, true>(fbits, g, parent, parts, pcount, cap_parts, overflow,
-                                                  (int)blockIdx.y, (int)blockIdx.x)) {
+    if (!ccl_local_tile<BX, GPT, LocalSmem::RUNS_FAST, true, SINGLE>(fbits, g, parent, parts, pcount, cap_parts, overflow,
+                                                                      nseg, (int)blockIdx.y, (int)blockIdx.x)) {
         if (threadIdx.x == 0) big_tiles[atomicAdd(big_count, 1)] = (int)(blockIdx.y * gridDim.x + blockIdx.x);
     }
 }
 
 // the listed tiles, with room for the worst case (usually none: the CTAs find an empty list and leave)
-template <int BX>
+template <int BX, int GPT, bool SINGLE>
 __global__ void __launch_bounds__(256)
 k_ccl_local_big(const uint32_t* __restrict__ fbits, Geom g, int* __restrict__ parent, Partial* __restrict__ parts,
                 int* __restrict__ pcount, int cap_parts, int32_t* __restrict__ overflow,
-                const int* __restrict__ big_tiles, const int* __restrict__ big_count, int tiles_per_frame) {
+                const int* __restrict__ big_tiles, const int* __restrict__ big_count, int tiles_per_frame,
+                int32_t* __restrict__ nseg) {
     wait_for_previous_kernel();
     let_next_kernel_launch();
     const int n = *big_count;
     for (int i = blockIdx.x; i < n; i += gridDim.x) {
         const int t = big_tiles[i];
-        ccl_local_tile<BX, LocalSmem::RUNS_MAX, false>(fbits, g, parent, parts, pcount, cap_parts, overflow,
-                                                t / tiles_per_frame, t % tiles_per_frame);
+        ccl_local_tile<BX, GPT, LocalSmem::runs_max(GPT), false, SINGLE>(fbits, g, parent, parts, pcount, cap_parts, overflow,
+                                                                         nseg, t / tiles_per_frame, t % tiles_per_frame);
         __syncthreads();                     // shared memory is reused by the next tile
     }
 }
@@ -773,6 +825,8 @@ k_ccl_offsets(int T, const int32_t* __restrict__ nseg, int32_t* segoff, const in
 __global__ void __launch_bounds__(256)
 k_seg_init(int T, int frame_base, const int32_t* __restrict__ nseg, const int32_t* __restrict__ segoff,
            swb_segment* __restrict__ rows, int cap_rows) {
+    wait_for_previous_kernel();
+    let_next_kernel_launch();
     const int f = blockIdx.y;
     const int n = nseg[f];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -1313,29 +1367,47 @@ k_gather_crops(const uint8_t* __restrict__ frames, long long frame_stride, long 
 
 }  // namespace
 
-template <int BX>
+template <int BX, int GPT, bool SINGLE>
 static void launch_local(cudaStream_t s, const uint32_t* fbits, int T, const Geom& g, const CclBuffers& b) {
-    constexpr int BY = 256 / BX;
+    constexpr int BY = GPT * 256 / BX;
     const int tiles = (g.BH + BY - 1) / BY;
     dim3 grid(tiles, T);
     static PerDeviceOnce once;
     if (once.need()) {
-        cudaFuncSetAttribute(k_ccl_local<BX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)LocalSmem::bytes(LocalSmem::RUNS_FAST, BX));
-        cudaFuncSetAttribute(k_ccl_local_big<BX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)LocalSmem::bytes(LocalSmem::RUNS_MAX, BX));
+        cudaFuncSetAttribute(k_ccl_local<BX, GPT, SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)LocalSmem::bytes(LocalSmem::RUNS_FAST, BX, GPT));
+        cudaFuncSetAttribute(k_ccl_local_big<BX, GPT, SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)LocalSmem::bytes(LocalSmem::runs_max(GPT), BX, GPT));
     }
     int* big_count = b.pcount + 1;
-    launch_dependent(k_ccl_local<BX>, grid, dim3(256), LocalSmem::bytes(LocalSmem::RUNS_FAST, BX), s, fbits, g, b.parent,
-                     b.parts, b.pcount, b.cap_parts, b.overflow, b.big_tiles, big_count);
+    launch_dependent(k_ccl_local<BX, GPT, SINGLE>, grid, dim3(256), LocalSmem::bytes(LocalSmem::RUNS_FAST, BX, GPT), s, fbits, g,
+                     b.parent, b.parts, b.pcount, b.cap_parts, b.overflow, b.big_tiles, big_count, b.nseg);
     const int big_grid = (int)std::min<long long>((long long)tiles * T, 148 * 4);
-    launch_dependent(k_ccl_local_big<BX>, dim3(big_grid), dim3(256), LocalSmem::bytes(LocalSmem::RUNS_MAX, BX), s,
-                     fbits, g, b.parent, b.parts, b.pcount, b.cap_parts, b.overflow, b.big_tiles, big_count, tiles);
+    launch_dependent(k_ccl_local_big<BX, GPT, SINGLE>, dim3(big_grid), dim3(256),
+                     LocalSmem::bytes(LocalSmem::runs_max(GPT), BX, GPT), s, fbits, g, b.parent, b.parts, b.pcount,
+                     b.cap_parts, b.overflow, b.big_tiles, big_count, tiles, b.nseg);
     const int n_boundaries = tiles - 1;
     if (n_boundaries > 0) {
         const int Q = g.wpr4 >> 2;
         dim3 bgrid((Q + 31) / 32, (n_boundaries + 7) / 8, T);
         launch_dependent(k_ccl_boundary, bgrid, dim3(32, 8), 0, s, fbits, g, BY, b.parent);
+    }
+}
+
+// frames that fit one tile of up to 4096 words: groups per thread (1, 2 or 4), or 0 when the frame needs several tiles
+static int single_tile_gpt(const Geom& g, int bx) {
+    if (bx > 8) return 0;
+    for (int gpt = 1; gpt <= 4; gpt *= 2)
+        if (gpt * 256 / bx >= g.BH) return gpt;
+    return 0;
+}
+
+template <int BX>
+static void launch_local_single(cudaStream_t s, const uint32_t* fbits, int T, const Geom& g, const CclBuffers& b, int gpt) {
+    if constexpr (BX <= 8) {
+        if (gpt == 1) launch_local<BX, 1, true>(s, fbits, T, g, b);
+        else if (gpt == 2) launch_local<BX, 2, true>(s, fbits, T, g, b);
+        else launch_local<BX, 4, true>(s, fbits, T, g, b);
     }
 }
 
@@ -1395,14 +1467,41 @@ cudaError_t launch_ccl(cudaStream_t s, const uint32_t* fbits, int T, const Geom&
     const bool tiled = Q <= 32;      // a tile spans the full width: frames up to 4096 pixels wide
     int launches = 0;
     if (!prepared) ccl_prepare(s, T, g, b, chain != nullptr);
+    const int single_gpt = tiled ? single_tile_gpt(g, bx) : 0;    // > 0: one CTA labels and ranks a whole frame
+    if (single_gpt > 0) {
+        switch (bx) {
+            case 1: launch_local_single<1>(s, fbits, T, g, b, single_gpt); break;
+            case 2: launch_local_single<2>(s, fbits, T, g, b, single_gpt); break;
+            case 4: launch_local_single<4>(s, fbits, T, g, b, single_gpt); break;
+            default: launch_local_single<8>(s, fbits, T, g, b, single_gpt); break;
+        }
+        launches += 2;
+        mark();
+        launch_dependent(k_ccl_offsets, dim3(1), dim3(1024), 0, s, T, b.nseg, b.segoff,
+                         chain ? chain->segoff_base : (const int32_t*)nullptr, b.cap_rows, b.overflow);
+        launch_dependent(k_seg_init, dim3(4, T), dim3(256), 0, s, T, chain ? chain->frame_base : 0, b.nseg, b.segoff, b.rows,
+                         b.cap_rows);
+        mark();
+        launch_dependent(k_props_final, dim3(PART_GRID), dim3(256), 0, s, b.parts, b.pcount, b.cap_parts, g, b.parent,
+                         b.segoff, b.rows, b.cap_rows);
+        launches += 3;
+        mark();
+        if (labels != nullptr) {
+            launch_write_labels(s, fbits, T, g, b, labels, label_elem_size, nullptr);
+            launches += 1;
+        }
+        mark();
+        if (n_launches) *n_launches += launches;
+        return cudaGetLastError();
+    }
     if (tiled) {
         switch (bx) {
-            case 1: launch_local<1>(s, fbits, T, g, b); break;
-            case 2: launch_local<2>(s, fbits, T, g, b); break;
-            case 4: launch_local<4>(s, fbits, T, g, b); break;
-            case 8: launch_local<8>(s, fbits, T, g, b); break;
-            case 16: launch_local<16>(s, fbits, T, g, b); break;
-            default: launch_local<32>(s, fbits, T, g, b); break;
+            case 1: launch_local<1, 1, false>(s, fbits, T, g, b); break;
+            case 2: launch_local<2, 1, false>(s, fbits, T, g, b); break;
+            case 4: launch_local<4, 1, false>(s, fbits, T, g, b); break;
+            case 8: launch_local<8, 1, false>(s, fbits, T, g, b); break;
+            case 16: launch_local<16, 1, false>(s, fbits, T, g, b); break;
+            default: launch_local<32, 1, false>(s, fbits, T, g, b); break;
         }
         launches += 3;
         mark();

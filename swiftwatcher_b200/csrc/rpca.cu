@@ -23,6 +23,7 @@
 // it is bit-identical (tests/golden/rpca_*.npz, produced by the reference's own rpca()).
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -596,6 +597,7 @@ cudaError_t rpca_alloc(RpcaWork& w, long long P, int nmax) {
     w.P = P;
     w.nmax = nmax;
     w.nctas = 148 * 4;
+    w.device_loop = -1;
     const size_t elems = (size_t)P * nmax;
     cudaError_t e;
     if ((e = cudaMalloc(&w.A0, elems * sizeof(double))) != cudaSuccess) return e;
@@ -665,6 +667,8 @@ __global__ void k_rpca_setup(const unsigned long long* __restrict__ sumsq, RpcaS
     r.itr = 0;
     r.done = r.zero;
     r.sweeps = 0;
+    r.cyc_eigen = r.cyc_jacobi = 0;
+    for (int i = 0; i < 8; ++i) r.sweeps_hist[i] = 0;
     *st = r;
     cudaGraphSetConditional(loop, r.zero ? 0u : 1u);                      // an all-black batch: E == 0, no iteration
 }
@@ -684,6 +688,7 @@ k_rpca_eigen21(const double* __restrict__ G, double* __restrict__ Wg, double* __
     __shared__ int pq[10][2];
     __shared__ int s_go;
     const int t = threadIdx.x, lane = t & 31;
+    const long long c_start = clock64();
     const bool warm = st->itr > 0;
     const double inv_mu = st->inv_mu;
     for (int q = t; q < n * n; q += 256) {
@@ -717,6 +722,7 @@ k_rpca_eigen21(const double* __restrict__ G, double* __restrict__ Wg, double* __
     }
     if (t < 32) {
         // ---- Jacobi sweeps, one warp
+        const long long c_j = clock64();
         int sweeps = 0;
         for (int sweep = 0; sweep < 100; ++sweep) {
             double off = 0.0, diag = 0.0;
@@ -728,7 +734,7 @@ k_rpca_eigen21(const double* __restrict__ G, double* __restrict__ Wg, double* __
                 off += __shfl_xor_sync(0xFFFFFFFFu, off, d);
                 diag += __shfl_xor_sync(0xFFFFFFFFu, diag, d);
             }
-            if (off <= 1e-34 * diag || off == 0.0) break;      // off-diagonal mass below eps^2 of the diagonal
+            if (off <= 1e-32 * diag || off == 0.0) break;      // off-diagonal mass below (eps / 10)^2 of the diagonal
             ++sweeps;
             for (int r = 0; r < n; ++r) {
                 // round r of the circle schedule on 22 players (player 21 = the bye, paired with r)
@@ -738,39 +744,50 @@ k_rpca_eigen21(const double* __restrict__ G, double* __restrict__ Wg, double* __
                     const double apq = a[p * LD + q];
                     double c = 1.0, sn = 0.0;
                     if (apq != 0.0) {
-                        const double app = a[p * LD + p], aqq = a[q * LD + q];
-                        const double theta = __ddiv_rn(aqq - app, __dmul_rn(2.0, apq));
-                        const double tt = __ddiv_rn(theta >= 0 ? 1.0 : -1.0,
-                                                    __dadd_rn(fabs(theta), sqrt(__dadd_rn(__dmul_rn(theta, theta), 1.0))));
-                        c = __ddiv_rn(1.0, sqrt(__dadd_rn(__dmul_rn(tt, tt), 1.0)));
-                        sn = __dmul_rn(tt, c);
+                        // tan of the rotation angle: t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)) with theta =
+                        // (aqq - app) / (2 apq), written without the division that forms theta:
+                        // t = sgn(d b) |b| / (|d| + sqrt(d^2 + b^2)), d = aqq - app, b = 2 apq  (three long
+                        // operations — sqrt, div, rsqrt — on the warp's critical path instead of five)
+                        const double d = a[q * LD + q] - a[p * LD + p], b2 = 2.0 * apq;
+                        const double tt = copysign(fabs(b2) / (fabs(d) + sqrt(fma(d, d, b2 * b2))), (d >= 0.0) == (b2 >= 0.0) ? 1.0 : -1.0);
+                        c = rsqrt(fma(tt, tt, 1.0));
+                        sn = tt * c;
                     }
                     cs[lane][0] = c; cs[lane][1] = sn;
                     pq[lane][0] = p; pq[lane][1] = q;
                 }
                 __syncwarp();
-                if (lane < n) {                                // columns p, q of a and of v, row `lane`
+                if (lane < n) {                                // columns p, q of a and of v, row `lane`: all loads, then the math
+                    double ap[10], aq[10], vp_[10], vq_[10];
+#pragma unroll
+                    for (int i = 0; i < 10; ++i) {
+                        const int p = pq[i][0], q = pq[i][1];
+                        ap[i] = a[lane * LD + p]; aq[i] = a[lane * LD + q];
+                        vp_[i] = v[lane * LD + p]; vq_[i] = v[lane * LD + q];
+                    }
 #pragma unroll
                     for (int i = 0; i < 10; ++i) {
                         const int p = pq[i][0], q = pq[i][1];
                         const double c = cs[i][0], sn = cs[i][1];
-                        const double akp = a[lane * LD + p], akq = a[lane * LD + q];
-                        a[lane * LD + p] = __dsub_rn(__dmul_rn(c, akp), __dmul_rn(sn, akq));
-                        a[lane * LD + q] = __dadd_rn(__dmul_rn(sn, akp), __dmul_rn(c, akq));
-                        const double vkp = v[lane * LD + p], vkq = v[lane * LD + q];
-                        v[lane * LD + p] = __dsub_rn(__dmul_rn(c, vkp), __dmul_rn(sn, vkq));
-                        v[lane * LD + q] = __dadd_rn(__dmul_rn(sn, vkp), __dmul_rn(c, vkq));
+                        a[lane * LD + p] = c * ap[i] - sn * aq[i];
+                        a[lane * LD + q] = sn * ap[i] + c * aq[i];
+                        v[lane * LD + p] = c * vp_[i] - sn * vq_[i];
+                        v[lane * LD + q] = sn * vp_[i] + c * vq_[i];
                     }
                 }
                 __syncwarp();
                 if (lane < n) {                                // rows p, q of a, column `lane`
+                    double ap[10], aq[10];
 #pragma unroll
                     for (int i = 0; i < 10; ++i) {
-                        const int p = pq[i][0], q = pq[i][1];
+                        ap[i] = a[pq[i][0] * LD + lane];
+                        aq[i] = a[pq[i][1] * LD + lane];
+                    }
+#pragma unroll
+                    for (int i = 0; i < 10; ++i) {
                         const double c = cs[i][0], sn = cs[i][1];
-                        const double apk = a[p * LD + lane], aqk = a[q * LD + lane];
-                        a[p * LD + lane] = __dsub_rn(__dmul_rn(c, apk), __dmul_rn(sn, aqk));
-                        a[q * LD + lane] = __dadd_rn(__dmul_rn(sn, apk), __dmul_rn(c, aqk));
+                        a[pq[i][0] * LD + lane] = c * ap[i] - sn * aq[i];
+                        a[pq[i][1] * LD + lane] = sn * ap[i] + c * aq[i];
                     }
                 }
                 __syncwarp();
@@ -781,7 +798,11 @@ k_rpca_eigen21(const double* __restrict__ G, double* __restrict__ Wg, double* __
             const double sv = d > 0.0 ? sqrt(d) : 0.0;
             dsc[lane] = sv > 0.0 ? __ddiv_rn(sv - inv_mu, sv) : 0.0;   // exactly dependent columns are skipped (see header)
         }
-        if (lane == 0) st->sweeps += sweeps;
+        if (lane == 0) {
+            st->sweeps += sweeps;
+            st->cyc_jacobi += clock64() - c_j;
+            if (st->itr < 8) st->sweeps_hist[st->itr] = sweeps;
+        }
     }
     __syncthreads();
     // V = Vp Vb (kept for the next warm start), then W = V diag(f) V^T
@@ -799,6 +820,8 @@ k_rpca_eigen21(const double* __restrict__ G, double* __restrict__ Wg, double* __
         for (int k = 0; k < n; ++k) acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(tmp[i * LD + k], dsc[k]), tmp[j * LD + k]));
         Wg[q] = acc;
     }
+    __syncthreads();
+    if (t == 0) st->cyc_eigen += clock64() - c_start;
     (void)s_go;
 }
 
@@ -921,8 +944,14 @@ cudaError_t rpca_run(cudaStream_t s, const uint8_t* X, int n, long long P, RpcaW
                      int* n_launches) {
     if (n < 1 || n > w.nmax || P > w.P) return cudaErrorInvalidValue;
     w.last_mode = 0;
-    static const bool host_loop = [] { const char* e = getenv("SWB_RPCA_HOST_LOOP"); return e && e[0] == '1'; }();
-    if (n == 21 && !host_loop) {
+    // Where the iteration loop runs.  Device (CUDA-graph WHILE node): nothing blocks, nothing is copied, but the
+    // 21 x 21 eigenproblem is one warp's work (~25 us per Jacobi sweep, 100-150 us per iteration); host: two
+    // stream synchronisations per iteration, eigenproblem in ~40 us.  Measured on a B200: 1080p full frame 9.8
+    // (device) vs 10.0 ms (host) per batch, 320x160 ROI 3.0 vs 2.6 ms.  Automatic choice: the device loop where
+    // an iteration's streaming pass outweighs the eigenproblem (>= 256 Ki pixels), the host loop below.
+    static const int env_loop = [] { const char* e = getenv("SWB_RPCA_HOST_LOOP"); return e ? (e[0] == '1' ? 0 : 1) : -1; }();
+    const int want = w.device_loop >= 0 ? w.device_loop : (env_loop >= 0 ? env_loop : (P >= (1 << 18) ? 1 : 0));
+    if (n == 21 && want == 1) {
         static PerDeviceOnce once_g;
         if (once_g.need()) {
             cudaFuncSetAttribute(k_rpca_gram21, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1093,6 +1122,12 @@ cudaError_t rpca_read_state(cudaStream_t s, RpcaWork& w, int* iters, int* sweeps
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
         if (e != cudaSuccess) return e;
         memcpy(&r, w.h_buf, sizeof(r));
+        static const bool dbg = [] { const char* e = getenv("SWB_RPCA_DEBUG"); return e && e[0] == '1'; }();
+        if (dbg)
+            fprintf(stderr, "rpca: %d iterations, %d sweeps (first eight: %d %d %d %d %d %d %d %d), eigen kernel %.1f us / iteration "
+                            "of which Jacobi %.1f us (at 1.965 GHz)\n", r.itr, r.sweeps, r.sweeps_hist[0], r.sweeps_hist[1],
+                    r.sweeps_hist[2], r.sweeps_hist[3], r.sweeps_hist[4], r.sweeps_hist[5], r.sweeps_hist[6], r.sweeps_hist[7],
+                    r.cyc_eigen / 1965.0 / std::max(r.itr, 1), r.cyc_jacobi / 1965.0 / std::max(r.itr, 1));
         if (iters) *iters = r.itr;
         if (sweeps) *sweeps = r.sweeps;
     } else {

@@ -135,6 +135,8 @@ struct RpcaState {
     double inv_mu_next, thr_next;    // the next iteration's (the fused pass prepares its Gram matrix)
     double dnorm, dual_norm;         // |X|_F;  max(|X|_2-ish, |X|_inf / lambda)  (image_filtering.py:269-275)
     int itr, done, zero, sweeps;     // iterations taken; stop flag; all-black batch; Jacobi sweeps so far
+    long long cyc_eigen, cyc_jacobi; // SM cycles spent in k_rpca_eigen21 / in its Jacobi sweeps (all iterations)
+    int sweeps_hist[8];              // Jacobi sweeps of the first eight iterations
 };
 
 struct RpcaWork {
@@ -152,6 +154,7 @@ struct RpcaWork {
     uint8_t* g_out;
     long long g_P;
     int graph_failed, last_mode, host_iters;   // last_mode: 1 = graph loop, 0 = host loop
+    int device_loop;                           // option "rpca_device_loop": 1 / 0 force the loop's place, -1 = automatic
 };
 cudaError_t rpca_alloc(RpcaWork& w, long long P, int nmax);
 void rpca_free(RpcaWork& w);

@@ -393,26 +393,6 @@ def test_sub_batches_equal_one_batch(n, T, se, close, mode):
         assert np.array_equal(ctx.labels(), labels_d)
 
 
-@pytest.mark.parametrize("mode,T", [("i32", 70), ("u8", 64), ("i32", 131)])
-def test_labelling_in_pieces_beside_the_label_writer(mode, T):
-    """Large device-resident submits are labelled in four pieces of frames on a second stream while the label
-    writer of the previous piece runs (forced here with the "label_overlap_min_px" option; real submits reach
-    it at 128 Mi label pixels): same masks, labels and table — offsets chained across the pieces — as the oracle."""
-    import torch
-    frames = synth.synth_video(34, 0, 0, T, 50, 110, 60)
-    region = [(5, 3), (108, 49)]
-    dev = torch.from_numpy(frames).cuda()
-    with swb.FilterContext(frames.shape[1:], region, label_mode=mode, max_frames=T) as ctx:
-        ctx.set_option("label_overlap_min_px", 1)
-        check_against_oracle(frames, region, mode=mode, ctx=ctx, submit_frames=dev, n_halo=0)
-        rows_a, counts_a = ctx.collect()
-        ctx.set_option("label_overlap", 0)
-        ctx.reset()
-        ctx.submit(dev, n_halo=0)
-        rows_b, counts_b = ctx.collect()
-        assert np.array_equal(rows_a, rows_b) and np.array_equal(counts_a, counts_b)
-
-
 def test_fuzz_small_shapes_and_parameters():
     """Seeded sweep over odd frame / ROI shapes (down to one pixel), every window length,
     both structuring elements, open / close combinations, thresholds, host and device frames."""
