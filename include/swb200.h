@@ -263,6 +263,12 @@ int swb_tracker_costs(swb_tracker* t, const double* prev_yx, const double* first
 const char* swb_tracker_last_error(const swb_tracker* t);
 int64_t swb_tracker_launch_count(const swb_tracker* t);
 
+/* Host-side helper of the drop-in (no device involved): copies n tiles of rows x row_bytes bytes, tile i starting at
+ * host address src[i] with `pitch` bytes between its rows, into dst[n][rows][row_bytes].  FrameQueue.segment_queue
+ * cuts the colour crops of all segments of a batch (extract_segment_images, image_filtering.py:338-369: views into the
+ * host frames) with one call instead of one numpy slice-and-copy per segment. */
+int swb_host_gather_tiles(const uint64_t* src, int64_t pitch, int32_t rows, int32_t row_bytes, int64_t n, uint8_t* dst);
+
 /* Page-locked host memory for frame ingest (io_video.py:11-165 decodes frames into host
  * arrays; frames decoded into these buffers reach the device by DMA at full PCIe speed
  * and asynchronously).  Portable across devices.  Needs a CUDA device like everything else. */

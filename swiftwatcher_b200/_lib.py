@@ -84,6 +84,7 @@ SYMBOLS = {
     "swb_tracker_costs": (C.c_int, [_P, _P, _P, _P, _I32, _P, _I32, C.POINTER(_P)]),
     "swb_tracker_last_error": (C.c_char_p, [_P]),
     "swb_tracker_launch_count": (_I64, [_P]),
+    "swb_host_gather_tiles": (C.c_int, [_P, _I64, _I32, _I32, _I64, _P]),
     "swb_host_alloc": (C.c_int, [C.POINTER(_P), C.c_uint64]),
     "swb_host_free": (C.c_int, [_P]),
     "swb_synth_frames": (C.c_int, [_I32, _P, _I32, _U32, _U32, _I32, _I32, _I32, _I32, _I32]),
@@ -126,6 +127,12 @@ def device_count():
     n = _I32(0)
     rc = load().swb_device_count(C.byref(n))
     return n.value if rc == SWB_OK else 0
+
+
+def gather_tiles(addresses, pitch, rows, row_bytes, out):
+    """``out[i] = rows x row_bytes bytes starting at host address addresses[i]`` (row pitch ``pitch``)."""
+    check(load().swb_host_gather_tiles(C.c_void_p(addresses.ctypes.data), int(pitch), int(rows), int(row_bytes),
+                                       len(addresses), C.c_void_p(out.ctypes.data)))
 
 
 def ptr(a):

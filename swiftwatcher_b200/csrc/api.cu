@@ -1032,6 +1032,17 @@ int swb_stage_bilateral(int32_t device, const uint8_t* in, int32_t h, int32_t w,
     return SWB_OK;
 }
 
+int swb_host_gather_tiles(const uint64_t* src, int64_t pitch, int32_t rows, int32_t row_bytes, int64_t n, uint8_t* dst) {
+    if ((n > 0 && (!src || !dst)) || rows <= 0 || row_bytes <= 0 || n < 0) return fail(nullptr, SWB_ERR_INVALID, "bad argument");
+    const size_t tile = (size_t)rows * row_bytes;
+    for (int64_t i = 0; i < n; ++i) {
+        const uint8_t* s = reinterpret_cast<const uint8_t*>(static_cast<uintptr_t>(src[i]));
+        uint8_t* d = dst + (size_t)i * tile;
+        for (int r = 0; r < rows; ++r) memcpy(d + (size_t)r * row_bytes, s + (size_t)r * pitch, (size_t)row_bytes);
+    }
+    return SWB_OK;
+}
+
 int swb_host_alloc(void** ptr, uint64_t bytes) {
     if (!ptr || bytes == 0) return fail(nullptr, SWB_ERR_INVALID, "bad argument");
     *ptr = nullptr;

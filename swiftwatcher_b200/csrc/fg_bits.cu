@@ -905,7 +905,7 @@ k_fg_bits_v2(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t on
 template <int V>
 struct IntC { static constexpr int value = V; };
 
-template <int C, int OCC>
+template <int C, int OCC, bool FMA_MERGE>
 __global__ void __launch_bounds__(V2_THREADS, OCC)
 k_fg_n9(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t one, uint8_t* __restrict__ raw_bits,
         const __grid_constant__ CUtensorMap tmap, int tile_rows, int n_long_blocks, int ts_tail) {
@@ -1159,8 +1159,10 @@ k_fg_n9(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t one, ui
             const uint32_t qq = vmin2(st[ia][2][q], st[ib][2][q]);
             const uint32_t uu = vmin2(st[ia][1][q], st[ib][1][q]);
             const uint32_t vv = fa.sub(fa.add(st[ia][1][q], st[ib][1][q]), uu);
-            const uint32_t m2 = vmin2(pp, uu), m5 = vmax2(qq, vv);
-            const uint32_t gg = vmax2(pp, uu), hh = vmin2(qq, vv);
+            const uint32_t m2 = vmin2(pp, uu), hh = vmin2(qq, vv);
+            // max(a, b) = a + b - min(a, b): two multiply-adds on the FMA pipe instead of one VIMNMX on the ALU pipe
+            const uint32_t gg = FMA_MERGE ? fa.sub(fa.add(pp, uu), m2) : vmax2(pp, uu);
+            const uint32_t m5 = FMA_MERGE ? fa.sub(fa.add(qq, vv), hh) : vmax2(qq, vv);
             const uint32_t m3 = vmin2(gg, hh);
             const uint32_t m4 = fa.sub(fa.add(gg, hh), m3);
             // (first | second << 8) per u16 half -> two lanes: one PRMT each (bytes 0, 2 / bytes 1, 3 into the low bytes)
@@ -1205,14 +1207,14 @@ k_fg_n9(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t one, ui
 // Column blocks of the N = 9 kernel over the machine: with `slots` CTAs resident at a time, the blocks of
 // the last, partial wave would run on a mostly idle GPU for as long as a full wave takes.  Those blocks are
 // cut into temporal sub-chunks short enough to spread them over all slots.
-template <int C, int OCC>
+template <int C, int OCC, bool FMA_MERGE>
 cudaError_t launch_n9(cudaStream_t s, const FrameSrc& src, int T, const Geom& g, int thresh, uint16_t* raw_bits,
                       int gpu_share) {
     constexpr int N = 9, L = 4, TB = 2 * L * C;
     constexpr int SMEM = 3 * 3 * CONSUMERS * TB + 2 * 3 * 8 + 16 + 3 * CONSUMERS * 16;
     static PerDeviceOnce once;
     if (once.need()) {
-        cudaError_t e = cudaFuncSetAttribute(k_fg_n9<C, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        cudaError_t e = cudaFuncSetAttribute(k_fg_n9<C, OCC, FMA_MERGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) return e;
     }
     const int gpr = g.wa / (2 * L);
@@ -1254,7 +1256,7 @@ cudaError_t launch_n9(cudaStream_t s, const FrameSrc& src, int T, const Geom& g,
     }
     const int per_tail = (T + ts_tail - 1) / ts_tail;
     const long long grid = (long long)n_long * per_long + (long long)(n_col_blocks - n_long) * per_tail;
-    k_fg_n9<C, OCC><<<(unsigned)grid, V2_THREADS, SMEM, s>>>(src, T, Ts, g.h, g.wa, thresh, 1u,
+    k_fg_n9<C, OCC, FMA_MERGE><<<(unsigned)grid, V2_THREADS, SMEM, s>>>(src, T, Ts, g.h, g.wa, thresh, 1u,
                                                             reinterpret_cast<uint8_t*>(raw_bits), tmap, tile_rows,
                                                             n_long, ts_tail);
     return cudaGetLastError();
@@ -1305,8 +1307,12 @@ cudaError_t launch_v2(cudaStream_t s, const FrameSrc& src, int T, const Geom& g,
         // the N = 9 loop fits 72 registers: three CTAs (24 consumer warps) per SM
         static const bool occ2 = [] { const char* e = getenv("SWB_K1_N9_OCC"); return e && e[0] == '2'; }();
         static const bool v2 = [] { const char* e = getenv("SWB_K1_N9_V2"); return e && e[0] == '1'; }();
-        if (!v2) return occ2 ? launch_n9<C, 2>(s, src, T, g, thresh, raw_bits, gpu_share)
-                             : launch_n9<C, 3>(s, src, T, g, thresh, raw_bits, gpu_share);
+        static const bool fma_merge = [] { const char* e = getenv("SWB_K1_N9_FMA_MERGE"); return !(e && e[0] == '0'); }();
+        if (!v2) {
+            if (occ2) return launch_n9<C, 2, false>(s, src, T, g, thresh, raw_bits, gpu_share);
+            return fma_merge ? launch_n9<C, 3, true>(s, src, T, g, thresh, raw_bits, gpu_share)
+                             : launch_n9<C, 3, false>(s, src, T, g, thresh, raw_bits, gpu_share);
+        }
         if (!occ2) return launch_v2_occ<N, C, 3>(s, src, T, g, thresh, raw_bits, gpu_share);
     }
     return launch_v2_occ<N, C, 2>(s, src, T, g, thresh, raw_bits, gpu_share);

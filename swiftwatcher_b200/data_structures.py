@@ -30,7 +30,7 @@ from pathlib import Path
 import numpy as np
 
 from . import image_filtering as img
-from ._lib import HALO_CARRY, MEM_HOST, is_pinned, pinned_empty
+from ._lib import HALO_CARRY, MEM_HOST, gather_tiles, is_pinned, pinned_empty
 from .pipeline import FilterContext, centroids, clamp_crop_region, props_from_rows  # noqa: F401
 
 
@@ -351,18 +351,42 @@ class FrameQueue(deque):
         offs = np.concatenate([[0], np.cumsum(counts)]).tolist()
         label, area, bbox = rows["label"].tolist(), rows["area"].tolist(), rows["bbox"].tolist()
         cen = centroids(rows).tolist() if len(rows) else []
-        box = img.expand_bboxes(rows["bbox"], min_seg_size, crop_region).tolist() if len(rows) else []
+        boxes = img.expand_bboxes(rows["bbox"], min_seg_size, crop_region) if len(rows) else np.zeros((0, 4), np.int64)
+        box = boxes.tolist()
+        # The common case — the grown bbox is exactly min_seg_size and inside the frame — is cut for the whole batch
+        # by one library call (row memcpys); anything else (larger birds, frame edges) keeps the reference's slice.
+        first = frames[0]
+        mh, mw = int(min_seg_size[0]), int(min_seg_size[1])
+        tiles, plain_l, tile_of = None, None, None
+        uniform = all(isinstance(f, np.ndarray) and f.dtype == np.uint8 and f.shape == first.shape and
+                      f.strides == first.strides and f.strides[-1] == 1 for f in frames)
+        if uniform and len(rows):
+            fh, fw = first.shape[0], first.shape[1]
+            pitch, px = first.strides[0], first.strides[1]
+            plain = ((boxes[:, 2] - boxes[:, 0] == mh) & (boxes[:, 3] - boxes[:, 1] == mw) & (boxes[:, 0] >= 0) &
+                     (boxes[:, 1] >= 0) & (boxes[:, 2] <= fh) & (boxes[:, 3] <= fw))
+            sel = np.flatnonzero(plain)
+            if len(sel):
+                base = np.array([f.__array_interface__["data"][0] for f in ordered], dtype=np.uint64)   # by frame index t
+                addr = base[rows["frame"][sel]] + (boxes[sel, 0] * pitch + boxes[sel, 1] * px).astype(np.uint64)
+                tiles = np.empty((len(sel), mh, mw) + first.shape[2:], np.uint8)
+                gather_tiles(np.ascontiguousarray(addr), pitch, mh, mw * px, tiles)
+                plain_l = plain.tolist()
+                tile_of = (np.cumsum(plain) - 1).tolist()      # table row -> its tile
         for pos in range(n):
             t = n - 1 - pos
             fr = self[pos]
             full, number, stamp = fr.frame, fr.frame_number, fr.timestamp
             segs = []
             for i in range(offs[t], offs[t + 1]):
-                b = box[i]
+                if plain_l is not None and plain_l[i]:
+                    image = tiles[tile_of[i]]
+                else:
+                    b = box[i]
+                    image = full[b[0]:b[2], b[1]:b[3]].copy()
                 seg = Segment.__new__(Segment)
-                seg.__dict__ = {"parent_frame_number": number, "parent_timestamp": stamp,
-                                "segment_image": full[b[0]:b[2], b[1]:b[3]].copy(), "segment_history": [],
-                                "status": None, "label": label[i], "area": area[i], "bbox": tuple(bbox[i]),
-                                "centroid": tuple(cen[i])}
+                seg.__dict__ = {"parent_frame_number": number, "parent_timestamp": stamp, "segment_image": image,
+                                "segment_history": [], "status": None, "label": label[i], "area": area[i],
+                                "bbox": tuple(bbox[i]), "centroid": tuple(cen[i])}
                 segs.append(seg)
             fr.segments = segs

@@ -167,3 +167,17 @@ def test_ingest_ring_peek_does_not_consume():
         assert np.array_equal(first[0][3], frames[3])
     finally:
         ring.close()
+
+
+def test_host_tile_gather_equals_numpy_slices():
+    """swb_host_gather_tiles (plain host memcpys; what segment_queue cuts the 24x24 segment images with)."""
+    from swiftwatcher_b200._lib import gather_tiles
+    rng = np.random.default_rng(3)
+    frames = rng.integers(0, 256, (3, 50, 70, 3), dtype=np.uint8)
+    boxes = [(0, 0, 0), (1, 26, 46), (2, 7, 13), (0, 20, 5)]
+    pitch, px = frames.strides[1], frames.strides[2]
+    addr = np.array([frames[t].__array_interface__["data"][0] + y * pitch + x * px for t, y, x in boxes], dtype=np.uint64)
+    out = np.empty((len(boxes), 24, 24, 3), np.uint8)
+    gather_tiles(addr, pitch, 24, 24 * px, out)
+    for k, (t, y, x) in enumerate(boxes):
+        assert np.array_equal(out[k], frames[t, y:y + 24, x:x + 24])
