@@ -273,6 +273,16 @@ def test_tall_narrow_frames_cross_tile_boundaries():
                              max_segments=100000)
 
 
+@pytest.mark.parametrize("se,do_close", [(3, False), (5, True), (3, True)])
+def test_wide_rois_span_several_morphology_slabs(se, do_close):
+    """ROIs wider than one 30-word slab of the morphology kernel, several strips of rows tall: unaligned ROI origin
+    (bit realignment across the slab's edge word), ROI touching the frame's borders, a frame width that is not a
+    multiple of 16 pixels behind the ROI."""
+    frames = synth.synth_video(35, 0, 0, 7, 150, 2100, 400)
+    for region in ([(37, 3), (1300, 148)], [(0, 0), (2048, 150)], [(845, 0), (2100, 150)]):
+        check_against_oracle(frames, region, n=5, se=se, do_close=do_close, mode="i32", max_segments=7 * 4096)
+
+
 def test_gray_input_frames():
     rng = np.random.default_rng(12)
     frames = rng.integers(0, 256, (6, 50, 90), dtype=np.uint8)
