@@ -13,7 +13,7 @@ import os
 import subprocess
 import sys
 
-GROUPS = [("k_fg_bits", "fg_bits"), ("k_morph_mask", "morph_mask"), ("k_ccl_local", "ccl_merge"),
+GROUPS = [("k_fg_bits", "fg_bits"), ("k_fg_n9", "fg_bits"), ("k_morph_mask", "morph_mask"), ("k_ccl_local", "ccl_merge"),
           ("k_ccl_boundary", "ccl_merge"), ("k_ccl_init", "ccl_merge"), ("k_ccl_merge", "ccl_merge"),
           ("k_root_count", "ccl_rank"), ("k_ccl_scan", "ccl_rank"), ("k_ccl_offsets", "ccl_rank"),
           ("k_seg_init", "ccl_rank"), ("k_root_place", "ccl_rank"), ("k_root_rank", "ccl_rank"),

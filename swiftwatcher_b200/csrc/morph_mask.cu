@@ -19,11 +19,46 @@
 // (origin X0a) to ROI-local columns (origin roi_x0), writes the final bit words
 // (rows padded to wpr4 words with zeros) and expands them to the {0,255} uint8
 // mask with 16-byte stores that are contiguous across the warp.
+#include <cuda.h>          // CUtensorMap (types only: the encoder is fetched through the runtime)
+
+#include <cstdlib>
+#include <cstring>
+
 #include "swb_internal.cuh"
 
 namespace swb {
 
 namespace {
+
+// ---- TMA staging (STAGED variant): one tensor-map box load brings every raw bit word a warp's strip needs.
+// The box starts at a word column that is a multiple of four (the innermost start of a tiled tensor load has to be
+// 16-byte aligned: an unaligned start is an illegal instruction, profiles/probes/tma_probe.cu) and at a row >= 0.
+__device__ __forceinline__ uint32_t k2_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+constexpr int BOXW = 36;   // words per staged row: up to 3 words of alignment slack + the slab's 32 words + the edge word
+
+typedef CUresult (*K2EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// raw bits as a tensor (words per row, rows, frames) of 32-bit elements; box = (BOXW, box_rows, 1)
+bool encode_raw_bits_tensor(CUtensorMap* tmap, const uint32_t* base, int wpr_raw, int h, int T, int box_rows) {
+    static K2EncodeFn encode = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            fn = nullptr;
+        return reinterpret_cast<K2EncodeFn>(fn);
+    }();
+    if (!encode || box_rows > 256 || (wpr_raw & 3) || (reinterpret_cast<uintptr_t>(base) & 15)) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)wpr_raw, (cuuint64_t)h, (cuuint64_t)T};
+    const cuuint64_t strides[2] = {(cuuint64_t)wpr_raw * 4, (cuuint64_t)wpr_raw * 4 * (cuuint64_t)h};
+    const cuuint32_t box[3] = {(cuuint32_t)BOXW, (cuuint32_t)box_rows, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    return encode(tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint32_t*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 constexpr int SLAB = 30;   // output words per warp
 constexpr int WPB = 4;     // warps per CTA
@@ -64,9 +99,12 @@ __device__ __forceinline__ uint32_t hop(uint32_t l, uint32_t c, uint32_t r, bool
 // SEG: lanes per frame.  32: the warp works on one frame.  16 (rows of at most 14 words: narrow ROIs): the two
 // half-warps work on the same rows of two consecutive frames, each with its own halo lanes, so a narrow
 // ROI keeps 28 of 32 lanes busy instead of 12; `live` is false for the half-warp past the last frame.
-template <int R, int PAT, bool INTERIOR, bool DX0, int SEG>
+// STAGED: the raw rows [row0, row0 + staged rows) of the strip, BOXW words each starting at word column col0, were
+// brought to shared memory (`srow`) by one TMA box load (rows / columns past the image arrived as zeros).
+template <int R, int PAT, bool INTERIOR, bool DX0, int SEG, bool STAGED = false>
 __device__ __forceinline__ void morph_strip(const uint32_t* __restrict__ raw_f, const Geom& g, uint32_t* __restrict__ fbits,
-                                            uint8_t* __restrict__ mask, int f, bool live, int slab, int lane, int y0) {
+                                            uint8_t* __restrict__ mask, int f, bool live, int slab, int lane, int y0,
+                                            const uint32_t* srow = nullptr, int row0 = 0, int col0 = 0) {
     constexpr int SLABW = SEG - 2;                           // output words per segment
     const int hl = lane & (SEG - 1);                         // lane within the segment
     const int seg0 = lane & ~(SEG - 1);
@@ -108,7 +146,14 @@ __device__ __forceinline__ void morph_strip(const uint32_t* __restrict__ raw_f, 
     auto fetch = [&](int y, uint32_t& lo, uint32_t& edge) {
         lo = 0u;
         edge = 0u;
-        if ((INTERIOR || (unsigned)y < (unsigned)g.h) && live) {
+        if constexpr (STAGED) {
+            const int yrel = y - row0;                               // rows above the image (and the one-row overshoot
+            if ((unsigned)yrel < (unsigned)(SR + 2 * HR) && j >= 0) {   // of the prefetch) read as zeros
+                const uint32_t* rowp = srow + yrel * BOXW + (j - col0);
+                lo = rowp[0];
+                if (!DX0 && hl == SEG - 1) edge = rowp[1];
+            }
+        } else if ((INTERIOR || (unsigned)y < (unsigned)g.h) && live) {
             const uint32_t* rowp = raw_f + (long long)y * g.wpr_raw;
             if (in_raw) lo = __ldg(rowp + j);
             if (!DX0 && hl == SEG - 1 && in_raw_next) edge = __ldg(rowp + j + 1);
@@ -212,6 +257,75 @@ k_morph_mask(const uint32_t* __restrict__ raw_bits, Geom g, int T, uint32_t* __r
     }
 }
 
+// The same strips with the raw rows staged by TMA (frames wider than one slab whose raw rows are 16-byte multiples):
+// the loads of a strip are all in flight at once instead of one row ahead of the arithmetic (the streaming kernel's
+// top stall was that load: 6.5 cycles of long-scoreboard stall per issued instruction at 4K).
+template <int R, int PAT>
+__global__ void __launch_bounds__(32 * WPB)
+k_morph_mask_staged(const __grid_constant__ CUtensorMap tmap, Geom g, int T, uint32_t* __restrict__ fbits,
+                    uint8_t* __restrict__ mask) {
+    constexpr int HR = n_ops(PAT) * R;
+    constexpr int SR = strip_rows(R, PAT);
+    constexpr int ROWS = SR + 2 * HR;
+    constexpr int REGION = (ROWS * BOXW * 4 + 127) / 128 * 128;   // per-warp staging area, 128-byte aligned for TMA
+    extern __shared__ __align__(128) uint8_t k2_smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    uint32_t* srow = reinterpret_cast<uint32_t*>(k2_smem + warp * REGION);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(k2_smem + WPB * REGION) + warp;
+    const int slab = blockIdx.x;
+    const int f = blockIdx.z;
+    const int y0 = (blockIdx.y * WPB + warp) * SR;
+    if (y0 >= g.h) return;                                   // warp-uniform
+    const int row0 = max(y0 - HR, 0);                        // box start: a row inside the image ...
+    const int col0 = max(slab * SLAB - 1, 0) & ~3;           // ... and a 16-byte aligned word column
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(k2_smem_u32(bar)), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    wait_for_previous_kernel();                              // launched as a dependent of K1 (raw bits)
+    if (lane == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(k2_smem_u32(bar)),
+                     "r"((uint32_t)(ROWS * BOXW * 4))
+                     : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                k2_smem_u32(srow)),
+            "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(col0), "r"(row0), "r"(f), "r"(k2_smem_u32(bar))
+            : "memory");
+    }
+    {
+        const uint32_t addr = k2_smem_u32(bar);
+        uint32_t done = 0;
+        int spins = 0;
+        while (true) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(addr), "r"(0u)
+                : "memory");
+            if (done) break;
+            if (++spins > (1 << 20)) __trap();               // never hang the GPU on a pipeline bug
+        }
+    }
+    const bool interior = (y0 - HR >= 0) && (y0 + SR + HR <= g.h);   // warp-uniform
+    if (g.dx == 0) {
+        if (interior) morph_strip<R, PAT, true, true, 32, true>(nullptr, g, fbits, mask, f, true, slab, lane, y0, srow, row0, col0);
+        else morph_strip<R, PAT, false, true, 32, true>(nullptr, g, fbits, mask, f, true, slab, lane, y0, srow, row0, col0);
+    } else {
+        if (interior) morph_strip<R, PAT, true, false, 32, true>(nullptr, g, fbits, mask, f, true, slab, lane, y0, srow, row0, col0);
+        else morph_strip<R, PAT, false, false, 32, true>(nullptr, g, fbits, mask, f, true, slab, lane, y0, srow, row0, col0);
+    }
+}
+
+bool k2_tma_enabled() {
+    static const bool on = [] { const char* e = getenv("SWB_K2_TMA"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 template <int R, int PAT>
 cudaError_t launch_pat(cudaStream_t s, const uint32_t* raw_bits, int T, const Geom& g, uint32_t* fbits,
                        uint8_t* mask) {
@@ -224,6 +338,21 @@ cudaError_t launch_pat(cudaStream_t s, const uint32_t* raw_bits, int T, const Ge
     }
     const int nslabs = (g.wpr4 + SLAB - 1) / SLAB;
     dim3 grid(nslabs, (nstrips + WPB - 1) / WPB, T);
+    // Measured on a B200: 5x5 open + close at 4K 0.566 -> 0.546 ms, 3x3 open at 1080p 0.468 -> 0.478 ms (the short
+    // chains are bound by the mask stores and their own arithmetic, not by the raw-row load): staged only where the
+    // vertical halo is deep (64-row strips).
+    if (k2_tma_enabled() && nslabs >= 2 && SR == 64) {
+        constexpr int ROWS = SR + 2 * n_ops(PAT) * R;
+        constexpr int SMEM = WPB * ((ROWS * BOXW * 4 + 127) / 128 * 128) + WPB * 8;
+        CUtensorMap tmap;
+        if (encode_raw_bits_tensor(&tmap, raw_bits, g.wpr_raw, g.h, T, ROWS)) {
+            static PerDeviceOnce once;
+            if (once.need())
+                cudaFuncSetAttribute(k_morph_mask_staged<R, PAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+            launch_dependent(k_morph_mask_staged<R, PAT>, grid, dim3(32 * WPB), (size_t)SMEM, s, tmap, g, T, fbits, mask);
+            return cudaGetLastError();
+        }
+    }
     launch_dependent(k_morph_mask<R, PAT, 32>, grid, dim3(32 * WPB), 0, s, raw_bits, g, T, fbits, mask);
     return cudaGetLastError();
 }
