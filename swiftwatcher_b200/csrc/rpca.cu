@@ -983,15 +983,19 @@ cudaError_t rpca_run(cudaStream_t s, const uint8_t* X, int n, long long P, RpcaW
     const int smem_gram = RP_NMAX * (RP_THREADS + 1) * (int)sizeof(double);
     const int smem_apply = (RP_NMAX * RP_NMAX + 2 * RP_NMAX * RP_THREADS) * (int)sizeof(double);
     if (once.need()) {
-        cudaFuncSetAttribute(k_rpca_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_gram);
-        cudaFuncSetAttribute(k_rpca_gram21, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_gram);
-        cudaFuncSetAttribute(k_rpca_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_apply);
-        cudaFuncSetAttribute(k_rpca_apply_n<21>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             21 * RP_THREADS * (int)sizeof(double));
-        cudaFuncSetAttribute(k_rpca_apply_pair<21, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             21 * (RP_THREADS / 2 + 8) * 17);
-        cudaFuncSetAttribute(k_rpca_apply_pair<21, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             21 * (RP_THREADS / 2 + 8) * 17);
+        // a failed shared-memory opt-in is reported here, not as a generic launch error later
+        cudaError_t ea[6] = {
+            cudaFuncSetAttribute(k_rpca_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_gram),
+            cudaFuncSetAttribute(k_rpca_gram21, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_gram),
+            cudaFuncSetAttribute(k_rpca_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_apply),
+            cudaFuncSetAttribute(k_rpca_apply_n<21>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 21 * RP_THREADS * (int)sizeof(double)),
+            cudaFuncSetAttribute(k_rpca_apply_pair<21, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 21 * (RP_THREADS / 2 + 8) * 17),
+            cudaFuncSetAttribute(k_rpca_apply_pair<21, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 21 * (RP_THREADS / 2 + 8) * 17)};
+        for (cudaError_t x : ea)
+            if (x != cudaSuccess) return x;
     }
 
     cudaMemsetAsync(w.sumsq, 0, 16, s);
@@ -1097,7 +1101,8 @@ cudaError_t rpca_run(cudaStream_t s, const uint8_t* X, int n, long long P, RpcaW
         else
             k_rpca_apply<<<nctas, RP_THREADS, (size_t)(n * n + 2 * n * RP_THREADS) * sizeof(double), s>>>(
                 X, Aold, Anew, w.Y, n, P, inv_mu, thr, mu, w.W, w.zpart, out);
-        cudaMemcpyAsync(hZ, w.zpart, (size_t)napply * sizeof(double), cudaMemcpyDeviceToHost, s);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;          // a failed launch of this iteration
+        if ((e = cudaMemcpyAsync(hZ, w.zpart, (size_t)napply * sizeof(double), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
         launches += 1;
         if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
         double zz = 0.0;
