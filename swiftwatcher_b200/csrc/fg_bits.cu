@@ -1093,8 +1093,12 @@ k_fg_n9(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t one, ui
     auto release = [&](int st, const uint32_t (&a)[L], const uint32_t (&b)[L], const uint32_t (&c)[L]) {
         // only after the loaded words have been consumed (the lanes depend on every LDS)
         asm volatile("" ::"r"(a[0]), "r"(a[L - 1]), "r"(b[0]), "r"(b[L - 1]), "r"(c[0]), "r"(c[L - 1]) : "memory");
-        __syncwarp();
-        if (lane0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_a + 8u * st) : "memory");
+        // elect.sync converges the warp (every lane has consumed its words by then) and picks the lane that arrives
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "elect.sync _|p, 0xffffffff;\n\t"
+            "@p mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}" ::"r"(empty_a + 8u * st)
+            : "memory");
     };
 
     const uint8_t* stage0 = smem;
