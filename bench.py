@@ -12,7 +12,8 @@ L2 flush is needed between steps).  Inputs are generated on the device by the
 seeded CUDA generator before the timed region.  `value` is device-timed (CUDA
 events on the launch stream, max over ranks); `e2e` runs the same chunks
 through the C ABI from pinned HOST buffers (H2D copy and D2H of the segment
-table inside the timed region).
+table inside the timed region; two contexts alternate so that the copy of the
+next chunk is queued while the table of the previous one is collected).
 """
 
 import argparse
@@ -777,16 +778,32 @@ def run_single(args, cfg, name, env, label_mode="i32", secondary=False):
         host = torch.empty((halo + T, H, W, 3), dtype=torch.uint8, pin_memory=True)
         host.copy_(bufs[0])
         torch.cuda.synchronize()
-        ctx_h.set_stream(stream.cuda_stream)
-        run_step(ctx_h, host)
-        rows_h, counts_h = ctx_h.collect()
+        two = clf is None and not rpca_mode         # two contexts alternate: chunk i+1 is on its way while chunk i is collected
+        ctxs = [ctx_h]
+        if two:
+            ctxs.append(swb.FilterContext((H, W, 3), roi, median_n=N, threshold=15, morph_size=cfg["se"], do_open=True,
+                                          do_close=cfg["do_close"], label_mode=label_mode, max_frames=T,
+                                          max_segments=T * 4096, device=local_rank))
+        else:
+            ctx_h.set_stream(stream.cuda_stream)
+        for c in ctxs:                                # untimed: staging buffers, pinned table buffers
+            run_step(c, host)
+            rows_h, counts_h = c.collect()
         d2h = 0
         env.barrier()
         t0 = time.perf_counter()
-        for i in range(e2e_steps):
-            run_step(ctx_h, host)
-            rows_h, counts_h = ctx_h.collect()
-            d2h = rows_h.nbytes + counts_h.nbytes + 4 * (T + 1) + (8 if clf is not None else 0)
+        if two:
+            for i in range(e2e_steps):
+                ctxs[i % 2].submit(host, n_halo=halo)
+                if i > 0:
+                    rows_h, counts_h = ctxs[(i - 1) % 2].collect()
+            rows_h, counts_h = ctxs[(e2e_steps - 1) % 2].collect()
+            d2h = rows_h.nbytes + counts_h.nbytes + 4 * (T + 1)
+        else:
+            for i in range(e2e_steps):
+                run_step(ctx_h, host)
+                rows_h, counts_h = ctx_h.collect()
+                d2h = rows_h.nbytes + counts_h.nbytes + 4 * (T + 1) + (8 if clf is not None else 0)
         torch.cuda.synchronize()
         dt = env.max_over_ranks(time.perf_counter() - t0)
         if roi is None:
@@ -798,8 +815,11 @@ def run_single(args, cfg, name, env, label_mode="i32", secondary=False):
         e2e = {"value": world * e2e_steps * T / dt, "unit": "frames/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                "note": "pinned host frames -> swb_submit (H2D) -> swb_collect (D2H segment table)"
-                       + (" -> device crops -> classifier -> kept count (D2H)" if clf is not None else "; PCIe-bound")}
-        ctx_h.close()
+                       + (" -> device crops -> classifier -> kept count (D2H)" if clf is not None else
+                          "; PCIe-bound; two contexts alternate, so that the copy of chunk i+1 is queued while the "
+                          "table of chunk i is collected" if two else "; PCIe-bound")}
+        for c in ctxs:
+            c.close()
         if roi is None and clf is None:
             # the roof of this number: the same bytes with one plain cudaMemcpyAsync per step on every rank at once
             gbs = h2d_attainable(env, host, bufs[0], max(e2e_steps, 2))
@@ -932,7 +952,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="only the headline config (no `also` sub-lines)")
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed oracle comparison")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--cpu-frames", type=int, default=0)
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
