@@ -225,7 +225,7 @@ struct DevTmp {
 
 extern "C" {
 
-const char* swb_version(void) { return "swb200 0.1 (sm_100a)"; }
+const char* swb_version(void) { return "swb200 0.2 (sm_100a)"; }
 
 const char* swb_last_error(const swb_ctx* ctx) { return ctx ? ctx->error.c_str() : g_error.c_str(); }
 
