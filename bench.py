@@ -982,9 +982,7 @@ def main():
     if default_run and not args.no_also:
         line["also"] = []
         for name, mode in ALSO:
-            sub = run(name, dict(CONFIGS[name]), mode, True)
-            sub.pop("cpu_baseline", None) if sub.get("cpu_baseline") is None else None
-            line["also"].append(sub)
+            line["also"].append(run(name, dict(CONFIGS[name]), mode, True))
     if env.world > 1 and not args.no_parity:
         line["partition_check"] = partition_check(env, cfg if not cfg.get("videos") else CONFIGS[DEFAULT_CONFIG])
     line["bench_wall_s"] = round(time.perf_counter() - t_start, 1)
