@@ -334,14 +334,20 @@ def soft_threshold(values, t):
     return np.maximum(values - t, 0) + np.minimum(values + t, 0)
 
 
-def inexact_augmented_lagrange_multiplier(X, lmbda=0.01, tol=0.001, maxiter=100):
+def inexact_augmented_lagrange_multiplier(X, lmbda=0.01, tol=0.001, maxiter=100, skip_null=False):
     """Robust PCA by the inexact ALM iteration of image_filtering.py:256-301 — the same float64
     operations in the same order (numpy + LAPACK svd), so that the result is bit-identical to the
     reference's; ``oracle/make_golden.py rpca`` asserts that.  Returns (low_rank, sparse, iterations).
 
     Per iteration: sparse = shrink(X - low_rank + Y/mu, lmbda/mu); thin SVD of X - sparse + Y/mu;
     low_rank = U diag(S - 1/mu) V (all singular values are kept: ``(S > 1/mu).shape[0]`` at :285 is
-    the length of S, not a count); residual Z = X - low_rank - sparse; Y += mu Z; mu *= 1.5."""
+    the length of S, not a count); residual Z = X - low_rank - sparse; Y += mu Z; mu *= 1.5.
+
+    ``skip_null=True`` is NOT the reference: it leaves out the components whose singular value is
+    (numerically) zero, which only exist when columns are exactly dependent — the all-zero frames the
+    reader pads the last batch of a video with (io_video.py:40-44).  The reference adds
+    -(1/mu) u_k v_k^T for them with whatever null-space basis LAPACK returns; the CUDA path skips them
+    (DESIGN.md §8), and tests/test_rpca.py pins that behaviour against this variant."""
     from numpy.linalg import norm, svd
     flat = X.ravel()
     two_norm = norm(flat, 2)
@@ -355,7 +361,7 @@ def inexact_augmented_lagrange_multiplier(X, lmbda=0.01, tol=0.001, maxiter=100)
     while not converged:
         sparse = soft_threshold(X - low_rank + (1 / mu) * multiplier, lmbda / mu)
         U, S, Vt = svd(X - sparse + (1 / mu) * multiplier, full_matrices=False)
-        kept = S.shape[0]
+        kept = int((S > 1e-12 * S[0]).sum()) if skip_null else S.shape[0]
         low_rank = np.dot(np.dot(U[:, :kept], np.diag(S[:kept] - 1 / mu)), Vt[:kept, :])
         residual = X - low_rank - sparse
         multiplier = multiplier + mu * residual
@@ -365,12 +371,12 @@ def inexact_augmented_lagrange_multiplier(X, lmbda=0.01, tol=0.001, maxiter=100)
     return low_rank, sparse, done
 
 
-def rpca(frame_list, want_iters=False):
+def rpca(frame_list, want_iters=False, skip_null=False):
     """image_filtering.py:220-253: list of gray frames -> list of uint8 "sparse" images
     (what is darker than the low-rank background)."""
     img_matrix = np.array(frame_list)
     col_matrix = np.transpose(img_matrix.reshape(img_matrix.shape[0], img_matrix.shape[1] * img_matrix.shape[2]))
-    _, s_columns, itr = inexact_augmented_lagrange_multiplier(col_matrix)
+    _, s_columns, itr = inexact_augmented_lagrange_multiplier(col_matrix, skip_null=skip_null)
     s_columns = np.negative(s_columns)
     s_columns = np.clip(s_columns, 0, 255).astype(np.uint8)
     out = [np.reshape(s_columns[:, i], (img_matrix.shape[1], img_matrix.shape[2]))

@@ -827,9 +827,11 @@ k_seg_init(int T, int frame_base, const int32_t* __restrict__ nseg, const int32_
            swb_segment* __restrict__ rows, int cap_rows) {
     wait_for_previous_kernel();
     let_next_kernel_launch();
-    const int f = blockIdx.y;
+    // one warp per frame (a frame has tens to a few hundred rows): T / 8 CTAs instead of 4 T mostly idle ones
+    const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (f >= T) return;
     const int n = nseg[f];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (int i = threadIdx.x & 31; i < n; i += 32) {
         const long long r = (long long)segoff[f] + i;
         if (r >= cap_rows) return;
         swb_segment s;
@@ -1479,7 +1481,7 @@ cudaError_t launch_ccl(cudaStream_t s, const uint32_t* fbits, int T, const Geom&
         mark();
         launch_dependent(k_ccl_offsets, dim3(1), dim3(1024), 0, s, T, b.nseg, b.segoff,
                          chain ? chain->segoff_base : (const int32_t*)nullptr, b.cap_rows, b.overflow);
-        launch_dependent(k_seg_init, dim3(4, T), dim3(256), 0, s, T, chain ? chain->frame_base : 0, b.nseg, b.segoff, b.rows,
+        launch_dependent(k_seg_init, dim3((T + 7) / 8), dim3(256), 0, s, T, chain ? chain->frame_base : 0, b.nseg, b.segoff, b.rows,
                          b.cap_rows);
         mark();
         launch_dependent(k_props_final, dim3(PART_GRID), dim3(256), 0, s, b.parts, b.pcount, b.cap_parts, g, b.parent,
@@ -1519,7 +1521,7 @@ cudaError_t launch_ccl(cudaStream_t s, const uint32_t* fbits, int T, const Geom&
     launch_dependent(k_ccl_offsets, dim3(1), dim3(1024), 0, s, T, b.nseg, b.segoff,
                      chain ? chain->segoff_base : (const int32_t*)nullptr, b.cap_rows, b.overflow);
     if (!tiled) {
-        dim3 grid(4, T);
+        dim3 grid((T + 7) / 8);
         k_seg_init<<<grid, 256, 0, s>>>(T, chain ? chain->frame_base : 0, b.nseg, b.segoff, b.rows, b.cap_rows);
         launches += 1;
     }

@@ -499,6 +499,23 @@ int pick_ts(int T, int n_col_blocks, int median_n, int gpu_share) {
     if (g_forced_ts > 0) return g_last_ts = std::min(T, (g_forced_ts + 5) / 6 * 6);
     return g_last_ts = pick_ts_impl(T, n_col_blocks, median_n, gpu_share);
 }
+// Cropped ROIs (tensor-map tiles): the kernel is short (~0.1 ms per 2048 frames of 320x240) and every sub-chunk
+// re-reads its (N-1)-frame warm-up, so ONE wave of long sub-chunks beats four waves of short ones (measured at
+// 320x240 / T = 2048: 0.1149 ms with one wave, 0.1175 with two, 0.1193 with three, 0.1211 with four).
+int roi_waves() {
+    static const int w = [] { const char* e = getenv("SWB_K1_ROI_WAVES"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 1; }();
+    return w;
+}
+// ... and the sub-chunk length is computed, not halved down, so that the grid is just UNDER a whole number of waves
+// (20 row blocks x 14 sub-chunks of 150 frames = 280 of 296 CTA slots at 320x240 / T = 2048).
+int pick_ts_roi(int T, int n_col_blocks, int median_n, int gpu_share, int occ) {
+    if (g_forced_ts > 0 || gpu_share > 1 || getenv("SWB_K1_TS")) return pick_ts(T, n_col_blocks, median_n, gpu_share);
+    const int chunks = std::max(1, roi_waves() * 148 * occ / std::max(n_col_blocks, 1));
+    int ts = (T + chunks - 1) / chunks;
+    ts = std::max(ts, std::max(8 * (median_n - 1), 1));
+    ts = std::min((ts + 5) / 6 * 6, T);
+    return g_last_ts = std::max(ts, 1);
+}
 
 // ---- tensor map of the ROI inside the frame stack: (row bytes / 8, ROI rows, frames) of 8-byte elements ----
 bool tma_enabled() {
@@ -1237,7 +1254,7 @@ cudaError_t launch_n9(cudaStream_t s, const FrameSrc& src, int T, const Geom& g,
             n_col_blocks = (g.h + rows - 1) / rows;
         }
     }
-    const int Ts = pick_ts(T, n_col_blocks, N, gpu_share);
+    const int Ts = tile_rows > 0 ? pick_ts_roi(T, n_col_blocks, N, gpu_share, OCC) : pick_ts(T, n_col_blocks, N, gpu_share);
     const int per_long = (T + Ts - 1) / Ts;
     // tail balancing (only when the context has the GPU to itself and nobody forced a sub-chunk length)
     int n_long = n_col_blocks, ts_tail = Ts;
@@ -1297,7 +1314,7 @@ cudaError_t launch_v2_occ(cudaStream_t s, const FrameSrc& src, int T, const Geom
             n_col_blocks = (g.h + rows - 1) / rows;
         }
     }
-    const int Ts = pick_ts(T, n_col_blocks, N, gpu_share);
+    const int Ts = tile_rows > 0 ? pick_ts_roi(T, n_col_blocks, N, gpu_share, OCC) : pick_ts(T, n_col_blocks, N, gpu_share);
     dim3 grid(n_col_blocks, (T + Ts - 1) / Ts);
     k_fg_bits_v2<N, C, S, L, OCC><<<grid, V2_THREADS, SMEM, s>>>(src, T, Ts, g.h, g.wa, thresh, 1u,
                                                                 reinterpret_cast<uint8_t*>(raw_bits), tmap, tile_rows);

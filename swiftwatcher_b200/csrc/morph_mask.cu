@@ -21,6 +21,7 @@
 // mask with 16-byte stores that are contiguous across the warp.
 #include <cuda.h>          // CUtensorMap (types only: the encoder is fetched through the runtime)
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -104,7 +105,7 @@ __device__ __forceinline__ uint32_t hop(uint32_t l, uint32_t c, uint32_t r, bool
 template <int R, int PAT, bool INTERIOR, bool DX0, int SEG, bool STAGED = false>
 __device__ __forceinline__ void morph_strip(const uint32_t* __restrict__ raw_f, const Geom& g, uint32_t* __restrict__ fbits,
                                             uint8_t* __restrict__ mask, int f, bool live, int slab, int lane, int y0,
-                                            const uint32_t* srow = nullptr, int row0 = 0, int col0 = 0) {
+                                            const uint32_t* srow = nullptr, int row0 = 0, int col0 = 0, int sr_rt = 0) {
     constexpr int SLABW = SEG - 2;                           // output words per segment
     const int hl = lane & (SEG - 1);                         // lane within the segment
     const int seg0 = lane & ~(SEG - 1);
@@ -130,7 +131,7 @@ __device__ __forceinline__ void morph_strip(const uint32_t* __restrict__ raw_f, 
 #pragma unroll
         for (int i = 0; i < W; ++i) win[s][i] = 0u;
 
-    const int y_end = min(y0 + SR, g.h);
+    const int y_end = min(y0 + (sr_rt > 0 ? sr_rt : SR), g.h);   // sr_rt: strip height chosen at launch (narrow ROIs)
     const int y_stop = y_end + HR;
     // mask output: lane -> two 16-byte chunks of the slab's row
     const bool st_bits = live && hl >= 1 && hl <= SLABW && j < g.wpr4;
@@ -257,6 +258,45 @@ k_morph_mask(const uint32_t* __restrict__ raw_bits, Geom g, int T, uint32_t* __r
     }
 }
 
+// Narrow ROIs (rows of at most 14 words): a warp works on one strip of TWO consecutive frames (SEG = 16), warps are
+// numbered linearly over (frame pair, strip) so that no CTA carries idle warps, and the strip height `sr` is chosen
+// at launch (narrow_strip_rows).
+template <int R, int PAT>
+__global__ void __launch_bounds__(32 * WPB)
+k_morph_mask_narrow(const uint32_t* __restrict__ raw_bits, Geom g, int T, uint32_t* __restrict__ fbits,
+                    uint8_t* __restrict__ mask, int sr, int nstrips) {
+    constexpr int HR = n_ops(PAT) * R;
+    wait_for_previous_kernel();                              // launched as a dependent of K1 (raw bits)
+    const int lane = threadIdx.x & 31;
+    const int wid = blockIdx.x * WPB + (threadIdx.x >> 5);
+    const int pair = wid / nstrips;
+    const int strip = wid - pair * nstrips;
+    if (2 * pair >= T) return;                               // warp-uniform
+    const int f = 2 * pair + (lane >> 4);                    // one frame per half-warp
+    const bool live = f < T;
+    const int y0 = strip * sr;
+    const uint32_t* raw_f = raw_bits + (long long)f * g.h * g.wpr_raw;
+    const bool interior = (y0 - HR >= 0) && (y0 + sr + HR <= g.h);   // warp-uniform
+    if (g.dx == 0) {
+        if (interior) morph_strip<R, PAT, true, true, 16>(raw_f, g, fbits, mask, f, live, 0, lane, y0, nullptr, 0, 0, sr);
+        else morph_strip<R, PAT, false, true, 16>(raw_f, g, fbits, mask, f, live, 0, lane, y0, nullptr, 0, 0, sr);
+    } else {
+        if (interior) morph_strip<R, PAT, true, false, 16>(raw_f, g, fbits, mask, f, live, 0, lane, y0, nullptr, 0, 0, sr);
+        else morph_strip<R, PAT, false, false, 16>(raw_f, g, fbits, mask, f, live, 0, lane, y0, nullptr, 0, 0, sr);
+    }
+}
+
+// Strip height for the narrow kernel: balanced strips of at most 24 rows.  Measured on a B200 at 320x240 /
+// T = 2048 (3x3 open): 12, 16 or 24 rows 0.0491 ms, 32 rows 0.0509, 48 rows (one exact wave of warps) 0.0508,
+// 60 rows 0.0525 — the kernel is bound by the latency of its stores, not by how its warps fill the machine,
+// so the shorter strips (more warps in flight per frame) win slightly and help the 21-frame queue batches most.
+int narrow_strip_rows(int h) {
+    static const int forced = [] { const char* e = getenv("SWB_K2_NARROW_SR"); return e ? atoi(e) : 0; }();
+    if (forced > 0) return std::min(forced, std::max(h, 1));
+    const int k = (h + 23) / 24;
+    return std::max(1, (h + k - 1) / std::max(k, 1));
+}
+
 // The same strips with the raw rows staged by TMA (frames wider than one slab whose raw rows are 16-byte multiples):
 // the loads of a strip are all in flight at once instead of one row ahead of the arithmetic (the streaming kernel's
 // top stall was that load: 6.5 cycles of long-scoreboard stall per issued instruction at 4K).
@@ -332,8 +372,11 @@ cudaError_t launch_pat(cudaStream_t s, const uint32_t* raw_bits, int T, const Ge
     constexpr int SR = strip_rows(R, PAT);
     const int nstrips = (g.h + SR - 1) / SR;
     if (g.wpr4 <= 14 && g.wpr_raw <= 15) {                   // narrow ROI: two frames per warp
-        dim3 grid(1, (nstrips + WPB - 1) / WPB, (T + 1) / 2);
-        launch_dependent(k_morph_mask<R, PAT, 16>, grid, dim3(32 * WPB), 0, s, raw_bits, g, T, fbits, mask);
+        const int sr = narrow_strip_rows(g.h);
+        const int strips = (g.h + sr - 1) / sr;
+        const long long warps = (long long)strips * ((T + 1) / 2);
+        dim3 grid((unsigned)((warps + WPB - 1) / WPB));
+        launch_dependent(k_morph_mask_narrow<R, PAT>, grid, dim3(32 * WPB), 0, s, raw_bits, g, T, fbits, mask, sr, strips);
         return cudaGetLastError();
     }
     const int nslabs = (g.wpr4 + SLAB - 1) / SLAB;
