@@ -79,8 +79,8 @@ typedef struct swb_config {
  * temporal history, n_halo is ignored, median_n is unused — then bilateralFilter(7, 15, 1),
  * threshold, opening and labelling as usual.  For the reference's batch of 21 frames the whole iteration
  * loop can run on the device (a CUDA-graph WHILE node: eigenproblem, stopping test and all; swb_submit is
- * then asynchronous as in the median mode): the default from 256 Ki pixels per frame, see the option
- * "rpca_device_loop".  Otherwise (smaller frames, other batch sizes) the stopping test and the n x n
+ * then asynchronous as in the median mode): the default for that batch size, see the option
+ * "rpca_device_loop".  Otherwise (other batch sizes, or the option set to 0) the stopping test and the n x n
  * eigenproblem run on the host and swb_submit BLOCKS until the decomposition has converged (it cannot be
  * used on a stream that is being captured). */
 #define SWB_BG_MEDIAN 0
@@ -162,7 +162,7 @@ int swb_collect_end(swb_ctx* ctx, int64_t* n_rows, int32_t* per_frame_counts);
  * sub-batches that are filtered while later frames are still being copied; default 1),
  * "sub_batch_min_px" (least work per sub-batch in pixels; default 64 Mi), "rpca_device_loop" (SWB_BG_RPCA, 21-frame batches: 1 = the
  * iteration loop as a CUDA-graph WHILE node on the device, swb_submit asynchronous; 0 = the host loop, swb_submit
- * blocks; -1 = automatic, the default: device from 256 Ki pixels per frame), "temporal_subchunk" (frames per
+ * blocks; -1 = automatic, the default: the device loop), "temporal_subchunk" (frames per
  * temporal sub-chunk of the filtering kernel, rounded up to a multiple of 6; 0 = chosen from the grid size). */
 int swb_set_option(swb_ctx* ctx, const char* name, int64_t value);
 /* Frames per temporal sub-chunk the filtering kernel used for the last submit (each sub-chunk

@@ -48,7 +48,22 @@ k_rpca_norms(const uint8_t* __restrict__ x, long long total, unsigned long long*
              unsigned int* __restrict__ vmax) {
     unsigned long long s = 0;
     unsigned int m = 0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x, gsize = (long long)gridDim.x * blockDim.x;
+    // 16 pixels per load where the stack is 16-byte aligned (it is: cudaMalloc), bytes for the tail
+    const long long nvec = (reinterpret_cast<uintptr_t>(x) & 15) == 0 ? total / 16 : 0;
+    const uint4* xv = reinterpret_cast<const uint4*>(x);
+    for (long long i = gtid; i < nvec; i += gsize) {
+        const uint4 q = __ldg(xv + i);
+        const uint32_t wds[4] = {q.x, q.y, q.z, q.w};
+        unsigned int part = 0;                       // 16 squares of bytes: < 2^21
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            part = __dp4a(wds[k], wds[k], part);     // sum of the four byte squares
+            m = max(m, max(max(wds[k] & 0xFFu, (wds[k] >> 8) & 0xFFu), max((wds[k] >> 16) & 0xFFu, wds[k] >> 24)));
+        }
+        s += part;
+    }
+    for (long long i = nvec * 16 + gtid; i < total; i += gsize) {
         const unsigned int v = x[i];
         s += (unsigned long long)(v * v);
         m = max(m, v);
@@ -138,7 +153,11 @@ k_rpca_gram(const uint8_t* __restrict__ X, const double* __restrict__ A, const d
 __global__ void __launch_bounds__(RP_THREADS)
 k_rpca_gram21(const uint8_t* __restrict__ X, const double* __restrict__ A, const double* __restrict__ Y,
               long long P, double inv_mu, double thr, double* __restrict__ gpart, const RpcaState* __restrict__ st) {
-    if (st) { inv_mu = st->inv_mu; thr = st->thr; }
+    // st != nullptr (graph loop): this is iteration 0, where A == 0 and Y == X / dual_norm are known without
+    // reading them (k_rpca_init does not run in the graph: 0.7 GB less to write and 0.7 GB less to read at 1080p)
+    const bool first = st != nullptr;
+    double dual_norm = 1.0;
+    if (st) { inv_mu = st->inv_mu; thr = st->thr; dual_norm = st->dual_norm; }
     constexpr int n = 21, NB = 7, NBLK = NB * (NB + 1) / 2, NS = 8;
     constexpr int npairs = n * (n + 1) / 2;
     extern __shared__ double sm[];                 // [n][LD]
@@ -168,8 +187,10 @@ k_rpca_gram21(const uint8_t* __restrict__ X, const double* __restrict__ A, const
             if (p < P) {
                 const long long idx = (long long)i * P + p;
                 const double x = (double)X[idx];
-                const double t2 = __dmul_rn(inv_mu, Y[idx]);           // numpy rounds the product, then the sum
-                const double e = shrink(__dadd_rn(x - A[idx], t2), thr);
+                const double y = first ? __ddiv_rn(x, dual_norm) : Y[idx];
+                const double a = first ? 0.0 : A[idx];
+                const double t2 = __dmul_rn(inv_mu, y);                // numpy rounds the product, then the sum
+                const double e = shrink(__dadd_rn(x - a, t2), thr);
                 m = __dadd_rn(x - e, t2);
             }
             sm[i * LD + t] = m;
@@ -363,7 +384,11 @@ k_rpca_apply_pair(const uint8_t* __restrict__ X, const double* A, double* Anew,
                   const double* __restrict__ Wg, double* __restrict__ zpart, uint8_t* __restrict__ out,
                   double inv_mu_next, double thr_next, double* __restrict__ gpart_next,
                   const RpcaState* __restrict__ st) {
+    bool first = false;                            // graph loop, iteration 0: A == 0 and Y == X / dual_norm, not read
+    double dual_norm = 1.0;
     if (st) {                                      // graph loop: parameters and the ping-pong role of the A buffers from the state
+        first = st->itr == 0;
+        dual_norm = st->dual_norm;
         inv_mu = st->inv_mu; thr = st->thr; mu = st->mu;
         inv_mu_next = st->inv_mu_next; thr_next = st->thr_next;
         if (st->itr & 1) { const double* t = A; A = Anew; Anew = const_cast<double*>(t); }
@@ -414,9 +439,15 @@ k_rpca_apply_pair(const uint8_t* __restrict__ X, const double* A, double* Anew,
             if (live && i < N) {
                 const long long idx = (long long)i * P + p;
                 xv[k] = X[idx];
-                av[k] = A[idx];
-                yv[k] = Y[idx];
+                if (!first) {
+                    av[k] = A[idx];
+                    yv[k] = Y[idx];
+                }
             }
+        }
+        if (first) {
+#pragma unroll
+            for (int k = 0; k < KH; ++k) yv[k] = __ddiv_rn((double)xv[k], dual_norm);
         }
         // ... then E and M; X, Y and E wait in shared memory for the update below (each lane reads back
         // only what it wrote: it owns frame i = 2k + par and column j = 2k + par)
@@ -534,17 +565,25 @@ k_rpca_apply_pair(const uint8_t* __restrict__ X, const double* A, double* Anew,
 __global__ void __launch_bounds__(RP_THREADS)
 k_crop_gray(const uint8_t* __restrict__ frames, long long frame_stride, long long pitch, int channels, int x0,
             int y0, int h, int w, int n, int newest_first, uint8_t* __restrict__ out) {
-    const long long P = (long long)h * w;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P * n; i += (long long)gridDim.x * blockDim.x) {
-        const int k = (int)(i / P);
-        const long long p = i - (long long)k * P;
-        const int y = (int)(p / w), x = (int)(p - (long long)y * w);
-        const int f = newest_first ? n - 1 - k : k;
-        const uint8_t* px = frames + (long long)f * frame_stride + (long long)(y0 + y) * pitch + (long long)(x0 + x) * channels;
-        uint8_t v;
-        if (channels == 3) v = (uint8_t)((3735u * px[0] + 19235u * px[1] + 9798u * px[2] + 16384u) >> 15);
-        else v = px[0];
-        out[i] = v;
+    // grid = (groups of four pixels along the row, rows, frames): no index divisions, one 32-bit store per thread
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y, k = blockIdx.z;
+    if (x4 >= w) return;
+    const int f = newest_first ? n - 1 - k : k;
+    const uint8_t* px = frames + (long long)f * frame_stride + (long long)(y0 + y) * pitch + (long long)(x0 + x4) * channels;
+    uint8_t* o = out + ((long long)k * h + y) * w + x4;
+    const int cnt = min(4, w - x4);
+    uint32_t packed = 0;
+    for (int i = 0; i < cnt; ++i) {
+        uint32_t v;
+        if (channels == 3) v = (3735u * px[3 * i] + 19235u * px[3 * i + 1] + 9798u * px[3 * i + 2] + 16384u) >> 15;
+        else v = px[i];
+        packed |= v << (8 * i);
+    }
+    if (cnt == 4 && (reinterpret_cast<uintptr_t>(o) & 3) == 0) {
+        *reinterpret_cast<uint32_t*>(o) = packed;
+    } else {
+        for (int i = 0; i < cnt; ++i) o[i] = (uint8_t)(packed >> (8 * i));
     }
 }
 
@@ -635,9 +674,11 @@ void rpca_free(RpcaWork& w) {
 
 cudaError_t launch_crop_gray(cudaStream_t s, const uint8_t* frames, long long frame_stride, long long pitch,
                              int channels, int x0, int y0, int h, int w, int n, int newest_first, uint8_t* out) {
-    const long long total = (long long)h * w * n;
-    const int grid = (int)std::min<long long>((total + RP_THREADS - 1) / RP_THREADS, 148 * 16);
-    k_crop_gray<<<grid, RP_THREADS, 0, s>>>(frames, frame_stride, pitch, channels, x0, y0, h, w, n, newest_first, out);
+    if (h < 1 || w < 1 || n < 1 || h > 65535 || n > 65535) return cudaErrorInvalidValue;
+    const int groups = (w + 3) / 4;
+    const int threads = groups >= 128 ? 128 : 32 * ((groups + 31) / 32);
+    const dim3 grid((groups + threads - 1) / threads, h, n);
+    k_crop_gray<<<grid, threads, 0, s>>>(frames, frame_stride, pitch, channels, x0, y0, h, w, n, newest_first, out);
     return cudaGetLastError();
 }
 
@@ -673,18 +714,28 @@ __global__ void k_rpca_setup(const unsigned long long* __restrict__ sumsq, RpcaS
     cudaGraphSetConditional(loop, r.zero ? 0u : 1u);                      // an all-black batch: E == 0, no iteration
 }
 
+// 1 / sqrt(x) from a float32 seed that is good to ~2^-22: with x y^2 = 1 - e, x^(-1/2) = y (1 + e/2 + 3 e^2 / 8 + O(e^3)),
+// i.e. ONE step with an error below 2^-64, four dependent double operations.  (A dependent FP64 operation costs
+// ~40 cycles on a B200: the rotation's chain of them, not its instruction count, is what a Jacobi round waits for.)
+__device__ __forceinline__ double rsqrt_refine(double x, float seed) {
+    const double y = (double)seed;
+    const double e = fma(-(x * y), y, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    const double q = y * e;
+    return fma(q, p, y);
+}
+
 // G (packed upper triangle) -> W = V diag((S - 1/mu) / S) V^T with G = V diag(S^2) V^T, for n = 21.
-// One CTA.  The eigenproblem is a parallel-order Jacobi iteration run by ONE warp on shared memory
-// (round-robin schedule: 21 rounds of 10 disjoint rotations per sweep, lane k owns row / column k, __syncwarp
-// between the three steps of a round), warm-started in the eigenbasis of the previous IALM iteration, where G
-// is nearly diagonal (two or three sweeps instead of seven).  The dense 21 x 21 products around it use all
-// 256 threads.  Rotation formulas and stopping rule are those of the host solver (jacobi_eigh).
+// One CTA.  The eigenproblem is a parallel-order Jacobi iteration on shared memory (round-robin schedule: 21 rounds
+// of 10 disjoint rotations per sweep), warm-started in the eigenbasis of the previous IALM iteration, where G
+// is nearly diagonal (four to six sweeps instead of seven).  Rotation formulas and stopping rule are those of the
+// host solver (jacobi_eigh).
 __global__ void __launch_bounds__(256)
 k_rpca_eigen21(const double* __restrict__ G, double* __restrict__ Wg, double* __restrict__ Vprev,
-               RpcaState* __restrict__ st) {
+               RpcaState* __restrict__ st, double jtol) {
     constexpr int n = 21, LD = 23;
     __shared__ double a[n * LD], v[n * LD], vp[n * LD], tmp[n * LD], dsc[n];
-    __shared__ double cs[10][2];
+    __shared__ double cs[10][2], red[8][2];
     __shared__ int pq[10][2];
     __shared__ int s_go;
     const int t = threadIdx.x, lane = t & 31;
@@ -720,89 +771,117 @@ k_rpca_eigen21(const double* __restrict__ G, double* __restrict__ Wg, double* __
         for (int r = 0, q = t; q < n * n; q += 256, ++r) a[(q / n) * LD + (q % n)] = mine[r];
         __syncthreads();
     }
-    if (t < 32) {
-        // ---- Jacobi sweeps, one warp
-        const long long c_j = clock64();
-        int sweeps = 0;
-        for (int sweep = 0; sweep < 100; ++sweep) {
+    // ---- Jacobi sweeps, all 256 threads.  A round has two steps separated by __syncthreads: ten lanes form the
+    // round's rotations; then thread (row, pair) rotates its two columns of v and thread (pair_i, pair_j) takes
+    // one 2 x 2 block of a through the column rotation of pair_j and the row rotation of pair_i (the same
+    // operations in the same order as the one-warp version, which walked columns then rows with a lane per
+    // row: a block needs nothing from outside itself, so the two passes fuse).  The bye of a round is index r.
+    const long long c_j = clock64();
+    int sweeps = 0;
+    for (int sweep = 0; sweep < 100; ++sweep) {
+        {
+            // stopping test: thread (i, j) squares one element of the upper triangle, warps add up with a fixed
+            // shuffle tree, warp 0 adds the eight partial sums
             double off = 0.0, diag = 0.0;
-            if (lane < n) {
-                diag = a[lane * LD + lane] * a[lane * LD + lane];
-                for (int j = lane + 1; j < n; ++j) off = fma(a[lane * LD + j], a[lane * LD + j], off);
+            if (t < n * (n + 1) / 2) {
+                int i = 0, q = t;
+                while (q >= n - i) { q -= n - i; ++i; }
+                const double x = a[i * LD + i + q];
+                if (q == 0) diag = x * x; else off = x * x;
             }
             for (int d = 16; d > 0; d >>= 1) {
                 off += __shfl_xor_sync(0xFFFFFFFFu, off, d);
                 diag += __shfl_xor_sync(0xFFFFFFFFu, diag, d);
             }
-            if (off <= 1e-32 * diag || off == 0.0) break;      // off-diagonal mass below (eps / 10)^2 of the diagonal
-            ++sweeps;
-            for (int r = 0; r < n; ++r) {
-                // round r of the circle schedule on 22 players (player 21 = the bye, paired with r)
-                if (lane < 10) {
-                    int p = (r + lane + 1) % n, q = (r + n - lane - 1) % n;
-                    if (p > q) { const int x = p; p = q; q = x; }
-                    const double apq = a[p * LD + q];
-                    double c = 1.0, sn = 0.0;
-                    if (apq != 0.0) {
-                        // tan of the rotation angle: t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)) with theta =
-                        // (aqq - app) / (2 apq), written without the division that forms theta:
-                        // t = sgn(d b) |b| / (|d| + sqrt(d^2 + b^2)), d = aqq - app, b = 2 apq  (three long
-                        // operations — sqrt, div, rsqrt — on the warp's critical path instead of five)
-                        const double d = a[q * LD + q] - a[p * LD + p], b2 = 2.0 * apq;
-                        const double tt = copysign(fabs(b2) / (fabs(d) + sqrt(fma(d, d, b2 * b2))), (d >= 0.0) == (b2 >= 0.0) ? 1.0 : -1.0);
-                        c = rsqrt(fma(tt, tt, 1.0));
-                        sn = tt * c;
-                    }
-                    cs[lane][0] = c; cs[lane][1] = sn;
-                    pq[lane][0] = p; pq[lane][1] = q;
-                }
-                __syncwarp();
-                if (lane < n) {                                // columns p, q of a and of v, row `lane`: all loads, then the math
-                    double ap[10], aq[10], vp_[10], vq_[10];
-#pragma unroll
-                    for (int i = 0; i < 10; ++i) {
-                        const int p = pq[i][0], q = pq[i][1];
-                        ap[i] = a[lane * LD + p]; aq[i] = a[lane * LD + q];
-                        vp_[i] = v[lane * LD + p]; vq_[i] = v[lane * LD + q];
-                    }
-#pragma unroll
-                    for (int i = 0; i < 10; ++i) {
-                        const int p = pq[i][0], q = pq[i][1];
-                        const double c = cs[i][0], sn = cs[i][1];
-                        a[lane * LD + p] = c * ap[i] - sn * aq[i];
-                        a[lane * LD + q] = sn * ap[i] + c * aq[i];
-                        v[lane * LD + p] = c * vp_[i] - sn * vq_[i];
-                        v[lane * LD + q] = sn * vp_[i] + c * vq_[i];
-                    }
-                }
-                __syncwarp();
-                if (lane < n) {                                // rows p, q of a, column `lane`
-                    double ap[10], aq[10];
-#pragma unroll
-                    for (int i = 0; i < 10; ++i) {
-                        ap[i] = a[pq[i][0] * LD + lane];
-                        aq[i] = a[pq[i][1] * LD + lane];
-                    }
-#pragma unroll
-                    for (int i = 0; i < 10; ++i) {
-                        const double c = cs[i][0], sn = cs[i][1];
-                        a[pq[i][0] * LD + lane] = c * ap[i] - sn * aq[i];
-                        a[pq[i][1] * LD + lane] = sn * ap[i] + c * aq[i];
-                    }
-                }
-                __syncwarp();
+            if (lane == 0) { red[t >> 5][0] = off; red[t >> 5][1] = diag; }
+            __syncthreads();
+            if (t == 0) {
+                off = diag = 0.0;
+                for (int wq = 0; wq < 8; ++wq) { off += red[wq][0]; diag += red[wq][1]; }
+                s_go = !(off <= jtol * diag || off == 0.0);   // off-diagonal mass below jtol of the diagonal (squares)
             }
         }
-        if (lane < n) {
-            const double d = a[lane * LD + lane];
-            const double sv = d > 0.0 ? sqrt(d) : 0.0;
-            dsc[lane] = sv > 0.0 ? __ddiv_rn(sv - inv_mu, sv) : 0.0;   // exactly dependent columns are skipped (see header)
+        __syncthreads();
+        if (!s_go) break;
+        ++sweeps;
+        for (int r = 0; r < n; ++r) {
+            // round r of the circle schedule on 22 players (player 21 = the bye, paired with r)
+            if (t < 10) {
+                int p = (r + t + 1) % n, q = (r + n - t - 1) % n;
+                if (p > q) { const int x = p; p = q; q = x; }
+                const double apq = a[p * LD + q];
+                double c = 1.0, sn = 0.0;
+                if (apq != 0.0) {
+                    // The rotation that zeroes a_pq: tan(2 phi) = b / d with d = aqq - app, b = 2 apq, |phi| <= pi / 4.
+                    // With r = 1 / sqrt(d^2 + b^2): cos(2 phi) = |d| r, cos^2(phi) = (1 + |d| r) / 2 = h,
+                    // c = h / sqrt(h), s = sgn(d b) |b| r / (2 sqrt(h)); h is in [1/2, 1], so nothing cancels.  The two
+                    // reciprocal square roots have arguments of known range (d and b are scaled by a power of two
+                    // first), so they are float32 MUFU seeds (computed ahead, in float32) + one cubic correction step
+                    // in double (rsqrt_refine) instead of the library's sqrt / div / rsqrt: the ten lanes that form a
+                    // round's rotations were ~1,100 of the round's ~1,500 cycles (clock64 instrumentation, round 2).
+                    const double d = a[q * LD + q] - a[p * LD + p], b2 = 2.0 * apq;
+                    // scale by the power of two that brings max(|d|, |b|) to [1, 2): exponent bits, two multiplies
+                    const int ef = min(max((__double2hiint(fmax(fabs(d), fabs(b2))) >> 20) & 0x7FF, 1), 2045);
+                    const double sc = __hiloint2double((2046 - ef) << 20, 0);
+                    const double ds = fabs(d) * sc, bs = fabs(b2) * sc;
+                    // float32 first (a few cycles per operation): the seeds of both reciprocal square roots
+                    const float dsf = (float)ds, bsf = (float)bs;
+                    const float rf = rsqrtf(fmaf(dsf, dsf, bsf * bsf));
+                    const float ihf = rsqrtf(fmaf(0.5f * dsf, rf, 0.5f));
+                    const double r = rsqrt_refine(fma(ds, ds, bs * bs), rf);   // the argument is in [1, 8)
+                    const double h = fma(0.5 * ds, r, 0.5);                    // [1/2, 1]
+                    const double ih = rsqrt_refine(h, ihf);
+                    c = h * ih;
+                    sn = copysign(0.5 * bs * r * ih, (d >= 0.0) == (b2 >= 0.0) ? 1.0 : -1.0);
+                }
+                cs[t][0] = c; cs[t][1] = sn;
+                pq[t][0] = p; pq[t][1] = q;
+            }
+            __syncthreads();
+            if (t < n * 10) {                                  // columns p, q of v, one row
+                const int row = t / 10, i = t - row * 10;
+                const int p = pq[i][0], q = pq[i][1];
+                const double c = cs[i][0], sn = cs[i][1];
+                const double vp_ = v[row * LD + p], vq_ = v[row * LD + q];
+                v[row * LD + p] = c * vp_ - sn * vq_;
+                v[row * LD + q] = sn * vp_ + c * vq_;
+            }
+            const int blk = 255 - t;                           // 11 x 11 blocks of a (pair 10 = the bye: one index, no rotation)
+            if (blk < 121) {
+                const int bi = blk / 11, bj = blk - bi * 11;
+                const bool ri = bi < 10, rj = bj < 10;
+                const int pi = ri ? pq[bi][0] : r, qi = ri ? pq[bi][1] : r;
+                const int pj = rj ? pq[bj][0] : r, qj = rj ? pq[bj][1] : r;
+                double x00 = a[pi * LD + pj], x01 = a[pi * LD + qj], x10 = a[qi * LD + pj], x11 = a[qi * LD + qj];
+                if (rj) {                                      // columns pj, qj (rows pi, qi)
+                    const double c = cs[bj][0], sn = cs[bj][1];
+                    const double u0 = c * x00 - sn * x01, u1 = sn * x00 + c * x01;
+                    const double w0 = c * x10 - sn * x11, w1 = sn * x10 + c * x11;
+                    x00 = u0; x01 = u1; x10 = w0; x11 = w1;
+                }
+                if (ri) {                                      // rows pi, qi (columns pj, qj)
+                    const double c = cs[bi][0], sn = cs[bi][1];
+                    const double u0 = c * x00 - sn * x10, u1 = sn * x00 + c * x10;
+                    const double w0 = c * x01 - sn * x11, w1 = sn * x01 + c * x11;
+                    x00 = u0; x10 = u1; x01 = w0; x11 = w1;
+                }
+                a[pi * LD + pj] = x00;
+                if (rj) a[pi * LD + qj] = x01;
+                if (ri) a[qi * LD + pj] = x10;
+                if (ri && rj) a[qi * LD + qj] = x11;
+            }
+            __syncthreads();
         }
-        if (lane == 0) {
-            st->sweeps += sweeps;
-            st->cyc_jacobi += clock64() - c_j;
-            if (st->itr < 8) st->sweeps_hist[st->itr] = sweeps;
-        }
+    }
+    if (t < n) {
+        const double d = a[t * LD + t];
+        const double sv = d > 0.0 ? sqrt(d) : 0.0;
+        dsc[t] = sv > 0.0 ? __ddiv_rn(sv - inv_mu, sv) : 0.0;   // exactly dependent columns are skipped (see header)
+    }
+    if (t == 0) {
+        st->sweeps += sweeps;
+        st->cyc_jacobi += clock64() - c_j;
+        if (st->itr < 8) st->sweeps_hist[st->itr] = sweeps;
     }
     __syncthreads();
     // V = Vp Vb (kept for the next warm start), then W = V diag(f) V^T
@@ -822,7 +901,6 @@ k_rpca_eigen21(const double* __restrict__ G, double* __restrict__ Wg, double* __
     }
     __syncthreads();
     if (t == 0) st->cyc_eigen += clock64() - c_start;
-    (void)s_go;
 }
 
 // |Z|_F^2 from the per-CTA partials (fixed order), the stopping test (image_filtering.py:296-298), mu *= rho
@@ -890,7 +968,7 @@ static cudaError_t rpca_run_graph(cudaStream_t s, const uint8_t* X, long long P,
         cudaMemsetAsync(w.sumsq, 0, 16, c1);
         k_rpca_norms<<<nctas, RP_THREADS, 0, c1>>>(X, total, w.sumsq, reinterpret_cast<unsigned int*>(w.sumsq + 1));
         k_rpca_setup<<<1, 32, 0, c1>>>(w.sumsq, st, lmbda, loop);
-        k_rpca_init<<<nctas, RP_THREADS, 0, c1>>>(X, total, 1.0, w.A0, w.Y, st, out);
+        cudaMemsetAsync(out, 0, (size_t)total, c1);       // what an all-black batch (no iteration at all) leaves behind
         k_rpca_gram21<<<nctas, RP_THREADS, 21 * (RP_THREADS + 8) * sizeof(double), c1>>>(X, w.A0, w.Y, P, 0.0, 0.0, w.gpart, st);
         if ((e = cudaGetLastError()) != cudaSuccess) return fail(e);
         if ((e = cudaStreamGetCaptureInfo(c1, &status, nullptr, &graph, &deps, &ndeps)) != cudaSuccess) return fail(e);
@@ -910,7 +988,8 @@ static cudaError_t rpca_run_graph(cudaStream_t s, const uint8_t* X, long long P,
             return fail(e);
         capturing2 = true;
         k_rpca_gram_reduce_st<<<(npairs * 32 + 127) / 128, 128, 0, c2>>>(w.gpart, nctas, napply, npairs, w.G, st);
-        k_rpca_eigen21<<<1, 256, 0, c2>>>(w.G, w.W, w.Vprev, st);
+        static const double jtol = [] { const char* e = getenv("SWB_RPCA_JTOL"); return e ? atof(e) : 1e-28; }();   // off-diagonal norm below 1e-14 of the diagonal norm
+        k_rpca_eigen21<<<1, 256, 0, c2>>>(w.G, w.W, w.Vprev, st, jtol);
         k_rpca_apply_pair<21, true><<<napply, RP_THREADS, 21 * (RP_THREADS / 2 + 8) * 17, c2>>>(
             X, w.A0, w.A1, w.Y, P, 0.0, 0.0, 0.0, w.W, w.zpart, out, 0.0, 0.0, w.gpart, st);
         k_rpca_check<<<1, 32, 0, c2>>>(w.zpart, napply, st, lmbda, tol, rho, maxiter, loop);
@@ -933,7 +1012,7 @@ static cudaError_t rpca_run_graph(cudaStream_t s, const uint8_t* X, long long P,
     }
     cudaError_t e = cudaGraphLaunch((cudaGraphExec_t)w.graph_exec, s);
     if (e != cudaSuccess) return e;
-    if (n_launches) *n_launches += 5;          // the loop's launches are counted when the state is read back
+    if (n_launches) *n_launches += 3;          // norms, setup, first Gram pass; the loop's launches are counted when the state is read back
     return cudaSuccess;
 }
 
@@ -944,13 +1023,13 @@ cudaError_t rpca_run(cudaStream_t s, const uint8_t* X, int n, long long P, RpcaW
                      int* n_launches) {
     if (n < 1 || n > w.nmax || P > w.P) return cudaErrorInvalidValue;
     w.last_mode = 0;
-    // Where the iteration loop runs.  Device (CUDA-graph WHILE node): nothing blocks, nothing is copied, but the
-    // 21 x 21 eigenproblem is one warp's work (~25 us per Jacobi sweep, 100-150 us per iteration); host: two
-    // stream synchronisations per iteration, eigenproblem in ~40 us.  Measured on a B200: 1080p full frame 9.8
-    // (device) vs 10.0 ms (host) per batch, 320x160 ROI 3.0 vs 2.6 ms.  Automatic choice: the device loop where
-    // an iteration's streaming pass outweighs the eigenproblem (>= 256 Ki pixels), the host loop below.
+    // Where the iteration loop runs.  Device (CUDA-graph WHILE node): nothing blocks, nothing is copied, the 21 x 21
+    // eigenproblem is one CTA's work (60-90 us per iteration); host: two stream synchronisations per iteration,
+    // eigenproblem in ~40 us.  Measured on a B200 (round 2, all 256 threads in the Jacobi rounds): 1080p full frame
+    // 9.26 ms (device) vs 9.67 (host) per batch, 320x160 ROI 2.10 vs 2.59 — the device loop is the default for the
+    // reference's batch size; SWB_RPCA_HOST_LOOP=1 / swb_set_option("rpca_device_loop", 0) select the host loop.
     static const int env_loop = [] { const char* e = getenv("SWB_RPCA_HOST_LOOP"); return e ? (e[0] == '1' ? 0 : 1) : -1; }();
-    const int want = w.device_loop >= 0 ? w.device_loop : (env_loop >= 0 ? env_loop : (P >= (1 << 18) ? 1 : 0));
+    const int want = w.device_loop >= 0 ? w.device_loop : (env_loop >= 0 ? env_loop : 1);
     if (n == 21 && want == 1) {
         static PerDeviceOnce once_g;
         if (once_g.need()) {
@@ -1289,11 +1368,116 @@ k_bilateral_r3(const uint8_t* __restrict__ in, int n, int h, int w, const Bilate
 
 }  // namespace
 
+// d = 7 (radius 3, 29 taps), rows that are multiples of four pixels: a thread filters FOUR adjacent pixels.
+// The one-pixel kernel above issues 29 byte loads + 58 shared-memory reads per pixel and is bound by the
+// load/store pipe (1.04 ms per 21 frames of 1080p); here a window row is three aligned 32-bit loads for the four
+// pixels (21 loads per thread instead of 116), the spatial weights sit in registers, and only the colour-weight
+// look-ups still go to shared memory.  Per pixel the taps are visited in the same order with the same float32
+// operations as k_bilateral: identical results.  block = (32, 8): a warp covers 128 pixels of a row, a CTA eight
+// adjacent rows (their windows overlap in L1); grid = (ceil(w / 128), ceil(h / 8), frames): no index divisions.
+__global__ void __launch_bounds__(256)
+k_bilateral_r3x4(const uint8_t* __restrict__ in, int n, int h, int w, const BilateralLut* __restrict__ lutp, int reverse,
+                 uint8_t* __restrict__ out, int thresh, uint32_t* __restrict__ bits, int wpr_bits) {
+    __shared__ float s_color[256];
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    s_color[tid] = lutp->color[tid];
+    float sp[29];
+#pragma unroll
+    for (int k = 0; k < 29; ++k) sp[k] = __ldg(&lutp->space[k]);
+    __syncthreads();
+    const int lane = threadIdx.x;
+    const int x4 = (blockIdx.x * 32 + lane) * 4;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    const int f = blockIdx.z;
+    if (y >= h) return;                                        // warp-uniform
+    const uint8_t* img = in + (long long)(reverse ? n - 1 - f : f) * h * w;
+    uint32_t res4 = 0;                                         // the four results, one per byte
+    if (x4 < w) {
+        if (y >= 3 && y < h - 3 && x4 >= 4 && x4 + 8 <= w) {
+            const uint8_t* row = img + (long long)y * w + x4;
+            const uint32_t cw = __ldg(reinterpret_cast<const uint32_t*>(row));
+            int c[4];
+            float sum[4], wsum[4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                c[p] = (cw >> (8 * p)) & 0xFFu;
+                sum[p] = wsum[p] = 0.f;
+            }
+            int k0 = 0;                                        // tap index of the row's first tap
+#pragma unroll
+            for (int i = -3; i <= 3; ++i) {
+                const uint32_t* rp = reinterpret_cast<const uint32_t*>(row + (long long)i * w);
+                const uint32_t wd[3] = {__ldg(rp - 1), __ldg(rp), __ldg(rp + 1)};   // pixels x4 - 4 .. x4 + 7
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    int k = k0;
+#pragma unroll
+                    for (int j = -3; j <= 3; ++j) {
+                        if (i * i + j * j > 9) continue;
+                        const int b = 4 + p + j;               // byte of the 12-byte window (compile-time)
+                        const int v = (wd[b >> 2] >> (8 * (b & 3))) & 0xFFu;
+                        const float wk = __fmul_rn(sp[k], s_color[abs(v - c[p])]);
+                        wsum[p] = __fadd_rn(wsum[p], wk);
+                        sum[p] = __fadd_rn(sum[p], __fmul_rn((float)v, wk));
+                        ++k;
+                    }
+                }
+#pragma unroll
+                for (int j = -3; j <= 3; ++j)
+                    if (i * i + j * j <= 9) ++k0;
+            }
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                int r = __float2int_rn(__fdiv_rn(sum[p], wsum[p]));
+                r = min(max(r, 0), 255);
+                res4 |= (uint32_t)r << (8 * p);
+            }
+        } else {
+            for (int p = 0; p < 4 && x4 + p < w; ++p) {        // frame border: reflected taps, one pixel at a time
+                const int x = x4 + p;
+                const int c = img[(long long)y * w + x];
+                float sum = 0.f, wsum = 0.f;
+                int k = 0;
+                for (int i = -3; i <= 3; ++i)
+                    for (int j = -3; j <= 3; ++j) {
+                        if (i * i + j * j > 9) continue;
+                        const int v = img[(long long)reflect101(y + i, h) * w + reflect101(x + j, w)];
+                        const float wk = __fmul_rn(__ldg(&lutp->space[k]), s_color[abs(v - c)]);
+                        wsum = __fadd_rn(wsum, wk);
+                        sum = __fadd_rn(sum, __fmul_rn((float)v, wk));
+                        ++k;
+                    }
+                int r = __float2int_rn(__fdiv_rn(sum, wsum));
+                r = min(max(r, 0), 255);
+                res4 |= (uint32_t)r << (8 * p);
+            }
+        }
+        if (out) *reinterpret_cast<uint32_t*>(out + ((long long)f * h + y) * w + x4) = res4;
+    }
+    if (bits) {
+        // lane -> nibble (lane & 7) of word lane / 8 of the warp's 128 pixels; OR over the eight lanes of a word
+        uint32_t nib = 0;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) nib |= ((int)((res4 >> (8 * p)) & 0xFFu) > thresh ? 1u : 0u) << p;
+        uint32_t word = nib << (4 * (lane & 7));
+        word |= __shfl_xor_sync(0xFFFFFFFFu, word, 1);
+        word |= __shfl_xor_sync(0xFFFFFFFFu, word, 2);
+        word |= __shfl_xor_sync(0xFFFFFFFFu, word, 4);
+        const int wi = x4 >> 5;
+        if ((lane & 7) == 0 && x4 < w && wi < wpr_bits) bits[((long long)f * h + y) * wpr_bits + wi] = word;
+    }
+}
+
 cudaError_t launch_bilateral(cudaStream_t s, const uint8_t* in, int n, int h, int w, const BilateralLut* d_lut,
                              int reverse, uint8_t* out, int thresh, uint32_t* bits, int wpr_bits, int radius) {
     const long long nwords = (long long)n * h * ((w + 31) / 32);
     const int grid = (int)std::min<long long>((nwords * 32 + 255) / 256, 148 * 32);
-    if (radius == 3 && h >= 7 && w >= 7)
+    static const bool x4 = [] { const char* e = getenv("SWB_BILATERAL_X4"); return !(e && e[0] == '0'); }();
+    if (radius == 3 && h >= 7 && w >= 16 && (w & 3) == 0 && x4 && h <= 65535 * 8 && n <= 65535 &&
+        (reinterpret_cast<uintptr_t>(in) & 3) == 0 && (out == nullptr || (reinterpret_cast<uintptr_t>(out) & 3) == 0))
+        k_bilateral_r3x4<<<dim3((w + 127) / 128, (h + 7) / 8, n), dim3(32, 8), 0, s>>>(in, n, h, w, d_lut, reverse, out, thresh,
+                                                                                  bits, wpr_bits);
+    else if (radius == 3 && h >= 7 && w >= 7)
         k_bilateral_r3<<<grid, 256, 0, s>>>(in, n, h, w, d_lut, reverse, out, thresh, bits, wpr_bits);
     else
         k_bilateral<<<grid, 256, 0, s>>>(in, n, h, w, d_lut, reverse, out, thresh, bits, wpr_bits);

@@ -146,8 +146,8 @@ class FilterContext:
     def submit(self, frames, n_halo=HALO_CARRY, n_frames=None):
         """frames: numpy (n_halo + n, H, W[, 3]) uint8 (host) or a CUDA torch
         tensor of that shape (device, zero-copy).  Asynchronous — except with bg_model="rpca" when the
-        iteration loop runs on the host (frames below 256 Ki pixels, batches other than 21 frames; see
-        the option "rpca_device_loop"): then the call returns when the decomposition has converged."""
+        iteration loop runs on the host (batches other than 21 frames, or the option "rpca_device_loop"
+        set to 0): then the call returns when the decomposition has converged."""
         if isinstance(frames, np.ndarray):
             if frames.dtype != np.uint8 or not frames.flags["C_CONTIGUOUS"]:
                 raise ValueError("frames must be C-contiguous uint8")

@@ -122,8 +122,8 @@ def test_fused_rpca_path_against_golden(golden_dir, name, mode):
     T = len(frames)
     for src in ("host", "device"):
         with swb.FilterContext(frames.shape[1:], roi, label_mode=mode, max_frames=T, bg_model="rpca") as ctx:
-            if src == "device":
-                ctx.set_option("rpca_device_loop", 1)          # small frames default to the host loop
+            if src == "host":
+                ctx.set_option("rpca_device_loop", 0)          # the host loop (21-frame batches default to the device loop)
             ctx.submit(frames if src == "host" else torch.from_numpy(frames).cuda(), n_halo=0)
             rows, counts = ctx.collect()
             masks, labels, sparse = ctx.masks(), ctx.labels(), ctx.rpca_images()
