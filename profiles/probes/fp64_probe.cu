@@ -32,6 +32,51 @@ __global__ void k_ffma_lat(float* out, int iters, float a, float b, long long* c
     if (threadIdx.x == 0) *cyc = c1 - c0;
 }
 
+__global__ void k_f2f_lat(double* out, int iters, long long* cyc) {
+    double x = 1.0 + threadIdx.x * 1e-3;
+    const long long c0 = clock64();
+    for (int it = 0; it < iters; ++it) {            // double -> float -> double round trip, dependent
+        float f = (float)x;
+        asm volatile("" : "+f"(f));
+        x = (double)f;
+        asm volatile("" : "+d"(x));
+    }
+    const long long c1 = clock64();
+    out[threadIdx.x] = x;
+    if (threadIdx.x == 0) *cyc = c1 - c0;
+}
+
+__global__ void k_rsq_lat(float* out, int iters, long long* cyc) {
+    float x = 1.0f + threadIdx.x * 1e-3f;
+    const long long c0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+        x = rsqrtf(x);
+        asm volatile("" : "+f"(x));
+    }
+    const long long c1 = clock64();
+    out[threadIdx.x] = x;
+    if (threadIdx.x == 0) *cyc = c1 - c0;
+}
+
+__global__ void k_lds_lat(int* out, int iters, long long* cyc) {
+    __shared__ int idx[256];
+    for (int i = threadIdx.x; i < 256; i += 32) idx[i] = (i * 7 + 3) & 255;
+    __syncwarp();
+    int x = threadIdx.x;
+    const long long c0 = clock64();
+    for (int it = 0; it < iters; ++it) x = idx[x];
+    const long long c1 = clock64();
+    out[threadIdx.x] = x;
+    if (threadIdx.x == 0) *cyc = c1 - c0;
+}
+
+__global__ void k_bar_lat(int* out, int iters, long long* cyc) {
+    const long long c0 = clock64();
+    for (int it = 0; it < iters; ++it) __syncthreads();
+    const long long c1 = clock64();
+    if (threadIdx.x == 0) { *cyc = c1 - c0; out[0] = 1; }
+}
+
 __global__ void k_dmma_tp(double* out, int iters, double a, double b) {
     double c[4][2];
     for (int i = 0; i < 4; ++i) c[i][0] = c[i][1] = threadIdx.x;
@@ -98,6 +143,18 @@ int main() {
     k_dmma_lat<<<1, 32>>>(out, iters, 1.0000001, 1e-9, cyc);
     cudaDeviceSynchronize();
     printf("DMMA dependent latency: %.1f cycles\n", (double)*cyc / iters);
+    k_f2f_lat<<<1, 32>>>(out, iters, cyc);
+    cudaDeviceSynchronize();
+    printf("F2F double->float->double round trip, dependent: %.1f cycles\n", (double)*cyc / iters);
+    k_rsq_lat<<<1, 32>>>((float*)out, iters, cyc);
+    cudaDeviceSynchronize();
+    printf("MUFU.RSQ dependent latency: %.1f cycles\n", (double)*cyc / iters);
+    k_lds_lat<<<1, 32>>>((int*)out, iters, cyc);
+    cudaDeviceSynchronize();
+    printf("LDS dependent (pointer chase) latency: %.1f cycles\n", (double)*cyc / iters);
+    k_bar_lat<<<1, 256>>>((int*)out, iters, cyc);
+    cudaDeviceSynchronize();
+    printf("__syncthreads, 8 warps, back to back: %.1f cycles\n", (double)*cyc / iters);
     printf("last error: %s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
