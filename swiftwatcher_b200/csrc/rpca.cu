@@ -725,6 +725,24 @@ __device__ __forceinline__ double rsqrt_refine(double x, float seed) {
     return fma(q, p, y);
 }
 
+// shared memory through explicit 32-bit shared-space addresses (see the Jacobi rounds of k_rpca_eigen21)
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t addr, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ int lds_s32(uint32_t addr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_s32(uint32_t addr, int v) {
+    asm volatile("st.shared.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
 // G (packed upper triangle) -> W = V diag((S - 1/mu) / S) V^T with G = V diag(S^2) V^T, for n = 21.
 // One CTA.  The eigenproblem is a parallel-order Jacobi iteration on shared memory (round-robin schedule: 21 rounds
 // of 10 disjoint rotations per sweep), warm-started in the eigenbasis of the previous IALM iteration, where G
@@ -777,6 +795,9 @@ k_rpca_eigen21(const double* __restrict__ G, double* __restrict__ Wg, double* __
     // operations in the same order as the one-warp version, which walked columns then rows with a lane per
     // row: a block needs nothing from outside itself, so the two passes fuse).  The bye of a round is index r.
     const long long c_j = clock64();
+    uint32_t a_s = (uint32_t)__cvta_generic_to_shared(a), v_s = (uint32_t)__cvta_generic_to_shared(v);
+    uint32_t cs_s = (uint32_t)__cvta_generic_to_shared(cs), pq_s = (uint32_t)__cvta_generic_to_shared(pq);
+    asm volatile("" : "+r"(a_s), "+r"(v_s), "+r"(cs_s), "+r"(pq_s));   // opaque: kept in registers, not re-derived per use
     int sweeps = 0;
     for (int sweep = 0; sweep < 100; ++sweep) {
         {
@@ -805,11 +826,14 @@ k_rpca_eigen21(const double* __restrict__ G, double* __restrict__ Wg, double* __
         if (!s_go) break;
         ++sweeps;
         for (int r = 0; r < n; ++r) {
-            // round r of the circle schedule on 22 players (player 21 = the bye, paired with r)
+            // round r of the circle schedule on 22 players (player 21 = the bye, paired with r).  Shared memory is
+            // addressed through 32-bit shared-space addresses formed once (a_s, v_s, cs_s, pq_s): with plain array
+            // accesses the compiler re-reads SR_CgaCtaId (S2R) in every divergent step of every round to rebuild the
+            // shared window base, right at the head of the round's critical path.
             if (t < 10) {
                 int p = (r + t + 1) % n, q = (r + n - t - 1) % n;
                 if (p > q) { const int x = p; p = q; q = x; }
-                const double apq = a[p * LD + q];
+                const double apq = lds_f64(a_s + 8 * (p * LD + q));
                 double c = 1.0, sn = 0.0;
                 if (apq != 0.0) {
                     // The rotation that zeroes a_pq: tan(2 phi) = b / d with d = aqq - app, b = 2 apq, |phi| <= pi / 4.
@@ -817,9 +841,8 @@ k_rpca_eigen21(const double* __restrict__ G, double* __restrict__ Wg, double* __
                     // c = h / sqrt(h), s = sgn(d b) |b| r / (2 sqrt(h)); h is in [1/2, 1], so nothing cancels.  The two
                     // reciprocal square roots have arguments of known range (d and b are scaled by a power of two
                     // first), so they are float32 MUFU seeds (computed ahead, in float32) + one cubic correction step
-                    // in double (rsqrt_refine) instead of the library's sqrt / div / rsqrt: the ten lanes that form a
-                    // round's rotations were ~1,100 of the round's ~1,500 cycles (clock64 instrumentation, round 2).
-                    const double d = a[q * LD + q] - a[p * LD + p], b2 = 2.0 * apq;
+                    // in double (rsqrt_refine) instead of the library's sqrt / div / rsqrt.
+                    const double d = lds_f64(a_s + 8 * (q * LD + q)) - lds_f64(a_s + 8 * (p * LD + p)), b2 = 2.0 * apq;
                     // scale by the power of two that brings max(|d|, |b|) to [1, 2): exponent bits, two multiplies
                     const int ef = min(max((__double2hiint(fmax(fabs(d), fabs(b2))) >> 20) & 0x7FF, 1), 2045);
                     const double sc = __hiloint2double((2046 - ef) << 20, 0);
@@ -828,47 +851,52 @@ k_rpca_eigen21(const double* __restrict__ G, double* __restrict__ Wg, double* __
                     const float dsf = (float)ds, bsf = (float)bs;
                     const float rf = rsqrtf(fmaf(dsf, dsf, bsf * bsf));
                     const float ihf = rsqrtf(fmaf(0.5f * dsf, rf, 0.5f));
-                    const double r = rsqrt_refine(fma(ds, ds, bs * bs), rf);   // the argument is in [1, 8)
-                    const double h = fma(0.5 * ds, r, 0.5);                    // [1/2, 1]
+                    const double rr = rsqrt_refine(fma(ds, ds, bs * bs), rf);  // the argument is in [1, 8)
+                    const double h = fma(0.5 * ds, rr, 0.5);                   // [1/2, 1]
                     const double ih = rsqrt_refine(h, ihf);
                     c = h * ih;
-                    sn = copysign(0.5 * bs * r * ih, (d >= 0.0) == (b2 >= 0.0) ? 1.0 : -1.0);
+                    sn = copysign(0.5 * bs * rr * ih, (d >= 0.0) == (b2 >= 0.0) ? 1.0 : -1.0);
                 }
-                cs[t][0] = c; cs[t][1] = sn;
-                pq[t][0] = p; pq[t][1] = q;
+                sts_f64(cs_s + 16 * t, c);
+                sts_f64(cs_s + 16 * t + 8, sn);
+                sts_s32(pq_s + 8 * t, p);
+                sts_s32(pq_s + 8 * t + 4, q);
             }
             __syncthreads();
             if (t < n * 10) {                                  // columns p, q of v, one row
                 const int row = t / 10, i = t - row * 10;
-                const int p = pq[i][0], q = pq[i][1];
-                const double c = cs[i][0], sn = cs[i][1];
-                const double vp_ = v[row * LD + p], vq_ = v[row * LD + q];
-                v[row * LD + p] = c * vp_ - sn * vq_;
-                v[row * LD + q] = sn * vp_ + c * vq_;
+                const int p = lds_s32(pq_s + 8 * i), q = lds_s32(pq_s + 8 * i + 4);
+                const double c = lds_f64(cs_s + 16 * i), sn = lds_f64(cs_s + 16 * i + 8);
+                const uint32_t ap = v_s + 8 * (row * LD + p), aq = v_s + 8 * (row * LD + q);
+                const double vp_ = lds_f64(ap), vq_ = lds_f64(aq);
+                sts_f64(ap, c * vp_ - sn * vq_);
+                sts_f64(aq, sn * vp_ + c * vq_);
             }
             const int blk = 255 - t;                           // 11 x 11 blocks of a (pair 10 = the bye: one index, no rotation)
             if (blk < 121) {
                 const int bi = blk / 11, bj = blk - bi * 11;
                 const bool ri = bi < 10, rj = bj < 10;
-                const int pi = ri ? pq[bi][0] : r, qi = ri ? pq[bi][1] : r;
-                const int pj = rj ? pq[bj][0] : r, qj = rj ? pq[bj][1] : r;
-                double x00 = a[pi * LD + pj], x01 = a[pi * LD + qj], x10 = a[qi * LD + pj], x11 = a[qi * LD + qj];
+                const int pi = ri ? lds_s32(pq_s + 8 * bi) : r, qi = ri ? lds_s32(pq_s + 8 * bi + 4) : r;
+                const int pj = rj ? lds_s32(pq_s + 8 * bj) : r, qj = rj ? lds_s32(pq_s + 8 * bj + 4) : r;
+                const uint32_t a00 = a_s + 8 * (pi * LD + pj), a01 = a_s + 8 * (pi * LD + qj);
+                const uint32_t a10 = a_s + 8 * (qi * LD + pj), a11 = a_s + 8 * (qi * LD + qj);
+                double x00 = lds_f64(a00), x01 = lds_f64(a01), x10 = lds_f64(a10), x11 = lds_f64(a11);
                 if (rj) {                                      // columns pj, qj (rows pi, qi)
-                    const double c = cs[bj][0], sn = cs[bj][1];
+                    const double c = lds_f64(cs_s + 16 * bj), sn = lds_f64(cs_s + 16 * bj + 8);
                     const double u0 = c * x00 - sn * x01, u1 = sn * x00 + c * x01;
                     const double w0 = c * x10 - sn * x11, w1 = sn * x10 + c * x11;
                     x00 = u0; x01 = u1; x10 = w0; x11 = w1;
                 }
                 if (ri) {                                      // rows pi, qi (columns pj, qj)
-                    const double c = cs[bi][0], sn = cs[bi][1];
+                    const double c = lds_f64(cs_s + 16 * bi), sn = lds_f64(cs_s + 16 * bi + 8);
                     const double u0 = c * x00 - sn * x10, u1 = sn * x00 + c * x10;
                     const double w0 = c * x01 - sn * x11, w1 = sn * x01 + c * x11;
                     x00 = u0; x10 = u1; x01 = w0; x11 = w1;
                 }
-                a[pi * LD + pj] = x00;
-                if (rj) a[pi * LD + qj] = x01;
-                if (ri) a[qi * LD + pj] = x10;
-                if (ri && rj) a[qi * LD + qj] = x11;
+                sts_f64(a00, x00);
+                if (rj) sts_f64(a01, x01);
+                if (ri) sts_f64(a10, x10);
+                if (ri && rj) sts_f64(a11, x11);
             }
             __syncthreads();
         }
