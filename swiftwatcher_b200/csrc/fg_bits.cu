@@ -509,7 +509,8 @@ int roi_waves() {
 // ... and the sub-chunk length is computed, not halved down, so that the grid is just UNDER a whole number of waves
 // (20 row blocks x 14 sub-chunks of 150 frames = 280 of 296 CTA slots at 320x240 / T = 2048).
 int pick_ts_roi(int T, int n_col_blocks, int median_n, int gpu_share, int occ) {
-    if (g_forced_ts > 0 || gpu_share > 1 || getenv("SWB_K1_TS")) return pick_ts(T, n_col_blocks, median_n, gpu_share);
+    static const bool env_ts = getenv("SWB_K1_TS") != nullptr;
+    if (g_forced_ts > 0 || gpu_share > 1 || env_ts) return pick_ts(T, n_col_blocks, median_n, gpu_share);
     const int chunks = std::max(1, roi_waves() * 148 * occ / std::max(n_col_blocks, 1));
     int ts = (T + chunks - 1) / chunks;
     ts = std::max(ts, std::max(8 * (median_n - 1), 1));
