@@ -35,6 +35,23 @@ namespace {
 // The box starts at a word column that is a multiple of four (the innermost start of a tiled tensor load has to be
 // 16-byte aligned: an unaligned start is an illegal instruction, profiles/probes/tma_probe.cu) and at a row >= 0.
 __device__ __forceinline__ uint32_t k2_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// wait for phase `parity` of an mbarrier (bounded: a pipeline bug traps instead of hanging the GPU)
+__device__ __forceinline__ void k2_mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = k2_smem_u32(bar);
+    uint32_t done = 0;
+    int spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (++spins > (1 << 20)) __trap();
+    }
+}
 constexpr int BOXW = 36;   // words per staged row: up to 3 words of alignment slack + the slab's 32 words + the edge word
 
 typedef CUresult (*K2EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -105,7 +122,8 @@ __device__ __forceinline__ uint32_t hop(uint32_t l, uint32_t c, uint32_t r, bool
 template <int R, int PAT, bool INTERIOR, bool DX0, int SEG, bool STAGED = false>
 __device__ __forceinline__ void morph_strip(const uint32_t* __restrict__ raw_f, const Geom& g, uint32_t* __restrict__ fbits,
                                             uint8_t* __restrict__ mask, int f, bool live, int slab, int lane, int y0,
-                                            const uint32_t* srow = nullptr, int row0 = 0, int col0 = 0, int sr_rt = 0) {
+                                            const uint32_t* srow = nullptr, int row0 = 0, int col0 = 0, int sr_rt = 0,
+                                            const CUtensorMap* tmap = nullptr, uint64_t* bar = nullptr) {
     constexpr int SLABW = SEG - 2;                           // output words per segment
     const int hl = lane & (SEG - 1);                         // lane within the segment
     const int seg0 = lane & ~(SEG - 1);
@@ -145,12 +163,33 @@ __device__ __forceinline__ void morph_strip(const uint32_t* __restrict__ raw_f, 
     }
     // raw words of row y (this lane's word; lane 31 also fetches the word after it), 0 outside the image
     auto fetch = [&](int y, uint32_t& lo, uint32_t& edge) {
+        const uint32_t lo_prev = lo;                         // the row fetched by the previous call
+        (void)lo_prev;
         lo = 0u;
         edge = 0u;
         if constexpr (STAGED) {
-            const int yrel = y - row0;                               // rows above the image (and the one-row overshoot
-            if ((unsigned)yrel < (unsigned)(SR + 2 * HR) && j >= 0) {   // of the prefetch) read as zeros
-                const uint32_t* rowp = srow + yrel * BOXW + (j - col0);
+            // The strip's SR + 2 HR raw rows pass through a staging buffer of HALF as many rows in two fills: when
+            // the (warp-uniform) row counter reaches the second half, every row of the first half has been read into
+            // registers, so the same buffer takes rows [row0 + HALF, row0 + 2 HALF).  Half the shared memory per
+            // warp = eight instead of four resident CTAs per SM; the second fill's latency is paid once per strip.
+            constexpr int HALF = (SR + 2 * HR) / 2;
+            const int yrel = y - row0;                               // rows above / below the image (and the one-row
+            if (yrel == HALF && y < g.h) {                           // overshoot of the prefetch) read as zeros
+                asm volatile("" ::"r"(__shfl_sync(0xFFFFFFFFu, lo_prev, 0)) : "memory");   // the first half's loads have landed
+                if (lane == 0) {
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(k2_smem_u32(bar)),
+                                 "r"((uint32_t)(HALF * BOXW * 4))
+                                 : "memory");
+                    asm volatile(
+                        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                            k2_smem_u32(srow)),
+                        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(col0), "r"(row0 + HALF), "r"(f), "r"(k2_smem_u32(bar))
+                        : "memory");
+                }
+                k2_mbar_wait(bar, 1u);
+            }
+            if ((unsigned)yrel < (unsigned)(2 * HALF) && j >= 0 && y < g.h) {
+                const uint32_t* rowp = srow + (yrel >= HALF ? yrel - HALF : yrel) * BOXW + (j - col0);
                 lo = rowp[0];
                 if (!DX0 && hl == SEG - 1) edge = rowp[1];
             }
@@ -162,7 +201,11 @@ __device__ __forceinline__ void morph_strip(const uint32_t* __restrict__ raw_f, 
     };
     uint32_t lo_n, edge_n;
     fetch(y0 - HR, lo_n, edge_n);
-    const long long orow0 = (long long)f * g.h;
+    // output pointers advance by one row per output row (the strip's rows come out in order, starting at y0):
+    // recomputing (f * h + y) * pitch + j per row was a fifth of the kernel's instructions (ncu source view)
+    const long long orow0 = (long long)f * g.h + y0;
+    uint32_t* fb_out = fbits + orow0 * g.wpr4 + j;
+    uint8_t* m_out = mask + orow0 * g.mpitch + (long long)slab * (SLABW * 32);
     for (int base = y0 - HR; base < y_stop; base += W) {
 #pragma unroll
         for (int u = 0; u < W; ++u) {
@@ -210,10 +253,11 @@ __device__ __forceinline__ void morph_strip(const uint32_t* __restrict__ raw_f, 
             // ---- outputs for row yin - HR
             const int yout = yin - HR;
             if (yout < y0) continue;                             // warp-uniform (pipeline warm-up)
-            const long long orow = orow0 + yout;
-            if (st_bits) fbits[orow * g.wpr4 + j] = cur;
+            if (st_bits) *fb_out = cur;
+            fb_out += g.wpr4;
             if (mask != nullptr) {
-                uint8_t* mrow = mask + orow * g.mpitch + (long long)slab * (SLABW * 32);
+                uint8_t* mrow = m_out;
+                m_out += g.mpitch;
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     const int c = half * SEG + hl;               // 16-byte chunk of the slab's row
@@ -306,8 +350,9 @@ k_morph_mask_staged(const __grid_constant__ CUtensorMap tmap, Geom g, int T, uin
                     uint8_t* __restrict__ mask) {
     constexpr int HR = n_ops(PAT) * R;
     constexpr int SR = strip_rows(R, PAT);
-    constexpr int ROWS = SR + 2 * HR;
-    constexpr int REGION = (ROWS * BOXW * 4 + 127) / 128 * 128;   // per-warp staging area, 128-byte aligned for TMA
+    constexpr int HALF = (SR + 2 * HR) / 2;                       // rows per fill of the staging buffer (two fills per strip)
+    static_assert((SR + 2 * HR) % 2 == 0, "two equal fills");
+    constexpr int REGION = (HALF * BOXW * 4 + 127) / 128 * 128;   // per-warp staging area, 128-byte aligned for TMA
     extern __shared__ __align__(128) uint8_t k2_smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -327,7 +372,7 @@ k_morph_mask_staged(const __grid_constant__ CUtensorMap tmap, Geom g, int T, uin
     wait_for_previous_kernel();                              // launched as a dependent of K1 (raw bits)
     if (lane == 0) {
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(k2_smem_u32(bar)),
-                     "r"((uint32_t)(ROWS * BOXW * 4))
+                     "r"((uint32_t)(HALF * BOXW * 4))
                      : "memory");
         asm volatile(
             "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
@@ -335,29 +380,14 @@ k_morph_mask_staged(const __grid_constant__ CUtensorMap tmap, Geom g, int T, uin
             "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(col0), "r"(row0), "r"(f), "r"(k2_smem_u32(bar))
             : "memory");
     }
-    {
-        const uint32_t addr = k2_smem_u32(bar);
-        uint32_t done = 0;
-        int spins = 0;
-        while (true) {
-            asm volatile(
-                "{\n\t.reg .pred p;\n\t"
-                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                "selp.u32 %0, 1, 0, p;\n\t}"
-                : "=r"(done)
-                : "r"(addr), "r"(0u)
-                : "memory");
-            if (done) break;
-            if (++spins > (1 << 20)) __trap();               // never hang the GPU on a pipeline bug
-        }
-    }
+    k2_mbar_wait(bar, 0u);
     const bool interior = (y0 - HR >= 0) && (y0 + SR + HR <= g.h);   // warp-uniform
     if (g.dx == 0) {
-        if (interior) morph_strip<R, PAT, true, true, 32, true>(nullptr, g, fbits, mask, f, true, slab, lane, y0, srow, row0, col0);
-        else morph_strip<R, PAT, false, true, 32, true>(nullptr, g, fbits, mask, f, true, slab, lane, y0, srow, row0, col0);
+        if (interior) morph_strip<R, PAT, true, true, 32, true>(nullptr, g, fbits, mask, f, true, slab, lane, y0, srow, row0, col0, 0, &tmap, bar);
+        else morph_strip<R, PAT, false, true, 32, true>(nullptr, g, fbits, mask, f, true, slab, lane, y0, srow, row0, col0, 0, &tmap, bar);
     } else {
-        if (interior) morph_strip<R, PAT, true, false, 32, true>(nullptr, g, fbits, mask, f, true, slab, lane, y0, srow, row0, col0);
-        else morph_strip<R, PAT, false, false, 32, true>(nullptr, g, fbits, mask, f, true, slab, lane, y0, srow, row0, col0);
+        if (interior) morph_strip<R, PAT, true, false, 32, true>(nullptr, g, fbits, mask, f, true, slab, lane, y0, srow, row0, col0, 0, &tmap, bar);
+        else morph_strip<R, PAT, false, false, 32, true>(nullptr, g, fbits, mask, f, true, slab, lane, y0, srow, row0, col0, 0, &tmap, bar);
     }
 }
 
@@ -385,7 +415,7 @@ cudaError_t launch_pat(cudaStream_t s, const uint32_t* raw_bits, int T, const Ge
     // chains are bound by the mask stores and their own arithmetic, not by the raw-row load): staged only where the
     // vertical halo is deep (64-row strips).
     if (k2_tma_enabled() && nslabs >= 2 && SR == 64) {
-        constexpr int ROWS = SR + 2 * n_ops(PAT) * R;
+        constexpr int ROWS = (SR + 2 * n_ops(PAT) * R) / 2;      // rows per fill: the strip's rows pass through in two fills
         constexpr int SMEM = WPB * ((ROWS * BOXW * 4 + 127) / 128 * 128) + WPB * 8;
         CUtensorMap tmap;
         if (encode_raw_bits_tensor(&tmap, raw_bits, g.wpr_raw, g.h, T, ROWS)) {
