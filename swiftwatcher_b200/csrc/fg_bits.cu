@@ -350,6 +350,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
     int spins = 0;
+    const long long t_wait0 = clock64();
     while (true) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -359,7 +360,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "r"(addr), "r"(parity), "r"(MBAR_SUSPEND_NS)
             : "memory");
         if (done) break;
-        if (++spins > (1 << 26)) __trap();   // never hang the GPU on a pipeline bug
+        // never hang the GPU on a pipeline bug: give up after ~2 s of SM clock (a try_wait may suspend for up to 1 ms)
+        if ((++spins & 63) == 0 && clock64() - t_wait0 > (1ll << 32)) __trap();
     }
 }
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
@@ -1099,6 +1101,7 @@ k_fg_n9(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t one, ui
         const uint32_t addr = full_a + 8u * st;
         uint32_t done = 0;
         int spins = 0;
+        const long long t_wait0 = clock64();
         while (true) {
             asm volatile(
                 "{\n\t.reg .pred p;\n\t"
@@ -1108,7 +1111,8 @@ k_fg_n9(FrameSrc src, int T, int Ts, int h, int wa, int thresh, uint32_t one, ui
                 : "r"(addr), "r"(parity), "r"(MBAR_SUSPEND_NS)
                 : "memory");
             if (done) break;
-            if (++spins > (1 << 26)) __trap();   // never hang the GPU on a pipeline bug
+            // never hang the GPU on a pipeline bug: give up after ~2 s of SM clock (a try_wait may suspend for up to 1 ms)
+        if ((++spins & 63) == 0 && clock64() - t_wait0 > (1ll << 32)) __trap();
         }
     };
     auto release = [&](int st, const uint32_t (&a)[L], const uint32_t (&b)[L], const uint32_t (&c)[L]) {
