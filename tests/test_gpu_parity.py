@@ -457,6 +457,31 @@ def test_device_roi_tiles_through_the_tensor_map(n):
                 t += k
 
 
+@pytest.mark.parametrize("n", [5, 9])
+def test_device_roi_tiles_over_several_temporal_subchunks(n):
+    """Cropped ROI in device-resident frames, long enough that K1 cuts the submit into several temporal
+    sub-chunks (the one-wave sizing of pick_ts_roi: every sub-chunk re-reads its n - 1 warm-up frames through
+    the tensor map), also with the sub-chunk length forced; every frame against the oracle."""
+    import torch
+    T = 90
+    frames = synth.synth_video(70 + n, 1, 0, T, 150, 704, 60)
+    dev = torch.from_numpy(frames).cuda()
+    region = [(64, 10), (384, 131)]
+    want = rp.run_path(frames, rp.PathParams(region, n, 15, 3, True, False, "i32"))
+    for forced in (0, 36):
+        with swb.FilterContext(frames.shape[1:], region, median_n=n, label_mode="i32", max_frames=T) as ctx:
+            if forced:
+                ctx.set_option("temporal_subchunk", forced)
+            ctx.submit(dev, n_halo=0)
+            rows, counts = ctx.collect()
+            ts = ctx.last_subchunk()
+            assert 0 < ts < T and (not forced or ts == forced), ts      # several sub-chunks
+            labels = ctx.labels()
+            for t in range(T):
+                assert np.array_equal(labels[t], want[t]["labels"]), (n, forced, t)
+                assert counts[t] == len(want[t]["props"])
+
+
 def test_concurrent_contexts_on_their_own_streams():
     """BASELINE configs[3]: several videos per GPU, one context + CUDA stream each, submits
     interleaved without synchronising in between — every context must still produce exactly
