@@ -104,7 +104,9 @@ def test_zero_padded_last_batch_is_pinned(golden_dir):
 def test_stage_bilateral_random_images():
     from swiftwatcher_b200 import image_filtering as img
     rng = np.random.default_rng(9)
-    for shape in [(97, 131), (5, 9), (1, 40), (33, 1)]:
+    # widths that are multiples of four take the four-pixels-per-thread kernel (k_bilateral_r3x4), the others the
+    # one-pixel kernels; heights below seven rows have no interior at all
+    for shape in [(97, 131), (5, 9), (1, 40), (33, 1), (40, 64), (7, 16), (33, 132), (8, 20), (64, 256)]:
         a = rng.integers(0, 256, shape, dtype=np.uint8)
         assert np.array_equal(img.bilateral_blur(a, 7, 15, 1), rp.bilateral_scalar(a))
     a = (rng.integers(0, 24, (200, 300)) + 90).astype(np.uint8)
