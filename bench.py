@@ -747,7 +747,7 @@ def run_single(args, cfg, name, env, label_mode="i32", secondary=False):
                                   "tf32": bool(torch.backends.cudnn.allow_tf32),
                                   "note": "torchvision SqueezeNet1.0 weights and layers as in the reference (float32, "
                                           "cuDNN, library code), evaluated on the window of positions the device-gathered "
-                                          "24x24 crop can influence + cached blank-canvas activations (WindowedSqueezeNet: "
+                                          "24x24 crop can influence + cached blank-canvas activations in persistent patch buffers (WindowedSqueezeNet: "
                                           "same scores as the padded 224x224 forward pass to 1e-4); the hot-path kernels "
                                           "in `kernels` are the filtering + labelling part of the step"}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")

@@ -7,7 +7,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libswb200.so")
-SOURCES = ["api.cu", "fg_bits.cu", "morph_mask.cu", "ccl.cu", "stages.cu", "synth.cu", "rpca.cu", "track.cu"]
+SOURCES = ["api.cu", "fg_bits.cu", "morph_mask.cu", "ccl.cu", "stages.cu", "synth.cu", "rpca.cu", "track.cu", "classify_glue.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",
               "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
 

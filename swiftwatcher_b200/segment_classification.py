@@ -116,6 +116,153 @@ class WindowedSqueezeNet:
         patch[:, :, a - na:b - na, a - na:b - na] = xw
         return patch
 
+    # -- the same evaluation with persistent patch buffers ---------------------------------------------
+    # Profiling the plain version below (profiles/classifier_timing.py) showed that the convolutions are ~15 % of its
+    # GPU time: the rest was glue — cloning the blank halo into a fresh patch for every layer and call, pasting the
+    # window in, concatenating the two expand branches of every Fire module, NHWC max-pooling.  Here every layer owns
+    # a patch buffer that is filled with the blank activations ONCE (the halo never changes); per call the producer
+    # writes its (ReLU'd) output straight into the buffer's interior (``clamp_min(out=view)``), and the 1x1 expand
+    # branch of a Fire module is the centre tap of a 3x3 kernel, so both branches are one convolution whose output is
+    # already the concatenation.  Same function, same float32 / TF32 library kernels.
+    def _build(self, offset, c, bmax, like):
+        F = torch.nn.functional
+        cl = like.is_contiguous(memory_format=torch.channels_last)
+        fmt = torch.channels_last if cl else torch.contiguous_format
+        glue = self._glue(like)
+
+        def buffer(blank, win, need, fill):
+            (a, b), (na, nb) = win, need
+            n = blank.shape[-1]
+            C = blank.shape[1]
+            buf = torch.empty((bmax, C, nb - na, nb - na), dtype=like.dtype, device=like.device).contiguous(memory_format=fmt)
+            buf.fill_(fill)
+            ia, ib = max(na, 0), min(nb, n)
+            buf[:, :, ia - na:ib - na, ia - na:ib - na] = blank[:, :, ia:ib, ia:ib]
+            return buf, (a - na, b - na)
+
+        steps = []
+        win = (offset, offset + c)
+        pending_relu = False                                   # the producer's ReLU is applied when its output is consumed
+        for kind, layer, blank in self.plan:
+            if kind == "relu":
+                pending_relu = True
+            elif kind == "conv":
+                k, st, p = layer.kernel_size[0], layer.stride[0], layer.padding[0]
+                n_out = (blank.shape[-1] + 2 * p - k) // st + 1
+                ow = self._out_window(win, k, st, p, n_out)
+                need = (ow[0] * st - p, (ow[1] - 1) * st - p + k)
+                buf, inner = buffer(blank, win, need, 0.0)
+                steps.append(("conv", buf, inner, pending_relu, layer.weight, layer.bias, st))
+                pending_relu, win = False, ow
+            elif kind == "pool":
+                k, st = layer.kernel_size, layer.stride
+                n_in = blank.shape[-1]
+                n_out = -((-(n_in - k)) // st) + 1 if layer.ceil_mode else (n_in - k) // st + 1
+                if layer.ceil_mode and (n_out - 1) * st >= n_in:
+                    n_out -= 1
+                ow = self._out_window(win, k, st, 0, n_out)
+                need = (ow[0] * st, (ow[1] - 1) * st + k)
+                if glue:                                       # swb_nhwc_maxpool on a channels-last patch
+                    buf, inner = buffer(blank, win, need, float("-inf"))
+                else:                                          # torch's NHWC max-pool kernel is 2-3x slower than its NCHW one here
+                    (a, b), (na, nb) = win, need
+                    n = blank.shape[-1]
+                    buf = torch.full((bmax, blank.shape[1], nb - na, nb - na), float("-inf"), dtype=like.dtype, device=like.device)
+                    ia, ib = max(na, 0), min(nb, n)
+                    buf[:, :, ia - na:ib - na, ia - na:ib - na] = blank[:, :, ia:ib, ia:ib]
+                    inner = (a - na, b - na)
+                steps.append(("pool", buf, inner, pending_relu, k, st, fmt))
+                pending_relu, win = False, ow
+            else:   # fire
+                n = blank.shape[-1]
+                ow = (max(win[0] - 1, 0), min(win[1] + 1, n))
+                need = (ow[0] - 1, ow[1] + 1)
+                buf, inner = buffer(blank, win, need, 0.0)     # blank = the squeeze activations of the blank canvas
+                w3, w1 = layer.expand3x3.weight, layer.expand1x1.weight
+                w1p = torch.zeros((w1.shape[0], w1.shape[1], 3, 3), dtype=w1.dtype, device=w1.device)
+                w1p[:, :, 1:2, 1:2] = w1
+                w = torch.cat([w1p, w3], 0).contiguous(memory_format=fmt)
+                bias = torch.cat([layer.expand1x1.bias, layer.expand3x3.bias], 0)
+                steps.append(("fire", buf, inner, pending_relu, layer.squeeze.weight, layer.squeeze.bias, w, bias))
+                pending_relu, win = True, ow                   # the module ends with ReLU on the concatenation
+        a, b = win
+        outside = self.blank_head.sum((2, 3)) - self.blank_head[:, :, a:b, a:b].sum((2, 3))
+        return steps, outside, pending_relu
+
+    @staticmethod
+    def _glue(like):
+        """The library's NHWC glue kernels (swb_nhwc_paste / swb_nhwc_maxpool) for channels-last CUDA float32 tensors."""
+        if like.device.type != "cuda" or like.dtype != torch.float32 or not like.is_contiguous(memory_format=torch.channels_last):
+            return None
+        from . import _lib
+        return _lib.load()
+
+    @staticmethod
+    def _paste(lib, x, buf, B, inner, relu):
+        """buf[:B, :, inner, inner] = relu?(x) with one streaming kernel (x: [B, C, h, w] channels-last)."""
+        from ._lib import check
+        Bx, C, h, w = x.shape
+        assert Bx == B and C == buf.shape[1]
+        if not x.is_contiguous(memory_format=torch.channels_last):
+            x = x.contiguous(memory_format=torch.channels_last)
+        check(lib.swb_nhwc_paste(x.data_ptr(), buf.data_ptr(), B, C, h, w, buf.shape[2], buf.shape[3], inner[0], inner[0],
+                                 1 if relu else 0, torch.cuda.current_stream(x.device).cuda_stream))
+
+    @torch.no_grad()
+    def forward_buffered(self, crops_norm, offset, bmax=2048):
+        """The evaluation of ``__call__`` on persistent buffers (at most ``bmax`` crops per call)."""
+        F = torch.nn.functional
+        B, c = int(crops_norm.shape[0]), int(crops_norm.shape[-1])
+        lib = self._glue(crops_norm)
+        key = (offset, c, crops_norm.device, crops_norm.is_contiguous(memory_format=torch.channels_last))
+        if getattr(self, "_built_key", None) != key or self._built_bmax < B:
+            self._steps, self._outside, self._last_relu = self._build(offset, c, max(bmax, B), crops_norm)
+            self._built_key, self._built_bmax = key, max(bmax, B)
+        x, relu = crops_norm, False
+        for step in self._steps:
+            kind, buf, (ia, ib) = step[0], step[1], step[2]
+            view = buf[:B, :, ia:ib, ia:ib]
+            if kind == "fire":
+                _, _, _, pre_relu, sw, sb, w, bias = step
+                if pre_relu:
+                    x = torch.relu_(x)
+                sq = F.conv2d(x, sw, sb)
+                if lib is not None:                                            # squeeze -> ReLU -> into the halo'd patch
+                    self._paste(lib, sq, buf, B, (ia, ib), True)
+                else:
+                    torch.clamp_min(sq, 0.0, out=view)
+                x = F.conv2d(buf[:B], w, bias)                                 # [expand1x1 | expand3x3], ReLU pending
+            elif kind == "conv":
+                _, _, _, pre_relu, w, bias, st = step
+                if lib is not None:
+                    self._paste(lib, x, buf, B, (ia, ib), pre_relu)
+                elif pre_relu:
+                    torch.clamp_min(x, 0.0, out=view)
+                else:
+                    view.copy_(x)
+                x = F.conv2d(buf[:B], w, bias, stride=st)
+            else:   # pool
+                _, _, _, pre_relu, k, st, fmt = step
+                if lib is not None:
+                    from ._lib import check
+                    self._paste(lib, x, buf, B, (ia, ib), pre_relu)
+                    n_in = int(buf.shape[2])
+                    n_out = (n_in - k) // st + 1
+                    x = torch.empty((B, buf.shape[1], n_out, n_out), dtype=buf.dtype, device=buf.device).contiguous(
+                        memory_format=torch.channels_last)
+                    check(lib.swb_nhwc_maxpool(buf.data_ptr(), x.data_ptr(), B, int(buf.shape[1]), n_in, n_in, k, st,
+                                               torch.cuda.current_stream(buf.device).cuda_stream))
+                    continue
+                if pre_relu:
+                    torch.clamp_min(x, 0.0, out=view)
+                else:
+                    view.copy_(x)
+                x = F.max_pool2d(buf[:B], k, st).contiguous(memory_format=fmt)
+        if self._last_relu:
+            x = torch.relu_(x)
+        head = torch.relu(F.conv2d(x, self.head.weight, self.head.bias))       # [B, 2, w, w]
+        return (head.sum((2, 3)) + self._outside) / float(self.blank_feat_hw * self.blank_feat_hw)
+
     @torch.no_grad()
     def __call__(self, crops_norm, offset):
         """crops_norm: [B, 3, c, c] normalised crops sitting at rows/cols [offset, offset + c) of the canvas."""
@@ -159,7 +306,7 @@ class WindowedSqueezeNet:
 
 
 class SegmentClassifier:
-    def __init__(self, model_path, device=None, batch_size=2048, channels_last=True, windowed=True):
+    def __init__(self, model_path, device=None, batch_size=2048, channels_last=True, windowed=True, buffered=True):
         if device is None:   # the reference's module-level choice (:10)
             device = torch.device("cuda:0" if torch.cuda.is_available() else "cpu")
         self.device = torch.device(device)
@@ -173,6 +320,7 @@ class SegmentClassifier:
         if self.channels_last:
             self.model = self.model.to(memory_format=torch.channels_last)
         self.batch_size = int(batch_size)
+        self.buffered = bool(buffered)       # persistent patch buffers (WindowedSqueezeNet.forward_buffered)
         self._mean = torch.tensor(_MEAN, dtype=torch.float32, device=self.device).view(1, 3, 1, 1)
         self._std = torch.tensor(_STD, dtype=torch.float32, device=self.device).view(1, 3, 1, 1)
         self.windowed = None
@@ -229,7 +377,9 @@ class SegmentClassifier:
         out = torch.empty((n, 2), dtype=torch.float32, device=self.device)
         for a in range(0, n, self.batch_size):
             b = min(n, a + self.batch_size)
-            if self.windowed is not None:
+            if self.windowed is not None and self.buffered:
+                out[a:b] = self.windowed.forward_buffered(self.preprocess_crops(crops[a:b]), PAD, self.batch_size)
+            elif self.windowed is not None:
                 out[a:b] = self.windowed(self.preprocess_crops(crops[a:b]), PAD)
             else:
                 out[a:b] = self.model(self.preprocess(crops[a:b]))

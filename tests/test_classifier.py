@@ -235,3 +235,44 @@ def test_pil_bilinear_restatement_equals_pillow():
             a = rng.integers(0, 256, (h, w, ch) if ch == 3 else (h, w), dtype=np.uint8)
             want = np.asarray(transforms.Resize((24, 24))(transforms.ToPILImage()(a)))
             assert np.array_equal(rc.pil_bilinear_resize(a, (24, 24)), want), (h, w, ch)
+
+
+@pytest.mark.gpu
+def test_gpu_glue_kernels_and_buffered_evaluation():
+    """swb_nhwc_paste / swb_nhwc_maxpool against the torch operations they replace (channel counts that take the
+    float4 and the scalar path, with and without ReLU, partial batches), and the buffered windowed evaluation against
+    the plain one and against the full forward pass, in both memory formats."""
+    import torch.nn.functional as F
+    from swiftwatcher_b200 import _lib
+    from swiftwatcher_b200._lib import check
+    from swiftwatcher_b200.segment_classification import SegmentClassifier, setup_model
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(5)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    for C, h, H, off, relu in [(3, 24, 36, 6, 0), (16, 8, 10, 1, 1), (96, 15, 17, 1, 1), (64, 5, 9, 3, 0)]:
+        for B in (1, 7):
+            x = torch.randn((B, C, h, h), generator=g).to(dev).contiguous(memory_format=torch.channels_last)
+            buf = torch.randn((B + 2, C, H, H), generator=g).to(dev).contiguous(memory_format=torch.channels_last)
+            want = buf.clone()
+            want[:B, :, off:off + h, off:off + h] = torch.relu(x) if relu else x
+            check(lib.swb_nhwc_paste(x.data_ptr(), buf.data_ptr(), B, C, h, h, H, H, off, off, relu, stream))
+            assert torch.equal(buf, want), (C, h, H, off, relu, B)
+    for C, H, k, s in [(96, 17, 3, 2), (256, 9, 3, 2), (8, 7, 2, 1)]:
+        x = torch.randn((5, C, H, H), generator=g).to(dev).contiguous(memory_format=torch.channels_last)
+        x[0, :, 0, :] = float("-inf")
+        n_out = (H - k) // s + 1
+        out = torch.empty((5, C, n_out, n_out), device=dev).contiguous(memory_format=torch.channels_last)
+        check(lib.swb_nhwc_maxpool(x.data_ptr(), out.data_ptr(), 5, C, H, H, k, s, stream))
+        assert torch.equal(out, F.max_pool2d(x, k, s)), (C, H, k, s)
+    assert lib.swb_nhwc_maxpool(x.data_ptr(), out.data_ptr(), 5, 6, 7, 7, 2, 1, stream) != 0   # channels not a multiple of 4
+    torch.manual_seed(3)
+    sd = setup_model(2, "cpu").state_dict()
+    crops = torch.randint(0, 256, (150, 24, 24, 3), dtype=torch.uint8, generator=g)
+    full = SegmentClassifier(sd, device="cuda:0", batch_size=64, windowed=False).scores(crops)
+    for cl in (True, False):
+        plain = SegmentClassifier(sd, device="cuda:0", batch_size=64, channels_last=cl, buffered=False)
+        buffered = SegmentClassifier(sd, device="cuda:0", batch_size=64, channels_last=cl, buffered=True)
+        a, b = plain.scores(crops), buffered.scores(crops)          # 150 = two full batches + a partial one
+        assert torch.allclose(a, b, rtol=TOL, atol=TOL) and torch.allclose(b, full, rtol=TOL, atol=TOL), cl
+        assert torch.allclose(buffered.scores(crops[:9]), full[:9], rtol=TOL, atol=TOL)
