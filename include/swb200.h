@@ -274,13 +274,14 @@ int swb_host_gather_tiles(const uint64_t* src, int64_t pitch, int32_t rows, int3
  * of positions the 24x24 crop can influence).  The convolutions are library kernels; these two kernels move a layer's
  * output into the next layer's input patch.  Device pointers, float32, NHWC (channels-last) layout, launched on
  * `stream` (a cudaStream_t, e.g. torch's current stream; NULL = the default stream), asynchronous.
- * swb_nhwc_paste:   dst[b][off_y + y][off_x + x][c] = src[b][y][x][c] (ReLU applied first when relu != 0); src is
- *                   [batch][h][w][channels], dst is [batch][dst_h][dst_w][channels].
+ * swb_nhwc_paste:   dst[b][off_y + y][off_x + x][c] = src[b][y][x][c] (+ bias[c] when bias != NULL, then ReLU when
+ *                   relu != 0); src is [batch][h][w][channels], dst is [batch][dst_h][dst_w][channels]; src == dst with
+ *                   the same geometry and zero offsets is the in-place bias + ReLU of a convolution output.
  * swb_nhwc_maxpool: out[b][oy][ox][c] = max of the kernel x kernel window at (oy * stride, ox * stride) of
  *                   in[batch][in_h][in_w][channels]; out is [batch][(in_h - kernel) / stride + 1][(in_w - kernel) / stride + 1]
  *                   [channels]; channels must be a multiple of 4 and both pointers 16-byte aligned. */
 int swb_nhwc_paste(const float* src, float* dst, int64_t batch, int32_t channels, int32_t h, int32_t w, int32_t dst_h,
-                   int32_t dst_w, int32_t off_y, int32_t off_x, int32_t relu, void* stream);
+                   int32_t dst_w, int32_t off_y, int32_t off_x, const float* bias, int32_t relu, void* stream);
 int swb_nhwc_maxpool(const float* in, float* out, int64_t batch, int32_t channels, int32_t in_h, int32_t in_w,
                      int32_t kernel, int32_t stride, void* stream);
 

@@ -85,7 +85,7 @@ SYMBOLS = {
     "swb_tracker_last_error": (C.c_char_p, [_P]),
     "swb_tracker_launch_count": (_I64, [_P]),
     "swb_host_gather_tiles": (C.c_int, [_P, _I64, _I32, _I32, _I64, _P]),
-    "swb_nhwc_paste": (C.c_int, [_P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
+    "swb_nhwc_paste": (C.c_int, [_P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _I32, _P]),
     "swb_nhwc_maxpool": (C.c_int, [_P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _P]),
     "swb_host_alloc": (C.c_int, [C.POINTER(_P), C.c_uint64]),
     "swb_host_free": (C.c_int, [_P]),

@@ -11,17 +11,27 @@
 
 namespace {
 
-// dst[b][oy + y][ox + x][c] = relu?(src[b][y][x][c]); a row of the window is w * C contiguous floats on both sides
+// dst[b][oy + y][ox + x][c] = relu?(src[b][y][x][c] + bias?[c]); a row of the window is w * C contiguous floats on both
+// sides.  src == dst with identical geometry is allowed (in-place bias + ReLU: every element is read and written by
+// the same thread), hence no __restrict__.
 template <typename V>
 __global__ void __launch_bounds__(256)
-k_nhwc_paste(const V* __restrict__ src, V* __restrict__ dst, int h, int row_v, long long src_img_v, long long dst_img_v,
-             int dst_row_v, long long dst_off_v, int relu) {
+k_nhwc_paste(const V* src, V* dst, int h, int row_v, long long src_img_v, long long dst_img_v, int dst_row_v,
+             long long dst_off_v, int relu, const V* __restrict__ bias, int c_v) {
     const int y = blockIdx.y;
     const long long b = blockIdx.z;
     const V* s = src + b * src_img_v + (long long)y * row_v;
     V* d = dst + b * dst_img_v + dst_off_v + (long long)y * dst_row_v;
     for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < row_v; x += gridDim.x * blockDim.x) {
         V v = s[x];
+        if (bias != nullptr) {
+            const V bv = bias[x % c_v];
+            if constexpr (sizeof(V) == 16) {
+                v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+            } else {
+                v += bv;
+            }
+        }
         if (relu) {
             if constexpr (sizeof(V) == 16) {
                 v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
@@ -61,7 +71,7 @@ k_nhwc_maxpool(const float4* __restrict__ in, float4* __restrict__ out, int W, i
 extern "C" {
 
 int swb_nhwc_paste(const float* src, float* dst, int64_t batch, int32_t channels, int32_t h, int32_t w, int32_t dst_h,
-                   int32_t dst_w, int32_t off_y, int32_t off_x, int32_t relu, void* stream) {
+                   int32_t dst_w, int32_t off_y, int32_t off_x, const float* bias, int32_t relu, void* stream) {
     if (!src || !dst || batch < 0 || channels < 1 || h < 1 || w < 1 || off_y < 0 || off_x < 0 || off_y + h > dst_h ||
         off_x + w > dst_w || batch > 65535 || h > 65535)
         return SWB_ERR_INVALID;
@@ -69,17 +79,18 @@ int swb_nhwc_paste(const float* src, float* dst, int64_t batch, int32_t channels
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const long long row = (long long)w * channels, dst_row = (long long)dst_w * channels;
     const long long dst_off = ((long long)off_y * dst_w + off_x) * channels;
-    const bool v4 = channels % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+    const bool v4 = channels % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(bias) & 15) == 0;
     if (v4) {
         const int row_v = (int)(row / 4);
         dim3 grid((row_v + 255) / 256, h, (unsigned)batch);
         k_nhwc_paste<float4><<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(dst), h, row_v,
                                                   (long long)h * row / 4, (long long)dst_h * dst_row / 4, (int)(dst_row / 4),
-                                                  dst_off / 4, relu);
+                                                  dst_off / 4, relu, reinterpret_cast<const float4*>(bias), channels / 4);
     } else {
         dim3 grid((unsigned)((row + 255) / 256), h, (unsigned)batch);
         k_nhwc_paste<float><<<grid, 256, 0, s>>>(src, dst, h, (int)row, (long long)h * row, (long long)dst_h * dst_row,
-                                                 (int)dst_row, dst_off, relu);
+                                                 (int)dst_row, dst_off, relu, bias, channels);
     }
     return cudaGetLastError() == cudaSuccess ? SWB_OK : SWB_ERR_CUDA;
 }

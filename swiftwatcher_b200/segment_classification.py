@@ -198,15 +198,15 @@ class WindowedSqueezeNet:
         return _lib.load()
 
     @staticmethod
-    def _paste(lib, x, buf, B, inner, relu):
-        """buf[:B, :, inner, inner] = relu?(x) with one streaming kernel (x: [B, C, h, w] channels-last)."""
+    def _paste(lib, x, buf, B, inner, relu, bias=None):
+        """buf[:B, :, inner, inner] = relu?(x + bias?) with one streaming kernel (x: [B, C, h, w] channels-last;
+        buf may be x itself with inner = (0, h): the in-place bias + ReLU of a convolution output)."""
         from ._lib import check
         Bx, C, h, w = x.shape
-        assert Bx == B and C == buf.shape[1]
-        if not x.is_contiguous(memory_format=torch.channels_last):
-            x = x.contiguous(memory_format=torch.channels_last)
+        assert Bx == B and C == buf.shape[1] and x.is_contiguous(memory_format=torch.channels_last)
         check(lib.swb_nhwc_paste(x.data_ptr(), buf.data_ptr(), B, C, h, w, buf.shape[2], buf.shape[3], inner[0], inner[0],
-                                 1 if relu else 0, torch.cuda.current_stream(x.device).cuda_stream))
+                                 None if bias is None else bias.data_ptr(), 1 if relu else 0,
+                                 torch.cuda.current_stream(x.device).cuda_stream))
 
     @torch.no_grad()
     def forward_buffered(self, crops_norm, offset, bmax=2048):
@@ -218,25 +218,34 @@ class WindowedSqueezeNet:
         if getattr(self, "_built_key", None) != key or self._built_bmax < B:
             self._steps, self._outside, self._last_relu = self._build(offset, c, max(bmax, B), crops_norm)
             self._built_key, self._built_bmax = key, max(bmax, B)
-        x, relu = crops_norm, False
+        cl = torch.channels_last
+        x = crops_norm
+        xb = None          # glue path: the bias of the convolution that produced x, not added yet (the library adds a
+                           # bias with a separate strided elementwise kernel: a third of the time before this)
         for step in self._steps:
             kind, buf, (ia, ib) = step[0], step[1], step[2]
             view = buf[:B, :, ia:ib, ia:ib]
             if kind == "fire":
                 _, _, _, pre_relu, sw, sb, w, bias = step
+                if lib is not None:
+                    x = x.contiguous(memory_format=cl)
+                    if pre_relu or xb is not None:                             # in place: + bias, ReLU
+                        self._paste(lib, x, x, B, (0, int(x.shape[2])), pre_relu, xb)
+                    sq = F.conv2d(x, sw, None).contiguous(memory_format=cl)
+                    self._paste(lib, sq, buf, B, (ia, ib), True, sb)           # squeeze + bias -> ReLU -> into the halo'd patch
+                    x, xb = F.conv2d(buf[:B], w, None), bias                   # [expand1x1 | expand3x3], bias and ReLU pending
+                    continue
                 if pre_relu:
                     x = torch.relu_(x)
-                sq = F.conv2d(x, sw, sb)
-                if lib is not None:                                            # squeeze -> ReLU -> into the halo'd patch
-                    self._paste(lib, sq, buf, B, (ia, ib), True)
-                else:
-                    torch.clamp_min(sq, 0.0, out=view)
-                x = F.conv2d(buf[:B], w, bias)                                 # [expand1x1 | expand3x3], ReLU pending
+                torch.clamp_min(F.conv2d(x, sw, sb), 0.0, out=view)
+                x = F.conv2d(buf[:B], w, bias)
             elif kind == "conv":
                 _, _, _, pre_relu, w, bias, st = step
                 if lib is not None:
-                    self._paste(lib, x, buf, B, (ia, ib), pre_relu)
-                elif pre_relu:
+                    self._paste(lib, x.contiguous(memory_format=cl), buf, B, (ia, ib), pre_relu, xb)
+                    x, xb = F.conv2d(buf[:B], w, None, stride=st), bias
+                    continue
+                if pre_relu:
                     torch.clamp_min(x, 0.0, out=view)
                 else:
                     view.copy_(x)
@@ -245,20 +254,23 @@ class WindowedSqueezeNet:
                 _, _, _, pre_relu, k, st, fmt = step
                 if lib is not None:
                     from ._lib import check
-                    self._paste(lib, x, buf, B, (ia, ib), pre_relu)
+                    self._paste(lib, x.contiguous(memory_format=cl), buf, B, (ia, ib), pre_relu, xb)
                     n_in = int(buf.shape[2])
                     n_out = (n_in - k) // st + 1
-                    x = torch.empty((B, buf.shape[1], n_out, n_out), dtype=buf.dtype, device=buf.device).contiguous(
-                        memory_format=torch.channels_last)
+                    x = torch.empty((B, buf.shape[1], n_out, n_out), dtype=buf.dtype, device=buf.device).contiguous(memory_format=cl)
                     check(lib.swb_nhwc_maxpool(buf.data_ptr(), x.data_ptr(), B, int(buf.shape[1]), n_in, n_in, k, st,
                                                torch.cuda.current_stream(buf.device).cuda_stream))
+                    xb = None
                     continue
                 if pre_relu:
                     torch.clamp_min(x, 0.0, out=view)
                 else:
                     view.copy_(x)
                 x = F.max_pool2d(buf[:B], k, st).contiguous(memory_format=fmt)
-        if self._last_relu:
+        if lib is not None and (self._last_relu or xb is not None):
+            x = x.contiguous(memory_format=cl)
+            self._paste(lib, x, x, B, (0, int(x.shape[2])), self._last_relu, xb)
+        elif self._last_relu:
             x = torch.relu_(x)
         head = torch.relu(F.conv2d(x, self.head.weight, self.head.bias))       # [B, 2, w, w]
         return (head.sum((2, 3)) + self._outside) / float(self.blank_feat_hw * self.blank_feat_hw)

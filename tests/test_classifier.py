@@ -256,8 +256,15 @@ def test_gpu_glue_kernels_and_buffered_evaluation():
             buf = torch.randn((B + 2, C, H, H), generator=g).to(dev).contiguous(memory_format=torch.channels_last)
             want = buf.clone()
             want[:B, :, off:off + h, off:off + h] = torch.relu(x) if relu else x
-            check(lib.swb_nhwc_paste(x.data_ptr(), buf.data_ptr(), B, C, h, h, H, H, off, off, relu, stream))
+            check(lib.swb_nhwc_paste(x.data_ptr(), buf.data_ptr(), B, C, h, h, H, H, off, off, None, relu, stream))
             assert torch.equal(buf, want), (C, h, H, off, relu, B)
+            bias = torch.randn((C,), generator=g).to(dev)
+            want[:B, :, off:off + h, off:off + h] = torch.relu(x + bias.view(1, C, 1, 1)) if relu else x + bias.view(1, C, 1, 1)
+            check(lib.swb_nhwc_paste(x.data_ptr(), buf.data_ptr(), B, C, h, h, H, H, off, off, bias.data_ptr(), relu, stream))
+            assert torch.equal(buf, want), (C, h, H, off, relu, B, "bias")
+            y = x.clone()                                          # in place: bias + ReLU of a convolution output
+            check(lib.swb_nhwc_paste(y.data_ptr(), y.data_ptr(), B, C, h, h, h, h, 0, 0, bias.data_ptr(), 1, stream))
+            assert torch.equal(y, torch.relu(x + bias.view(1, C, 1, 1)))
     for C, H, k, s in [(96, 17, 3, 2), (256, 9, 3, 2), (8, 7, 2, 1)]:
         x = torch.randn((5, C, H, H), generator=g).to(dev).contiguous(memory_format=torch.channels_last)
         x[0, :, 0, :] = float("-inf")
