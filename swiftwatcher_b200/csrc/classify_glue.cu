@@ -5,6 +5,7 @@
 // (profiles/classifier_timing.py).  Both are plain NHWC (channels-last) float32 streaming kernels.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 
 #include "../../include/swb200.h"
@@ -18,12 +19,16 @@ template <typename V>
 __global__ void __launch_bounds__(256)
 k_nhwc_paste(const V* src, V* dst, int h, int row_v, long long src_img_v, long long dst_img_v, int dst_row_v,
              long long dst_off_v, int relu, const V* __restrict__ bias, int c_v) {
-    const int y = blockIdx.y;
-    const long long b = blockIdx.z;
-    const V* s = src + b * src_img_v + (long long)y * row_v;
-    V* d = dst + b * dst_img_v + dst_off_v + (long long)y * dst_row_v;
-    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < row_v; x += gridDim.x * blockDim.x) {
-        V v = s[x];
+    // one thread per vector of the (contiguous) source image: windows are small (5..36 rows of 10..1500 vectors), a block
+    // per row would leave most of its threads idle
+    const long long b = blockIdx.y;
+    const V* s = src + b * src_img_v;
+    V* dimg = dst + b * dst_img_v + dst_off_v;
+    const int n = h * row_v;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int y = i / row_v, x = i - y * row_v;
+        V* d = dimg + (long long)y * dst_row_v;
+        V v = s[i];
         if (bias != nullptr) {
             const V bv = bias[x % c_v];
             if constexpr (sizeof(V) == 16) {
@@ -41,7 +46,6 @@ k_nhwc_paste(const V* src, V* dst, int h, int row_v, long long src_img_v, long l
         }
         d[x] = v;
     }
-    (void)h;
 }
 
 // out[b][oy][ox][c] = max over the k x k window at (oy * s, ox * s) of in[b][.][.][c]; in is H x W, out is OH x OW
@@ -73,7 +77,7 @@ extern "C" {
 int swb_nhwc_paste(const float* src, float* dst, int64_t batch, int32_t channels, int32_t h, int32_t w, int32_t dst_h,
                    int32_t dst_w, int32_t off_y, int32_t off_x, const float* bias, int32_t relu, void* stream) {
     if (!src || !dst || batch < 0 || channels < 1 || h < 1 || w < 1 || off_y < 0 || off_x < 0 || off_y + h > dst_h ||
-        off_x + w > dst_w || batch > 65535 || h > 65535)
+        off_x + w > dst_w || batch > 65535 || (long long)h * w * channels > 0x7FFFFFFF)
         return SWB_ERR_INVALID;
     if (batch == 0) return SWB_OK;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -83,12 +87,12 @@ int swb_nhwc_paste(const float* src, float* dst, int64_t batch, int32_t channels
                     (reinterpret_cast<uintptr_t>(bias) & 15) == 0;
     if (v4) {
         const int row_v = (int)(row / 4);
-        dim3 grid((row_v + 255) / 256, h, (unsigned)batch);
+        dim3 grid((unsigned)std::min<long long>(((long long)h * row_v + 255) / 256, 64), (unsigned)batch);
         k_nhwc_paste<float4><<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(dst), h, row_v,
                                                   (long long)h * row / 4, (long long)dst_h * dst_row / 4, (int)(dst_row / 4),
                                                   dst_off / 4, relu, reinterpret_cast<const float4*>(bias), channels / 4);
     } else {
-        dim3 grid((unsigned)((row + 255) / 256), h, (unsigned)batch);
+        dim3 grid((unsigned)std::min<long long>((h * row + 255) / 256, 64), (unsigned)batch);
         k_nhwc_paste<float><<<grid, 256, 0, s>>>(src, dst, h, (int)row, (long long)h * row, (long long)dst_h * dst_row,
                                                  (int)dst_row, dst_off, relu, bias, channels);
     }
